@@ -1,0 +1,169 @@
+/*
+ * nettracer_b200.h — C ABI of the B200 intersect-and-shade path.
+ *
+ * Drop-in boundary.  The reference interface each entry point would
+ * replace CANNOT be cited: /root/reference holds a single README (README:1-3, a URL), so
+ * there is no Java render API to bind against.  The surface below is the one SURVEY.md
+ * §8(b) proposes — host (Java via Panama FFM / JNI, or any FFI) keeps scene parsing,
+ * camera set-up and image output and hands flat arrays across; see INTEGRATION.md.
+ *
+ * Rules: plain C types only; errors are negative ints (never exceptions); the text of
+ * the last error on the calling thread is nt_last_error(); there is no CPU fallback —
+ * every compute entry point fails with NT_ERR_NO_DEVICE when no sm_100 GPU is usable.
+ * The shading rules are SPEC-PROVISIONAL.md (this repository's own; parity with
+ * NetTracer is unpinned).
+ */
+#ifndef NETTRACER_B200_H
+#define NETTRACER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NT_ABI_VERSION 1
+
+enum nt_status {
+    NT_OK = 0,
+    NT_ERR_INVALID = -1,   /* bad argument / malformed scene */
+    NT_ERR_NO_DEVICE = -2, /* no usable sm_100 device */
+    NT_ERR_CUDA = -3,      /* CUDA runtime error, text in nt_last_error() */
+    NT_ERR_NOMEM = -4
+};
+
+enum nt_precision {
+    NT_F64_STRICT = 0, /* binary64, no FMA contraction, SPEC-PROVISIONAL §1-6 */
+    NT_F32_FAST = 1    /* binary32 fast mode, SPEC-PROVISIONAL §7 */
+};
+
+enum nt_layout {
+    NT_LAYOUT_FULL = 0,   /* pixel (x,y) at out + y*stride + 4*x; only owned rows are written */
+    NT_LAYOUT_COMPACT = 1 /* owned row bands packed back to back, stride bytes per row */
+};
+
+/* Camera resolved by the host (SPEC-PROVISIONAL §2). */
+typedef struct nt_camera {
+    double eye[3];
+    double p00[3];
+    double dx[3];
+    double dy[3];
+} nt_camera;
+
+/* Flat row-major arrays owned by the caller; nt_scene_create copies what it needs. */
+typedef struct nt_scene_desc {
+    uint32_t struct_size; /* sizeof(nt_scene_desc), for ABI evolution */
+    uint32_t n_spheres, n_planes, n_triangles, n_materials, n_lights;
+    const double *spheres;        /* [n_spheres][4]   cx cy cz r */
+    const int32_t *sphere_mat;    /* [n_spheres] */
+    const double *planes;         /* [n_planes][4]    nx ny nz d */
+    const int32_t *plane_mat;     /* [n_planes] */
+    const double *triangles;      /* [n_triangles][9] v0 v1 v2 */
+    const int32_t *triangle_mat;  /* [n_triangles] */
+    const double *materials;      /* [n_materials][10] r g b ka kd ks shininess kr kt ior */
+    const double *lights;         /* [n_lights][6]    px py pz r g b */
+    double ambient[3];
+    double background[3];
+} nt_scene_desc;
+
+typedef struct nt_render_params {
+    uint32_t struct_size; /* sizeof(nt_render_params) */
+    uint32_t width, height;
+    uint32_t spp;         /* perfect square, 1..64 */
+    uint32_t max_depth;   /* 1..NT_MAX_DEPTH; 1 = primary + shadow rays only */
+    uint32_t precision;   /* enum nt_precision */
+    double ray_epsilon;   /* <= 0 selects the default 1e-6 */
+    nt_camera camera;
+    /* Image sharding for multi-GPU: rows are cut into bands of band_rows rows; band b is
+     * owned by shard (b mod shard_count).  shard_count = 1 renders everything. */
+    uint32_t shard_index, shard_count, band_rows;
+    uint32_t layout;      /* enum nt_layout */
+} nt_render_params;
+
+#define NT_MAX_DEPTH 16
+
+typedef struct nt_render_stats {
+    uint64_t rays_primary;
+    uint64_t rays_secondary; /* reflection + transmission */
+    uint64_t rays_shadow;
+    /* Algorithmic work executed, by kind (the roofline numerators). */
+    uint64_t sphere_tests;
+    uint64_t plane_tests;
+    uint64_t triangle_tests;
+    uint64_t box_tests;      /* BVH child boxes tested (0 for flat scenes) */
+    uint64_t light_evals;    /* unoccluded light contributions shaded */
+    double kernel_ms;        /* device time of the render kernel(s), CUDA events; nt_render only */
+    double total_ms;         /* host wall time of the whole nt_render call */
+} nt_render_stats;
+
+typedef struct nt_scene nt_scene;
+
+/* ---- library ---- */
+int nt_abi_version(void);
+const char *nt_last_error(void);
+int nt_device_count(int *count);
+
+/* ---- scene ---- */
+/* Validates, derives per-primitive constants, builds the BVH when the scene has more bounded
+ * primitives than fit the flat kernel, and uploads to `device`. */
+int nt_scene_create(const nt_scene_desc *desc, int device, nt_scene **out);
+void nt_scene_destroy(nt_scene *scene);
+/* info[0]=uses_bvh info[1]=bvh_nodes info[2]=device_bytes info[3]=device */
+int nt_scene_info(const nt_scene *scene, uint64_t info[4]);
+
+/* ---- render ---- */
+/* Host buffer (pageable or pinned), blocking.  Renders the shard named in params, copies the
+ * result to rgba_out.  stats may be NULL. */
+int nt_render(nt_scene *scene, const nt_render_params *params, uint8_t *rgba_out,
+              size_t row_stride_bytes, nt_render_stats *stats);
+
+/* Device buffer on the scene's device, asynchronous on `cuda_stream` (a cudaStream_t, may be
+ * NULL for the default stream).  rgba_out_dev may be a peer-mapped pointer of another GPU
+ * (NVLink): with NT_LAYOUT_FULL every shard can store straight into one remote framebuffer. */
+int nt_render_device(nt_scene *scene, const nt_render_params *params, void *rgba_out_dev,
+                     size_t row_stride_bytes, void *cuda_stream);
+/* Synchronises `cuda_stream` and returns the counters of the last nt_render_device call. */
+int nt_render_device_stats(nt_scene *scene, void *cuda_stream, nt_render_stats *stats);
+
+/* ---- unit-level entry point (parity tests of the intersectors) ---- */
+/* Nearest hit of n rays (host arrays origins[n][3], dirs[n][3], used as given — not normalised)
+ * against the scene under SPEC-PROVISIONAL §3.  t_out[i] = hit distance or -1; prim_out[i] =
+ * global primitive id or -1.  precision as in nt_render_params; ray_epsilon <= 0 = default. */
+int nt_trace_rays(nt_scene *scene, uint32_t n, const double *origins, const double *dirs,
+                  uint32_t precision, double ray_epsilon, double *t_out, int32_t *prim_out);
+
+/* Rows a shard owns / bytes its compact buffer needs (pure host arithmetic). */
+uint32_t nt_shard_rows(uint32_t height, uint32_t band_rows, uint32_t shard_index,
+                       uint32_t shard_count);
+
+/* Rank-0 side of the gather: scatter `shard_count` compact buffers, laid out back to back with
+ * `shard_stride_bytes` between them, into a full frame.  Device pointers, async on stream. */
+int nt_deinterleave_device(const void *compact_all, size_t shard_stride_bytes, void *full_out,
+                           size_t row_stride_bytes, uint32_t width, uint32_t height,
+                           uint32_t band_rows, uint32_t shard_count, int device,
+                           void *cuda_stream);
+
+/* ---- peer framebuffer (NVLink store path) ---- */
+/* Export / open a CUDA IPC handle (64 bytes) for a device allocation, so that every rank's
+ * render kernel can store its pixels directly into rank 0's framebuffer. */
+int nt_ipc_export(const void *dev_ptr, int device, uint8_t handle_out[64]);
+int nt_ipc_open(const uint8_t handle[64], int device, void **dev_ptr_out);
+int nt_ipc_close(void *dev_ptr, int device);
+
+/* ---- roofline denominators ---- */
+typedef struct nt_peaks {
+    double f64_fma_gflops;   /* DFMA chain, 2 flops per instruction */
+    double f64_nofma_gflops; /* alternating DMUL / DADD, 1 flop per instruction */
+    double f32_fma_gflops;   /* FFMA chain */
+    double f32_nofma_gflops;
+    double sm_clock_mhz_est; /* clock64 ticks / elapsed time during the DFMA run */
+    int sm_count;
+} nt_peaks;
+/* Issue-rate micro-benchmark on all SMs of `device`: ~50 ms per figure. */
+int nt_measure_peaks(int device, nt_peaks *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NETTRACER_B200_H */

@@ -1,0 +1,83 @@
+"""ctypes mirror of include/nettracer_b200.h (the C-ABI drop-in boundary).
+
+No reference interface can be cited: /root/reference/README:1-3 is the whole reference.
+The same structs are consumed by the CUDA library and by the test-only CPU oracle.
+"""
+import ctypes as C
+
+NT_ABI_VERSION = 1
+NT_OK, NT_ERR_INVALID, NT_ERR_NO_DEVICE, NT_ERR_CUDA, NT_ERR_NOMEM = 0, -1, -2, -3, -4
+NT_F64_STRICT, NT_F32_FAST = 0, 1
+NT_LAYOUT_FULL, NT_LAYOUT_COMPACT = 0, 1
+NT_MAX_DEPTH = 16
+
+_pd = C.POINTER(C.c_double)
+_pi = C.POINTER(C.c_int32)
+
+
+class nt_camera(C.Structure):
+    _fields_ = [("eye", C.c_double * 3), ("p00", C.c_double * 3),
+                ("dx", C.c_double * 3), ("dy", C.c_double * 3)]
+
+
+class nt_scene_desc(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32),
+                ("n_spheres", C.c_uint32), ("n_planes", C.c_uint32), ("n_triangles", C.c_uint32),
+                ("n_materials", C.c_uint32), ("n_lights", C.c_uint32),
+                ("spheres", _pd), ("sphere_mat", _pi),
+                ("planes", _pd), ("plane_mat", _pi),
+                ("triangles", _pd), ("triangle_mat", _pi),
+                ("materials", _pd), ("lights", _pd),
+                ("ambient", C.c_double * 3), ("background", C.c_double * 3)]
+
+
+class nt_render_params(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32),
+                ("width", C.c_uint32), ("height", C.c_uint32),
+                ("spp", C.c_uint32), ("max_depth", C.c_uint32), ("precision", C.c_uint32),
+                ("ray_epsilon", C.c_double),
+                ("camera", nt_camera),
+                ("shard_index", C.c_uint32), ("shard_count", C.c_uint32), ("band_rows", C.c_uint32),
+                ("layout", C.c_uint32)]
+
+
+class nt_render_stats(C.Structure):
+    _fields_ = [("rays_primary", C.c_uint64), ("rays_secondary", C.c_uint64),
+                ("rays_shadow", C.c_uint64),
+                ("sphere_tests", C.c_uint64), ("plane_tests", C.c_uint64),
+                ("triangle_tests", C.c_uint64), ("box_tests", C.c_uint64),
+                ("light_evals", C.c_uint64),
+                ("kernel_ms", C.c_double), ("total_ms", C.c_double)]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["rays"] = self.rays_primary + self.rays_secondary + self.rays_shadow
+        return d
+
+
+class nt_peaks(C.Structure):
+    _fields_ = [("f64_fma_gflops", C.c_double), ("f64_nofma_gflops", C.c_double),
+                ("f32_fma_gflops", C.c_double), ("f32_nofma_gflops", C.c_double),
+                ("sm_clock_mhz_est", C.c_double), ("sm_count", C.c_int)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# Every symbol include/nettracer_b200.h declares (tests check the .so exports each one).
+EXPORTS = [
+    "nt_abi_version", "nt_last_error", "nt_device_count",
+    "nt_scene_create", "nt_scene_destroy", "nt_scene_info",
+    "nt_render", "nt_render_device", "nt_render_device_stats", "nt_trace_rays",
+    "nt_shard_rows", "nt_deinterleave_device",
+    "nt_ipc_export", "nt_ipc_open", "nt_ipc_close",
+    "nt_measure_peaks",
+]
+
+# Flop-counting convention fixed in SURVEY.md §8(d) (FMA = 2, div/sqrt = 1).
+FLOPS = {"sphere_tests": 17, "plane_tests": 11, "triangle_tests": 39, "box_tests": 18,
+         "light_evals": 40}
+
+
+def algorithmic_flops(stats: dict) -> int:
+    return sum(stats[k] * v for k, v in FLOPS.items())

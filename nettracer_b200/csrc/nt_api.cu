@@ -1,0 +1,472 @@
+// nt_api.cu — the C ABI of include/nettracer_b200.h: validation, scene flattening + upload,
+// launch configuration, host/device render entry points, sharding helpers, CUDA IPC wrappers.
+// Host logic only; the arithmetic lives in nt_trace.cuh.  No CPU fallback anywhere: every compute
+// entry point needs an sm_100 device and fails with NT_ERR_NO_DEVICE / NT_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/nettracer_b200.h"
+#include "nt_bvh.h"
+#include "nt_device.h"
+
+static_assert(NT_MAX_DEPTH == NT_MAX_DEPTH_DEV, "depth limits must agree");
+
+// ---------------- errors ----------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(NT_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));  \
+    } while (0)
+
+extern "C" int nt_abi_version(void) { return NT_ABI_VERSION; }
+extern "C" const char *nt_last_error(void) { return g_err; }
+
+extern "C" int nt_device_count(int *count) {
+    if (!count) return fail(NT_ERR_INVALID, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); *count = 0; return fail(NT_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    *count = n;
+    return NT_OK;
+}
+
+static int check_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { cudaGetLastError(); return fail(NT_ERR_NO_DEVICE, "no CUDA device (%s)", cudaGetErrorString(e)); }
+    if (device < 0 || device >= n) return fail(NT_ERR_NO_DEVICE, "device %d out of range (%d devices)", device, n);
+    int major = 0;
+    CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) return fail(NT_ERR_NO_DEVICE, "device %d is sm_%d0, this library is built for sm_100a only", device, major);
+    return NT_OK;
+}
+
+// ---------------- scene ----------------
+struct nt_scene {
+    int device = 0;
+    NtDevScene ds{};
+    std::vector<void *> allocs;
+    size_t device_bytes = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    unsigned long long *d_counters = nullptr, *h_counters = nullptr;
+    uint8_t *d_fb = nullptr;
+    size_t fb_bytes = 0;
+    std::mutex mu;
+};
+
+template <typename T>
+static int upload(nt_scene *sc, const std::vector<T> &v, const T **out) {
+    *out = nullptr;
+    const size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? NT_ERR_NOMEM : NT_ERR_CUDA, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    sc->allocs.push_back(p);
+    sc->device_bytes += bytes;
+    if (!v.empty()) CU(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T *)p;
+    return NT_OK;
+}
+
+static int validate_desc(const nt_scene_desc *d) {
+    if (!d) return fail(NT_ERR_INVALID, "desc is NULL");
+    if (d->struct_size != sizeof(nt_scene_desc)) return fail(NT_ERR_INVALID, "nt_scene_desc.struct_size %u != %zu", d->struct_size, sizeof(nt_scene_desc));
+    if (d->n_materials == 0 || !d->materials) return fail(NT_ERR_INVALID, "scene needs at least one material");
+    if ((d->n_spheres && (!d->spheres || !d->sphere_mat)) || (d->n_planes && (!d->planes || !d->plane_mat)) ||
+        (d->n_triangles && (!d->triangles || !d->triangle_mat)) || (d->n_lights && !d->lights))
+        return fail(NT_ERR_INVALID, "array pointer is NULL for a non-zero count");
+    for (uint32_t i = 0; i < d->n_spheres; ++i) {
+        if (d->sphere_mat[i] < 0 || (uint32_t)d->sphere_mat[i] >= d->n_materials) return fail(NT_ERR_INVALID, "sphere %u: material %d out of range", i, d->sphere_mat[i]);
+        const double *s = d->spheres + 4 * (size_t)i;
+        if (!(s[3] > 0) || !std::isfinite(s[0] + s[1] + s[2] + s[3])) return fail(NT_ERR_INVALID, "sphere %u: radius must be > 0 and all values finite", i);
+    }
+    for (uint32_t i = 0; i < d->n_planes; ++i) {
+        if (d->plane_mat[i] < 0 || (uint32_t)d->plane_mat[i] >= d->n_materials) return fail(NT_ERR_INVALID, "plane %u: material %d out of range", i, d->plane_mat[i]);
+        const double *p = d->planes + 4 * (size_t)i;
+        if (!std::isfinite(p[0] + p[1] + p[2] + p[3])) return fail(NT_ERR_INVALID, "plane %u: non-finite value", i);
+    }
+    for (uint32_t i = 0; i < d->n_triangles; ++i) {
+        if (d->triangle_mat[i] < 0 || (uint32_t)d->triangle_mat[i] >= d->n_materials) return fail(NT_ERR_INVALID, "triangle %u: material %d out of range", i, d->triangle_mat[i]);
+        const double *t = d->triangles + 9 * (size_t)i;
+        double sum = 0;
+        for (int k = 0; k < 9; ++k) sum += t[k];
+        if (!std::isfinite(sum)) return fail(NT_ERR_INVALID, "triangle %u: non-finite value", i);
+    }
+    return NT_OK;
+}
+
+static const size_t kSmemBudget = 40 * 1024;
+static const uint32_t kFlatMaxBounded = 64;
+
+extern "C" void nt_scene_destroy(nt_scene *sc) {
+    if (!sc) return;
+    cudaSetDevice(sc->device);
+    for (void *p : sc->allocs) cudaFree(p);
+    if (sc->d_fb) cudaFree(sc->d_fb);
+    if (sc->d_counters) cudaFree(sc->d_counters);
+    if (sc->h_counters) cudaFreeHost(sc->h_counters);
+    if (sc->ev0) cudaEventDestroy(sc->ev0);
+    if (sc->ev1) cudaEventDestroy(sc->ev1);
+    if (sc->stream) cudaStreamDestroy(sc->stream);
+    delete sc;
+}
+
+static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
+    CU(cudaSetDevice(device));
+    sc->device = device;
+    const uint32_t ns = d->n_spheres, np = d->n_planes, nt = d->n_triangles, nm = d->n_materials, nl = d->n_lights;
+
+    // flat (everything staged in shared memory) or BVH (bounded primitives in HBM behind a tree)
+    bool use_bvh = ns + nt > kFlatMaxBounded ||
+                   ((size_t)ns * 4 + (size_t)np * 4 + (size_t)nt * NT_TRI_STRIDE) * sizeof(double) > kSmemBudget;
+    if (const char *e = getenv("NT_BVH")) {
+        if (e[0] == '1') use_bvh = true;
+        else if (e[0] == '0' && ((size_t)ns * 4 + (size_t)np * 4 + (size_t)nt * NT_TRI_STRIDE) * sizeof(double) <= kSmemBudget) use_bvh = false;
+    }
+    if ((size_t)np * 4 * sizeof(double) > kSmemBudget) return fail(NT_ERR_INVALID, "too many planes (%u): planes are staged in shared memory, limit %zu", np, kSmemBudget / 32);
+
+    NtBvhBuild bvh;
+    std::vector<int> sph_order(ns), tri_order(nt);
+    for (uint32_t i = 0; i < ns; ++i) sph_order[i] = (int)i;
+    for (uint32_t i = 0; i < nt; ++i) tri_order[i] = (int)i;
+    if (use_bvh) {
+        int leaf_max = 4;
+        if (const char *e = getenv("NT_BVH_LEAF")) leaf_max = atoi(e);
+        nt_bvh_build(d->spheres, ns, d->triangles, nt, leaf_max, bvh);
+        sph_order = bvh.sph_order;
+        tri_order = bvh.tri_order;
+    }
+
+    // SPEC-PROVISIONAL §1 derived quantities, in binary64; the float view is the rounded double view
+    std::vector<double> sph(4 * (size_t)ns), sph_invr(ns), pln(4 * (size_t)np), tri(NT_TRI_STRIDE * (size_t)nt),
+        mat(NT_MAT_STRIDE * (size_t)nm), lights(6 * (size_t)nl), globals(8, 0.0);
+    std::vector<int> sph_mat(ns), sph_gid(ns), pln_mat(np), tri_mat(nt), tri_gid(nt);
+    for (uint32_t k = 0; k < ns; ++k) {
+        const int i = sph_order[k];
+        const double *s = d->spheres + 4 * (size_t)i;
+        sph[4 * (size_t)k] = s[0]; sph[4 * (size_t)k + 1] = s[1]; sph[4 * (size_t)k + 2] = s[2];
+        sph[4 * (size_t)k + 3] = s[3] * s[3];
+        sph_invr[k] = 1.0 / s[3];
+        sph_mat[k] = d->sphere_mat[i];
+        sph_gid[k] = i;
+    }
+    for (uint32_t i = 0; i < np; ++i) {
+        for (int k = 0; k < 4; ++k) pln[4 * (size_t)i + k] = d->planes[4 * (size_t)i + k];
+        pln_mat[i] = d->plane_mat[i];
+    }
+    for (uint32_t k = 0; k < nt; ++k) {
+        const int i = tri_order[k];
+        const double *t = d->triangles + 9 * (size_t)i;
+        double *o = tri.data() + NT_TRI_STRIDE * (size_t)k;
+        const double e1[3] = { t[3] - t[0], t[4] - t[1], t[5] - t[2] }, e2[3] = { t[6] - t[0], t[7] - t[1], t[8] - t[2] };
+        const double c[3] = { e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0] };
+        const double inv = 1.0 / std::sqrt((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
+        for (int a = 0; a < 3; ++a) { o[a] = t[a]; o[3 + a] = e1[a]; o[6 + a] = e2[a]; o[9 + a] = c[a] * inv; }
+        tri_mat[k] = d->triangle_mat[i];
+        tri_gid[k] = (int)(ns + np) + i;
+    }
+    for (uint32_t i = 0; i < nm; ++i) {
+        const double *m = d->materials + 10 * (size_t)i;
+        double *o = mat.data() + NT_MAT_STRIDE * (size_t)i;
+        for (int k = 0; k < 10; ++k) o[k] = m[k];
+        o[10] = 1.0 / m[9];
+        o[11] = 0;
+    }
+    for (size_t i = 0; i < 6 * (size_t)nl; ++i) lights[i] = d->lights[i];
+    for (int k = 0; k < 3; ++k) { globals[k] = d->ambient[k]; globals[3 + k] = d->background[k]; }
+
+    auto to_f = [](const std::vector<double> &v) { std::vector<float> f(v.size()); for (size_t i = 0; i < v.size(); ++i) f[i] = (float)v[i]; return f; };
+    NtDevScene &ds = sc->ds;
+    ds.ns = ns; ds.np = np; ds.nt = nt; ds.nm = nm; ds.nl = nl;
+    ds.use_bvh = use_bvh ? 1 : 0;
+    ds.n_nodes = use_bvh && ns + nt > 0 ? (uint32_t)bvh.nodes.size() : 0;
+    ds.max_abs = bvh.max_abs;
+    int rc;
+#define UP(vec, dst) if ((rc = upload(sc, vec, &(dst))) != NT_OK) return rc
+    UP(sph, ds.v64.sph); UP(sph_invr, ds.v64.sph_invr); UP(pln, ds.v64.pln); UP(tri, ds.v64.tri);
+    UP(mat, ds.v64.mat); UP(lights, ds.v64.lights); UP(globals, ds.v64.globals);
+    const std::vector<float> fsph = to_f(sph), fir = to_f(sph_invr), fpln = to_f(pln), ftri = to_f(tri),
+                             fmat = to_f(mat), fl = to_f(lights), fg = to_f(globals);
+    UP(fsph, ds.v32.sph); UP(fir, ds.v32.sph_invr); UP(fpln, ds.v32.pln); UP(ftri, ds.v32.tri);
+    UP(fmat, ds.v32.mat); UP(fl, ds.v32.lights); UP(fg, ds.v32.globals);
+    UP(sph_mat, ds.sph_mat); UP(sph_gid, ds.sph_gid); UP(pln_mat, ds.pln_mat); UP(tri_mat, ds.tri_mat); UP(tri_gid, ds.tri_gid);
+    UP(bvh.nodes, ds.nodes);
+#undef UP
+    CU(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&sc->ev0));
+    CU(cudaEventCreate(&sc->ev1));
+    CU(cudaMalloc(&sc->d_counters, sizeof(unsigned long long) * NT_COUNTER_SLOTS * NT_NCOUNTERS));
+    CU(cudaMallocHost(&sc->h_counters, sizeof(unsigned long long) * NT_COUNTER_SLOTS * NT_NCOUNTERS));
+    return NT_OK;
+}
+
+extern "C" int nt_scene_create(const nt_scene_desc *desc, int device, nt_scene **out) {
+    if (!out) return fail(NT_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int rc = validate_desc(desc);
+    if (rc) return rc;
+    if ((rc = check_device(device)) != NT_OK) return rc;
+    nt_scene *sc = new (std::nothrow) nt_scene;
+    if (!sc) return fail(NT_ERR_NOMEM, "out of host memory");
+    rc = scene_create_impl(desc, device, sc);
+    if (rc) { nt_scene_destroy(sc); return rc; }
+    *out = sc;
+    return NT_OK;
+}
+
+extern "C" int nt_scene_info(const nt_scene *sc, uint64_t info[4]) {
+    if (!sc || !info) return fail(NT_ERR_INVALID, "NULL argument");
+    info[0] = sc->ds.use_bvh; info[1] = sc->ds.n_nodes; info[2] = sc->device_bytes; info[3] = (uint64_t)sc->device;
+    return NT_OK;
+}
+
+// ---------------- sharding arithmetic ----------------
+extern "C" uint32_t nt_shard_rows(uint32_t height, uint32_t band_rows, uint32_t shard_index, uint32_t shard_count) {
+    if (band_rows == 0 || shard_count == 0 || shard_index >= shard_count) return 0;
+    const uint32_t nb = (height + band_rows - 1) / band_rows;
+    uint32_t rows = 0;
+    for (uint32_t b = shard_index; b < nb; b += shard_count) {
+        const uint32_t y0 = b * band_rows, y1 = y0 + band_rows > height ? height : y0 + band_rows;
+        rows += y1 - y0;
+    }
+    return rows;
+}
+
+// ---------------- render ----------------
+static int make_args(const nt_render_params *p, size_t stride, NtRenderArgs *a) {
+    if (!p) return fail(NT_ERR_INVALID, "params is NULL");
+    if (p->struct_size != sizeof(nt_render_params)) return fail(NT_ERR_INVALID, "nt_render_params.struct_size %u != %zu", p->struct_size, sizeof(nt_render_params));
+    if (p->width == 0 || p->height == 0 || p->width > 65536 || p->height > 65536) return fail(NT_ERR_INVALID, "bad image size %ux%u", p->width, p->height);
+    uint32_t n = 0;
+    for (uint32_t k = 1; k <= 8; ++k) if (k * k == p->spp) n = k;
+    if (!n) return fail(NT_ERR_INVALID, "spp %u is not a perfect square in 1..64", p->spp);
+    if (p->max_depth < 1 || p->max_depth > NT_MAX_DEPTH) return fail(NT_ERR_INVALID, "max_depth %u not in 1..%d", p->max_depth, NT_MAX_DEPTH);
+    if (p->precision != NT_F64_STRICT && p->precision != NT_F32_FAST) return fail(NT_ERR_INVALID, "unknown precision %u", p->precision);
+    if (p->layout != NT_LAYOUT_FULL && p->layout != NT_LAYOUT_COMPACT) return fail(NT_ERR_INVALID, "unknown layout %u", p->layout);
+    const uint32_t scount = p->shard_count ? p->shard_count : 1, band = p->band_rows ? p->band_rows : 1;
+    if (p->shard_index >= scount) return fail(NT_ERR_INVALID, "shard_index %u >= shard_count %u", p->shard_index, scount);
+    if (stride < (size_t)p->width * 4 || stride % 4) return fail(NT_ERR_INVALID, "row stride %zu must be >= 4*width and a multiple of 4", stride);
+    memset(a, 0, sizeof *a);
+    a->width = p->width; a->height = p->height; a->spp = p->spp; a->n = n; a->max_depth = p->max_depth;
+    a->shard_index = p->shard_index; a->shard_count = scount; a->band_rows = band; a->layout = p->layout;
+    a->vrows = nt_shard_rows(p->height, band, p->shard_index, scount);
+    uint32_t L = 1;
+    while (L < 32 && p->spp % (L * 2) == 0) L *= 2;
+    a->lanes = L;
+    static const uint32_t tw[6][2] = { { 8, 4 }, { 4, 4 }, { 4, 2 }, { 2, 2 }, { 2, 1 }, { 1, 1 } }; // L = 1,2,4,8,16,32
+    int li = 0;
+    while ((1u << li) < L) ++li;
+    a->twx = tw[li][0]; a->twy = tw[li][1];
+    a->tiles_x = (p->width + 4 * a->twx - 1) / (4 * a->twx);
+    a->tiles_y = (a->vrows + 2 * a->twy - 1) / (2 * a->twy);
+    a->eps = p->ray_epsilon > 0 ? p->ray_epsilon : 1e-6;
+    if (p->precision == NT_F32_FAST && a->eps < 1e-4) a->eps = 1e-4; // SPEC-PROVISIONAL §7
+    for (int k = 0; k < 3; ++k) {
+        a->cam[k] = p->camera.eye[k]; a->cam[3 + k] = p->camera.p00[k];
+        a->cam[6 + k] = p->camera.dx[k]; a->cam[9 + k] = p->camera.dy[k];
+    }
+    a->stride = stride;
+    return NT_OK;
+}
+
+static int launch(nt_scene *sc, const NtRenderArgs &a, uint32_t precision, cudaStream_t st) {
+    if (a.vrows == 0) return NT_OK;
+    if (a.tiles_y > 65535) return fail(NT_ERR_INVALID, "image too tall for one launch (%u row tiles)", a.tiles_y);
+    const int e = precision == NT_F64_STRICT ? nt_launch_render_f64(sc->ds, a, st) : nt_launch_render_f32(sc->ds, a, st);
+    if (e) return fail(NT_ERR_CUDA, "render kernel launch: %s", cudaGetErrorString((cudaError_t)e));
+    return NT_OK;
+}
+
+static void sum_counters(const unsigned long long *h, nt_render_stats *s) {
+    unsigned long long t[NT_NCOUNTERS] = { 0 };
+    for (int slot = 0; slot < NT_COUNTER_SLOTS; ++slot)
+        for (int i = 0; i < NT_NCOUNTERS; ++i) t[i] += h[slot * NT_NCOUNTERS + i];
+    s->rays_primary = t[0]; s->rays_secondary = t[1]; s->rays_shadow = t[2];
+    s->sphere_tests = t[3]; s->plane_tests = t[4]; s->triangle_tests = t[5]; s->box_tests = t[6]; s->light_evals = t[7];
+}
+
+extern "C" int nt_render(nt_scene *sc, const nt_render_params *p, uint8_t *rgba_out, size_t stride,
+                         nt_render_stats *stats) {
+    if (!sc || !rgba_out) return fail(NT_ERR_INVALID, "NULL argument");
+    const auto t0 = std::chrono::steady_clock::now();
+    std::lock_guard<std::mutex> lock(sc->mu);
+    NtRenderArgs a;
+    int rc = make_args(p, (size_t)(p ? p->width : 0) * 4, &a); // device frame is tightly packed
+    if (rc) return rc;
+    if (stride < (size_t)p->width * 4) return fail(NT_ERR_INVALID, "row stride %zu < 4*width", stride);
+    CU(cudaSetDevice(sc->device));
+    const size_t pitch = (size_t)p->width * 4;
+    const uint32_t out_rows = p->layout == NT_LAYOUT_COMPACT ? a.vrows : p->height;
+    const size_t need = pitch * out_rows;
+    if (need > sc->fb_bytes) {
+        if (sc->d_fb) cudaFree(sc->d_fb);
+        sc->d_fb = nullptr; sc->fb_bytes = 0;
+        cudaError_t e = cudaMalloc((void **)&sc->d_fb, need);
+        if (e != cudaSuccess) return fail(NT_ERR_NOMEM, "framebuffer cudaMalloc(%zu): %s", need, cudaGetErrorString(e));
+        sc->fb_bytes = need;
+    }
+    a.out = sc->d_fb;
+    a.counters = sc->d_counters;
+    const size_t cbytes = sizeof(unsigned long long) * NT_COUNTER_SLOTS * NT_NCOUNTERS;
+    CU(cudaMemsetAsync(sc->d_counters, 0, cbytes, sc->stream));
+    CU(cudaEventRecord(sc->ev0, sc->stream));
+    if ((rc = launch(sc, a, p->precision, sc->stream)) != NT_OK) return rc;
+    CU(cudaEventRecord(sc->ev1, sc->stream));
+    if (a.vrows) {
+        if (p->layout == NT_LAYOUT_COMPACT || a.shard_count == 1) {
+            CU(cudaMemcpy2DAsync(rgba_out, stride, sc->d_fb, pitch, pitch, out_rows, cudaMemcpyDeviceToHost, sc->stream));
+        } else { // full layout, sharded: only the owned bands reach the caller's buffer
+            const uint32_t nb = (p->height + a.band_rows - 1) / a.band_rows;
+            for (uint32_t b = a.shard_index; b < nb; b += a.shard_count) {
+                const uint32_t y0 = b * a.band_rows, y1 = std::min(p->height, y0 + a.band_rows);
+                CU(cudaMemcpy2DAsync(rgba_out + (size_t)y0 * stride, stride, sc->d_fb + (size_t)y0 * pitch, pitch, pitch, y1 - y0, cudaMemcpyDeviceToHost, sc->stream));
+            }
+        }
+    }
+    CU(cudaMemcpyAsync(sc->h_counters, sc->d_counters, cbytes, cudaMemcpyDeviceToHost, sc->stream));
+    CU(cudaStreamSynchronize(sc->stream));
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        sum_counters(sc->h_counters, stats);
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, sc->ev0, sc->ev1));
+        stats->kernel_ms = ms;
+        stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return NT_OK;
+}
+
+extern "C" int nt_render_device(nt_scene *sc, const nt_render_params *p, void *rgba_out_dev, size_t stride,
+                                void *cuda_stream) {
+    if (!sc || !rgba_out_dev) return fail(NT_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lock(sc->mu);
+    NtRenderArgs a;
+    int rc = make_args(p, stride, &a);
+    if (rc) return rc;
+    if (((uintptr_t)rgba_out_dev) % 4) return fail(NT_ERR_INVALID, "output pointer must be 4-byte aligned");
+    CU(cudaSetDevice(sc->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    a.out = (uint8_t *)rgba_out_dev;
+    a.counters = sc->d_counters;
+    CU(cudaMemsetAsync(sc->d_counters, 0, sizeof(unsigned long long) * NT_COUNTER_SLOTS * NT_NCOUNTERS, st));
+    return launch(sc, a, p->precision, st);
+}
+
+extern "C" int nt_render_device_stats(nt_scene *sc, void *cuda_stream, nt_render_stats *stats) {
+    if (!sc || !stats) return fail(NT_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lock(sc->mu);
+    CU(cudaSetDevice(sc->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CU(cudaMemcpyAsync(sc->h_counters, sc->d_counters, sizeof(unsigned long long) * NT_COUNTER_SLOTS * NT_NCOUNTERS, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memset(stats, 0, sizeof *stats);
+    sum_counters(sc->h_counters, stats);
+    return NT_OK;
+}
+
+// ---------------- unit-level nearest-hit queries ----------------
+extern "C" int nt_trace_rays(nt_scene *sc, uint32_t n, const double *origins, const double *dirs, uint32_t precision,
+                             double ray_epsilon, double *t_out, int32_t *prim_out) {
+    if (!sc || (n && (!origins || !dirs || !t_out || !prim_out))) return fail(NT_ERR_INVALID, "NULL argument");
+    if (precision != NT_F64_STRICT && precision != NT_F32_FAST) return fail(NT_ERR_INVALID, "unknown precision %u", precision);
+    if (n == 0) return NT_OK;
+    std::lock_guard<std::mutex> lock(sc->mu);
+    CU(cudaSetDevice(sc->device));
+    double *d_o = nullptr, *d_d = nullptr, *d_t = nullptr;
+    int *d_p = nullptr;
+    const size_t vb = sizeof(double) * 3 * (size_t)n;
+    int rc = NT_OK;
+    do {
+        cudaError_t e;
+        if ((e = cudaMalloc((void **)&d_o, vb)) || (e = cudaMalloc((void **)&d_d, vb)) || (e = cudaMalloc((void **)&d_t, sizeof(double) * n)) ||
+            (e = cudaMalloc((void **)&d_p, sizeof(int) * n))) { rc = fail(NT_ERR_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); break; }
+        if ((e = cudaMemcpyAsync(d_o, origins, vb, cudaMemcpyHostToDevice, sc->stream)) || (e = cudaMemcpyAsync(d_d, dirs, vb, cudaMemcpyHostToDevice, sc->stream))) {
+            rc = fail(NT_ERR_CUDA, "H2D: %s", cudaGetErrorString(e)); break;
+        }
+        NtTraceArgs a;
+        a.n = n;
+        a.eps = ray_epsilon > 0 ? ray_epsilon : 1e-6;
+        if (precision == NT_F32_FAST && a.eps < 1e-4) a.eps = 1e-4;
+        a.origins = d_o; a.dirs = d_d; a.t_out = d_t; a.prim_out = d_p;
+        const int le = precision == NT_F64_STRICT ? nt_launch_trace_f64(sc->ds, a, sc->stream) : nt_launch_trace_f32(sc->ds, a, sc->stream);
+        if (le) { rc = fail(NT_ERR_CUDA, "trace kernel launch: %s", cudaGetErrorString((cudaError_t)le)); break; }
+        if ((e = cudaMemcpyAsync(t_out, d_t, sizeof(double) * n, cudaMemcpyDeviceToHost, sc->stream)) ||
+            (e = cudaMemcpyAsync(prim_out, d_p, sizeof(int) * n, cudaMemcpyDeviceToHost, sc->stream)) || (e = cudaStreamSynchronize(sc->stream))) {
+            rc = fail(NT_ERR_CUDA, "D2H: %s", cudaGetErrorString(e)); break;
+        }
+    } while (0);
+    cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_p);
+    return rc;
+}
+
+// ---------------- gather helper: compact shard buffers -> full frame ----------------
+__global__ void deinterleave_kernel(const uint32_t *__restrict__ compact, size_t shard_stride_words, uint32_t *__restrict__ full,
+                                    size_t row_stride_words, uint32_t width, uint32_t height, uint32_t band, uint32_t shards) {
+    const uint32_t y = blockIdx.y;
+    const uint32_t b = y / band, shard = b % shards, vr = (b / shards) * band + y % band;
+    const uint32_t *src = compact + shard * shard_stride_words + (size_t)vr * width;
+    uint32_t *dst = full + (size_t)y * row_stride_words;
+    for (uint32_t x = blockIdx.x * blockDim.x + threadIdx.x; x < width; x += gridDim.x * blockDim.x) dst[x] = __ldg(src + x);
+}
+
+extern "C" int nt_deinterleave_device(const void *compact_all, size_t shard_stride_bytes, void *full_out, size_t row_stride_bytes,
+                                      uint32_t width, uint32_t height, uint32_t band_rows, uint32_t shard_count, int device,
+                                      void *cuda_stream) {
+    if (!compact_all || !full_out || !width || !height || !band_rows || !shard_count) return fail(NT_ERR_INVALID, "bad argument");
+    if (shard_stride_bytes % 4 || row_stride_bytes % 4 || row_stride_bytes < (size_t)width * 4) return fail(NT_ERR_INVALID, "strides must be multiples of 4 and >= 4*width");
+    if (height > 65535) return fail(NT_ERR_INVALID, "height %u too large", height);
+    int rc = check_device(device);
+    if (rc) return rc;
+    CU(cudaSetDevice(device));
+    dim3 grid((width + 255) / 256 > 8 ? 8 : (width + 255) / 256, height), block(256);
+    deinterleave_kernel<<<grid, block, 0, (cudaStream_t)cuda_stream>>>((const uint32_t *)compact_all, shard_stride_bytes / 4, (uint32_t *)full_out,
+                                                                       row_stride_bytes / 4, width, height, band_rows, shard_count);
+    CU(cudaGetLastError());
+    return NT_OK;
+}
+
+// ---------------- CUDA IPC (peer framebuffer over NVLink) ----------------
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+
+extern "C" int nt_ipc_export(const void *dev_ptr, int device, uint8_t handle_out[64]) {
+    if (!dev_ptr || !handle_out) return fail(NT_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, (void *)dev_ptr));
+    memcpy(handle_out, &h, 64);
+    return NT_OK;
+}
+
+extern "C" int nt_ipc_open(const uint8_t handle[64], int device, void **dev_ptr_out) {
+    if (!handle || !dev_ptr_out) return fail(NT_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(dev_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return NT_OK;
+}
+
+extern "C" int nt_ipc_close(void *dev_ptr, int device) {
+    if (!dev_ptr) return fail(NT_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(device));
+    CU(cudaIpcCloseMemHandle(dev_ptr));
+    return NT_OK;
+}

@@ -1,0 +1,169 @@
+// nt_bvh.cpp — host-side BVH2 builder (binned SAH, 16 bins) for the bounded primitives of a scene.
+// Two trees (spheres, triangles) hang off one root so every leaf holds a single primitive kind and
+// indexes a contiguous run of the BVH-ordered device array of that kind.
+// Boxes are float, rounded outward: they may only ever cull (SPEC-PROVISIONAL §3 "conservative
+// culling only").  On-GPU build is SURVEY.md §8 row (f3), not this round.
+#include "nt_bvh.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+namespace {
+
+struct Box {
+    float lo[3], hi[3];
+    void reset() {
+        for (int a = 0; a < 3; ++a) { lo[a] = std::numeric_limits<float>::infinity(); hi[a] = -lo[a]; }
+    }
+    void grow(const Box &b) {
+        for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); }
+    }
+    float half_area() const {
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        return dx * dy + dy * dz + dz * dx;
+    }
+};
+
+inline float f_down(double x) {
+    float f = (float)x;
+    return (double)f > x ? std::nextafterf(f, -std::numeric_limits<float>::infinity()) : f;
+}
+inline float f_up(double x) {
+    float f = (float)x;
+    return (double)f < x ? std::nextafterf(f, std::numeric_limits<float>::infinity()) : f;
+}
+
+struct Ref { Box box; int c; int n; };
+
+struct Builder {
+    std::vector<NtBvhNode> &nodes;
+    const std::vector<Box> &boxes;
+    std::vector<float> cen[3];
+    std::vector<int> &order;
+    int type_flag, leaf_max;
+
+    Builder(std::vector<NtBvhNode> &n, const std::vector<Box> &b, std::vector<int> &o, int tf, int lm)
+        : nodes(n), boxes(b), order(o), type_flag(tf), leaf_max(lm) {
+        for (int a = 0; a < 3; ++a) {
+            cen[a].resize(b.size());
+            for (size_t i = 0; i < b.size(); ++i) cen[a][i] = 0.5f * (b[i].lo[a] + b[i].hi[a]);
+        }
+    }
+
+    Ref build(int b, int e, int depth) {
+        Box bounds, cb;
+        bounds.reset(); cb.reset();
+        for (int i = b; i < e; ++i) {
+            const int p = order[i];
+            bounds.grow(boxes[p]);
+            for (int a = 0; a < 3; ++a) { cb.lo[a] = std::min(cb.lo[a], cen[a][p]); cb.hi[a] = std::max(cb.hi[a], cen[a][p]); }
+        }
+        const int count = e - b;
+        if (count <= leaf_max) return Ref{ bounds, b, count | type_flag };
+
+        int mid = -1;
+        if (depth < 40) {
+            constexpr int NB = 16;
+            float best_cost = std::numeric_limits<float>::infinity();
+            int best_axis = -1, best_bin = -1;
+            for (int a = 0; a < 3; ++a) {
+                const float ext = cb.hi[a] - cb.lo[a];
+                if (!(ext > 0)) continue;
+                Box bb[NB]; int bc[NB];
+                for (int i = 0; i < NB; ++i) { bb[i].reset(); bc[i] = 0; }
+                const float sc = NB / ext;
+                for (int i = b; i < e; ++i) {
+                    const int p = order[i];
+                    int bi = (int)((cen[a][p] - cb.lo[a]) * sc);
+                    bi = bi < 0 ? 0 : bi >= NB ? NB - 1 : bi;
+                    bb[bi].grow(boxes[p]); bc[bi]++;
+                }
+                float ra[NB]; int rc[NB];
+                Box acc; acc.reset(); int cnt = 0;
+                for (int i = NB - 1; i > 0; --i) { acc.grow(bb[i]); cnt += bc[i]; ra[i] = acc.half_area(); rc[i] = cnt; }
+                acc.reset(); cnt = 0;
+                for (int i = 0; i < NB - 1; ++i) {
+                    acc.grow(bb[i]); cnt += bc[i];
+                    if (cnt == 0 || rc[i + 1] == 0) continue;
+                    const float cost = acc.half_area() * cnt + ra[i + 1] * rc[i + 1];
+                    if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = i; }
+                }
+            }
+            if (best_axis >= 0) {
+                const int a = best_axis;
+                const float sc = 16 / (cb.hi[a] - cb.lo[a]), lo = cb.lo[a];
+                auto it = std::partition(order.begin() + b, order.begin() + e, [&](int p) {
+                    int bi = (int)((cen[a][p] - lo) * sc);
+                    bi = bi < 0 ? 0 : bi >= 16 ? 15 : bi;
+                    return bi <= best_bin;
+                });
+                mid = (int)(it - order.begin());
+                if (mid == b || mid == e) mid = -1;
+            }
+        }
+        if (mid < 0) { // degenerate or too deep: median split on the widest centroid axis
+            int a = 0;
+            if (cb.hi[1] - cb.lo[1] > cb.hi[a] - cb.lo[a]) a = 1;
+            if (cb.hi[2] - cb.lo[2] > cb.hi[a] - cb.lo[a]) a = 2;
+            mid = b + count / 2;
+            std::nth_element(order.begin() + b, order.begin() + mid, order.begin() + e,
+                             [&](int x, int y) { return cen[a][x] < cen[a][y]; });
+        }
+        const int id = (int)nodes.size();
+        nodes.emplace_back();
+        const Ref l = build(b, mid, depth + 1), r = build(mid, e, depth + 1);
+        nt_bvh_set_children(nodes[id], l.box.lo, l.box.hi, l.c, l.n, r.box.lo, r.box.hi, r.c, r.n);
+        return Ref{ bounds, id, 0 };
+    }
+};
+
+Ref build_set(std::vector<NtBvhNode> &nodes, const std::vector<Box> &boxes, std::vector<int> &order,
+              int type_flag, int leaf_max) {
+    order.resize(boxes.size());
+    for (size_t i = 0; i < boxes.size(); ++i) order[i] = (int)i;
+    if (boxes.empty()) {
+        Ref r; r.box.reset(); r.c = 0; r.n = -1;
+        return r;
+    }
+    Builder bld(nodes, boxes, order, type_flag, leaf_max);
+    return bld.build(0, (int)boxes.size(), 0);
+}
+
+} // namespace
+
+void nt_bvh_set_children(NtBvhNode &n, const float *lo0, const float *hi0, int c0, int n0,
+                         const float *lo1, const float *hi1, int c1, int n1) {
+    for (int a = 0; a < 3; ++a) { n.lo0[a] = lo0[a]; n.hi0[a] = hi0[a]; n.lo1[a] = lo1[a]; n.hi1[a] = hi1[a]; }
+    n.c0 = c0; n.c1 = c1; n.n0 = n0; n.n1 = n1;
+}
+
+void nt_bvh_build(const double *spheres, uint32_t ns, const double *triangles, uint32_t nt,
+                  int leaf_max, NtBvhBuild &out) {
+    if (leaf_max < 1) leaf_max = 1;
+    if (leaf_max > 255) leaf_max = 255;
+    std::vector<Box> sb(ns), tb(nt);
+    float max_abs = 0;
+    for (uint32_t i = 0; i < ns; ++i) {
+        const double *s = spheres + 4 * (size_t)i;
+        for (int a = 0; a < 3; ++a) { sb[i].lo[a] = f_down(s[a] - s[3]); sb[i].hi[a] = f_up(s[a] + s[3]); }
+    }
+    for (uint32_t i = 0; i < nt; ++i) {
+        const double *t = triangles + 9 * (size_t)i;
+        for (int a = 0; a < 3; ++a) {
+            tb[i].lo[a] = f_down(std::min(t[a], std::min(t[3 + a], t[6 + a])));
+            tb[i].hi[a] = f_up(std::max(t[a], std::max(t[3 + a], t[6 + a])));
+        }
+    }
+    for (const auto *v : { &sb, &tb })
+        for (const Box &b : *v)
+            for (int a = 0; a < 3; ++a) max_abs = std::max(max_abs, std::max(std::fabs(b.lo[a]), std::fabs(b.hi[a])));
+    out.nodes.clear();
+    out.nodes.reserve((size_t)(ns + nt) / 2 + 8);
+    out.nodes.emplace_back(); // root joins the two trees
+    const Ref rs = build_set(out.nodes, sb, out.sph_order, 0, leaf_max);
+    const Ref rt = build_set(out.nodes, tb, out.tri_order, 0x100, leaf_max);
+    nt_bvh_set_children(out.nodes[0], rs.box.lo, rs.box.hi, rs.c, rs.n, rt.box.lo, rt.box.hi, rt.c, rt.n);
+    out.max_abs = max_abs;
+}

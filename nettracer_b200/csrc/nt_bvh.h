@@ -1,0 +1,18 @@
+// nt_bvh.h — host BVH builder interface (see nt_bvh.cpp).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "nt_device.h"
+
+struct NtBvhBuild {
+    std::vector<NtBvhNode> nodes;  // nodes[0] is the root
+    std::vector<int> sph_order;    // BVH-ordered position -> original sphere index
+    std::vector<int> tri_order;    // BVH-ordered position -> original triangle index
+    float max_abs = 0;
+};
+
+void nt_bvh_set_children(NtBvhNode &n, const float *lo0, const float *hi0, int c0, int n0,
+                         const float *lo1, const float *hi1, int c1, int n1);
+void nt_bvh_build(const double *spheres, uint32_t ns, const double *triangles, uint32_t nt,
+                  int leaf_max, NtBvhBuild &out);

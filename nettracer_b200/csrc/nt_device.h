@@ -1,0 +1,74 @@
+// nt_device.h — structs shared by the host API (nt_api.cu) and the kernels (nt_trace.cuh).
+// Data layout in HBM is documented in DESIGN.md §3.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+#define NT_TRI_STRIDE 12   // v0[3] e1[3] e2[3] ng[3]  (R units; 16-byte aligned rows)
+#define NT_MAT_STRIDE 12   // r g b ka kd ks shininess kr kt ior inv_ior pad
+#define NT_COUNTER_SLOTS 32
+#define NT_NCOUNTERS 8     // primary secondary shadow sphere plane triangle box light
+#define NT_BLOCK_THREADS 256
+#define NT_BVH_STACK 64
+#define NT_MAX_DEPTH_DEV 16 // == NT_MAX_DEPTH of the public header
+
+// 64-byte BVH2 node: both child boxes (float, rounded outward) + child links.
+//   q0 = lo0.x lo0.y lo0.z hi0.x | q1 = hi0.y hi0.z lo1.x lo1.y | q2 = lo1.z hi1.x hi1.y hi1.z
+//   q3 = c0 c1 n0 n1 (ints).  n == 0: inner child, c = node index.  n > 0: leaf, c = first
+//   primitive (index into the BVH-ordered sphere or triangle array), n & 0xff = count,
+//   n & 0x100 = triangles (else spheres).  n < 0: empty child.
+struct NtBvhNode {
+    float lo0[3], hi0[3];
+    float lo1[3], hi1[3];
+    int c0, c1, n0, n1;
+};
+static_assert(sizeof(NtBvhNode) == 64, "node must be 64 bytes");
+
+template <typename R>
+struct NtSceneView {
+    const R *sph;      // [ns][4]  cx cy cz r2
+    const R *sph_invr; // [ns]
+    const R *pln;      // [np][4]  nx ny nz d
+    const R *tri;      // [nt][NT_TRI_STRIDE]
+    const R *mat;      // [nm][NT_MAT_STRIDE]
+    const R *lights;   // [nl][6]
+    const R *globals;  // ambient[3] background[3] pad[2]
+};
+
+struct NtDevScene {
+    uint32_t ns, np, nt, nm, nl;
+    uint32_t use_bvh, n_nodes;
+    float max_abs; // largest |coordinate| of any bounded primitive (box-test margin)
+    const int *sph_mat, *sph_gid, *pln_mat, *tri_mat, *tri_gid;
+    const NtBvhNode *nodes;
+    NtSceneView<double> v64;
+    NtSceneView<float> v32;
+};
+
+struct NtRenderArgs {
+    uint32_t width, height, spp, n, max_depth;
+    uint32_t shard_index, shard_count, band_rows, layout, vrows;
+    uint32_t lanes;    // lanes per pixel (power of two dividing spp, <= 32)
+    uint32_t twx, twy; // warp tile in pixels, twx*twy*lanes == 32
+    uint32_t tiles_x, tiles_y; // block tiles over the virtual image
+    double eps;
+    double cam[12];    // eye p00 dx dy
+    uint8_t *out;
+    size_t stride;
+    unsigned long long *counters; // [NT_COUNTER_SLOTS][NT_NCOUNTERS]
+};
+
+struct NtTraceArgs {
+    uint32_t n;
+    double eps;
+    const double *origins, *dirs;
+    double *t_out;
+    int *prim_out;
+};
+
+// Launchers, one translation unit per precision (strict: -fmad=false; fast: FMA + fast math).
+int nt_launch_render_f64(const NtDevScene &s, const NtRenderArgs &a, void *stream);
+int nt_launch_render_f32(const NtDevScene &s, const NtRenderArgs &a, void *stream);
+int nt_launch_trace_f64(const NtDevScene &s, const NtTraceArgs &a, void *stream);
+int nt_launch_trace_f32(const NtDevScene &s, const NtTraceArgs &a, void *stream);
+size_t nt_flat_smem_bytes(const NtDevScene &s, int precision);

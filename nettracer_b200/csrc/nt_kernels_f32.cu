@@ -1,0 +1,13 @@
+// Fast binary32 instantiation (SPEC-PROVISIONAL §7): FMA contraction and -use_fast_math.
+#include "nt_trace.cuh"
+
+int nt_launch_render_f32(const NtDevScene &s, const NtRenderArgs &a, void *stream) {
+    return nt::launch_render<float>(s, a, (cudaStream_t)stream);
+}
+int nt_launch_trace_f32(const NtDevScene &s, const NtTraceArgs &a, void *stream) {
+    return nt::launch_trace<float>(s, a, (cudaStream_t)stream);
+}
+size_t nt_flat_smem_bytes(const NtDevScene &s, int precision) {
+    return precision == 0 ? nt::flat_smem_bytes<double>(s, s.use_bvh != 0)
+                          : nt::flat_smem_bytes<float>(s, s.use_bvh != 0);
+}

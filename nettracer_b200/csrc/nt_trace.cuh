@@ -1,0 +1,572 @@
+// nt_trace.cuh — the intersect-and-shade hot path, templated on the arithmetic
+// type R: double = strict mode (this header is then compiled with -fmad=false so no multiply-add
+// is fused and every operation happens in the order SPEC-PROVISIONAL.md writes it), float = fast
+// mode (FMA contraction, approximate div/sqrt/pow).  No reference file can be cited — the spec is
+// this repository's own (SPEC-PROVISIONAL.md §n is quoted beside each routine).
+//
+// One thread traces one image sample: its whole ray tree, depth-first in pre-order with an explicit
+// stack (SPEC §4).  `lanes` adjacent lanes own the samples of one pixel and combine them with
+// shuffles in sample order (SPEC §5), so supersampling never leaves registers.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include <type_traits>
+
+#include "nt_device.h"
+
+namespace nt {
+
+template <typename R> struct V3 { R x, y, z; };
+
+template <typename R> __device__ __forceinline__ R dot(const V3<R> &a, const V3<R> &b) {
+    return (a.x * b.x + a.y * b.y) + a.z * b.z;
+}
+template <typename R> __device__ __forceinline__ V3<R> cross(const V3<R> &a, const V3<R> &b) {
+    return { a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x };
+}
+template <typename R> __device__ __forceinline__ V3<R> sub(const V3<R> &a, const V3<R> &b) {
+    return { a.x - b.x, a.y - b.y, a.z - b.z };
+}
+template <typename R> __device__ __forceinline__ V3<R> scale(const V3<R> &a, R s) {
+    return { a.x * s, a.y * s, a.z * s };
+}
+
+template <typename R> struct Math;
+template <> struct Math<double> {
+    static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+    static __device__ __forceinline__ double div(double a, double b) { return a / b; }
+    static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+    static __device__ __forceinline__ double pow_(double a, double b) { return pow(a, b); }
+    static __device__ __forceinline__ float up(double x) { return __double2float_ru(x); }
+    static __device__ __forceinline__ double inf() { return CUDART_INF; }
+};
+template <> struct Math<float> {
+    static __device__ __forceinline__ float rcp(float x) { return 1.0f / x; }
+    static __device__ __forceinline__ float div(float a, float b) { return a / b; }
+    static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float pow_(float a, float b) { return __powf(a, b); }
+    static __device__ __forceinline__ float up(float x) { return x; }
+    static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
+};
+
+// ---- loads: 128-bit, read-only path for global data, plain LDS for staged data ----
+template <bool GLOBAL> __device__ __forceinline__ void load4(const double *p, double *o) {
+    double2 a, b;
+    if (GLOBAL) { a = __ldg((const double2 *)p); b = __ldg((const double2 *)p + 1); }
+    else { a = *(const double2 *)p; b = *((const double2 *)p + 1); }
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+template <bool GLOBAL> __device__ __forceinline__ void load4(const float *p, float *o) {
+    float4 a = GLOBAL ? __ldg((const float4 *)p) : *(const float4 *)p;
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+}
+template <bool GLOBAL> __device__ __forceinline__ void load9(const double *p, double *o) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        double2 a = GLOBAL ? __ldg((const double2 *)p + i) : *((const double2 *)p + i);
+        o[2 * i] = a.x;
+        if (i < 4) o[2 * i + 1] = a.y;
+    }
+}
+template <bool GLOBAL> __device__ __forceinline__ void load9(const float *p, float *o) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float4 a = GLOBAL ? __ldg((const float4 *)p + i) : *((const float4 *)p + i);
+        o[4 * i] = a.x;
+        if (i < 2) { o[4 * i + 1] = a.y; o[4 * i + 2] = a.z; o[4 * i + 3] = a.w; }
+    }
+}
+
+struct Counters {
+    unsigned prim, sec, shadow, sph, pln, tri, box, light;
+};
+
+// ---- SPEC §3 intersections ----
+template <typename R, bool GLOBAL>
+__device__ __forceinline__ bool hit_sphere(const R *__restrict__ s, const V3<R> &o, const V3<R> &d,
+                                           R eps, R &t_out) {
+    R q[4];
+    load4<GLOBAL>(s, q);
+    V3<R> oc = { o.x - q[0], o.y - q[1], o.z - q[2] };
+    R b = dot(oc, d);
+    R cc = dot(oc, oc) - q[3];
+    R disc = b * b - cc;
+    if (disc < R(0)) return false;
+    R sq = Math<R>::sqrt_(disc);
+    R t = -b - sq;
+    if (!(t > eps)) t = -b + sq;
+    if (!(t > eps)) return false;
+    t_out = t;
+    return true;
+}
+
+template <typename R>
+__device__ __forceinline__ bool hit_plane(const R *__restrict__ p, const V3<R> &o, const V3<R> &d,
+                                          R eps, R &t_out) {
+    R q[4];
+    load4<false>(p, q);
+    V3<R> n = { q[0], q[1], q[2] };
+    R dn = dot(n, d);
+    if (dn == R(0)) return false;
+    R t = Math<R>::div(q[3] - dot(n, o), dn);
+    if (!(t > eps)) return false;
+    t_out = t;
+    return true;
+}
+
+template <typename R, bool GLOBAL>
+__device__ __forceinline__ bool hit_triangle(const R *__restrict__ tr, const V3<R> &o,
+                                             const V3<R> &d, R eps, R &t_out) {
+    R q[9];
+    load9<GLOBAL>(tr, q);
+    V3<R> v0 = { q[0], q[1], q[2] }, e1 = { q[3], q[4], q[5] }, e2 = { q[6], q[7], q[8] };
+    V3<R> p = cross(d, e2);
+    R det = dot(e1, p);
+    if (det == R(0)) return false;
+    R inv = Math<R>::rcp(det);
+    V3<R> tv = sub(o, v0);
+    R u = dot(tv, p) * inv;
+    if (u < R(0) || u > R(1)) return false;
+    V3<R> qv = cross(tv, e1);
+    R v = dot(d, qv) * inv;
+    if (v < R(0) || u + v > R(1)) return false;
+    R t = dot(e2, qv) * inv;
+    if (!(t > eps)) return false;
+    t_out = t;
+    return true;
+}
+
+// ---- scene context of one block ----
+template <typename R, bool BVH> struct Ctx {
+    const NtDevScene *s;
+    const NtSceneView<R> *v;
+    const R *sph; // staged in shared memory when !BVH, global (BVH order) otherwise
+    const R *pln; // always staged in shared memory
+    const R *tri; // as sph
+    R eps;
+    unsigned max_depth;
+};
+
+struct Hit {
+    int kind; // 0 sphere, 1 plane, 2 triangle, -1 none
+    int idx;  // index into the device array of that kind
+    int gid;  // global primitive id (tie-break)
+};
+
+__device__ __forceinline__ void slab(float lo, float hi, float o, float inv, float m, float &tn,
+                                     float &tf) {
+    float a = (lo - m - o) * inv, b = (hi + m - o) * inv;
+    tn = fmaxf(tn, fminf(a, b));
+    tf = fminf(tf, fmaxf(a, b));
+}
+
+// BVH traversal over the bounded primitives.  Boxes are float and only ever cull: they are rounded
+// outward at build time and widened here by a margin that covers rounding the ray to float, so the
+// survivors are exactly those the brute-force loop of SPEC §3 would accept (tests/test_parity_*
+// compare both).  ANY = occlusion query (first hit with t < tb ends it).
+template <typename R, bool ANY>
+__device__ __forceinline__ bool bvh_traverse(const Ctx<R, true> &c, const V3<R> &o, const V3<R> &d,
+                                             R &tb, Hit &best, Counters &k) {
+    if (c.s->n_nodes == 0) return false;
+    const float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
+    const float ix = 1.0f / (float)d.x, iy = 1.0f / (float)d.y, iz = 1.0f / (float)d.z;
+    const float m = 4e-6f * (fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz)) + c.s->max_abs);
+    float tmaxf = Math<R>::up(tb);
+    int2 stack[NT_BVH_STACK];
+    int sp = 0, node = 0;
+    bool found = false;
+    for (;;) {
+        const float4 *q = (const float4 *)(c.s->nodes + node);
+        const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+        const int4 q3 = __ldg((const int4 *)(q + 3));
+        float n0 = 0.0f, f0 = CUDART_INF_F, n1 = 0.0f, f1 = CUDART_INF_F;
+        slab(q0.x, q0.w, ox, ix, m, n0, f0);
+        slab(q0.y, q1.x, oy, iy, m, n0, f0);
+        slab(q0.z, q1.y, oz, iz, m, n0, f0);
+        slab(q1.z, q2.y, ox, ix, m, n1, f1);
+        slab(q1.w, q2.z, oy, iy, m, n1, f1);
+        slab(q2.x, q2.w, oz, iz, m, n1, f1);
+        k.box += 2;
+        bool h0 = q3.z >= 0 && n0 <= f0 && n0 <= tmaxf;
+        bool h1 = q3.w >= 0 && n1 <= f1 && n1 <= tmaxf;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            const bool h = ch ? h1 : h0;
+            const int cnt = ch ? q3.w : q3.z, start = ch ? q3.y : q3.x;
+            if (h && cnt > 0) {
+                if (ch && !((ch ? n1 : n0) <= tmaxf)) continue; // leaf 0 may have shrunk the bound
+                const int num = cnt & 0xff;
+                for (int j = 0; j < num; ++j) {
+                    const int idx = start + j;
+                    R t;
+                    bool hit;
+                    if (cnt & 0x100) { k.tri++; hit = hit_triangle<R, true>(c.tri + (size_t)idx * NT_TRI_STRIDE, o, d, c.eps, t); }
+                    else { k.sph++; hit = hit_sphere<R, true>(c.sph + (size_t)idx * 4, o, d, c.eps, t); }
+                    if (!hit) continue;
+                    if (ANY) { if (t < tb) return true; }
+                    else {
+                        const int kind = (cnt & 0x100) ? 2 : 0;
+                        if (t < tb) {
+                            tb = t; best.kind = kind; best.idx = idx;
+                            best.gid = __ldg((kind ? c.s->tri_gid : c.s->sph_gid) + idx);
+                            tmaxf = Math<R>::up(tb); found = true;
+                        } else if (t == tb) {
+                            const int gid = __ldg((kind ? c.s->tri_gid : c.s->sph_gid) + idx);
+                            if (gid < best.gid) { best.kind = kind; best.idx = idx; best.gid = gid; found = true; }
+                        }
+                    }
+                }
+            }
+        }
+        h0 = h0 && q3.z == 0 && n0 <= tmaxf;
+        h1 = h1 && q3.w == 0 && n1 <= tmaxf;
+        if (h0 && h1) {
+            const bool first1 = n1 < n0;
+            const int far_node = first1 ? q3.x : q3.y;
+            const float far_t = first1 ? n0 : n1;
+            node = first1 ? q3.y : q3.x;
+            stack[sp++] = make_int2(far_node, __float_as_int(far_t));
+        } else if (h0) node = q3.x;
+        else if (h1) node = q3.y;
+        else {
+            bool got = false;
+            while (sp > 0) {
+                const int2 e = stack[--sp];
+                if (__int_as_float(e.y) <= tmaxf) { node = e.x; got = true; break; }
+            }
+            if (!got) break;
+        }
+    }
+    return found;
+}
+
+// SPEC §3 nearest hit: smallest t; equal t -> smallest global primitive id.
+template <typename R, bool BVH>
+__device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o, const V3<R> &d,
+                                            R &tb, Hit &best, Counters &k) {
+    const NtDevScene &s = *c.s;
+    tb = Math<R>::inf();
+    best.kind = -1; best.idx = -1; best.gid = 0x7fffffff;
+    R t;
+    if constexpr (!BVH) {
+        for (unsigned i = 0; i < s.ns; ++i)
+            if (hit_sphere<R, false>(c.sph + 4 * i, o, d, c.eps, t) && t < tb) { tb = t; best.kind = 0; best.idx = (int)i; }
+        k.sph += s.ns;
+    }
+    for (unsigned i = 0; i < s.np; ++i)
+        if (hit_plane<R>(c.pln + 4 * i, o, d, c.eps, t) && t < tb) { tb = t; best.kind = 1; best.idx = (int)i; best.gid = (int)(s.ns + i); }
+    k.pln += s.np;
+    if constexpr (!BVH) {
+        for (unsigned i = 0; i < s.nt; ++i)
+            if (hit_triangle<R, false>(c.tri + NT_TRI_STRIDE * i, o, d, c.eps, t) && t < tb) { tb = t; best.kind = 2; best.idx = (int)i; }
+        k.tri += s.nt;
+    } else {
+        bvh_traverse<R, false>(c, o, d, tb, best, k);
+    }
+    return best.kind >= 0;
+}
+
+// SPEC §3 occlusion: any primitive hit (t > eps) with t < dist; first found ends the query.
+template <typename R, bool BVH>
+__device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, const V3<R> &d, R dist,
+                                         Counters &k) {
+    const NtDevScene &s = *c.s;
+    R t;
+    if constexpr (!BVH) {
+        for (unsigned i = 0; i < s.ns; ++i) {
+            k.sph++;
+            if (hit_sphere<R, false>(c.sph + 4 * i, o, d, c.eps, t) && t < dist) return true;
+        }
+    }
+    for (unsigned i = 0; i < s.np; ++i) {
+        k.pln++;
+        if (hit_plane<R>(c.pln + 4 * i, o, d, c.eps, t) && t < dist) return true;
+    }
+    if constexpr (!BVH) {
+        for (unsigned i = 0; i < s.nt; ++i) {
+            k.tri++;
+            if (hit_triangle<R, false>(c.tri + NT_TRI_STRIDE * i, o, d, c.eps, t) && t < dist) return true;
+        }
+        return false;
+    } else {
+        Hit h;
+        R tb = dist;
+        return bvh_traverse<R, true>(c, o, d, tb, h, k);
+    }
+}
+
+// SPEC §4: radiance of one sample = sum over its ray tree in depth-first pre-order of W * local.
+template <typename R, bool BVH>
+__device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R> d, R acc[3],
+                                             Counters &k) {
+    const NtDevScene &s = *c.s;
+    const NtSceneView<R> &v = *c.v;
+    // deferred transmission children (reflection children are followed immediately)
+    R st[NT_MAX_DEPTH_DEV][7];
+    unsigned st_depth[NT_MAX_DEPTH_DEV];
+    int sp = 0;
+    R W = R(1);
+    unsigned depth = 1;
+    for (;;) {
+        R t;
+        Hit h;
+        bool descend = false;
+        if (!nearest_hit<R, BVH>(c, o, d, t, h, k)) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) acc[ch] = acc[ch] + W * __ldg(v.globals + 3 + ch);
+        } else {
+            const V3<R> P = { o.x + d.x * t, o.y + d.y * t, o.z + d.z * t };
+            V3<R> Ng;
+            int mat;
+            if (h.kind == 0) {
+                const R *sp4 = BVH ? v.sph + 4 * (size_t)h.idx : c.sph + 4 * h.idx;
+                R q[4];
+                if (BVH) load4<true>(sp4, q); else load4<false>(sp4, q);
+                const R ir = __ldg(v.sph_invr + h.idx);
+                Ng = { (P.x - q[0]) * ir, (P.y - q[1]) * ir, (P.z - q[2]) * ir };
+                mat = __ldg(s.sph_mat + h.idx);
+            } else if (h.kind == 1) {
+                R q[4];
+                load4<false>(c.pln + 4 * h.idx, q);
+                Ng = { q[0], q[1], q[2] };
+                mat = __ldg(s.pln_mat + h.idx);
+            } else {
+                const R *tp = v.tri + (size_t)h.idx * NT_TRI_STRIDE + 9;
+                Ng = { __ldg(tp), __ldg(tp + 1), __ldg(tp + 2) };
+                mat = __ldg(s.tri_mat + h.idx);
+            }
+            const R *mp = v.mat + (size_t)mat * NT_MAT_STRIDE;
+            R mq[12];
+            load4<true>(mp, mq); load4<true>(mp + 4, mq + 4); load4<true>(mp + 8, mq + 8);
+            const R ka = mq[3], kd = mq[4], ks = mq[5], shin = mq[6], kr = mq[7], kt = mq[8];
+            const R cosd = dot(d, Ng);
+            const bool entering = cosd < R(0);
+            V3<R> N = Ng;
+            if (!entering) { N.x = -Ng.x; N.y = -Ng.y; N.z = -Ng.z; }
+            R local[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) local[ch] = __ldg(v.globals + ch) * (ka * mq[ch]);
+            for (unsigned l = 0; l < s.nl; ++l) {
+                const R *lp = v.lights + 6 * l;
+                const V3<R> Lv = { __ldg(lp) - P.x, __ldg(lp + 1) - P.y, __ldg(lp + 2) - P.z };
+                const R d2 = dot(Lv, Lv);
+                const R dist = Math<R>::sqrt_(d2);
+                const V3<R> L = scale(Lv, Math<R>::rcp(dist));
+                const R ndl = dot(N, L);
+                if (!(ndl > R(0))) continue;
+                k.shadow++;
+                if (occluded<R, BVH>(c, P, L, dist, k)) continue;
+                k.light++;
+                const R kdn = kd * ndl;
+                const R lc[3] = { __ldg(lp + 3), __ldg(lp + 4), __ldg(lp + 5) };
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) local[ch] = local[ch] + lc[ch] * (mq[ch] * kdn);
+                const R two = R(2) * ndl;
+                const V3<R> Rv = { N.x * two - L.x, N.y * two - L.y, N.z * two - L.z };
+                const R rv = -dot(Rv, d);
+                if (ks > R(0) && rv > R(0)) {
+                    const R sterm = ks * Math<R>::pow_(rv, shin);
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) local[ch] = local[ch] + lc[ch] * sterm;
+                }
+            }
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) acc[ch] = acc[ch] + W * local[ch];
+
+            if (depth < c.max_depth) {
+                const R cosi = -dot(d, N);
+                R wr = kr, wt = R(0);
+                V3<R> T = { R(0), R(0), R(0) };
+                if (kt > R(0)) {
+                    const R eta = entering ? mq[10] : mq[9];
+                    const R kk = R(1) - (eta * eta) * (R(1) - cosi * cosi);
+                    if (kk < R(0)) wr = kr + kt;
+                    else {
+                        wt = kt;
+                        const R sterm = eta * cosi - Math<R>::sqrt_(kk);
+                        T = { d.x * eta + N.x * sterm, d.y * eta + N.y * sterm, d.z * eta + N.z * sterm };
+                    }
+                }
+                if (wt > R(0)) {
+                    k.sec++;
+                    if (wr > R(0)) { // defer: reflection subtree comes first in pre-order
+                        st[sp][0] = P.x; st[sp][1] = P.y; st[sp][2] = P.z;
+                        st[sp][3] = T.x; st[sp][4] = T.y; st[sp][5] = T.z;
+                        st[sp][6] = W * wt; st_depth[sp] = depth + 1;
+                        ++sp;
+                    }
+                }
+                if (wr > R(0)) {
+                    k.sec++;
+                    const R two = R(2) * cosi;
+                    const V3<R> Rd = { d.x + N.x * two, d.y + N.y * two, d.z + N.z * two };
+                    o = P; d = Rd; W = W * wr; depth = depth + 1;
+                    descend = true;
+                } else if (wt > R(0)) {
+                    o = P; d = T; W = W * wt; depth = depth + 1;
+                    descend = true;
+                }
+            }
+        }
+        if (descend) continue;
+        if (sp == 0) break;
+        --sp;
+        o = { st[sp][0], st[sp][1], st[sp][2] };
+        d = { st[sp][3], st[sp][4], st[sp][5] };
+        W = st[sp][6];
+        depth = st_depth[sp];
+    }
+}
+
+// ---- block-level plumbing ----
+
+// Stage the flat intersection data in shared memory with 128-bit loads.
+template <typename R, bool BVH>
+__device__ __forceinline__ void stage_scene(const NtDevScene &s, const NtSceneView<R> &v, R *smem,
+                                            Ctx<R, BVH> &c) {
+    const unsigned n_sph = BVH ? 0 : s.ns * 4, n_pln = s.np * 4, n_tri = BVH ? 0 : s.nt * NT_TRI_STRIDE;
+    R *s_sph = smem, *s_pln = smem + n_sph, *s_tri = s_pln + n_pln;
+    constexpr int VEC = 16 / sizeof(R);
+    typedef typename std::conditional<sizeof(R) == 8, double2, float4>::type VT;
+    for (unsigned i = threadIdx.x; i < n_sph / VEC; i += blockDim.x) ((VT *)s_sph)[i] = __ldg((const VT *)v.sph + i);
+    for (unsigned i = threadIdx.x; i < n_pln / VEC; i += blockDim.x) ((VT *)s_pln)[i] = __ldg((const VT *)v.pln + i);
+    for (unsigned i = threadIdx.x; i < n_tri / VEC; i += blockDim.x) ((VT *)s_tri)[i] = __ldg((const VT *)v.tri + i);
+    __syncthreads();
+    c.sph = BVH ? v.sph : s_sph;
+    c.pln = s_pln;
+    c.tri = BVH ? v.tri : s_tri;
+}
+
+__device__ __forceinline__ void flush_counters(const Counters &k, unsigned long long *counters,
+                                               unsigned *s_cnt) {
+    const unsigned vals[NT_NCOUNTERS] = { k.prim, k.sec, k.shadow, k.sph, k.pln, k.tri, k.box, k.light };
+    if (threadIdx.x < NT_NCOUNTERS) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NT_NCOUNTERS; ++i) {
+        const unsigned w = __reduce_add_sync(0xffffffffu, vals[i]);
+        if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_cnt[i], w);
+    }
+    __syncthreads();
+    if (threadIdx.x < NT_NCOUNTERS && s_cnt[threadIdx.x]) {
+        const unsigned slot = (blockIdx.x + blockIdx.y * gridDim.x) % NT_COUNTER_SLOTS;
+        atomicAdd(&counters[slot * NT_NCOUNTERS + threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+    }
+}
+
+template <typename R, bool BVH>
+__global__ void __launch_bounds__(NT_BLOCK_THREADS)
+render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRenderArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned s_cnt[NT_NCOUNTERS];
+    const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
+    Ctx<R, BVH> c;
+    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.max_depth = a.max_depth;
+    stage_scene<R, BVH>(s, v, (R *)smem_raw, c);
+
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned L = a.lanes, j = lane & (L - 1), pw = lane / L;
+    // block tile = 4 x 2 warp tiles of twx x twy pixels over the virtual image (owned rows only)
+    const unsigned px = (blockIdx.x * 4 + (warp & 3)) * a.twx + pw % a.twx;
+    const unsigned vr = (blockIdx.y * 2 + (warp >> 2)) * a.twy + pw / a.twx;
+    const bool live = px < a.width && vr < a.vrows;
+    const unsigned y = ((vr / a.band_rows) * a.shard_count + a.shard_index) * a.band_rows + vr % a.band_rows;
+
+    Counters k = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    R sum[3] = { R(0), R(0), R(0) };
+    const V3<R> eye = { (R)a.cam[0], (R)a.cam[1], (R)a.cam[2] };
+    const R rn = (R)a.n;
+    const unsigned rounds = a.spp / L;
+    for (unsigned r = 0; r < rounds; ++r) {
+        R acc[3] = { R(0), R(0), R(0) };
+        if (live) {
+            // SPEC §2: regular n x n grid, sample s = r*L + j
+            const unsigned sidx = r * L + j;
+            const unsigned si = sidx % a.n, sj = sidx / a.n;
+            const R ox = Math<R>::div((R)si + R(0.5), rn), oy = Math<R>::div((R)sj + R(0.5), rn);
+            const R fx = (R)px + ox, fy = (R)y + oy;
+            const V3<R> D = { ((R)a.cam[3] + (R)a.cam[6] * fx) + (R)a.cam[9] * fy,
+                              ((R)a.cam[4] + (R)a.cam[7] * fx) + (R)a.cam[10] * fy,
+                              ((R)a.cam[5] + (R)a.cam[8] * fx) + (R)a.cam[11] * fy };
+            const V3<R> dir = scale(D, Math<R>::rcp(Math<R>::sqrt_(dot(D, D))));
+            k.prim++;
+            trace_sample<R, BVH>(c, eye, dir, acc, k);
+        }
+        // SPEC §5: samples are added in sample order; lanes of one pixel are adjacent
+        if (L == 1) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) sum[ch] = sum[ch] + acc[ch];
+        } else {
+            const unsigned base = lane & ~(L - 1);
+            for (unsigned jj = 0; jj < L; ++jj)
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) sum[ch] = sum[ch] + __shfl_sync(0xffffffffu, acc[ch], base + jj);
+        }
+    }
+    if (live && j == 0) {
+        const R inv_spp = Math<R>::rcp((R)a.spp);
+        unsigned rgba = 0xff000000u;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const R cv = sum[ch] * inv_spp;
+            const unsigned q = cv <= R(0) ? 0u : cv >= R(1) ? 255u : (unsigned)(int)(cv * R(255) + R(0.5));
+            rgba |= q << (8 * ch);
+        }
+        const size_t row = a.layout == 1 ? vr : y;
+        *(unsigned *)(a.out + row * a.stride + 4 * (size_t)px) = rgba;
+    }
+    flush_counters(k, a.counters, s_cnt);
+}
+
+// Unit-level entry: nearest hit of arbitrary rays (nt_trace_rays).
+template <typename R, bool BVH>
+__global__ void __launch_bounds__(NT_BLOCK_THREADS)
+trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtTraceArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
+    Ctx<R, BVH> c;
+    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.max_depth = 1;
+    stage_scene<R, BVH>(s, v, (R *)smem_raw, c);
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const V3<R> o = { (R)a.origins[3 * i], (R)a.origins[3 * i + 1], (R)a.origins[3 * i + 2] };
+    const V3<R> d = { (R)a.dirs[3 * i], (R)a.dirs[3 * i + 1], (R)a.dirs[3 * i + 2] };
+    Counters k = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    R t;
+    Hit h;
+    if (nearest_hit<R, BVH>(c, o, d, t, h, k)) {
+        a.t_out[i] = (double)t;
+        a.prim_out[i] = h.kind == 1 ? h.gid : (BVH ? h.gid : (h.kind == 0 ? h.idx : (int)(s.ns + s.np) + h.idx));
+    } else {
+        a.t_out[i] = -1.0;
+        a.prim_out[i] = -1;
+    }
+}
+
+template <typename R>
+inline size_t flat_smem_bytes(const NtDevScene &s, bool bvh) {
+    size_t n = (size_t)s.np * 4;
+    if (!bvh) n += (size_t)s.ns * 4 + (size_t)s.nt * NT_TRI_STRIDE;
+    return n * sizeof(R);
+}
+
+template <typename R>
+inline int launch_render(const NtDevScene &s, const NtRenderArgs &a, cudaStream_t st) {
+    dim3 grid(a.tiles_x, a.tiles_y), block(NT_BLOCK_THREADS);
+    const size_t smem = flat_smem_bytes<R>(s, s.use_bvh != 0);
+    if (s.use_bvh) render_kernel<R, true><<<grid, block, smem, st>>>(s, a);
+    else render_kernel<R, false><<<grid, block, smem, st>>>(s, a);
+    return (int)cudaGetLastError();
+}
+
+template <typename R>
+inline int launch_trace(const NtDevScene &s, const NtTraceArgs &a, cudaStream_t st) {
+    dim3 grid((a.n + NT_BLOCK_THREADS - 1) / NT_BLOCK_THREADS), block(NT_BLOCK_THREADS);
+    const size_t smem = flat_smem_bytes<R>(s, s.use_bvh != 0);
+    if (s.use_bvh) trace_kernel<R, true><<<grid, block, smem, st>>>(s, a);
+    else trace_kernel<R, false><<<grid, block, smem, st>>>(s, a);
+    return (int)cudaGetLastError();
+}
+
+} // namespace nt

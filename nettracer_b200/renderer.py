@@ -1,0 +1,97 @@
+"""Host-side renderer over the C ABI (include/nettracer_b200.h): the call a NetTracer host would
+make in place of its per-pixel intersect-and-shade loop.  The reference's render API is unknown
+(/root/reference/README:1-3); this mirrors SURVEY.md §8(b)'s proposed surface one to one.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .lib import check, load
+from .scene import Camera, Scene, make_params, owned_rows, shard_rows
+
+
+class Renderer:
+    """One scene resident on one GPU.  `render()` = nt_render (host buffer, blocking);
+    `render_device()` = nt_render_device (device buffer, asynchronous on a stream)."""
+
+    def __init__(self, scene: Scene, device: int = 0):
+        self._lib = load()
+        self._h = C.c_void_p()
+        desc, keep = scene.to_desc()
+        check(self._lib.nt_scene_create(C.byref(desc), int(device), C.byref(self._h)))
+        del keep
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.nt_scene_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def info(self) -> dict:
+        a = (C.c_uint64 * 4)()
+        check(self._lib.nt_scene_info(self._h, a))
+        return {"uses_bvh": bool(a[0]), "bvh_nodes": int(a[1]), "device_bytes": int(a[2]), "device": int(a[3])}
+
+    # -- host path --
+    def render_params(self, params: abi.nt_render_params, out: np.ndarray | None = None):
+        """out: uint8 [rows, width, 4] C-contiguous host array (rows = height for FULL, owned rows for
+        COMPACT).  Returns (out, stats dict)."""
+        rows = params.height if params.layout == abi.NT_LAYOUT_FULL else shard_rows(
+            params.height, params.band_rows or 1, params.shard_index, params.shard_count or 1)
+        if out is None:
+            out = np.zeros((rows, params.width, 4), dtype=np.uint8)
+        assert out.dtype == np.uint8 and out.flags.c_contiguous and out.shape == (rows, params.width, 4)
+        st = abi.nt_render_stats()
+        check(self._lib.nt_render(self._h, C.byref(params), out.ctypes.data, params.width * 4, C.byref(st)))
+        return out, st.as_dict()
+
+    def render(self, camera: Camera, width, height, spp=1, max_depth=1, precision=abi.NT_F64_STRICT,
+               out=None, **kw):
+        p = make_params(width, height, spp, max_depth, camera.resolve(width, height), precision, **kw)
+        return self.render_params(p, out)
+
+    # -- device path --
+    def render_device(self, params: abi.nt_render_params, dev_ptr: int, row_stride_bytes: int, stream: int = 0):
+        check(self._lib.nt_render_device(self._h, C.byref(params), C.c_void_p(dev_ptr), row_stride_bytes,
+                                         C.c_void_p(stream)))
+
+    def device_stats(self, stream: int = 0) -> dict:
+        st = abi.nt_render_stats()
+        check(self._lib.nt_render_device_stats(self._h, C.c_void_p(stream), C.byref(st)))
+        return st.as_dict()
+
+    # -- unit-level --
+    def trace_rays(self, origins, dirs, precision=abi.NT_F64_STRICT, ray_epsilon=0.0):
+        o = np.ascontiguousarray(origins, dtype=np.float64).reshape(-1, 3)
+        d = np.ascontiguousarray(dirs, dtype=np.float64).reshape(-1, 3)
+        t = np.zeros(len(o), dtype=np.float64)
+        prim = np.zeros(len(o), dtype=np.int32)
+        check(self._lib.nt_trace_rays(self._h, len(o), o.ctypes.data, d.ctypes.data, int(precision),
+                                      float(ray_epsilon), t.ctypes.data, prim.ctypes.data))
+        return t, prim
+
+
+def measure_peaks(device=0) -> dict:
+    p = abi.nt_peaks()
+    check(load().nt_measure_peaks(int(device), C.byref(p)))
+    return p.as_dict()
+
+
+def deinterleave_host(compact_shards, height, width, band_rows):
+    """Host twin of nt_deinterleave_device (used by CPU tests of the sharding arithmetic)."""
+    n = len(compact_shards)
+    full = np.zeros((height, width, 4), dtype=np.uint8)
+    for i, buf in enumerate(compact_shards):
+        full[owned_rows(height, band_rows, i, n)] = buf
+    return full
