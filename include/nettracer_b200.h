@@ -145,6 +145,9 @@ int nt_deinterleave_device(const void *compact_all, size_t shard_stride_bytes, v
                            void *cuda_stream);
 
 /* ---- peer framebuffer (NVLink store path) ---- */
+/* A plain cudaMalloc'd buffer on `device` (so that its IPC handle has offset 0), and its release. */
+int nt_device_malloc(int device, size_t bytes, void **dev_ptr_out);
+int nt_device_free(int device, void *dev_ptr);
 /* Export / open a CUDA IPC handle (64 bytes) for a device allocation, so that every rank's
  * render kernel can store its pixels directly into rank 0's framebuffer. */
 int nt_ipc_export(const void *dev_ptr, int device, uint8_t handle_out[64]);

@@ -70,7 +70,7 @@ EXPORTS = [
     "nt_scene_create", "nt_scene_destroy", "nt_scene_info",
     "nt_render", "nt_render_device", "nt_render_device_stats", "nt_trace_rays",
     "nt_shard_rows", "nt_deinterleave_device",
-    "nt_ipc_export", "nt_ipc_open", "nt_ipc_close",
+    "nt_device_malloc", "nt_device_free", "nt_ipc_export", "nt_ipc_open", "nt_ipc_close",
     "nt_measure_peaks",
 ]
 

@@ -446,6 +446,24 @@ extern "C" int nt_deinterleave_device(const void *compact_all, size_t shard_stri
 // ---------------- CUDA IPC (peer framebuffer over NVLink) ----------------
 static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
 
+extern "C" int nt_device_malloc(int device, size_t bytes, void **dev_ptr_out) {
+    if (!dev_ptr_out || bytes == 0) return fail(NT_ERR_INVALID, "bad argument");
+    *dev_ptr_out = nullptr;
+    int rc = check_device(device);
+    if (rc) return rc;
+    CU(cudaSetDevice(device));
+    cudaError_t e = cudaMalloc(dev_ptr_out, bytes);
+    if (e != cudaSuccess) return fail(NT_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return NT_OK;
+}
+
+extern "C" int nt_device_free(int device, void *dev_ptr) {
+    if (!dev_ptr) return NT_OK;
+    CU(cudaSetDevice(device));
+    CU(cudaFree(dev_ptr));
+    return NT_OK;
+}
+
 extern "C" int nt_ipc_export(const void *dev_ptr, int device, uint8_t handle_out[64]) {
     if (!dev_ptr || !handle_out) return fail(NT_ERR_INVALID, "NULL argument");
     CU(cudaSetDevice(device));

@@ -90,8 +90,17 @@ __device__ __forceinline__ bool hit_sphere(const R *__restrict__ s, const V3<R> 
     load4<GLOBAL>(s, q);
     V3<R> oc = { o.x - q[0], o.y - q[1], o.z - q[2] };
     R b = dot(oc, d);
-    R cc = dot(oc, oc) - q[3];
-    R disc = b * b - cc;
+    R disc;
+    if constexpr (sizeof(R) == 8) {
+        R cc = dot(oc, oc) - q[3];
+        disc = b * b - cc;
+    } else {
+        // fast mode (SPEC §7): b*b - (|oc|^2 - r^2) cancels catastrophically in binary32 for distant
+        // spheres (hit points land ~1e-4 off the surface and refracted rays re-hit it), so take the
+        // discriminant from the component of oc perpendicular to the (unit) direction instead
+        V3<R> l = { oc.x - b * d.x, oc.y - b * d.y, oc.z - b * d.z };
+        disc = q[3] - dot(l, l);
+    }
     if (disc < R(0)) return false;
     R sq = Math<R>::sqrt_(disc);
     R t = -b - sq;

@@ -39,6 +39,8 @@ def load():
         "nt_trace_rays": (C.c_int, [vp, u32, vp, vp, u32, C.c_double, vp, vp]),
         "nt_shard_rows": (u32, [u32, u32, u32, u32]),
         "nt_deinterleave_device": (C.c_int, [vp, C.c_size_t, vp, C.c_size_t, u32, u32, u32, u32, C.c_int, vp]),
+        "nt_device_malloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(vp)]),
+        "nt_device_free": (C.c_int, [C.c_int, vp]),
         "nt_ipc_export": (C.c_int, [vp, C.c_int, vp]),
         "nt_ipc_open": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
         "nt_ipc_close": (C.c_int, [vp, C.c_int]),

@@ -1,0 +1,15 @@
+"""Render one config a few times (profiling target): python scripts/gpu_one.py <config> <f64|f32> [iters]"""
+import sys
+
+sys.path.insert(0, ".")
+from nettracer_b200 import abi, scenes  # noqa: E402
+from nettracer_b200.renderer import Renderer  # noqa: E402
+
+name, prec = sys.argv[1], sys.argv[2]
+iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+factory, w, h, spp, depth = scenes.CONFIGS[name]
+scene, cam = factory()
+with Renderer(scene) as r:
+    for _ in range(iters):
+        img, st = r.render(cam, w, h, spp, depth, abi.NT_F64_STRICT if prec == "f64" else abi.NT_F32_FAST)
+    print(name, prec, st)

@@ -1,0 +1,138 @@
+"""CPU tests of the oracle (test infrastructure).  PARITY UNPINNED w.r.t. NetTracer: the reference
+tree holds no source, test or golden vector (/root/reference/README:1-3), so the oracle is pinned
+to (1) analytic known answers, (2) an independent pure-Python restatement of SPEC-PROVISIONAL.md,
+(3) its own committed golden fixtures, (4) brute force == BVH."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from nettracer_b200 import abi, scenes
+from nettracer_b200.scene import Camera, Material, Scene, make_params, owned_rows, shard_rows
+from oracle import oracle
+from tests.make_golden import CASES, KEYS
+from tests.py_restatement import PyTracer
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_known_answer_intersections():
+    s = Scene()
+    m = s.add_material(Material())
+    s.add_sphere((0, 0, -5), 1.0, m)          # id 0
+    s.add_plane((0, 1, 0), -2.0, m)           # id 1: y = -2
+    s.add_triangle((-1, -1, -10), (1, -1, -10), (0, 1, -10), m)  # id 2
+    o = np.array([[0, 0, 0], [0, 0, 0], [0, 0, 0], [5, 5, 0], [0, 0, -5], [0, 0, 0], [0, 0, -7]], dtype=float)
+    d = np.array([[0, 0, -1], [0, -1, 0], [0.3, 0.2, -1], [0, 1, 0], [0, 0, -1], [0.0, 0.99, -10], [0, 0, -1]], dtype=float)
+    t, prim = oracle.trace_rays(s, o, d)
+    assert prim[0] == 0 and t[0] == 4.0                    # front of the sphere
+    assert prim[1] == 1 and t[1] == 2.0                    # plane below
+    assert prim[3] == -1 and t[3] == -1.0                  # away from everything
+    assert prim[4] == 0 and t[4] == 1.0                    # from the centre: far root
+    assert prim[6] == 2 and t[6] == 3.0                    # behind the sphere: triangle only
+    # tie-break: identical spheres -> the lowest id wins
+    s2 = Scene(); m2 = s2.add_material(Material())
+    s2.add_sphere((0, 0, -5), 1.0, m2); s2.add_sphere((0, 0, -5), 1.0, m2)
+    t2, p2 = oracle.trace_rays(s2, [[0, 0, 0]], [[0, 0, -1]])
+    assert p2[0] == 0
+    # epsilon: a ray starting on the sphere surface leaves it
+    t3, p3 = oracle.trace_rays(s2, [[0, 0, -4]], [[0, 0, 1]])
+    assert p3[0] == -1
+
+
+def test_known_answer_shading_single_pixel():
+    """One diffuse sphere, one light, head on: pixel = ka*amb*col + lcol*col*kd*ndl with ndl = 1."""
+    s = Scene(ambient=(0.5, 0.5, 0.5), background=(0, 0, 0))
+    m = s.add_material(Material((0.8, 0.4, 0.2), ka=0.1, kd=0.5))
+    s.add_sphere((0, 0, -5), 1.0, m)
+    s.add_light((0, 0, 10), (1.0, 1.0, 1.0))
+    cam = Camera((0, 0, 0), (0, 0, -1), vfov_deg=1.0)
+    img, st, rad = oracle.render(s, make_params(1, 1, 1, 1, cam.resolve(1, 1)), radiance=True)
+    want = [0.5 * (0.1 * c) + 1.0 * (c * (0.5 * 1.0)) for c in (0.8, 0.4, 0.2)]
+    assert np.allclose(rad[0, 0], want, rtol=0, atol=1e-12)
+    assert st["rays_primary"] == 1 and st["rays_shadow"] == 1 and st["light_evals"] == 1
+    assert list(img[0, 0]) == [int(v * 255 + 0.5) for v in want] + [255]
+
+
+@pytest.mark.parametrize("seed,depth", [(3, 1), (5, 4)])
+def test_c_oracle_equals_python_restatement(seed, depth):
+    s, cam = scenes.random_mixed(5, 2, 6, seed=seed)
+    w, h, spp = 20, 14, 4
+    p = make_params(w, h, spp, depth, cam.resolve(w, h))
+    img, st = oracle.render(s, p)
+    py = PyTracer(s.arrays(), s.ambient, s.background, 1e-6, depth)
+    ref = np.array(py.render(p.camera, w, h, spp), dtype=np.uint8)
+    assert np.array_equal(img, ref)
+    assert py.rays == st["rays"]
+
+
+def test_python_restatement_on_cornell_tile():
+    s, cam = scenes.cornell_box()
+    w, h = 24, 14
+    p = make_params(w, h, 1, 3, cam.resolve(w, h))
+    img, st = oracle.render(s, p)
+    py = PyTracer(s.arrays(), s.ambient, s.background, 1e-6, 3)
+    assert np.array_equal(img, np.array(py.render(p.camera, w, h, 1), dtype=np.uint8))
+    assert py.rays == st["rays"]
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_reproduces_golden(name):
+    factory, kw, w, h, spp, depth = CASES[name]
+    scene, cam = factory(**kw)
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    img, st = oracle.render(scene, make_params(w, h, spp, depth, cam.resolve(w, h)), accel=0)
+    assert np.array_equal(img, g["rgba"])
+    assert [st[k] for k in KEYS] == list(g["counters"])
+
+
+@pytest.mark.parametrize("seed", [21, 22])
+def test_oracle_bvh_equals_bruteforce(seed):
+    s, cam = scenes.random_mixed(80, 2, 120, seed=seed)
+    p = make_params(96, 64, 4, 4, cam.resolve(96, 64))
+    a, sa, ra = oracle.render(s, p, accel=0, radiance=True)
+    b, sb, rb = oracle.render(s, p, accel=1, radiance=True)
+    assert np.array_equal(a, b) and np.array_equal(ra.view(np.uint64), rb.view(np.uint64))
+    for k in KEYS:
+        assert sa[k] == sb[k]
+    rng = np.random.default_rng(seed)
+    o = rng.uniform(-8, 8, (2000, 3)); o[:, 2] += 10
+    d = rng.normal(size=(2000, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    t0, p0 = oracle.trace_rays(s, o, d, accel=0)
+    t1, p1 = oracle.trace_rays(s, o, d, accel=1)
+    assert np.array_equal(p0, p1) and np.array_equal(t0.view(np.uint64), t1.view(np.uint64))
+
+
+def test_oracle_threads_and_shards_agree():
+    s, cam = scenes.cornell_box()
+    w, h, band, n = 64, 50, 8, 3
+    p = make_params(w, h, 4, 3, cam.resolve(w, h))
+    full, st = oracle.render(s, p, n_threads=1)
+    full4, st4 = oracle.render(s, p, n_threads=4)
+    assert np.array_equal(full, full4) and st["rays"] == st4["rays"]
+    acc = np.zeros_like(full)
+    rays = 0
+    for i in range(n):
+        pc = make_params(w, h, 4, 3, cam.resolve(w, h), shard_index=i, shard_count=n, band_rows=band,
+                         layout=abi.NT_LAYOUT_COMPACT)
+        rows = shard_rows(h, band, i, n)
+        part, sti = oracle.render(s, pc, compact_rows=rows)
+        acc[owned_rows(h, band, i, n)] = part
+        rays += sti["rays"]
+    assert np.array_equal(acc, full) and rays == st["rays"]
+
+
+def test_oracle_rejects_bad_input():
+    s, cam = scenes.cornell_box()
+    with pytest.raises(RuntimeError):
+        oracle.render(s, make_params(8, 8, 3, 1, cam.resolve(8, 8)))
+    s.sphere_mat[0] = 99
+    with pytest.raises(RuntimeError):
+        oracle.render(s, make_params(8, 8, 1, 1, cam.resolve(8, 8)))
+
+
+def test_flop_convention():
+    st = {"sphere_tests": 1, "plane_tests": 1, "triangle_tests": 1, "box_tests": 1, "light_evals": 1}
+    assert abi.algorithmic_flops(st) == 17 + 11 + 39 + 18 + 40
+    assert math.isclose(1.0, 1.0)

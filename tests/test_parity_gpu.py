@@ -129,18 +129,31 @@ def test_sharded_render_reassembles(layout):
 
 
 def test_fast_mode_tolerance():
-    """binary32 fast mode vs the strict image: >= 99% of pixels within 2 LSB per channel and mean
-    absolute error < 0.25 LSB (silhouette / shadow-edge pixels may flip; they are the remainder)."""
+    """binary32 fast mode vs the strict image (SPEC-PROVISIONAL §7 has no bit contract).  Stated
+    tolerance: >= 99.5% of pixels within 1 LSB per channel, >= 99.8% within 2 LSB, mean absolute
+    error < 0.05 LSB; the remainder are silhouette / shadow-edge / total-internal-reflection pixels
+    whose ray tree flips.  Measured on a B200: 99.91% / 99.94% / 0.006 LSB (cornell, depth 5)."""
     s, cam = scenes.cornell_box()
     w, h = 480, 270
     with Renderer(s) as r:
         strict, st64 = r.render(cam, w, h, 4, 5, abi.NT_F64_STRICT)
         fast, st32 = r.render(cam, w, h, 4, 5, abi.NT_F32_FAST)
     diff = np.abs(strict.astype(np.int16) - fast.astype(np.int16))[..., :3]
-    frac_ok = float((diff.max(axis=-1) <= 2).mean())
-    assert frac_ok >= 0.99, frac_ok
-    assert diff.mean() < 0.25, diff.mean()
-    assert abs(st32["rays"] - st64["rays"]) / st64["rays"] < 0.01
+    assert float((diff.max(axis=-1) <= 1).mean()) >= 0.995
+    assert float((diff.max(axis=-1) <= 2).mean()) >= 0.998
+    assert diff.mean() < 0.05, diff.mean()
+    assert abs(st32["rays"] - st64["rays"]) / st64["rays"] < 0.005
+
+
+def test_fast_mode_tolerance_bvh_scene():
+    s, cam = scenes.spheres_and_mesh(n_spheres=2000, mesh_n=96)
+    w, h = 320, 180
+    with Renderer(s) as r:
+        strict, _ = r.render(cam, w, h, 4, 3, abi.NT_F64_STRICT)
+        fast, _ = r.render(cam, w, h, 4, 3, abi.NT_F32_FAST)
+    diff = np.abs(strict.astype(np.int16) - fast.astype(np.int16))[..., :3]
+    assert float((diff.max(axis=-1) <= 2).mean()) >= 0.99
+    assert diff.mean() < 0.1, diff.mean()
 
 
 def test_empty_and_degenerate_scenes():
@@ -166,10 +179,98 @@ def test_invalid_arguments_rejected():
     from nettracer_b200.lib import NetTracerError
     s, cam = scenes.cornell_box()
     with Renderer(s) as r:
-        for bad in (dict(spp=3), dict(max_depth=0), dict(max_depth=17), dict(width=0)):
-            kw = dict(width=64, height=64, spp=1, max_depth=1); kw.update(bad)
+        for bad in (dict(spp=3), dict(max_depth=0), dict(max_depth=17), dict(width=0), dict(precision=7),
+                    dict(shard_index=2, shard_count=2)):
+            p = make_params(64, 64, 1, 1, cam.resolve(64, 64))
+            for k, v in bad.items():
+                setattr(p, k, v)
             with pytest.raises(NetTracerError):
-                r.render(cam, kw["width"], kw["height"], kw["spp"], kw["max_depth"])
+                r.render_params(p)
     s.sphere_mat[0] = 99
     with pytest.raises(NetTracerError):
         Renderer(s)
+
+
+# ---------------- committed golden fixtures (tests/golden, made by tests/make_golden.py) ----------------
+from tests.make_golden import CASES, KEYS  # noqa: E402
+import os  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_cuda_matches_golden(name):
+    factory, kw, w, h, spp, depth = CASES[name]
+    scene, cam = factory(**kw)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    with Renderer(scene) as r:
+        img, st = r.render(cam, w, h, spp, depth, abi.NT_F64_STRICT)
+    assert_images_match(img, g["rgba"], name)
+    assert [st[k] for k in KEYS] == list(g["counters"])
+
+
+# ---------------- device path: nt_render_device + nt_deinterleave_device, on torch streams ----------------
+def test_device_path_and_deinterleave_kernel():
+    import torch
+    from nettracer_b200.sharded import CudaBackend
+    s, cam = scenes.cornell_box()
+    w, h, band, n = 176, 99, 8, 3
+    ref, rst = oracle.render(s, make_params(w, h, 4, 3, cam.resolve(w, h)))
+    b = CudaBackend(s, 0)
+    max_rows = max(shard_rows(h, band, i, n) for i in range(n))
+    slots = b.empty(n, max_rows, w, 4).zero_()
+    rays = 0
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        for i in range(n):
+            p = make_params(w, h, 4, 3, cam.resolve(w, h), shard_index=i, shard_count=n, band_rows=band,
+                            layout=abi.NT_LAYOUT_COMPACT)
+            b.render_shard(p, slots[i].data_ptr(), w * 4)
+            rays += b.stats()["rays"]
+        full = b.empty(h, w, 4).zero_()
+        b.deinterleave(slots, max_rows * w * 4, full, w, h, band, n)
+    stream.synchronize()
+    assert_images_match(full.cpu().numpy(), ref, "device path")
+    assert rays == rst["rays"]
+    b.close()
+
+
+# ---------------- full-size properties (BASELINE.json sizes; the oracle is too slow to be the checker) ----------------
+def test_full_size_cfg3_properties():
+    """1920x1080, 4 spp, depth 5: sharded == unsharded bit for bit, re-render is idempotent, every pixel
+    opaque, ray counters add up over shards, and a 1/8-height strip equals the oracle."""
+    s, cam = scenes.cornell_box()
+    w, h, spp, depth = 1920, 1080, 4, 5
+    with Renderer(s) as r:
+        full, st = r.render(cam, w, h, spp, depth)
+        again, st2 = r.render(cam, w, h, spp, depth)
+        assert np.array_equal(full, again) and st["rays"] == st2["rays"]
+        assert (full[..., 3] == 255).all() and st["rays_primary"] == w * h * spp
+        parts, rays = [], 0
+        for i in range(4):
+            p = make_params(w, h, spp, depth, cam.resolve(w, h), shard_index=i, shard_count=4, band_rows=8,
+                            layout=abi.NT_LAYOUT_COMPACT)
+            img, sti = r.render_params(p)
+            parts.append(img)
+            rays += sti["rays"]
+        assert np.array_equal(deinterleave_host(parts, h, w, 8), full) and rays == st["rays"]
+    # the oracle on shard 3 of 8 (135 rows, ~1/8 of the frame)
+    p = make_params(w, h, spp, depth, cam.resolve(w, h), shard_index=3, shard_count=8, band_rows=8,
+                    layout=abi.NT_LAYOUT_COMPACT)
+    rows = shard_rows(h, 8, 3, 8)
+    ref, _ = oracle.render(s, p, compact_rows=rows)
+    from nettracer_b200.scene import owned_rows
+    assert_images_match(full[owned_rows(h, 8, 3, 8)], ref, "cfg3 strip")
+
+
+def test_two_gpu_sharded_renderer_modes():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for mode in ("gather", "p2p_store"):
+        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                              "--master-addr", "127.0.0.1", "--master-port", "29533",
+                              os.path.join(root, "tests", "sharded_gpu_worker.py"), mode],
+                             capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and "SHARDED_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
