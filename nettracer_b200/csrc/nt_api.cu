@@ -114,6 +114,7 @@ static int validate_desc(const nt_scene_desc *d) {
 }
 
 static const size_t kSmemBudget = 40 * 1024;
+static const size_t kCounterBytes = sizeof(unsigned long long) * (NT_COUNTER_SLOTS * NT_NCOUNTERS + 1);
 static const uint32_t kFlatMaxBounded = 64;
 
 extern "C" void nt_scene_destroy(nt_scene *sc) {
@@ -213,8 +214,8 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
     CU(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&sc->ev0));
     CU(cudaEventCreate(&sc->ev1));
-    CU(cudaMalloc(&sc->d_counters, sizeof(unsigned long long) * NT_COUNTER_SLOTS * NT_NCOUNTERS));
-    CU(cudaMallocHost(&sc->h_counters, sizeof(unsigned long long) * NT_COUNTER_SLOTS * NT_NCOUNTERS));
+    CU(cudaMalloc(&sc->d_counters, kCounterBytes));
+    CU(cudaMallocHost(&sc->h_counters, kCounterBytes));
     return NT_OK;
 }
 
@@ -275,8 +276,8 @@ static int make_args(const nt_render_params *p, size_t stride, NtRenderArgs *a) 
     int li = 0;
     while ((1u << li) < L) ++li;
     a->twx = tw[li][0]; a->twy = tw[li][1];
-    a->tiles_x = (p->width + 4 * a->twx - 1) / (4 * a->twx);
-    a->tiles_y = (a->vrows + 2 * a->twy - 1) / (2 * a->twy);
+    a->tiles_x = (p->width + a->twx - 1) / a->twx;
+    a->tiles_y = (a->vrows + a->twy - 1) / a->twy;
     a->eps = p->ray_epsilon > 0 ? p->ray_epsilon : 1e-6;
     if (p->precision == NT_F32_FAST && a->eps < 1e-4) a->eps = 1e-4; // SPEC-PROVISIONAL §7
     for (int k = 0; k < 3; ++k) {
@@ -289,7 +290,6 @@ static int make_args(const nt_render_params *p, size_t stride, NtRenderArgs *a) 
 
 static int launch(nt_scene *sc, const NtRenderArgs &a, uint32_t precision, cudaStream_t st) {
     if (a.vrows == 0) return NT_OK;
-    if (a.tiles_y > 65535) return fail(NT_ERR_INVALID, "image too tall for one launch (%u row tiles)", a.tiles_y);
     const int e = precision == NT_F64_STRICT ? nt_launch_render_f64(sc->ds, a, st) : nt_launch_render_f32(sc->ds, a, st);
     if (e) return fail(NT_ERR_CUDA, "render kernel launch: %s", cudaGetErrorString((cudaError_t)e));
     return NT_OK;
@@ -325,7 +325,7 @@ extern "C" int nt_render(nt_scene *sc, const nt_render_params *p, uint8_t *rgba_
     }
     a.out = sc->d_fb;
     a.counters = sc->d_counters;
-    const size_t cbytes = sizeof(unsigned long long) * NT_COUNTER_SLOTS * NT_NCOUNTERS;
+    const size_t cbytes = kCounterBytes;
     CU(cudaMemsetAsync(sc->d_counters, 0, cbytes, sc->stream));
     CU(cudaEventRecord(sc->ev0, sc->stream));
     if ((rc = launch(sc, a, p->precision, sc->stream)) != NT_OK) return rc;
@@ -366,7 +366,7 @@ extern "C" int nt_render_device(nt_scene *sc, const nt_render_params *p, void *r
     cudaStream_t st = (cudaStream_t)cuda_stream;
     a.out = (uint8_t *)rgba_out_dev;
     a.counters = sc->d_counters;
-    CU(cudaMemsetAsync(sc->d_counters, 0, sizeof(unsigned long long) * NT_COUNTER_SLOTS * NT_NCOUNTERS, st));
+    CU(cudaMemsetAsync(sc->d_counters, 0, kCounterBytes, st));
     return launch(sc, a, p->precision, st);
 }
 
@@ -375,7 +375,7 @@ extern "C" int nt_render_device_stats(nt_scene *sc, void *cuda_stream, nt_render
     std::lock_guard<std::mutex> lock(sc->mu);
     CU(cudaSetDevice(sc->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    CU(cudaMemcpyAsync(sc->h_counters, sc->d_counters, sizeof(unsigned long long) * NT_COUNTER_SLOTS * NT_NCOUNTERS, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(sc->h_counters, sc->d_counters, kCounterBytes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     memset(stats, 0, sizeof *stats);
     sum_counters(sc->h_counters, stats);

@@ -9,6 +9,9 @@
 #define NT_COUNTER_SLOTS 32
 #define NT_NCOUNTERS 8     // primary secondary shadow sphere plane triangle box light
 #define NT_BLOCK_THREADS 256
+#ifndef NT_MIN_BLOCKS
+#define NT_MIN_BLOCKS 3     // resident blocks per SM the render kernels are compiled for
+#endif
 #define NT_BVH_STACK 64
 #define NT_MAX_DEPTH_DEV 16 // == NT_MAX_DEPTH of the public header
 
@@ -50,12 +53,12 @@ struct NtRenderArgs {
     uint32_t shard_index, shard_count, band_rows, layout, vrows;
     uint32_t lanes;    // lanes per pixel (power of two dividing spp, <= 32)
     uint32_t twx, twy; // warp tile in pixels, twx*twy*lanes == 32
-    uint32_t tiles_x, tiles_y; // block tiles over the virtual image
+    uint32_t tiles_x, tiles_y; // warp tiles over the virtual image (owned rows only)
     double eps;
     double cam[12];    // eye p00 dx dy
     uint8_t *out;
     size_t stride;
-    unsigned long long *counters; // [NT_COUNTER_SLOTS][NT_NCOUNTERS]
+    unsigned long long *counters; // [NT_COUNTER_SLOTS][NT_NCOUNTERS] + 1 (next warp tile)
 };
 
 struct NtTraceArgs {

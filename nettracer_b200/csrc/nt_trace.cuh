@@ -50,47 +50,71 @@ template <> struct Math<float> {
     static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
 };
 
-// ---- loads: 128-bit, read-only path for global data, plain LDS for staged data ----
-template <bool GLOBAL> __device__ __forceinline__ void load4(const double *p, double *o) {
-    double2 a, b;
-    if (GLOBAL) { a = __ldg((const double2 *)p); b = __ldg((const double2 *)p + 1); }
-    else { a = *(const double2 *)p; b = *((const double2 *)p + 1); }
-    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
-}
-template <bool GLOBAL> __device__ __forceinline__ void load4(const float *p, float *o) {
-    float4 a = GLOBAL ? __ldg((const float4 *)p) : *(const float4 *)p;
-    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
-}
-template <bool GLOBAL> __device__ __forceinline__ void load9(const double *p, double *o) {
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        double2 a = GLOBAL ? __ldg((const double2 *)p + i) : *((const double2 *)p + i);
-        o[2 * i] = a.x;
-        if (i < 4) o[2 * i + 1] = a.y;
+// ---- loads: 128-bit; read-only path for global data, ld.shared by 32-bit shared address for the
+// staged data (an explicit state space: a generic pointer made the compiler rebuild the shared
+// window base inside the loops) ----
+template <typename R> struct Ld;
+template <> struct Ld<double> {
+    static __device__ __forceinline__ void g4(const double *p, double *o) {
+        const double2 a = __ldg((const double2 *)p), b = __ldg((const double2 *)p + 1);
+        o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
     }
-}
-template <bool GLOBAL> __device__ __forceinline__ void load9(const float *p, float *o) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        float4 a = GLOBAL ? __ldg((const float4 *)p + i) : *((const float4 *)p + i);
-        o[4 * i] = a.x;
-        if (i < 2) { o[4 * i + 1] = a.y; o[4 * i + 2] = a.z; o[4 * i + 3] = a.w; }
+    static __device__ __forceinline__ void s4(unsigned addr, double *o) {
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "r"(addr));
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+16];" : "=d"(o[2]), "=d"(o[3]) : "r"(addr));
     }
-}
+    static __device__ __forceinline__ void g9(const double *p, double *o) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const double2 a = __ldg((const double2 *)p + i);
+            o[2 * i] = a.x;
+            if (i < 4) o[2 * i + 1] = a.y;
+        }
+    }
+    static __device__ __forceinline__ void s9(unsigned addr, double *o) {
+        double pad;
+        (void)&pad;
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "r"(addr));
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+16];" : "=d"(o[2]), "=d"(o[3]) : "r"(addr));
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+32];" : "=d"(o[4]), "=d"(o[5]) : "r"(addr));
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+48];" : "=d"(o[6]), "=d"(o[7]) : "r"(addr));
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+64];" : "=d"(o[8]), "=d"(pad) : "r"(addr));
+    }
+};
+template <> struct Ld<float> {
+    static __device__ __forceinline__ void g4(const float *p, float *o) {
+        const float4 a = __ldg((const float4 *)p);
+        o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+    }
+    static __device__ __forceinline__ void s4(unsigned addr, float *o) {
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "r"(addr));
+    }
+    static __device__ __forceinline__ void g9(const float *p, float *o) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float4 a = __ldg((const float4 *)p + i);
+            o[4 * i] = a.x;
+            if (i < 2) { o[4 * i + 1] = a.y; o[4 * i + 2] = a.z; o[4 * i + 3] = a.w; }
+        }
+    }
+    static __device__ __forceinline__ void s9(unsigned addr, float *o) {
+        float p0, p1, p2;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "r"(addr));
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(o[4]), "=f"(o[5]), "=f"(o[6]), "=f"(o[7]) : "r"(addr));
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+32];" : "=f"(o[8]), "=f"(p0), "=f"(p1), "=f"(p2) : "r"(addr));
+    }
+};
 
 struct Counters {
     unsigned prim, sec, shadow, sph, pln, tri, box, light;
 };
 
 // ---- SPEC §3 intersections ----
-template <typename R, bool GLOBAL>
-__device__ __forceinline__ bool hit_sphere(const R *__restrict__ s, const V3<R> &o, const V3<R> &d,
-                                           R eps, R &t_out) {
-    R q[4];
-    load4<GLOBAL>(s, q);
+// Sphere, part 1 (branch-free, so two spheres can be interleaved): b and the discriminant.
+template <typename R>
+__device__ __forceinline__ void sphere_eval(const R q[4], const V3<R> &o, const V3<R> &d, R &b, R &disc) {
     V3<R> oc = { o.x - q[0], o.y - q[1], o.z - q[2] };
-    R b = dot(oc, d);
-    R disc;
+    b = dot(oc, d);
     if constexpr (sizeof(R) == 8) {
         R cc = dot(oc, oc) - q[3];
         disc = b * b - cc;
@@ -101,7 +125,12 @@ __device__ __forceinline__ bool hit_sphere(const R *__restrict__ s, const V3<R> 
         V3<R> l = { oc.x - b * d.x, oc.y - b * d.y, oc.z - b * d.z };
         disc = q[3] - dot(l, l);
     }
-    if (disc < R(0)) return false;
+}
+// Sphere, part 2: roots (only reached when disc >= 0).  Deliberately NOT inlined: the binary64 sqrt
+// expands to ~30 instructions and this is reached from six places; one shared copy keeps the kernel
+// inside the instruction cache (the profile showed no_instruction stalls at 60 KB of code).
+template <typename R>
+__device__ __noinline__ bool sphere_finish(R b, R disc, R eps, R &t_out) {
     R sq = Math<R>::sqrt_(disc);
     R t = -b - sq;
     if (!(t > eps)) t = -b + sq;
@@ -109,26 +138,43 @@ __device__ __forceinline__ bool hit_sphere(const R *__restrict__ s, const V3<R> 
     t_out = t;
     return true;
 }
-
+// The plane quotient, shared for the same reason (binary64 division is ~30 instructions).
 template <typename R>
-__device__ __forceinline__ bool hit_plane(const R *__restrict__ p, const V3<R> &o, const V3<R> &d,
-                                          R eps, R &t_out) {
-    R q[4];
-    load4<false>(p, q);
+__device__ __noinline__ R plane_quotient(R num, R dn) { return Math<R>::div(num, dn); }
+template <typename R>
+__device__ __forceinline__ bool hit_sphere(const R q[4], const V3<R> &o, const V3<R> &d, R eps, R &t_out) {
+    R b, disc;
+    sphere_eval<R>(q, o, d, b, disc);
+    if (disc < R(0)) return false;
+    return sphere_finish<R>(b, disc, eps, t_out);
+}
+
+// Plane.  Returns true with t when the plane is hit (t > eps) AND t could be < tmax; when it returns
+// false the plane is either missed or certainly not nearer than tmax.  The strict mode avoids the
+// binary64 division (~15 FP64-pipe instructions) unless the quotient can matter:
+//   * num and dn of different sign            -> t < 0, a miss
+//   * |num| >= (|dn| * tmax) * (1 + 1e-15)     -> the correctly rounded quotient is >= tmax
+// Both tests are implied by the exact rule, so the result is bit-identical to dividing always.
+template <typename R>
+__device__ __forceinline__ bool hit_plane(const R q[4], const V3<R> &o, const V3<R> &d, R eps, R tmax,
+                                          R &t_out) {
     V3<R> n = { q[0], q[1], q[2] };
     R dn = dot(n, d);
+    R num = q[3] - dot(n, o);
+    if constexpr (sizeof(R) == 8) {
+        if ((__double2hiint(num) ^ __double2hiint(dn)) < 0) return false;
+        if (fabs(num) >= (fabs(dn) * tmax) * (1.0 + 1e-15)) return false;
+    }
     if (dn == R(0)) return false;
-    R t = Math<R>::div(q[3] - dot(n, o), dn);
+    R t;
+    if constexpr (sizeof(R) == 8) t = plane_quotient<R>(num, dn); else t = Math<R>::div(num, dn);
     if (!(t > eps)) return false;
     t_out = t;
     return true;
 }
 
-template <typename R, bool GLOBAL>
-__device__ __forceinline__ bool hit_triangle(const R *__restrict__ tr, const V3<R> &o,
-                                             const V3<R> &d, R eps, R &t_out) {
-    R q[9];
-    load9<GLOBAL>(tr, q);
+template <typename R>
+__device__ __forceinline__ bool hit_triangle(const R q[9], const V3<R> &o, const V3<R> &d, R eps, R &t_out) {
     V3<R> v0 = { q[0], q[1], q[2] }, e1 = { q[3], q[4], q[5] }, e2 = { q[6], q[7], q[8] };
     V3<R> p = cross(d, e2);
     R det = dot(e1, p);
@@ -147,14 +193,25 @@ __device__ __forceinline__ bool hit_triangle(const R *__restrict__ tr, const V3<
 }
 
 // ---- scene context of one block ----
+// Dynamic shared memory: the flat intersection data staged by stage_scene().  Addressed through this
+// symbol (plus element offsets kept in Ctx) so that every access is a plain LDS with an immediate
+// base; pointers kept in a struct made the compiler rebuild the shared window address per iteration.
+extern __shared__ __align__(16) unsigned char nt_smem[];
+
 template <typename R, bool BVH> struct Ctx {
     const NtDevScene *s;
     const NtSceneView<R> *v;
-    const R *sph; // staged in shared memory when !BVH, global (BVH order) otherwise
-    const R *pln; // always staged in shared memory
-    const R *tri; // as sph
+    unsigned sph_addr, pln_addr, tri_addr; // 32-bit shared-memory byte addresses of the staged arrays
     R eps;
     unsigned max_depth;
+    __device__ __forceinline__ void ld_sph(unsigned i, R *q) const {
+        if constexpr (BVH) Ld<R>::g4(v->sph + 4 * (size_t)i, q); else Ld<R>::s4(sph_addr + i * (4 * (unsigned)sizeof(R)), q);
+    }
+    __device__ __forceinline__ void ld_pln(unsigned i, R *q) const { Ld<R>::s4(pln_addr + i * (4 * (unsigned)sizeof(R)), q); }
+    __device__ __forceinline__ void ld_tri(unsigned i, R *q) const {
+        if constexpr (BVH) Ld<R>::g9(v->tri + NT_TRI_STRIDE * (size_t)i, q);
+        else Ld<R>::s9(tri_addr + i * (NT_TRI_STRIDE * (unsigned)sizeof(R)), q);
+    }
 };
 
 struct Hit {
@@ -210,8 +267,8 @@ __device__ __forceinline__ bool bvh_traverse(const Ctx<R, true> &c, const V3<R> 
                     const int idx = start + j;
                     R t;
                     bool hit;
-                    if (cnt & 0x100) { k.tri++; hit = hit_triangle<R, true>(c.tri + (size_t)idx * NT_TRI_STRIDE, o, d, c.eps, t); }
-                    else { k.sph++; hit = hit_sphere<R, true>(c.sph + (size_t)idx * 4, o, d, c.eps, t); }
+                    if (cnt & 0x100) { R q[9]; c.ld_tri(idx, q); k.tri++; hit = hit_triangle<R>(q, o, d, c.eps, t); }
+                    else { R q[4]; c.ld_sph(idx, q); k.sph++; hit = hit_sphere<R>(q, o, d, c.eps, t); }
                     if (!hit) continue;
                     if (ANY) { if (t < tb) return true; }
                     else {
@@ -259,16 +316,36 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
     best.kind = -1; best.idx = -1; best.gid = 0x7fffffff;
     R t;
     if constexpr (!BVH) {
-        for (unsigned i = 0; i < s.ns; ++i)
-            if (hit_sphere<R, false>(c.sph + 4 * i, o, d, c.eps, t) && t < tb) { tb = t; best.kind = 0; best.idx = (int)i; }
+        // two spheres per iteration: the two discriminant chains are independent and interleave
+        unsigned i = 0;
+        for (; i + 2 <= s.ns; i += 2) {
+            R q0[4], q1[4], b0, b1, d0, d1;
+            c.ld_sph(i, q0);
+            c.ld_sph(i + 1, q1);
+            sphere_eval<R>(q0, o, d, b0, d0);
+            sphere_eval<R>(q1, o, d, b1, d1);
+            if (!(d0 < R(0)) && sphere_finish<R>(b0, d0, c.eps, t) && t < tb) { tb = t; best.kind = 0; best.idx = (int)i; }
+            if (!(d1 < R(0)) && sphere_finish<R>(b1, d1, c.eps, t) && t < tb) { tb = t; best.kind = 0; best.idx = (int)i + 1; }
+        }
+        if (i < s.ns) {
+            R q[4];
+            c.ld_sph(i, q);
+            if (hit_sphere<R>(q, o, d, c.eps, t) && t < tb) { tb = t; best.kind = 0; best.idx = (int)i; }
+        }
         k.sph += s.ns;
     }
-    for (unsigned i = 0; i < s.np; ++i)
-        if (hit_plane<R>(c.pln + 4 * i, o, d, c.eps, t) && t < tb) { tb = t; best.kind = 1; best.idx = (int)i; best.gid = (int)(s.ns + i); }
+    for (unsigned i = 0; i < s.np; ++i) {
+        R q[4];
+        c.ld_pln(i, q);
+        if (hit_plane<R>(q, o, d, c.eps, tb, t) && t < tb) { tb = t; best.kind = 1; best.idx = (int)i; best.gid = (int)(s.ns + i); }
+    }
     k.pln += s.np;
     if constexpr (!BVH) {
-        for (unsigned i = 0; i < s.nt; ++i)
-            if (hit_triangle<R, false>(c.tri + NT_TRI_STRIDE * i, o, d, c.eps, t) && t < tb) { tb = t; best.kind = 2; best.idx = (int)i; }
+        for (unsigned i = 0; i < s.nt; ++i) {
+            R q[9];
+            c.ld_tri(i, q);
+            if (hit_triangle<R>(q, o, d, c.eps, t) && t < tb) { tb = t; best.kind = 2; best.idx = (int)i; }
+        }
         k.tri += s.nt;
     } else {
         bvh_traverse<R, false>(c, o, d, tb, best, k);
@@ -277,26 +354,43 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
 }
 
 // SPEC §3 occlusion: any primitive hit (t > eps) with t < dist; first found ends the query.
+// Counters follow the sequential rule (tests up to and including the first occluder).
 template <typename R, bool BVH>
 __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, const V3<R> &d, R dist,
                                          Counters &k) {
     const NtDevScene &s = *c.s;
     R t;
     if constexpr (!BVH) {
-        for (unsigned i = 0; i < s.ns; ++i) {
-            k.sph++;
-            if (hit_sphere<R, false>(c.sph + 4 * i, o, d, c.eps, t) && t < dist) return true;
+        unsigned i = 0;
+        for (; i + 2 <= s.ns; i += 2) {
+            R q0[4], q1[4], b0, b1, d0, d1;
+            c.ld_sph(i, q0);
+            c.ld_sph(i + 1, q1);
+            sphere_eval<R>(q0, o, d, b0, d0);
+            sphere_eval<R>(q1, o, d, b1, d1);
+            if (!(d0 < R(0)) && sphere_finish<R>(b0, d0, c.eps, t) && t < dist) { k.sph += i + 1; return true; }
+            if (!(d1 < R(0)) && sphere_finish<R>(b1, d1, c.eps, t) && t < dist) { k.sph += i + 2; return true; }
         }
+        if (i < s.ns) {
+            R q[4];
+            c.ld_sph(i, q);
+            if (hit_sphere<R>(q, o, d, c.eps, t) && t < dist) { k.sph += s.ns; return true; }
+        }
+        k.sph += s.ns;
     }
     for (unsigned i = 0; i < s.np; ++i) {
-        k.pln++;
-        if (hit_plane<R>(c.pln + 4 * i, o, d, c.eps, t) && t < dist) return true;
+        R q[4];
+        c.ld_pln(i, q);
+        if (hit_plane<R>(q, o, d, c.eps, dist, t) && t < dist) { k.pln += i + 1; return true; }
     }
+    k.pln += s.np;
     if constexpr (!BVH) {
         for (unsigned i = 0; i < s.nt; ++i) {
-            k.tri++;
-            if (hit_triangle<R, false>(c.tri + NT_TRI_STRIDE * i, o, d, c.eps, t) && t < dist) return true;
+            R q[9];
+            c.ld_tri(i, q);
+            if (hit_triangle<R>(q, o, d, c.eps, t) && t < dist) { k.tri += i + 1; return true; }
         }
+        k.tri += s.nt;
         return false;
     } else {
         Hit h;
@@ -329,15 +423,14 @@ __device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R
             V3<R> Ng;
             int mat;
             if (h.kind == 0) {
-                const R *sp4 = BVH ? v.sph + 4 * (size_t)h.idx : c.sph + 4 * h.idx;
                 R q[4];
-                if (BVH) load4<true>(sp4, q); else load4<false>(sp4, q);
+                c.ld_sph(h.idx, q);
                 const R ir = __ldg(v.sph_invr + h.idx);
                 Ng = { (P.x - q[0]) * ir, (P.y - q[1]) * ir, (P.z - q[2]) * ir };
                 mat = __ldg(s.sph_mat + h.idx);
             } else if (h.kind == 1) {
                 R q[4];
-                load4<false>(c.pln + 4 * h.idx, q);
+                c.ld_pln(h.idx, q);
                 Ng = { q[0], q[1], q[2] };
                 mat = __ldg(s.pln_mat + h.idx);
             } else {
@@ -347,7 +440,7 @@ __device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R
             }
             const R *mp = v.mat + (size_t)mat * NT_MAT_STRIDE;
             R mq[12];
-            load4<true>(mp, mq); load4<true>(mp + 4, mq + 4); load4<true>(mp + 8, mq + 8);
+            Ld<R>::g4(mp, mq); Ld<R>::g4(mp + 4, mq + 4); Ld<R>::g4(mp + 8, mq + 8);
             const R ka = mq[3], kd = mq[4], ks = mq[5], shin = mq[6], kr = mq[7], kt = mq[8];
             const R cosd = dot(d, Ng);
             const bool entering = cosd < R(0);
@@ -432,98 +525,119 @@ __device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R
 
 // Stage the flat intersection data in shared memory with 128-bit loads.
 template <typename R, bool BVH>
-__device__ __forceinline__ void stage_scene(const NtDevScene &s, const NtSceneView<R> &v, R *smem,
-                                            Ctx<R, BVH> &c) {
-    const unsigned n_sph = BVH ? 0 : s.ns * 4, n_pln = s.np * 4, n_tri = BVH ? 0 : s.nt * NT_TRI_STRIDE;
-    R *s_sph = smem, *s_pln = smem + n_sph, *s_tri = s_pln + n_pln;
+__device__ __forceinline__ void stage_scene(const NtDevScene &s, const NtSceneView<R> &v, Ctx<R, BVH> &c) {
+    const unsigned n_sph = BVH ? 0u : s.ns * 4, n_pln = s.np * 4, n_tri = BVH ? 0u : s.nt * NT_TRI_STRIDE;
+    R *smem = (R *)nt_smem;
     constexpr int VEC = 16 / sizeof(R);
     typedef typename std::conditional<sizeof(R) == 8, double2, float4>::type VT;
-    for (unsigned i = threadIdx.x; i < n_sph / VEC; i += blockDim.x) ((VT *)s_sph)[i] = __ldg((const VT *)v.sph + i);
-    for (unsigned i = threadIdx.x; i < n_pln / VEC; i += blockDim.x) ((VT *)s_pln)[i] = __ldg((const VT *)v.pln + i);
-    for (unsigned i = threadIdx.x; i < n_tri / VEC; i += blockDim.x) ((VT *)s_tri)[i] = __ldg((const VT *)v.tri + i);
+    if constexpr (!BVH)
+#pragma unroll 1
+        for (unsigned i = threadIdx.x; i < n_sph / VEC; i += blockDim.x) ((VT *)smem)[i] = __ldg((const VT *)v.sph + i);
+#pragma unroll 1
+    for (unsigned i = threadIdx.x; i < n_pln / VEC; i += blockDim.x) ((VT *)(smem + n_sph))[i] = __ldg((const VT *)v.pln + i);
+    if constexpr (!BVH)
+#pragma unroll 1
+        for (unsigned i = threadIdx.x; i < n_tri / VEC; i += blockDim.x) ((VT *)(smem + n_sph + n_pln))[i] = __ldg((const VT *)v.tri + i);
     __syncthreads();
-    c.sph = BVH ? v.sph : s_sph;
-    c.pln = s_pln;
-    c.tri = BVH ? v.tri : s_tri;
+    unsigned base = (unsigned)__cvta_generic_to_shared(nt_smem);
+    asm volatile("" : "+r"(base)); // opaque: otherwise ptxas re-derives the window base (S2R + 5 ops) per use
+    c.sph_addr = base;
+    c.pln_addr = base + n_sph * (unsigned)sizeof(R);
+    c.tri_addr = base + (n_sph + n_pln) * (unsigned)sizeof(R);
 }
 
+// Per-thread counters -> one atomic per counter per block, spread over NT_COUNTER_SLOTS slots.
 __device__ __forceinline__ void flush_counters(const Counters &k, unsigned long long *counters,
-                                               unsigned *s_cnt) {
+                                               unsigned long long *s_cnt) {
     const unsigned vals[NT_NCOUNTERS] = { k.prim, k.sec, k.shadow, k.sph, k.pln, k.tri, k.box, k.light };
     if (threadIdx.x < NT_NCOUNTERS) s_cnt[threadIdx.x] = 0;
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < NT_NCOUNTERS; ++i) {
         const unsigned w = __reduce_add_sync(0xffffffffu, vals[i]);
-        if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_cnt[i], w);
+        if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_cnt[i], (unsigned long long)w);
     }
     __syncthreads();
     if (threadIdx.x < NT_NCOUNTERS && s_cnt[threadIdx.x]) {
-        const unsigned slot = (blockIdx.x + blockIdx.y * gridDim.x) % NT_COUNTER_SLOTS;
-        atomicAdd(&counters[slot * NT_NCOUNTERS + threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+        const unsigned slot = blockIdx.x % NT_COUNTER_SLOTS;
+        atomicAdd(&counters[slot * NT_NCOUNTERS + threadIdx.x], s_cnt[threadIdx.x]);
     }
 }
 
+// Persistent warps: the grid is sized to fill the machine once (SM count x resident blocks); every
+// warp pulls warp-tiles (twx x twy pixels x `lanes` samples = 32 samples) from one atomic counter until
+// the image is exhausted, so no block waits at a barrier for its slowest tile and an expensive region
+// (glass, mirrors) is spread over all SMs.  The only block barriers are the scene staging at the start
+// and the counter flush at the end.
 template <typename R, bool BVH>
-__global__ void __launch_bounds__(NT_BLOCK_THREADS)
+__global__ void __launch_bounds__(NT_BLOCK_THREADS, NT_MIN_BLOCKS)
 render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRenderArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ unsigned s_cnt[NT_NCOUNTERS];
+    __shared__ unsigned long long s_cnt[NT_NCOUNTERS];
     const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
     Ctx<R, BVH> c;
     c.s = &s; c.v = &v; c.eps = (R)a.eps; c.max_depth = a.max_depth;
-    stage_scene<R, BVH>(s, v, (R *)smem_raw, c);
+    stage_scene<R, BVH>(s, v, c);
 
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lane = threadIdx.x & 31;
     const unsigned L = a.lanes, j = lane & (L - 1), pw = lane / L;
-    // block tile = 4 x 2 warp tiles of twx x twy pixels over the virtual image (owned rows only)
-    const unsigned px = (blockIdx.x * 4 + (warp & 3)) * a.twx + pw % a.twx;
-    const unsigned vr = (blockIdx.y * 2 + (warp >> 2)) * a.twy + pw / a.twx;
-    const bool live = px < a.width && vr < a.vrows;
-    const unsigned y = ((vr / a.band_rows) * a.shard_count + a.shard_index) * a.band_rows + vr % a.band_rows;
-
-    Counters k = { 0, 0, 0, 0, 0, 0, 0, 0 };
-    R sum[3] = { R(0), R(0), R(0) };
+    const unsigned lx = pw % a.twx, ly = pw / a.twx;
+    const unsigned warps_per_block = NT_BLOCK_THREADS / 32, total_warps = gridDim.x * warps_per_block;
+    const unsigned n_tiles = a.tiles_x * a.tiles_y;
+    unsigned long long *next_tile = a.counters + NT_COUNTER_SLOTS * NT_NCOUNTERS;
     const V3<R> eye = { (R)a.cam[0], (R)a.cam[1], (R)a.cam[2] };
     const R rn = (R)a.n;
+    const R inv_spp = Math<R>::rcp((R)a.spp);
     const unsigned rounds = a.spp / L;
-    for (unsigned r = 0; r < rounds; ++r) {
-        R acc[3] = { R(0), R(0), R(0) };
-        if (live) {
-            // SPEC §2: regular n x n grid, sample s = r*L + j
-            const unsigned sidx = r * L + j;
-            const unsigned si = sidx % a.n, sj = sidx / a.n;
-            const R ox = Math<R>::div((R)si + R(0.5), rn), oy = Math<R>::div((R)sj + R(0.5), rn);
-            const R fx = (R)px + ox, fy = (R)y + oy;
-            const V3<R> D = { ((R)a.cam[3] + (R)a.cam[6] * fx) + (R)a.cam[9] * fy,
-                              ((R)a.cam[4] + (R)a.cam[7] * fx) + (R)a.cam[10] * fy,
-                              ((R)a.cam[5] + (R)a.cam[8] * fx) + (R)a.cam[11] * fy };
-            const V3<R> dir = scale(D, Math<R>::rcp(Math<R>::sqrt_(dot(D, D))));
-            k.prim++;
-            trace_sample<R, BVH>(c, eye, dir, acc, k);
-        }
-        // SPEC §5: samples are added in sample order; lanes of one pixel are adjacent
-        if (L == 1) {
+    Counters k = { 0, 0, 0, 0, 0, 0, 0, 0 };
+
+    unsigned tile = blockIdx.x * warps_per_block + (threadIdx.x >> 5); // first tile: no atomic needed
+    while (tile < n_tiles) {
+        const unsigned px = (tile % a.tiles_x) * a.twx + lx;
+        const unsigned vr = (tile / a.tiles_x) * a.twy + ly;
+        const bool live = px < a.width && vr < a.vrows;
+        const unsigned y = ((vr / a.band_rows) * a.shard_count + a.shard_index) * a.band_rows + vr % a.band_rows;
+        R sum[3] = { R(0), R(0), R(0) };
+        for (unsigned r = 0; r < rounds; ++r) {
+            R acc[3] = { R(0), R(0), R(0) };
+            if (live) {
+                // SPEC §2: regular n x n grid, sample s = r*L + j
+                const unsigned sidx = r * L + j;
+                const unsigned si = sidx % a.n, sj = sidx / a.n;
+                const R ox = Math<R>::div((R)si + R(0.5), rn), oy = Math<R>::div((R)sj + R(0.5), rn);
+                const R fx = (R)px + ox, fy = (R)y + oy;
+                const V3<R> D = { ((R)a.cam[3] + (R)a.cam[6] * fx) + (R)a.cam[9] * fy,
+                                  ((R)a.cam[4] + (R)a.cam[7] * fx) + (R)a.cam[10] * fy,
+                                  ((R)a.cam[5] + (R)a.cam[8] * fx) + (R)a.cam[11] * fy };
+                const V3<R> dir = scale(D, Math<R>::rcp(Math<R>::sqrt_(dot(D, D))));
+                k.prim++;
+                trace_sample<R, BVH>(c, eye, dir, acc, k);
+            }
+            // SPEC §5: samples are added in sample order; the lanes of one pixel are adjacent
+            if (L == 1) {
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) sum[ch] = sum[ch] + acc[ch];
-        } else {
-            const unsigned base = lane & ~(L - 1);
-            for (unsigned jj = 0; jj < L; ++jj)
+                for (int ch = 0; ch < 3; ++ch) sum[ch] = sum[ch] + acc[ch];
+            } else {
+                const unsigned base = lane & ~(L - 1);
+#pragma unroll 1
+                for (unsigned jj = 0; jj < L; ++jj)
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) sum[ch] = sum[ch] + __shfl_sync(0xffffffffu, acc[ch], base + jj);
+                    for (int ch = 0; ch < 3; ++ch) sum[ch] = sum[ch] + __shfl_sync(0xffffffffu, acc[ch], base + jj);
+            }
         }
-    }
-    if (live && j == 0) {
-        const R inv_spp = Math<R>::rcp((R)a.spp);
-        unsigned rgba = 0xff000000u;
+        if (live && j == 0) {
+            unsigned rgba = 0xff000000u;
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const R cv = sum[ch] * inv_spp;
-            const unsigned q = cv <= R(0) ? 0u : cv >= R(1) ? 255u : (unsigned)(int)(cv * R(255) + R(0.5));
-            rgba |= q << (8 * ch);
+            for (int ch = 0; ch < 3; ++ch) {
+                const R cv = sum[ch] * inv_spp;
+                const unsigned q = cv <= R(0) ? 0u : cv >= R(1) ? 255u : (unsigned)(int)(cv * R(255) + R(0.5));
+                rgba |= q << (8 * ch);
+            }
+            const size_t row = a.layout == 1 ? vr : y;
+            *(unsigned *)(a.out + row * a.stride + 4 * (size_t)px) = rgba;
         }
-        const size_t row = a.layout == 1 ? vr : y;
-        *(unsigned *)(a.out + row * a.stride + 4 * (size_t)px) = rgba;
+        unsigned long long nt = 0;
+        if (lane == 0) nt = atomicAdd(next_tile, 1ull) + total_warps;
+        tile = (unsigned)__shfl_sync(0xffffffffu, nt, 0);
     }
     flush_counters(k, a.counters, s_cnt);
 }
@@ -532,11 +646,10 @@ render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRe
 template <typename R, bool BVH>
 __global__ void __launch_bounds__(NT_BLOCK_THREADS)
 trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtTraceArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
     Ctx<R, BVH> c;
     c.s = &s; c.v = &v; c.eps = (R)a.eps; c.max_depth = 1;
-    stage_scene<R, BVH>(s, v, (R *)smem_raw, c);
+    stage_scene<R, BVH>(s, v, c);
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
     const V3<R> o = { (R)a.origins[3 * i], (R)a.origins[3 * i + 1], (R)a.origins[3 * i + 2] };
@@ -560,13 +673,28 @@ inline size_t flat_smem_bytes(const NtDevScene &s, bool bvh) {
     return n * sizeof(R);
 }
 
+template <typename R, bool BVH>
+inline int launch_render_t(const NtDevScene &s, const NtRenderArgs &a, cudaStream_t st) {
+    static int blocks_per_sm[64] = { 0 }, sms[64] = { 0 }; // per device, resolved once
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t smem = flat_smem_bytes<R>(s, BVH);
+    if (dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
+    if (!sms[dev]) {
+        cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[dev], render_kernel<R, BVH>, NT_BLOCK_THREADS, 4096);
+        if (blocks_per_sm[dev] < 1) blocks_per_sm[dev] = 1;
+    }
+    const unsigned n_tiles = a.tiles_x * a.tiles_y, wpb = NT_BLOCK_THREADS / 32;
+    unsigned grid = (unsigned)(sms[dev] * blocks_per_sm[dev]);
+    if (grid > (n_tiles + wpb - 1) / wpb) grid = (n_tiles + wpb - 1) / wpb;
+    render_kernel<R, BVH><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
+    return (int)cudaGetLastError();
+}
+
 template <typename R>
 inline int launch_render(const NtDevScene &s, const NtRenderArgs &a, cudaStream_t st) {
-    dim3 grid(a.tiles_x, a.tiles_y), block(NT_BLOCK_THREADS);
-    const size_t smem = flat_smem_bytes<R>(s, s.use_bvh != 0);
-    if (s.use_bvh) render_kernel<R, true><<<grid, block, smem, st>>>(s, a);
-    else render_kernel<R, false><<<grid, block, smem, st>>>(s, a);
-    return (int)cudaGetLastError();
+    return s.use_bvh ? launch_render_t<R, true>(s, a, st) : launch_render_t<R, false>(s, a, st);
 }
 
 template <typename R>

@@ -7,7 +7,7 @@ import os
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnettracer_b200.so")
+LIB_PATH = os.environ.get("NT_LIB_PATH") or os.path.join(_HERE, "libnettracer_b200.so")  # override: experiments only
 _LIB = None
 
 
