@@ -69,6 +69,8 @@ struct nt_scene {
     unsigned long long *d_counters = nullptr, *h_counters = nullptr;
     uint8_t *d_fb = nullptr;
     size_t fb_bytes = 0;
+    void *d_samples = nullptr; // BVH scenes: per-sample radiance scratch
+    size_t samples_bytes = 0;
     std::mutex mu;
 };
 
@@ -122,6 +124,7 @@ extern "C" void nt_scene_destroy(nt_scene *sc) {
     cudaSetDevice(sc->device);
     for (void *p : sc->allocs) cudaFree(p);
     if (sc->d_fb) cudaFree(sc->d_fb);
+    if (sc->d_samples) cudaFree(sc->d_samples);
     if (sc->d_counters) cudaFree(sc->d_counters);
     if (sc->h_counters) cudaFreeHost(sc->h_counters);
     if (sc->ev0) cudaEventDestroy(sc->ev0);
@@ -142,6 +145,7 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
         if (e[0] == '1') use_bvh = true;
         else if (e[0] == '0' && ((size_t)ns * 4 + (size_t)np * 4 + (size_t)nt * NT_TRI_STRIDE) * sizeof(double) <= kSmemBudget) use_bvh = false;
     }
+    if (ns >= (1u << 26) || nt >= (1u << 26)) return fail(NT_ERR_INVALID, "more than 2^26 spheres or triangles");
     if ((size_t)np * 4 * sizeof(double) > kSmemBudget) return fail(NT_ERR_INVALID, "too many planes (%u): planes are staged in shared memory, limit %zu", np, kSmemBudget / 32);
 
     NtBvhBuild bvh;
@@ -200,6 +204,7 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
     ds.use_bvh = use_bvh ? 1 : 0;
     ds.n_nodes = use_bvh && ns + nt > 0 ? (uint32_t)bvh.nodes.size() : 0;
     ds.max_abs = bvh.max_abs;
+    for (int a = 0; a < 3; ++a) { ds.blo[a] = bvh.blo[a]; ds.bhi[a] = bvh.bhi[a]; }
     int rc;
 #define UP(vec, dst) if ((rc = upload(sc, vec, &(dst))) != NT_OK) return rc
     UP(sph, ds.v64.sph); UP(sph_invr, ds.v64.sph_invr); UP(pln, ds.v64.pln); UP(tri, ds.v64.tri);
@@ -288,8 +293,18 @@ static int make_args(const nt_render_params *p, size_t stride, NtRenderArgs *a) 
     return NT_OK;
 }
 
-static int launch(nt_scene *sc, const NtRenderArgs &a, uint32_t precision, cudaStream_t st) {
+static int launch(nt_scene *sc, NtRenderArgs &a, uint32_t precision, cudaStream_t st) {
     if (a.vrows == 0) return NT_OK;
+    if (a.vrows > 65535) return fail(NT_ERR_INVALID, "more than 65535 owned rows in one launch");
+    const size_t need = nt_sample_buffer_bytes(sc->ds, a, (int)precision);
+    if (need > sc->samples_bytes) { // grows on demand; cudaFree waits for kernels still using the old one
+        if (sc->d_samples) cudaFree(sc->d_samples);
+        sc->d_samples = nullptr; sc->samples_bytes = 0;
+        cudaError_t e = cudaMalloc(&sc->d_samples, need);
+        if (e != cudaSuccess) return fail(NT_ERR_NOMEM, "sample buffer cudaMalloc(%zu): %s", need, cudaGetErrorString(e));
+        sc->samples_bytes = need;
+    }
+    a.samples = sc->d_samples;
     const int e = precision == NT_F64_STRICT ? nt_launch_render_f64(sc->ds, a, st) : nt_launch_render_f32(sc->ds, a, st);
     if (e) return fail(NT_ERR_CUDA, "render kernel launch: %s", cudaGetErrorString((cudaError_t)e));
     return NT_OK;

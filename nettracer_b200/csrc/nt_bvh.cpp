@@ -133,16 +133,22 @@ Ref build_set(std::vector<NtBvhNode> &nodes, const std::vector<Box> &boxes, std:
 
 } // namespace
 
+static int make_ref(int c, int n) {
+    if (n == 0) return c;          // inner node
+    if (n < 0) return -1;          // empty
+    return -2 - (c | (((n & 0xff) - 1) << 26) | (((n >> 8) & 1) << 28));
+}
+
 void nt_bvh_set_children(NtBvhNode &n, const float *lo0, const float *hi0, int c0, int n0,
                          const float *lo1, const float *hi1, int c1, int n1) {
     for (int a = 0; a < 3; ++a) { n.lo0[a] = lo0[a]; n.hi0[a] = hi0[a]; n.lo1[a] = lo1[a]; n.hi1[a] = hi1[a]; }
-    n.c0 = c0; n.c1 = c1; n.n0 = n0; n.n1 = n1;
+    n.c0 = make_ref(c0, n0); n.c1 = make_ref(c1, n1); n.n0 = n0; n.n1 = n1;
 }
 
 void nt_bvh_build(const double *spheres, uint32_t ns, const double *triangles, uint32_t nt,
                   int leaf_max, NtBvhBuild &out) {
     if (leaf_max < 1) leaf_max = 1;
-    if (leaf_max > 255) leaf_max = 255;
+    if (leaf_max > NT_LEAF_MAX) leaf_max = NT_LEAF_MAX;
     std::vector<Box> sb(ns), tb(nt);
     float max_abs = 0;
     for (uint32_t i = 0; i < ns; ++i) {
@@ -166,4 +172,7 @@ void nt_bvh_build(const double *spheres, uint32_t ns, const double *triangles, u
     const Ref rt = build_set(out.nodes, tb, out.tri_order, 0x100, leaf_max);
     nt_bvh_set_children(out.nodes[0], rs.box.lo, rs.box.hi, rs.c, rs.n, rt.box.lo, rt.box.hi, rt.c, rt.n);
     out.max_abs = max_abs;
+    Box all = rs.box;
+    all.grow(rt.box);
+    for (int a = 0; a < 3; ++a) { out.blo[a] = all.lo[a]; out.bhi[a] = all.hi[a]; }
 }

@@ -10,6 +10,7 @@ struct NtBvhBuild {
     std::vector<int> sph_order;    // BVH-ordered position -> original sphere index
     std::vector<int> tri_order;    // BVH-ordered position -> original triangle index
     float max_abs = 0;
+    float blo[3] = { 0, 0, 0 }, bhi[3] = { 0, 0, 0 }; // union of all primitive boxes
 };
 
 void nt_bvh_set_children(NtBvhNode &n, const float *lo0, const float *hi0, int c0, int n0,

@@ -1,0 +1,478 @@
+// nt_bvh_trace.cuh — the intersect-and-shade path for scenes whose bounded primitives live in HBM
+// behind a BVH (BASELINE.json configs[3], [4]).  Same arithmetic as nt_trace.cuh (SPEC-PROVISIONAL
+// §2-§5, same operation order, so strict mode stays bit-exact), different control structure:
+//
+//   Every lane runs a small state machine over its sample's ray tree.  At any moment a lane has at
+//   most ONE ray query in flight (nearest hit of a tree node, or the occlusion query of one light), and
+//   ALL kinds of query run through the same traversal code.  The warp alternates between
+//     (A) traversal rounds — one inner-node step and/or one leaf step per lane per round — and
+//     (B) advance — lanes whose query has finished shade, pick the next light, spawn children or
+//         finish — which is short.
+//   With a recursive-looking per-lane structure (nt_trace.cuh's) the occlusion traversal and the
+//   nearest-hit traversal are separate instruction streams and lanes that drift apart serialise: ncu
+//   measured 6.1 of 32 threads active per instruction on the 1M-triangle scene (profiles/r01_*).
+//   Here lanes drift in *state*, not in program counter.
+//
+//   Lanes are also refilled: a lane whose sample is complete stores the sample's radiance to the
+//   per-sample buffer and, once enough lanes of the warp are idle, the warp claims that many new
+//   samples with ONE atomicAdd (ballot + popc prefix gives each idle lane its sample id).  Ray trees
+//   differ wildly on these scenes (a terrain hit is 3 queries, a glass sphere up to 21 at depth 3), so
+//   with a static lane -> sample binding most lanes of a warp idle behind the deepest tree.  A small
+//   resolve kernel then adds the samples of each pixel in sample order (SPEC §5) and quantises.
+#pragma once
+#include "nt_trace.cuh"
+
+namespace nt {
+
+#define NT_REF_EMPTY (-1)
+// leaf ref = -2 - (first | (count-1) << 26 | type << 28); inner ref = node index >= 0
+__device__ __forceinline__ bool ref_is_leaf(int r) { return r <= -2; }
+
+template <typename R> struct BvhQuery { // scalars only: lives in registers (the stack is a separate array)
+    V3<R> o, d;
+    R tb;          // nearest: best t so far; any: the distance bound
+    Hit best;
+    float ox, oy, oz, ix, iy, iz, m, tmaxf; // binary32 copy of the ray for the box tests, origin shifted by tshift
+    R tshift;      // box-test frame: t' = t - tshift (0 unless the origin lies outside the scene bounds)
+    int cur;       // ref being visited, NT_REF_EMPTY when the query needs a pop
+    int sp;
+    bool any, done, found;
+};
+
+// Start a query: planes (unbounded, staged in shared memory) are tested here, then the tree is armed.
+template <typename R>
+__device__ __forceinline__ void query_start(const Ctx<R, true> &c, BvhQuery<R> &q, const V3<R> &o, const V3<R> &d,
+                                            R tmax, bool any, Counters &k) {
+    const NtDevScene &s = *c.s;
+    q.o = o; q.d = d; q.tb = tmax; q.any = any; q.done = false; q.found = false;
+    q.best.kind = -1; q.best.idx = -1; q.best.gid = 0x7fffffff;
+    q.cur = NT_REF_EMPTY; q.sp = 0;
+    R t;
+    for (unsigned i = 0; i < s.np; ++i) {
+        R pq[4];
+        c.ld_pln(i, pq);
+        k.pln++;
+        if (hit_plane<R>(pq, o, d, c.eps, q.tb, t) && t < q.tb) {
+            if (any) { q.done = true; q.found = true; return; }
+            q.tb = t; q.best.kind = 1; q.best.idx = (int)i; q.best.gid = (int)(s.ns + i); q.found = true;
+        }
+    }
+    if (s.n_nodes == 0) { q.done = true; return; }
+    float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
+    q.ix = 1.0f / (float)d.x; q.iy = 1.0f / (float)d.y; q.iz = 1.0f / (float)d.z;
+    // Box margin: covers rounding the ray to binary32 (origin, direction, reciprocal, slab products).
+    // It grows with |origin|, so a far origin (a camera outside the scene, a hit on an unbounded plane
+    // kilometres away) is first slid along the exact ray to where it enters the scene bounds: only the
+    // box tests use the shifted copy, the primitive tests keep the original ray.
+    float m = 4e-6f * (fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz)) + s.max_abs);
+    float tn = 0.0f, tf = CUDART_INF_F;
+    slab(s.blo[0], s.bhi[0], ox, q.ix, m, tn, tf);
+    slab(s.blo[1], s.bhi[1], oy, q.iy, m, tn, tf);
+    slab(s.blo[2], s.bhi[2], oz, q.iz, m, tn, tf);
+    if (!(tn <= tf) || tn > Math<R>::up(q.tb)) { q.done = true; return; } // misses every bounded primitive
+    q.tshift = R(0);
+    if (tn > 0.0f) {
+        const R ts = (R)tn;
+        const V3<R> os = { o.x + d.x * ts, o.y + d.y * ts, o.z + d.z * ts }; // a point of the exact ray
+        ox = (float)os.x; oy = (float)os.y; oz = (float)os.z;
+        m = 4e-6f * (fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz)) + s.max_abs);
+        q.tshift = ts;
+    }
+    q.ox = ox; q.oy = oy; q.oz = oz; q.m = m;
+    q.tmaxf = Math<R>::up(q.tb - q.tshift);
+    q.cur = 0;
+}
+
+template <typename R> __device__ __forceinline__ void query_pop(BvhQuery<R> &q, const int2 *stack) {
+    while (q.sp > 0) {
+        const int2 e = stack[--q.sp];
+        if (__int_as_float(e.y) <= q.tmaxf) { q.cur = e.x; return; }
+    }
+    q.cur = NT_REF_EMPTY;
+    q.done = true;
+}
+
+// One inner node: both child boxes (binary32, conservative), near child next, far child pushed.
+template <typename R>
+__device__ __forceinline__ void query_inner_step(const Ctx<R, true> &c, BvhQuery<R> &q, int2 *stack, Counters &k) {
+    const float4 *n = (const float4 *)(c.s->nodes + q.cur);
+    const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2);
+    const int4 q3 = __ldg((const int4 *)(n + 3));
+    float n0 = 0.0f, f0 = CUDART_INF_F, n1 = 0.0f, f1 = CUDART_INF_F;
+    slab(q0.x, q0.w, q.ox, q.ix, q.m, n0, f0);
+    slab(q0.y, q1.x, q.oy, q.iy, q.m, n0, f0);
+    slab(q0.z, q1.y, q.oz, q.iz, q.m, n0, f0);
+    slab(q1.z, q2.y, q.ox, q.ix, q.m, n1, f1);
+    slab(q1.w, q2.z, q.oy, q.iy, q.m, n1, f1);
+    slab(q2.x, q2.w, q.oz, q.iz, q.m, n1, f1);
+    k.box += 2;
+    const bool h0 = q3.x != NT_REF_EMPTY && n0 <= f0 && n0 <= q.tmaxf;
+    const bool h1 = q3.y != NT_REF_EMPTY && n1 <= f1 && n1 <= q.tmaxf;
+    if (h0 && h1) {
+        const bool first1 = n1 < n0;
+        q.cur = first1 ? q3.y : q3.x;
+        stack[q.sp++] = make_int2(first1 ? q3.x : q3.y, __float_as_int(first1 ? n0 : n1));
+    } else if (h0) q.cur = q3.x;
+    else if (h1) q.cur = q3.y;
+    else query_pop(q, stack);
+}
+
+// One leaf: up to 4 primitives of one kind, exact tests in R.
+template <typename R>
+__device__ __forceinline__ void query_leaf_step(const Ctx<R, true> &c, BvhQuery<R> &q, const int2 *stack, Counters &k) {
+    const int code = -2 - q.cur;
+    const int first = code & 0x3ffffff, count = ((code >> 26) & 3) + 1;
+    const bool is_tri = (code >> 28) & 1;
+    for (int j = 0; j < count; ++j) {
+        const int idx = first + j;
+        R t;
+        bool hit;
+        if (is_tri) { R p[9]; c.ld_tri(idx, p); k.tri++; hit = hit_triangle<R>(p, q.o, q.d, c.eps, t); }
+        else { R p[4]; c.ld_sph(idx, p); k.sph++; hit = hit_sphere<R>(p, q.o, q.d, c.eps, t); }
+        if (!hit) continue;
+        if (q.any) {
+            if (t < q.tb) { q.found = true; q.done = true; q.cur = NT_REF_EMPTY; return; }
+        } else {
+            const int kind = is_tri ? 2 : 0;
+            if (t < q.tb) {
+                q.tb = t; q.best.kind = kind; q.best.idx = idx;
+                q.best.gid = __ldg((is_tri ? c.s->tri_gid : c.s->sph_gid) + idx);
+                q.tmaxf = Math<R>::up(q.tb - q.tshift); q.found = true;
+            } else if (t == q.tb) { // SPEC §3 tie-break: the smallest global primitive id wins
+                const int gid = __ldg((is_tri ? c.s->tri_gid : c.s->sph_gid) + idx);
+                if (gid < q.best.gid) { q.best.kind = kind; q.best.idx = idx; q.best.gid = gid; q.found = true; }
+            }
+        }
+    }
+    query_pop(q, stack);
+}
+
+// ---- per-lane ray-tree state machine (scalars only; the deferred-children stack is a separate array) ----
+template <typename R> struct Lane {
+    V3<R> d;         // direction of the tree node being shaded (its origin and hit point live in the query)
+    V3<R> N;
+    R W, ndl, local[3], acc[3];
+    unsigned depth, sid;
+    int phase;       // 0: nearest-hit query in flight; 1 + l: occlusion query of light l in flight
+    int mat, sp;
+    bool active, entering;
+};
+template <typename R> struct ChildStack {
+    R v[NT_MAX_DEPTH_DEV][7];
+    unsigned depth[NT_MAX_DEPTH_DEV];
+};
+
+// Sample finished: hand its radiance to the resolve pass.
+template <typename R>
+__device__ __forceinline__ void lane_finish(Lane<R> &ln, R *samples) {
+    R *dst = samples + 3 * (size_t)ln.sid;
+    dst[0] = ln.acc[0]; dst[1] = ln.acc[1]; dst[2] = ln.acc[2];
+    ln.active = false;
+}
+
+// Node finished: next ray of the tree (reflection child first, deferred transmission children after),
+// or the sample is complete.  Starts the nearest-hit query of that ray.
+template <typename R>
+__device__ __forceinline__ void lane_next_ray(const Ctx<R, true> &c, Lane<R> &ln, BvhQuery<R> &q, ChildStack<R> &cs,
+                                              bool descend, const V3<R> &o, R *samples, Counters &k) {
+    V3<R> ro = o;
+    if (!descend) {
+        if (ln.sp == 0) { lane_finish<R>(ln, samples); q.done = true; return; }
+        const int sp = --ln.sp;
+        ro = { cs.v[sp][0], cs.v[sp][1], cs.v[sp][2] };
+        ln.d = { cs.v[sp][3], cs.v[sp][4], cs.v[sp][5] };
+        ln.W = cs.v[sp][6];
+        ln.depth = cs.depth[sp];
+    }
+    ln.phase = 0;
+    query_start<R>(c, q, ro, ln.d, Math<R>::inf(), false, k);
+}
+
+// SPEC §4, light loop from light `l` on: arm the occlusion query of the next light that faces the
+// surface; when none is left, add the node to the sample, spawn its children and move on.
+// P (the hit point) is the origin of the shadow queries, so it is passed around instead of stored.
+template <typename R>
+__device__ __forceinline__ void lane_lights_from(const Ctx<R, true> &c, Lane<R> &ln, BvhQuery<R> &q, ChildStack<R> &cs,
+                                                 const V3<R> &P, unsigned l, R *samples, Counters &k) {
+    const NtDevScene &s = *c.s;
+    const NtSceneView<R> &v = *c.v;
+    for (; l < s.nl; ++l) {
+        const R *lp = v.lights + 6 * l;
+        const V3<R> Lv = { __ldg(lp) - P.x, __ldg(lp + 1) - P.y, __ldg(lp + 2) - P.z };
+        const R d2 = dot(Lv, Lv);
+        const R dist = Math<R>::sqrt_(d2);
+        const V3<R> L = scale(Lv, Math<R>::rcp(dist));
+        const R ndl = dot(ln.N, L);
+        if (!(ndl > R(0))) continue;
+        k.shadow++;
+        ln.ndl = ndl; ln.phase = 1 + (int)l;
+        query_start<R>(c, q, P, L, dist, true, k);
+        return;
+    }
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) ln.acc[ch] = ln.acc[ch] + ln.W * ln.local[ch];
+    bool descend = false;
+    if (ln.depth < c.max_depth) {
+        const R *mp = v.mat + (size_t)ln.mat * NT_MAT_STRIDE;
+        R m2[4];
+        Ld<R>::g4(mp + 8, m2); // kt ior inv_ior pad
+        const R kr = __ldg(mp + 7), kt = m2[0];
+        const V3<R> d = ln.d, N = ln.N;
+        const R cosi = -dot(d, N);
+        R wr = kr, wt = R(0);
+        V3<R> T = { R(0), R(0), R(0) };
+        if (kt > R(0)) {
+            const R eta = ln.entering ? m2[2] : m2[1];
+            const R kk = R(1) - (eta * eta) * (R(1) - cosi * cosi);
+            if (kk < R(0)) wr = kr + kt;
+            else {
+                wt = kt;
+                const R sterm = eta * cosi - Math<R>::sqrt_(kk);
+                T = { d.x * eta + N.x * sterm, d.y * eta + N.y * sterm, d.z * eta + N.z * sterm };
+            }
+        }
+        if (wt > R(0)) {
+            k.sec++;
+            if (wr > R(0)) { // defer: the reflection subtree comes first in pre-order
+                const int sp = ln.sp;
+                cs.v[sp][0] = P.x; cs.v[sp][1] = P.y; cs.v[sp][2] = P.z;
+                cs.v[sp][3] = T.x; cs.v[sp][4] = T.y; cs.v[sp][5] = T.z;
+                cs.v[sp][6] = ln.W * wt; cs.depth[sp] = ln.depth + 1;
+                ln.sp = sp + 1;
+            }
+        }
+        if (wr > R(0)) {
+            k.sec++;
+            const R two = R(2) * cosi;
+            ln.d = { d.x + N.x * two, d.y + N.y * two, d.z + N.z * two };
+            ln.W = ln.W * wr; ln.depth = ln.depth + 1;
+            descend = true;
+        } else if (wt > R(0)) {
+            ln.d = T; ln.W = ln.W * wt; ln.depth = ln.depth + 1;
+            descend = true;
+        }
+    }
+    lane_next_ray<R>(c, ln, q, cs, descend, P, samples, k);
+}
+
+// The lane's query has finished: consume its result and arm the next one.
+template <typename R>
+__device__ __forceinline__ void lane_advance(const Ctx<R, true> &c, Lane<R> &ln, BvhQuery<R> &q, ChildStack<R> &cs,
+                                             R *samples, Counters &k) {
+    const NtDevScene &s = *c.s;
+    const NtSceneView<R> &v = *c.v;
+    if (ln.phase == 0) {
+        if (q.best.kind < 0) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) ln.acc[ch] = ln.acc[ch] + ln.W * __ldg(v.globals + 3 + ch);
+            lane_next_ray<R>(c, ln, q, cs, false, q.o, samples, k);
+            return;
+        }
+        const R t = q.tb;
+        const Hit h = q.best;
+        const V3<R> o = q.o, d = ln.d;
+        const V3<R> P = { o.x + d.x * t, o.y + d.y * t, o.z + d.z * t };
+        V3<R> Ng;
+        int mat;
+        if (h.kind == 0) {
+            R p[4];
+            c.ld_sph(h.idx, p);
+            const R ir = __ldg(v.sph_invr + h.idx);
+            Ng = { (P.x - p[0]) * ir, (P.y - p[1]) * ir, (P.z - p[2]) * ir };
+            mat = __ldg(s.sph_mat + h.idx);
+        } else if (h.kind == 1) {
+            R p[4];
+            c.ld_pln(h.idx, p);
+            Ng = { p[0], p[1], p[2] };
+            mat = __ldg(s.pln_mat + h.idx);
+        } else {
+            const R *tp = v.tri + (size_t)h.idx * NT_TRI_STRIDE + 9;
+            Ng = { __ldg(tp), __ldg(tp + 1), __ldg(tp + 2) };
+            mat = __ldg(s.tri_mat + h.idx);
+        }
+        const R *mp = v.mat + (size_t)mat * NT_MAT_STRIDE;
+        R m0[4];
+        Ld<R>::g4(mp, m0); // r g b ka
+        const bool entering = dot(d, Ng) < R(0);
+        ln.mat = mat; ln.entering = entering;
+        ln.N = entering ? Ng : V3<R>{ -Ng.x, -Ng.y, -Ng.z };
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) ln.local[ch] = __ldg(v.globals + ch) * (m0[3] * m0[ch]);
+        lane_lights_from<R>(c, ln, q, cs, P, 0, samples, k);
+        return;
+    }
+    // occlusion query of light l finished; q.o is the hit point P and q.d the unit vector to the light
+    const unsigned l = (unsigned)(ln.phase - 1);
+    const V3<R> P = q.o;
+    if (!q.found) {
+        k.light++;
+        const V3<R> L = q.d;
+        const R *mp = v.mat + (size_t)ln.mat * NT_MAT_STRIDE;
+        R m0[4], m1[4];
+        Ld<R>::g4(mp, m0);     // r g b ka
+        Ld<R>::g4(mp + 4, m1); // kd ks shininess kr
+        const R *lp = v.lights + 6 * l;
+        const R lc[3] = { __ldg(lp + 3), __ldg(lp + 4), __ldg(lp + 5) };
+        const R kdn = m1[0] * ln.ndl;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) ln.local[ch] = ln.local[ch] + lc[ch] * (m0[ch] * kdn);
+        const R two = R(2) * ln.ndl;
+        const V3<R> Rv = { ln.N.x * two - L.x, ln.N.y * two - L.y, ln.N.z * two - L.z };
+        const R rv = -dot(Rv, ln.d);
+        if (m1[1] > R(0) && rv > R(0)) {
+            const R sterm = m1[1] * Math<R>::pow_(rv, m1[2]);
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) ln.local[ch] = ln.local[ch] + lc[ch] * sterm;
+        }
+    }
+    lane_lights_from<R>(c, ln, q, cs, P, l + 1, samples, k);
+}
+
+// Sample id -> pixel and sub-sample (the inverse is in resolve_kernel).  sid = (tile*rounds + r)*32 + slot,
+// slot = pixel-in-tile * lanes + j, sample index s = r*lanes + j.
+struct SampleMap {
+    unsigned px, vr, y, sidx;
+    bool live;
+};
+__device__ __forceinline__ SampleMap map_sample(const NtRenderArgs &a, unsigned sid) {
+    SampleMap m;
+    const unsigned rounds = a.spp / a.lanes;
+    const unsigned tile = sid / (rounds * 32), rem = sid % (rounds * 32);
+    const unsigned r = rem / 32, slot = rem % 32, pw = slot / a.lanes, j = slot % a.lanes;
+    m.px = (tile % a.tiles_x) * a.twx + pw % a.twx;
+    m.vr = (tile / a.tiles_x) * a.twy + pw / a.twx;
+    m.live = m.px < a.width && m.vr < a.vrows;
+    m.y = ((m.vr / a.band_rows) * a.shard_count + a.shard_index) * a.band_rows + m.vr % a.band_rows;
+    m.sidx = r * a.lanes + j;
+    return m;
+}
+
+// Persistent-warp trace kernel for BVH scenes: writes one radiance triple per sample.
+template <typename R>
+__global__ void __launch_bounds__(NT_BLOCK_THREADS, NT_MIN_BLOCKS_BVH)
+render_bvh_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRenderArgs a) {
+    __shared__ unsigned long long s_cnt[NT_NCOUNTERS];
+    const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
+    Ctx<R, true> c;
+    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.max_depth = a.max_depth;
+    stage_scene<R, true>(s, v, c);
+
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned n_sids = a.tiles_x * a.tiles_y * (a.spp / a.lanes) * 32;
+    unsigned long long *next_sid = a.counters + NT_COUNTER_SLOTS * NT_NCOUNTERS;
+    R *samples = (R *)a.samples;
+    const R rn = (R)a.n;
+    Counters k = { 0, 0, 0, 0, 0, 0, 0, 0 };
+
+    Lane<R> ln;
+    BvhQuery<R> q;
+    ChildStack<R> cs;
+    int2 bstack[NT_BVH_STACK];
+    ln.active = false; ln.sp = 0; ln.phase = 0;
+    q.done = true; q.cur = NT_REF_EMPTY; q.sp = 0; q.found = false; q.any = false;
+    bool exhausted = false;
+
+    for (;;) {
+        // ---- refill: idle lanes claim new samples, one atomic per warp ----
+        const unsigned idle = __ballot_sync(0xffffffffu, !ln.active);
+        if (!exhausted && (__popc(idle) >= NT_REFILL_THRESHOLD || idle == 0xffffffffu)) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(next_sid, (unsigned long long)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + __popc(idle) >= n_sids) exhausted = true;
+            if (!ln.active) {
+                const unsigned long long sid = base + __popc(idle & ((1u << lane) - 1));
+                if (sid < n_sids) {
+                    const SampleMap m = map_sample(a, (unsigned)sid);
+                    if (m.live) {
+                        // SPEC §2: regular n x n grid
+                        const unsigned si = m.sidx % a.n, sj = m.sidx / a.n;
+                        const R ox = Math<R>::div((R)si + R(0.5), rn), oy = Math<R>::div((R)sj + R(0.5), rn);
+                        const R fx = (R)m.px + ox, fy = (R)m.y + oy;
+                        const V3<R> D = { ((R)a.cam[3] + (R)a.cam[6] * fx) + (R)a.cam[9] * fy,
+                                          ((R)a.cam[4] + (R)a.cam[7] * fx) + (R)a.cam[10] * fy,
+                                          ((R)a.cam[5] + (R)a.cam[8] * fx) + (R)a.cam[11] * fy };
+                        const V3<R> eye = { (R)a.cam[0], (R)a.cam[1], (R)a.cam[2] };
+                        ln.d = scale(D, Math<R>::rcp(Math<R>::sqrt_(dot(D, D))));
+                        ln.sid = (unsigned)sid; ln.W = R(1); ln.depth = 1; ln.sp = 0; ln.phase = 0; ln.active = true;
+                        ln.acc[0] = ln.acc[1] = ln.acc[2] = R(0);
+                        k.prim++;
+                        query_start<R>(c, q, eye, ln.d, Math<R>::inf(), false, k);
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, ln.active) == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- (A) traversal rounds ----
+        for (;;) {
+            const bool trav = ln.active && !q.done;
+            if (__ballot_sync(0xffffffffu, trav) == 0) break;
+            if (trav && q.cur >= 0) query_inner_step<R>(c, q, bstack, k);
+            if (ln.active && !q.done && ref_is_leaf(q.cur)) query_leaf_step<R>(c, q, bstack, k);
+            const unsigned parked = __ballot_sync(0xffffffffu, !ln.active || q.done);
+            if (__popc(parked) >= NT_ADVANCE_THRESHOLD) break;
+        }
+        // ---- (B) advance the lanes whose query is complete ----
+        if (ln.active && q.done) lane_advance<R>(c, ln, q, cs, samples, k);
+    }
+    flush_counters(k, a.counters, s_cnt);
+}
+
+// Resolve: SPEC §5 — the samples of a pixel are added in sample order, scaled, quantised to RGBA8.
+template <typename R>
+__global__ void __launch_bounds__(256)
+resolve_kernel(const __grid_constant__ NtRenderArgs a) {
+    const unsigned px = blockIdx.x * blockDim.x + threadIdx.x, vr = blockIdx.y;
+    if (px >= a.width || vr >= a.vrows) return;
+    const R *samples = (const R *)a.samples;
+    const unsigned rounds = a.spp / a.lanes;
+    const unsigned tile = (vr / a.twy) * a.tiles_x + px / a.twx;
+    const unsigned pw = (vr % a.twy) * a.twx + px % a.twx;
+    R sum[3] = { R(0), R(0), R(0) };
+    for (unsigned r = 0; r < rounds; ++r)
+        for (unsigned j = 0; j < a.lanes; ++j) {
+            const R *sp = samples + 3 * ((size_t)(tile * rounds + r) * 32 + pw * a.lanes + j);
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) sum[ch] = sum[ch] + sp[ch];
+        }
+    const R inv_spp = Math<R>::rcp((R)a.spp);
+    unsigned rgba = 0xff000000u;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const R cv = sum[ch] * inv_spp;
+        const unsigned qv = cv <= R(0) ? 0u : cv >= R(1) ? 255u : (unsigned)(int)(cv * R(255) + R(0.5));
+        rgba |= qv << (8 * ch);
+    }
+    const unsigned y = ((vr / a.band_rows) * a.shard_count + a.shard_index) * a.band_rows + vr % a.band_rows;
+    const size_t row = a.layout == 1 ? vr : y;
+    *(unsigned *)(a.out + row * a.stride + 4 * (size_t)px) = rgba;
+}
+
+// Unit-level entry for BVH scenes: nearest hit of arbitrary rays (nt_trace_rays).
+template <typename R>
+__global__ void __launch_bounds__(NT_BLOCK_THREADS)
+trace_bvh_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtTraceArgs a) {
+    const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
+    Ctx<R, true> c;
+    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.max_depth = 1;
+    stage_scene<R, true>(s, v, c);
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const V3<R> o = { (R)a.origins[3 * i], (R)a.origins[3 * i + 1], (R)a.origins[3 * i + 2] };
+    const V3<R> d = { (R)a.dirs[3 * i], (R)a.dirs[3 * i + 1], (R)a.dirs[3 * i + 2] };
+    Counters k = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    BvhQuery<R> q;
+    int2 bstack[NT_BVH_STACK];
+    query_start<R>(c, q, o, d, Math<R>::inf(), false, k);
+    while (!q.done) {
+        if (q.cur >= 0) query_inner_step<R>(c, q, bstack, k);
+        else query_leaf_step<R>(c, q, bstack, k);
+    }
+    a.t_out[i] = q.best.kind >= 0 ? (double)q.tb : -1.0;
+    a.prim_out[i] = q.best.kind >= 0 ? q.best.gid : -1;
+}
+
+} // namespace nt

@@ -13,13 +13,23 @@
 #define NT_MIN_BLOCKS 3     // resident blocks per SM the render kernels are compiled for
 #endif
 #define NT_BVH_STACK 64
+#ifndef NT_MIN_BLOCKS_BVH
+#define NT_MIN_BLOCKS_BVH 2 // the BVH state machine keeps more per-lane state
+#endif
+#ifndef NT_ADVANCE_THRESHOLD
+#define NT_ADVANCE_THRESHOLD 8 // lanes parked with a finished query before the warp leaves traversal
+#endif
+#ifndef NT_REFILL_THRESHOLD
+#define NT_REFILL_THRESHOLD 8  // idle lanes before the warp claims new samples
+#endif
+#define NT_LEAF_MAX 4       // (count-1) is stored in 2 bits of a leaf ref
 #define NT_MAX_DEPTH_DEV 16 // == NT_MAX_DEPTH of the public header
 
-// 64-byte BVH2 node: both child boxes (float, rounded outward) + child links.
+// 64-byte BVH2 node: both child boxes (float, rounded outward) + child refs.
 //   q0 = lo0.x lo0.y lo0.z hi0.x | q1 = hi0.y hi0.z lo1.x lo1.y | q2 = lo1.z hi1.x hi1.y hi1.z
-//   q3 = c0 c1 n0 n1 (ints).  n == 0: inner child, c = node index.  n > 0: leaf, c = first
-//   primitive (index into the BVH-ordered sphere or triangle array), n & 0xff = count,
-//   n & 0x100 = triangles (else spheres).  n < 0: empty child.
+//   q3 = c0 c1 n0 n1 (ints).  c = child ref: >= 0 inner node index; -1 empty; <= -2 leaf, with
+//   -2 - c = first | (count-1) << 26 | kind << 28  (first = index into the BVH-ordered sphere (kind 0)
+//   or triangle (kind 1) array, count 1..4).  n0/n1 keep the builder's count|kind<<8 (diagnostics).
 struct NtBvhNode {
     float lo0[3], hi0[3];
     float lo1[3], hi1[3];
@@ -42,6 +52,7 @@ struct NtDevScene {
     uint32_t ns, np, nt, nm, nl;
     uint32_t use_bvh, n_nodes;
     float max_abs; // largest |coordinate| of any bounded primitive (box-test margin)
+    float blo[3], bhi[3]; // bounds of all bounded primitives (float, rounded outward)
     const int *sph_mat, *sph_gid, *pln_mat, *tri_mat, *tri_gid;
     const NtBvhNode *nodes;
     NtSceneView<double> v64;
@@ -58,7 +69,8 @@ struct NtRenderArgs {
     double cam[12];    // eye p00 dx dy
     uint8_t *out;
     size_t stride;
-    unsigned long long *counters; // [NT_COUNTER_SLOTS][NT_NCOUNTERS] + 1 (next warp tile)
+    unsigned long long *counters; // [NT_COUNTER_SLOTS][NT_NCOUNTERS] + 1 (next warp tile / next sample id)
+    void *samples;                // BVH scenes: per-sample radiance, R[3] each (see nt_bvh_trace.cuh)
 };
 
 struct NtTraceArgs {
@@ -75,3 +87,4 @@ int nt_launch_render_f32(const NtDevScene &s, const NtRenderArgs &a, void *strea
 int nt_launch_trace_f64(const NtDevScene &s, const NtTraceArgs &a, void *stream);
 int nt_launch_trace_f32(const NtDevScene &s, const NtTraceArgs &a, void *stream);
 size_t nt_flat_smem_bytes(const NtDevScene &s, int precision);
+size_t nt_sample_buffer_bytes(const NtDevScene &s, const NtRenderArgs &a, int precision); // 0 for flat scenes

@@ -11,3 +11,8 @@ size_t nt_flat_smem_bytes(const NtDevScene &s, int precision) {
     return precision == 0 ? nt::flat_smem_bytes<double>(s, s.use_bvh != 0)
                           : nt::flat_smem_bytes<float>(s, s.use_bvh != 0);
 }
+size_t nt_sample_buffer_bytes(const NtDevScene &s, const NtRenderArgs &a, int precision) {
+    if (!s.use_bvh) return 0;
+    const size_t n = (size_t)a.tiles_x * a.tiles_y * (a.spp / a.lanes) * 32;
+    return n * 3 * (precision == 0 ? sizeof(double) : sizeof(float));
+}

@@ -227,86 +227,6 @@ __device__ __forceinline__ void slab(float lo, float hi, float o, float inv, flo
     tf = fminf(tf, fmaxf(a, b));
 }
 
-// BVH traversal over the bounded primitives.  Boxes are float and only ever cull: they are rounded
-// outward at build time and widened here by a margin that covers rounding the ray to float, so the
-// survivors are exactly those the brute-force loop of SPEC §3 would accept (tests/test_parity_*
-// compare both).  ANY = occlusion query (first hit with t < tb ends it).
-template <typename R, bool ANY>
-__device__ __forceinline__ bool bvh_traverse(const Ctx<R, true> &c, const V3<R> &o, const V3<R> &d,
-                                             R &tb, Hit &best, Counters &k) {
-    if (c.s->n_nodes == 0) return false;
-    const float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
-    const float ix = 1.0f / (float)d.x, iy = 1.0f / (float)d.y, iz = 1.0f / (float)d.z;
-    const float m = 4e-6f * (fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz)) + c.s->max_abs);
-    float tmaxf = Math<R>::up(tb);
-    int2 stack[NT_BVH_STACK];
-    int sp = 0, node = 0;
-    bool found = false;
-    for (;;) {
-        const float4 *q = (const float4 *)(c.s->nodes + node);
-        const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
-        const int4 q3 = __ldg((const int4 *)(q + 3));
-        float n0 = 0.0f, f0 = CUDART_INF_F, n1 = 0.0f, f1 = CUDART_INF_F;
-        slab(q0.x, q0.w, ox, ix, m, n0, f0);
-        slab(q0.y, q1.x, oy, iy, m, n0, f0);
-        slab(q0.z, q1.y, oz, iz, m, n0, f0);
-        slab(q1.z, q2.y, ox, ix, m, n1, f1);
-        slab(q1.w, q2.z, oy, iy, m, n1, f1);
-        slab(q2.x, q2.w, oz, iz, m, n1, f1);
-        k.box += 2;
-        bool h0 = q3.z >= 0 && n0 <= f0 && n0 <= tmaxf;
-        bool h1 = q3.w >= 0 && n1 <= f1 && n1 <= tmaxf;
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-            const bool h = ch ? h1 : h0;
-            const int cnt = ch ? q3.w : q3.z, start = ch ? q3.y : q3.x;
-            if (h && cnt > 0) {
-                if (ch && !((ch ? n1 : n0) <= tmaxf)) continue; // leaf 0 may have shrunk the bound
-                const int num = cnt & 0xff;
-                for (int j = 0; j < num; ++j) {
-                    const int idx = start + j;
-                    R t;
-                    bool hit;
-                    if (cnt & 0x100) { R q[9]; c.ld_tri(idx, q); k.tri++; hit = hit_triangle<R>(q, o, d, c.eps, t); }
-                    else { R q[4]; c.ld_sph(idx, q); k.sph++; hit = hit_sphere<R>(q, o, d, c.eps, t); }
-                    if (!hit) continue;
-                    if (ANY) { if (t < tb) return true; }
-                    else {
-                        const int kind = (cnt & 0x100) ? 2 : 0;
-                        if (t < tb) {
-                            tb = t; best.kind = kind; best.idx = idx;
-                            best.gid = __ldg((kind ? c.s->tri_gid : c.s->sph_gid) + idx);
-                            tmaxf = Math<R>::up(tb); found = true;
-                        } else if (t == tb) {
-                            const int gid = __ldg((kind ? c.s->tri_gid : c.s->sph_gid) + idx);
-                            if (gid < best.gid) { best.kind = kind; best.idx = idx; best.gid = gid; found = true; }
-                        }
-                    }
-                }
-            }
-        }
-        h0 = h0 && q3.z == 0 && n0 <= tmaxf;
-        h1 = h1 && q3.w == 0 && n1 <= tmaxf;
-        if (h0 && h1) {
-            const bool first1 = n1 < n0;
-            const int far_node = first1 ? q3.x : q3.y;
-            const float far_t = first1 ? n0 : n1;
-            node = first1 ? q3.y : q3.x;
-            stack[sp++] = make_int2(far_node, __float_as_int(far_t));
-        } else if (h0) node = q3.x;
-        else if (h1) node = q3.y;
-        else {
-            bool got = false;
-            while (sp > 0) {
-                const int2 e = stack[--sp];
-                if (__int_as_float(e.y) <= tmaxf) { node = e.x; got = true; break; }
-            }
-            if (!got) break;
-        }
-    }
-    return found;
-}
-
 // SPEC §3 nearest hit: smallest t; equal t -> smallest global primitive id.
 template <typename R, bool BVH>
 __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o, const V3<R> &d,
@@ -347,8 +267,6 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
             if (hit_triangle<R>(q, o, d, c.eps, t) && t < tb) { tb = t; best.kind = 2; best.idx = (int)i; }
         }
         k.tri += s.nt;
-    } else {
-        bvh_traverse<R, false>(c, o, d, tb, best, k);
     }
     return best.kind >= 0;
 }
@@ -391,12 +309,8 @@ __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, c
             if (hit_triangle<R>(q, o, d, c.eps, t) && t < dist) { k.tri += i + 1; return true; }
         }
         k.tri += s.nt;
-        return false;
-    } else {
-        Hit h;
-        R tb = dist;
-        return bvh_traverse<R, true>(c, o, d, tb, h, k);
     }
+    return false;
 }
 
 // SPEC §4: radiance of one sample = sum over its ray tree in depth-first pre-order of W * local.
@@ -659,7 +573,7 @@ trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtTra
     Hit h;
     if (nearest_hit<R, BVH>(c, o, d, t, h, k)) {
         a.t_out[i] = (double)t;
-        a.prim_out[i] = h.kind == 1 ? h.gid : (BVH ? h.gid : (h.kind == 0 ? h.idx : (int)(s.ns + s.np) + h.idx));
+        a.prim_out[i] = h.kind == 1 ? h.gid : (h.kind == 0 ? h.idx : (int)(s.ns + s.np) + h.idx);
     } else {
         a.t_out[i] = -1.0;
         a.prim_out[i] = -1;
@@ -673,6 +587,12 @@ inline size_t flat_smem_bytes(const NtDevScene &s, bool bvh) {
     return n * sizeof(R);
 }
 
+} // namespace nt
+
+#include "nt_bvh_trace.cuh"
+
+namespace nt {
+
 template <typename R, bool BVH>
 inline int launch_render_t(const NtDevScene &s, const NtRenderArgs &a, cudaStream_t st) {
     static int blocks_per_sm[64] = { 0 }, sms[64] = { 0 }; // per device, resolved once
@@ -682,13 +602,17 @@ inline int launch_render_t(const NtDevScene &s, const NtRenderArgs &a, cudaStrea
     if (dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
     if (!sms[dev]) {
         cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[dev], render_kernel<R, BVH>, NT_BLOCK_THREADS, 4096);
+        if (BVH) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[dev], render_bvh_kernel<R>, NT_BLOCK_THREADS, 4096);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[dev], render_kernel<R, false>, NT_BLOCK_THREADS, 4096);
         if (blocks_per_sm[dev] < 1) blocks_per_sm[dev] = 1;
     }
     const unsigned n_tiles = a.tiles_x * a.tiles_y, wpb = NT_BLOCK_THREADS / 32;
     unsigned grid = (unsigned)(sms[dev] * blocks_per_sm[dev]);
     if (grid > (n_tiles + wpb - 1) / wpb) grid = (n_tiles + wpb - 1) / wpb;
-    render_kernel<R, BVH><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
+    if (BVH) {
+        render_bvh_kernel<R><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
+        resolve_kernel<R><<<dim3((a.width + 255) / 256, a.vrows), 256, 0, st>>>(a);
+    } else render_kernel<R, false><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
     return (int)cudaGetLastError();
 }
 
@@ -701,7 +625,7 @@ template <typename R>
 inline int launch_trace(const NtDevScene &s, const NtTraceArgs &a, cudaStream_t st) {
     dim3 grid((a.n + NT_BLOCK_THREADS - 1) / NT_BLOCK_THREADS), block(NT_BLOCK_THREADS);
     const size_t smem = flat_smem_bytes<R>(s, s.use_bvh != 0);
-    if (s.use_bvh) trace_kernel<R, true><<<grid, block, smem, st>>>(s, a);
+    if (s.use_bvh) trace_bvh_kernel<R><<<grid, block, smem, st>>>(s, a);
     else trace_kernel<R, false><<<grid, block, smem, st>>>(s, a);
     return (int)cudaGetLastError();
 }

@@ -1,4 +1,5 @@
-"""Render one config a few times (profiling target): python scripts/gpu_one.py <config> <f64|f32> [iters]"""
+"""Render one config a few times (profiling target):
+   python scripts/gpu_one.py <config> <f64|f32> [iters] [WxH] [spp] [depth]"""
 import sys
 
 sys.path.insert(0, ".")
@@ -8,8 +9,14 @@ from nettracer_b200.renderer import Renderer  # noqa: E402
 name, prec = sys.argv[1], sys.argv[2]
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 factory, w, h, spp, depth = scenes.CONFIGS[name]
+if len(sys.argv) > 4:
+    w, h = map(int, sys.argv[4].split("x"))
+if len(sys.argv) > 5:
+    spp = int(sys.argv[5])
+if len(sys.argv) > 6:
+    depth = int(sys.argv[6])
 scene, cam = factory()
 with Renderer(scene) as r:
     for _ in range(iters):
         img, st = r.render(cam, w, h, spp, depth, abi.NT_F64_STRICT if prec == "f64" else abi.NT_F32_FAST)
-    print(name, prec, st)
+    print(name, prec, w, h, spp, depth, st)
