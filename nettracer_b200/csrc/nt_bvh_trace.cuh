@@ -406,14 +406,22 @@ render_bvh_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ 
             if (exhausted) break;
             continue;
         }
-        // ---- (A) traversal rounds ----
+        // ---- (A) traversal rounds: descend until (nearly) every traversing lane holds a leaf, then
+        //      test the leaves together — the exact primitive tests are the expensive part and must
+        //      not run with a handful of lanes ----
         for (;;) {
-            const bool trav = ln.active && !q.done;
-            if (__ballot_sync(0xffffffffu, trav) == 0) break;
-            if (trav && q.cur >= 0) query_inner_step<R>(c, q, bstack, k);
-            if (ln.active && !q.done && ref_is_leaf(q.cur)) query_leaf_step<R>(c, q, bstack, k);
+            for (;;) {
+                const bool inner = ln.active && !q.done && q.cur >= 0;
+                const unsigned im = __ballot_sync(0xffffffffu, inner);
+                if (im == 0) break;
+                if (inner) query_inner_step<R>(c, q, bstack, k);
+                if (__popc(im) < NT_DESCEND_MIN &&
+                    __ballot_sync(0xffffffffu, ln.active && !q.done && ref_is_leaf(q.cur)) != 0) break;
+            }
+            const bool leaf = ln.active && !q.done && ref_is_leaf(q.cur);
+            if (leaf) query_leaf_step<R>(c, q, bstack, k);
             const unsigned parked = __ballot_sync(0xffffffffu, !ln.active || q.done);
-            if (__popc(parked) >= NT_ADVANCE_THRESHOLD) break;
+            if (parked == 0xffffffffu || __popc(parked) >= NT_ADVANCE_THRESHOLD) break;
         }
         // ---- (B) advance the lanes whose query is complete ----
         if (ln.active && q.done) lane_advance<R>(c, ln, q, cs, samples, k);

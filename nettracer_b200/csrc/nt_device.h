@@ -14,13 +14,16 @@
 #endif
 #define NT_BVH_STACK 64
 #ifndef NT_MIN_BLOCKS_BVH
-#define NT_MIN_BLOCKS_BVH 2 // the BVH state machine keeps more per-lane state
+#define NT_MIN_BLOCKS_BVH 4 // measured best on configs[3] (2: 93.7 ms, 3: 78.2 ms, 4: 75.2 ms) despite spills
 #endif
 #ifndef NT_ADVANCE_THRESHOLD
-#define NT_ADVANCE_THRESHOLD 8 // lanes parked with a finished query before the warp leaves traversal
+#define NT_ADVANCE_THRESHOLD 32 // lanes parked with a finished query before the warp shades (8: 123 ms, 16: 106, 32: 94)
+#endif
+#ifndef NT_DESCEND_MIN
+#define NT_DESCEND_MIN 4      // fewer lanes than this still descending -> go test the waiting leaves
 #endif
 #ifndef NT_REFILL_THRESHOLD
-#define NT_REFILL_THRESHOLD 8  // idle lanes before the warp claims new samples
+#define NT_REFILL_THRESHOLD 32 // idle lanes before the warp claims new samples (8: 105 ms, 24: 78.2, 32: 75.8)
 #endif
 #define NT_LEAF_MAX 4       // (count-1) is stored in 2 bits of a leaf ref
 #define NT_MAX_DEPTH_DEV 16 // == NT_MAX_DEPTH of the public header

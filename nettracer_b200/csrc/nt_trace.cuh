@@ -99,6 +99,7 @@ template <> struct Ld<float> {
     }
     static __device__ __forceinline__ void s9(unsigned addr, float *o) {
         float p0, p1, p2;
+        (void)&p0; (void)&p1; (void)&p2;
         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "r"(addr));
         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(o[4]), "=f"(o[5]), "=f"(o[6]), "=f"(o[7]) : "r"(addr));
         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+32];" : "=f"(o[8]), "=f"(p0), "=f"(p1), "=f"(p2) : "r"(addr));
