@@ -305,7 +305,11 @@ def main():
         peak_gf = peaks["f64_nofma_gflops"] if strict else peaks["f32_fma_gflops"]
         achieved_tf = flops_local / (kernel_ms_local * 1e-3) / 1e12
         roof = {"bound": "fp64" if strict else "fp32", "achieved": achieved_tf, "peak": peak_gf / 1e3, "unit": "TFLOP/s",
-                "frac": achieved_tf / (peak_gf / 1e3), "traffic": None,
+                "frac": achieved_tf / (peak_gf / 1e3),
+                "traffic": ({"cfg3_cornell_1080p_4spp_d5": 5.38e7}.get(a.workload) if strict else None),
+                "traffic_note": "dram read+write bytes of one render launch inside this bench (ncu --set full, "
+                                "profiles/r01_c_cfg3_f64_final.md): 1.2 MB read + 52.6 MB written, of which 8.3 MB is the "
+                                "frame and the rest dirty L2 lines of the 256 MiB flush; the kernel is not HBM bound (0.3 %)",
                 "kernel": "render_kernel<%s,%s>" % ("double" if strict else "float", "bvh" if info["uses_bvh"] else "flat"),
                 "kernel_ms": kernel_ms_local, "algorithmic_flops_per_launch": flops_local,
                 "peak_source": "nt_measure_peaks in this process: " + ("FP64 mul/add issue rate without FMA (strict mode may not fuse)"
