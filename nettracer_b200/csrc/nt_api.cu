@@ -164,6 +164,7 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
     std::vector<double> sph(4 * (size_t)ns), sph_invr(ns), pln(4 * (size_t)np), tri(NT_TRI_STRIDE * (size_t)nt),
         mat(NT_MAT_STRIDE * (size_t)nm), lights(6 * (size_t)nl), globals(8, 0.0);
     std::vector<int> sph_mat(ns), sph_gid(ns), pln_mat(np), tri_mat(nt), tri_gid(nt);
+    std::vector<unsigned> pln_code((np + 15) / 16 + 1, 0u);
     for (uint32_t k = 0; k < ns; ++k) {
         const int i = sph_order[k];
         const double *s = d->spheres + 4 * (size_t)i;
@@ -176,6 +177,11 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
     for (uint32_t i = 0; i < np; ++i) {
         for (int k = 0; k < 4; ++k) pln[4 * (size_t)i + k] = d->planes[4 * (size_t)i + k];
         pln_mat[i] = d->plane_mat[i];
+        const double *n = d->planes + 4 * (size_t)i;
+        unsigned code = 3; // exact axis-aligned unit normals take the one-product fast path (bit-identical)
+        for (int k = 0; k < 3; ++k)
+            if (std::fabs(n[k]) == 1.0 && n[(k + 1) % 3] == 0.0 && n[(k + 2) % 3] == 0.0) code = (unsigned)k;
+        pln_code[i / 16] |= code << (2 * (i % 16));
     }
     for (uint32_t k = 0; k < nt; ++k) {
         const int i = tri_order[k];
@@ -213,7 +219,7 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
                              fmat = to_f(mat), fl = to_f(lights), fg = to_f(globals);
     UP(fsph, ds.v32.sph); UP(fir, ds.v32.sph_invr); UP(fpln, ds.v32.pln); UP(ftri, ds.v32.tri);
     UP(fmat, ds.v32.mat); UP(fl, ds.v32.lights); UP(fg, ds.v32.globals);
-    UP(sph_mat, ds.sph_mat); UP(sph_gid, ds.sph_gid); UP(pln_mat, ds.pln_mat); UP(tri_mat, ds.tri_mat); UP(tri_gid, ds.tri_gid);
+    UP(sph_mat, ds.sph_mat); UP(sph_gid, ds.sph_gid); UP(pln_mat, ds.pln_mat); UP(pln_code, ds.pln_code); UP(tri_mat, ds.tri_mat); UP(tri_gid, ds.tri_gid);
     UP(bvh.nodes, ds.nodes);
 #undef UP
     CU(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
@@ -330,22 +336,39 @@ extern "C" int nt_render(nt_scene *sc, const nt_render_params *p, uint8_t *rgba_
     CU(cudaSetDevice(sc->device));
     const size_t pitch = (size_t)p->width * 4;
     const uint32_t out_rows = p->layout == NT_LAYOUT_COMPACT ? a.vrows : p->height;
-    const size_t need = pitch * out_rows;
-    if (need > sc->fb_bytes) {
-        if (sc->d_fb) cudaFree(sc->d_fb);
-        sc->d_fb = nullptr; sc->fb_bytes = 0;
-        cudaError_t e = cudaMalloc((void **)&sc->d_fb, need);
-        if (e != cudaSuccess) return fail(NT_ERR_NOMEM, "framebuffer cudaMalloc(%zu): %s", need, cudaGetErrorString(e));
-        sc->fb_bytes = need;
+    // Pinned (page-locked) caller buffer: the kernel stores the RGBA8 words straight into it over PCIe
+    // (UVA maps pinned host memory into the device address space), so the device->host transfer overlaps
+    // the tracing instead of following it.  Pageable buffers go through a device frame + cudaMemcpy2D.
+    uint8_t *mapped = nullptr;
+    {
+        static const bool allow = [] { const char *e = getenv("NT_ZEROCOPY"); return !(e && e[0] == '0'); }();
+        cudaPointerAttributes at;
+        if (allow && stride % 4 == 0 && ((uintptr_t)rgba_out) % 4 == 0 &&
+            cudaPointerGetAttributes(&at, rgba_out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+            mapped = (uint8_t *)at.devicePointer;
+        cudaGetLastError();
     }
-    a.out = sc->d_fb;
+    if (mapped) {
+        a.out = mapped;
+        a.stride = stride;
+    } else {
+        const size_t need = pitch * out_rows;
+        if (need > sc->fb_bytes) {
+            if (sc->d_fb) cudaFree(sc->d_fb);
+            sc->d_fb = nullptr; sc->fb_bytes = 0;
+            cudaError_t e = cudaMalloc((void **)&sc->d_fb, need);
+            if (e != cudaSuccess) return fail(NT_ERR_NOMEM, "framebuffer cudaMalloc(%zu): %s", need, cudaGetErrorString(e));
+            sc->fb_bytes = need;
+        }
+        a.out = sc->d_fb;
+    }
     a.counters = sc->d_counters;
     const size_t cbytes = kCounterBytes;
     CU(cudaMemsetAsync(sc->d_counters, 0, cbytes, sc->stream));
     CU(cudaEventRecord(sc->ev0, sc->stream));
     if ((rc = launch(sc, a, p->precision, sc->stream)) != NT_OK) return rc;
     CU(cudaEventRecord(sc->ev1, sc->stream));
-    if (a.vrows) {
+    if (a.vrows && !mapped) {
         if (p->layout == NT_LAYOUT_COMPACT || a.shard_count == 1) {
             CU(cudaMemcpy2DAsync(rgba_out, stride, sc->d_fb, pitch, pitch, out_rows, cudaMemcpyDeviceToHost, sc->stream));
         } else { // full layout, sharded: only the owned bands reach the caller's buffer

@@ -48,11 +48,15 @@ __device__ __forceinline__ void query_start(const Ctx<R, true> &c, BvhQuery<R> &
     q.best.kind = -1; q.best.idx = -1; q.best.gid = 0x7fffffff;
     q.cur = NT_REF_EMPTY; q.sp = 0;
     R t;
+    unsigned codes = 0;
     for (unsigned i = 0; i < s.np; ++i) {
         R pq[4];
+        if ((i & 15) == 0) codes = c.pln_codes(i >> 4);
         c.ld_pln(i, pq);
+        const int code = (int)(codes & 3u);
+        codes >>= 2;
         k.pln++;
-        if (hit_plane<R>(pq, o, d, c.eps, q.tb, t) && t < q.tb) {
+        if (hit_plane<R>(pq, code, o, d, c.eps, q.tb, t) && t < q.tb) {
             if (any) { q.done = true; q.found = true; return; }
             q.tb = t; q.best.kind = 1; q.best.idx = (int)i; q.best.gid = (int)(s.ns + i); q.found = true;
         }

@@ -57,6 +57,7 @@ struct NtDevScene {
     float max_abs; // largest |coordinate| of any bounded primitive (box-test margin)
     float blo[3], bhi[3]; // bounds of all bounded primitives (float, rounded outward)
     const int *sph_mat, *sph_gid, *pln_mat, *tri_mat, *tri_gid;
+    const unsigned *pln_code; // 2 bits per plane, 16 planes per word: 0..2 normal == +-e_k, 3 general
     const NtBvhNode *nodes;
     NtSceneView<double> v64;
     NtSceneView<float> v32;

@@ -15,6 +15,18 @@
 
 #include "nt_device.h"
 
+// what-if timing hooks (experiments only; the shipped build defines none of them)
+#ifdef NT_EXP_NOPLANES
+#define NT_EXP_NP(x) 0u
+#else
+#define NT_EXP_NP(x) (x)
+#endif
+#ifdef NT_EXP_NOSPHERES
+#define NT_EXP_NS(x) 0u
+#else
+#define NT_EXP_NS(x) (x)
+#endif
+
 namespace nt {
 
 template <typename R> struct V3 { R x, y, z; };
@@ -37,7 +49,11 @@ template <> struct Math<double> {
     static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
     static __device__ __forceinline__ double div(double a, double b) { return a / b; }
     static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+#ifdef NT_EXP_NOPOW
+    static __device__ __forceinline__ double pow_(double a, double b) { return a * b; }
+#else
     static __device__ __forceinline__ double pow_(double a, double b) { return pow(a, b); }
+#endif
     static __device__ __forceinline__ float up(double x) { return __double2float_ru(x); }
     static __device__ __forceinline__ double inf() { return CUDART_INF; }
 };
@@ -157,11 +173,24 @@ __device__ __forceinline__ bool hit_sphere(const R q[4], const V3<R> &o, const V
 //   * |num| >= (|dn| * tmax) * (1 + 1e-15)     -> the correctly rounded quotient is >= tmax
 // Both tests are implied by the exact rule, so the result is bit-identical to dividing always.
 template <typename R>
-__device__ __forceinline__ bool hit_plane(const R q[4], const V3<R> &o, const V3<R> &d, R eps, R tmax,
+__device__ __forceinline__ bool hit_plane(const R q[4], int code, const V3<R> &o, const V3<R> &d, R eps, R tmax,
                                           R &t_out) {
-    V3<R> n = { q[0], q[1], q[2] };
-    R dn = dot(n, d);
-    R num = q[3] - dot(n, o);
+    // code (warp-uniform: every lane tests the same plane): 0..2 = the normal is +-e_k, 3 = general.
+    // For an axis-aligned unit normal the two dot products of SPEC §3 reduce EXACTLY to one product:
+    // (0*a + n_k*b) + 0*c == n_k*b in IEEE arithmetic for finite inputs and n_k = +-1, so 8 of the 10
+    // multiply/adds are skipped with bit-identical dn and num.  Uniform switch: no divergence.
+    R dn, dno;
+    switch (sizeof(R) == 8 ? code : 3) { // strict mode only: in binary32 the products are cheaper than the switch
+    case 0: dn = q[0] * d.x; dno = q[0] * o.x; break;
+    case 1: dn = q[1] * d.y; dno = q[1] * o.y; break;
+    case 2: dn = q[2] * d.z; dno = q[2] * o.z; break;
+    default: {
+        V3<R> n = { q[0], q[1], q[2] };
+        dn = dot(n, d);
+        dno = dot(n, o);
+    }
+    }
+    R num = q[3] - dno;
     if constexpr (sizeof(R) == 8) {
         if ((__double2hiint(num) ^ __double2hiint(dn)) < 0) return false;
         if (fabs(num) >= (fabs(dn) * tmax) * (1.0 + 1e-15)) return false;
@@ -202,13 +231,19 @@ extern __shared__ __align__(16) unsigned char nt_smem[];
 template <typename R, bool BVH> struct Ctx {
     const NtDevScene *s;
     const NtSceneView<R> *v;
-    unsigned sph_addr, pln_addr, tri_addr; // 32-bit shared-memory byte addresses of the staged arrays
+    unsigned sph_addr, pln_addr, tri_addr, code_addr; // 32-bit shared-memory byte addresses of the staged arrays
     R eps;
     unsigned max_depth;
     __device__ __forceinline__ void ld_sph(unsigned i, R *q) const {
         if constexpr (BVH) Ld<R>::g4(v->sph + 4 * (size_t)i, q); else Ld<R>::s4(sph_addr + i * (4 * (unsigned)sizeof(R)), q);
     }
     __device__ __forceinline__ void ld_pln(unsigned i, R *q) const { Ld<R>::s4(pln_addr + i * (4 * (unsigned)sizeof(R)), q); }
+    // plane classes, 2 bits per plane, 16 planes per word
+    __device__ __forceinline__ unsigned pln_codes(unsigned word) const {
+        unsigned v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(code_addr + 4 * word));
+        return v;
+    }
     __device__ __forceinline__ void ld_tri(unsigned i, R *q) const {
         if constexpr (BVH) Ld<R>::g9(v->tri + NT_TRI_STRIDE * (size_t)i, q);
         else Ld<R>::s9(tri_addr + i * (NT_TRI_STRIDE * (unsigned)sizeof(R)), q);
@@ -239,7 +274,7 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
     if constexpr (!BVH) {
         // two spheres per iteration: the two discriminant chains are independent and interleave
         unsigned i = 0;
-        for (; i + 2 <= s.ns; i += 2) {
+        for (; i + 2 <= NT_EXP_NS(s.ns); i += 2) {
             R q0[4], q1[4], b0, b1, d0, d1;
             c.ld_sph(i, q0);
             c.ld_sph(i + 1, q1);
@@ -255,10 +290,14 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
         }
         k.sph += s.ns;
     }
-    for (unsigned i = 0; i < s.np; ++i) {
+    unsigned codes = 0;
+    for (unsigned i = 0; i < NT_EXP_NP(s.np); ++i) {
         R q[4];
+        if ((i & 15) == 0) codes = c.pln_codes(i >> 4);
         c.ld_pln(i, q);
-        if (hit_plane<R>(q, o, d, c.eps, tb, t) && t < tb) { tb = t; best.kind = 1; best.idx = (int)i; best.gid = (int)(s.ns + i); }
+        const int code = (int)(codes & 3u);
+        codes >>= 2;
+        if (hit_plane<R>(q, code, o, d, c.eps, tb, t) && t < tb) { tb = t; best.kind = 1; best.idx = (int)i; best.gid = (int)(s.ns + i); }
     }
     k.pln += s.np;
     if constexpr (!BVH) {
@@ -281,7 +320,7 @@ __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, c
     R t;
     if constexpr (!BVH) {
         unsigned i = 0;
-        for (; i + 2 <= s.ns; i += 2) {
+        for (; i + 2 <= NT_EXP_NS(s.ns); i += 2) {
             R q0[4], q1[4], b0, b1, d0, d1;
             c.ld_sph(i, q0);
             c.ld_sph(i + 1, q1);
@@ -297,10 +336,14 @@ __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, c
         }
         k.sph += s.ns;
     }
-    for (unsigned i = 0; i < s.np; ++i) {
+    unsigned codes = 0;
+    for (unsigned i = 0; i < NT_EXP_NP(s.np); ++i) {
         R q[4];
+        if ((i & 15) == 0) codes = c.pln_codes(i >> 4);
         c.ld_pln(i, q);
-        if (hit_plane<R>(q, o, d, c.eps, dist, t) && t < dist) { k.pln += i + 1; return true; }
+        const int code = (int)(codes & 3u);
+        codes >>= 2;
+        if (hit_plane<R>(q, code, o, d, c.eps, dist, t) && t < dist) { k.pln += i + 1; return true; }
     }
     k.pln += s.np;
     if constexpr (!BVH) {
@@ -453,12 +496,15 @@ __device__ __forceinline__ void stage_scene(const NtDevScene &s, const NtSceneVi
     if constexpr (!BVH)
 #pragma unroll 1
         for (unsigned i = threadIdx.x; i < n_tri / VEC; i += blockDim.x) ((VT *)(smem + n_sph + n_pln))[i] = __ldg((const VT *)v.tri + i);
+    unsigned *codes = (unsigned *)(smem + n_sph + n_pln + n_tri);
+    for (unsigned i = threadIdx.x; i < (s.np + 15) / 16; i += blockDim.x) codes[i] = __ldg(s.pln_code + i);
     __syncthreads();
     unsigned base = (unsigned)__cvta_generic_to_shared(nt_smem);
     asm volatile("" : "+r"(base)); // opaque: otherwise ptxas re-derives the window base (S2R + 5 ops) per use
     c.sph_addr = base;
     c.pln_addr = base + n_sph * (unsigned)sizeof(R);
     c.tri_addr = base + (n_sph + n_pln) * (unsigned)sizeof(R);
+    c.code_addr = base + (n_sph + n_pln + n_tri) * (unsigned)sizeof(R);
 }
 
 // Per-thread counters -> one atomic per counter per block, spread over NT_COUNTER_SLOTS slots.
@@ -585,7 +631,7 @@ template <typename R>
 inline size_t flat_smem_bytes(const NtDevScene &s, bool bvh) {
     size_t n = (size_t)s.np * 4;
     if (!bvh) n += (size_t)s.ns * 4 + (size_t)s.nt * NT_TRI_STRIDE;
-    return n * sizeof(R);
+    return n * sizeof(R) + (size_t)((s.np + 15) / 16) * sizeof(unsigned);
 }
 
 } // namespace nt
