@@ -210,6 +210,13 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
     ds.use_bvh = use_bvh ? 1 : 0;
     ds.n_nodes = use_bvh && ns + nt > 0 ? (uint32_t)bvh.nodes.size() : 0;
     ds.max_abs = bvh.max_abs;
+    if (!use_bvh) { // flat scenes: extent of the bounded primitives, for the binary32 filter margin
+        double mx = 0;
+        for (uint32_t i = 0; i < ns; ++i)
+            for (int a = 0; a < 3; ++a) mx = std::max(mx, std::fabs(d->spheres[4 * (size_t)i + a]) + d->spheres[4 * (size_t)i + 3]);
+        for (size_t i = 0; i < 9 * (size_t)nt; ++i) mx = std::max(mx, std::fabs(d->triangles[i]));
+        ds.max_abs = (float)mx * 1.000001f;
+    }
     for (int a = 0; a < 3; ++a) { ds.blo[a] = bvh.blo[a]; ds.bhi[a] = bvh.bhi[a]; }
     int rc;
 #define UP(vec, dst) if ((rc = upload(sc, vec, &(dst))) != NT_OK) return rc

@@ -13,6 +13,15 @@
 #define NT_MIN_BLOCKS 3     // resident blocks per SM the render kernels are compiled for
 #endif
 #define NT_BVH_STACK 64
+#ifndef NT_FILTER_BATCH
+#define NT_FILTER_BATCH 4   // filter evaluations interleaved per loop iteration
+#endif
+#ifndef NT_SPHERE_FILTER
+#define NT_SPHERE_FILTER 0  // strict flat scenes: binary32 conservative pre-filter before the exact sphere test.
+                           // Bit-exact (tests pass with it on) but SLOWER on configs[2]: 1.49 ms (one at a time), 1.90 ms
+                           // (batch 4), 2.27 ms (batch 8) vs 1.39 ms without -- the kernel is register-bound at 80
+                           // registers and the extra live state spills; kept for the next round's register diet
+#endif
 #ifndef NT_MIN_BLOCKS_BVH
 #define NT_MIN_BLOCKS_BVH 4 // measured best on configs[3] (2: 93.7 ms, 3: 78.2 ms, 4: 75.2 ms) despite spills
 #endif

@@ -222,6 +222,44 @@ __device__ __forceinline__ bool hit_triangle(const R q[9], const V3<R> &o, const
     return true;
 }
 
+// ---- binary32 pre-filter for the strict sphere test (flat scenes) ----
+// The strict mode must return exactly what the binary64 rule of SPEC §3 returns, but it does not have
+// to evaluate that rule for a sphere that provably cannot matter.  The filter works on a binary32 copy
+// of the ray and of the sphere (centre rounded to nearest, radius rounded up) and answers one question
+// conservatively: could this sphere have a hit with t in (0, tmax]?  It reports "no" only if
+//   * the centre is farther from the ray's line than r + m            (clear miss), or
+//   * the whole chord lies behind the origin, t_far + m < 0            (both roots negative), or
+//   * the chord starts beyond the bound, t_near - m > tmax.
+// m = 4e-5 * (|origin|_inf + scene extent) is ~20x the worst-case binary32 error of the quantities
+// involved (conversions 2^-24 relative, then <= ~12 roundings on values bounded by 2*(|o|+extent)); the
+// comparisons are written so that NaN/overflow answers "maybe".  Every "maybe" gets the exact test, in
+// the original order, so results are bit-identical (tests/test_parity_gpu.py compares against the
+// oracle, which has no filter).  Counters still count every sphere as tested.
+struct SphFilterRay {
+    float ox, oy, oz, dx, dy, dz, m;
+};
+__device__ __forceinline__ bool sphere_maybe(const SphFilterRay &r, float4 s /*cx cy cz r_up*/, float tmaxf) {
+    // branch-free on purpose: NT_FILTER_BATCH of these are evaluated back to back so that their
+    // (4-cycle-latency) dependency chains interleave; the kernel is latency-, not throughput-bound
+    const float x = r.ox - s.x, y = r.oy - s.y, z = r.oz - s.z;
+    const float b = __fmaf_rn(z, r.dz, __fmaf_rn(y, r.dy, x * r.dx));
+    const float lx = __fmaf_rn(-b, r.dx, x), ly = __fmaf_rn(-b, r.dy, y), lz = __fmaf_rn(-b, r.dz, z);
+    const float l2 = __fmaf_rn(lz, lz, __fmaf_rn(ly, ly, lx * lx));
+    const float rm = s.w + r.m, rm2 = rm * rm * 1.000001f;
+    const float h = sqrtf(fmaxf(rm2 - l2, 0.0f)) * 1.000001f;
+    const bool no = (l2 > rm2) | (-b + h + r.m < 0.0f) | (-b - h - r.m > tmaxf);
+    return !no;
+}
+
+template <typename R>
+__device__ __forceinline__ SphFilterRay make_filter_ray(const V3<R> &o, const V3<R> &d, float scene_max_abs) {
+    SphFilterRay r;
+    r.ox = (float)o.x; r.oy = (float)o.y; r.oz = (float)o.z;
+    r.dx = (float)d.x; r.dy = (float)d.y; r.dz = (float)d.z;
+    r.m = 4e-5f * (fmaxf(fmaxf(fabsf(r.ox), fabsf(r.oy)), fabsf(r.oz)) + scene_max_abs);
+    return r;
+}
+
 // ---- scene context of one block ----
 // Dynamic shared memory: the flat intersection data staged by stage_scene().  Addressed through this
 // symbol (plus element offsets kept in Ctx) so that every access is a plain LDS with an immediate
@@ -231,13 +269,18 @@ extern __shared__ __align__(16) unsigned char nt_smem[];
 template <typename R, bool BVH> struct Ctx {
     const NtDevScene *s;
     const NtSceneView<R> *v;
-    unsigned sph_addr, pln_addr, tri_addr, code_addr; // 32-bit shared-memory byte addresses of the staged arrays
+    unsigned sph_addr, pln_addr, tri_addr, code_addr, fsph_addr; // 32-bit shared-memory byte addresses of the staged arrays
     R eps;
     unsigned max_depth;
     __device__ __forceinline__ void ld_sph(unsigned i, R *q) const {
         if constexpr (BVH) Ld<R>::g4(v->sph + 4 * (size_t)i, q); else Ld<R>::s4(sph_addr + i * (4 * (unsigned)sizeof(R)), q);
     }
     __device__ __forceinline__ void ld_pln(unsigned i, R *q) const { Ld<R>::s4(pln_addr + i * (4 * (unsigned)sizeof(R)), q); }
+    __device__ __forceinline__ float4 ld_fsph(unsigned i) const {
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(fsph_addr + 16 * i));
+        return v;
+    }
     // plane classes, 2 bits per plane, 16 planes per word
     __device__ __forceinline__ unsigned pln_codes(unsigned word) const {
         unsigned v;
@@ -271,7 +314,24 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
     tb = Math<R>::inf();
     best.kind = -1; best.idx = -1; best.gid = 0x7fffffff;
     R t;
-    if constexpr (!BVH) {
+    if constexpr (!BVH && sizeof(R) == 8 && NT_SPHERE_FILTER) {
+        const SphFilterRay fr = make_filter_ray(o, d, s.max_abs);
+        float tbf = CUDART_INF_F;
+        for (unsigned i0 = 0; i0 < NT_EXP_NS(s.ns); i0 += NT_FILTER_BATCH) {
+            unsigned mask = 0;
+#pragma unroll
+            for (int u = 0; u < NT_FILTER_BATCH; ++u)
+                if (i0 + u < s.ns && sphere_maybe(fr, c.ld_fsph(i0 + u), tbf)) mask |= 1u << u;
+            while (mask) { // exact tests of the survivors, in index order
+                const unsigned i = i0 + (unsigned)__ffs((int)mask) - 1;
+                mask &= mask - 1;
+                R q[4];
+                c.ld_sph(i, q);
+                if (hit_sphere<R>(q, o, d, c.eps, t) && t < tb) { tb = t; best.kind = 0; best.idx = (int)i; tbf = Math<R>::up(tb); }
+            }
+        }
+        k.sph += s.ns;
+    } else if constexpr (!BVH) {
         // two spheres per iteration: the two discriminant chains are independent and interleave
         unsigned i = 0;
         for (; i + 2 <= NT_EXP_NS(s.ns); i += 2) {
@@ -318,7 +378,24 @@ __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, c
                                          Counters &k) {
     const NtDevScene &s = *c.s;
     R t;
-    if constexpr (!BVH) {
+    if constexpr (!BVH && sizeof(R) == 8 && NT_SPHERE_FILTER) {
+        const SphFilterRay fr = make_filter_ray(o, d, s.max_abs);
+        const float distf = Math<R>::up(dist);
+        for (unsigned i0 = 0; i0 < NT_EXP_NS(s.ns); i0 += NT_FILTER_BATCH) {
+            unsigned mask = 0;
+#pragma unroll
+            for (int u = 0; u < NT_FILTER_BATCH; ++u)
+                if (i0 + u < s.ns && sphere_maybe(fr, c.ld_fsph(i0 + u), distf)) mask |= 1u << u;
+            while (mask) {
+                const unsigned i = i0 + (unsigned)__ffs((int)mask) - 1;
+                mask &= mask - 1;
+                R q[4];
+                c.ld_sph(i, q);
+                if (hit_sphere<R>(q, o, d, c.eps, t) && t < dist) { k.sph += i + 1; return true; }
+            }
+        }
+        k.sph += s.ns;
+    } else if constexpr (!BVH) {
         unsigned i = 0;
         for (; i + 2 <= NT_EXP_NS(s.ns); i += 2) {
             R q0[4], q1[4], b0, b1, d0, d1;
@@ -498,6 +575,14 @@ __device__ __forceinline__ void stage_scene(const NtDevScene &s, const NtSceneVi
         for (unsigned i = threadIdx.x; i < n_tri / VEC; i += blockDim.x) ((VT *)(smem + n_sph + n_pln))[i] = __ldg((const VT *)v.tri + i);
     unsigned *codes = (unsigned *)(smem + n_sph + n_pln + n_tri);
     for (unsigned i = threadIdx.x; i < (s.np + 15) / 16; i += blockDim.x) codes[i] = __ldg(s.pln_code + i);
+    const unsigned code_words = (s.np + 15) / 16, fs_off = (code_words + 3) & ~3u; // float4-aligned
+    if constexpr (!BVH && sizeof(R) == 8) {
+        float4 *fs = (float4 *)(codes + fs_off);
+        for (unsigned i = threadIdx.x; i < s.ns; i += blockDim.x) {
+            const double2 a = __ldg((const double2 *)v.sph + 2 * i), b2 = __ldg((const double2 *)v.sph + 2 * i + 1);
+            fs[i] = make_float4((float)a.x, (float)a.y, (float)b2.x, __double2float_ru(sqrt(b2.y)));
+        }
+    }
     __syncthreads();
     unsigned base = (unsigned)__cvta_generic_to_shared(nt_smem);
     asm volatile("" : "+r"(base)); // opaque: otherwise ptxas re-derives the window base (S2R + 5 ops) per use
@@ -505,6 +590,7 @@ __device__ __forceinline__ void stage_scene(const NtDevScene &s, const NtSceneVi
     c.pln_addr = base + n_sph * (unsigned)sizeof(R);
     c.tri_addr = base + (n_sph + n_pln) * (unsigned)sizeof(R);
     c.code_addr = base + (n_sph + n_pln + n_tri) * (unsigned)sizeof(R);
+    c.fsph_addr = c.code_addr + 4 * fs_off;
 }
 
 // Per-thread counters -> one atomic per counter per block, spread over NT_COUNTER_SLOTS slots.
@@ -631,7 +717,9 @@ template <typename R>
 inline size_t flat_smem_bytes(const NtDevScene &s, bool bvh) {
     size_t n = (size_t)s.np * 4;
     if (!bvh) n += (size_t)s.ns * 4 + (size_t)s.nt * NT_TRI_STRIDE;
-    return n * sizeof(R) + (size_t)((s.np + 15) / 16) * sizeof(unsigned);
+    size_t bytes = n * sizeof(R) + (size_t)((((s.np + 15) / 16) + 3) & ~3u) * sizeof(unsigned);
+    if (!bvh && sizeof(R) == 8) bytes += (size_t)s.ns * sizeof(float4); // binary32 filter spheres
+    return bytes;
 }
 
 } // namespace nt
