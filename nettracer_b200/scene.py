@@ -88,7 +88,7 @@ class Scene:
 
     def add_plane(self, n, d, mat):
         n = _vec(n)
-        ln = math.sqrt(float(n @ n))
+        ln = math.sqrt((float(n[0]) * float(n[0]) + float(n[1]) * float(n[1])) + float(n[2]) * float(n[2]))
         self.planes.append((*(n / ln), float(d) / ln))
         self.plane_mat.append(int(mat))
 
