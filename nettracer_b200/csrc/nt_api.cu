@@ -156,6 +156,7 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
         int leaf_max = 4;
         if (const char *e = getenv("NT_BVH_LEAF")) leaf_max = atoi(e);
         nt_bvh_build(d->spheres, ns, d->triangles, nt, leaf_max, bvh);
+        if (3 * bvh.depth4 + 4 > NT_BVH_STACK) return fail(NT_ERR_INVALID, "BVH too deep (%d levels) for the %d-entry traversal stack", bvh.depth4, NT_BVH_STACK);
         sph_order = bvh.sph_order;
         tri_order = bvh.tri_order;
     }
@@ -208,7 +209,7 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
     NtDevScene &ds = sc->ds;
     ds.ns = ns; ds.np = np; ds.nt = nt; ds.nm = nm; ds.nl = nl;
     ds.use_bvh = use_bvh ? 1 : 0;
-    ds.n_nodes = use_bvh && ns + nt > 0 ? (uint32_t)bvh.nodes.size() : 0;
+    ds.n_nodes = use_bvh && ns + nt > 0 ? (uint32_t)bvh.nodes4.size() : 0;
     ds.max_abs = bvh.max_abs;
     if (!use_bvh) { // flat scenes: extent of the bounded primitives, for the binary32 filter margin
         double mx = 0;
@@ -227,7 +228,7 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
     UP(fsph, ds.v32.sph); UP(fir, ds.v32.sph_invr); UP(fpln, ds.v32.pln); UP(ftri, ds.v32.tri);
     UP(fmat, ds.v32.mat); UP(fl, ds.v32.lights); UP(fg, ds.v32.globals);
     UP(sph_mat, ds.sph_mat); UP(sph_gid, ds.sph_gid); UP(pln_mat, ds.pln_mat); UP(pln_code, ds.pln_code); UP(tri_mat, ds.tri_mat); UP(tri_gid, ds.tri_gid);
-    UP(bvh.nodes, ds.nodes);
+    UP(bvh.nodes4, ds.nodes);
 #undef UP
     CU(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&sc->ev0));

@@ -145,6 +145,55 @@ void nt_bvh_set_children(NtBvhNode &n, const float *lo0, const float *hi0, int c
     n.c0 = make_ref(c0, n0); n.c1 = make_ref(c1, n1); n.n0 = n0; n.n1 = n1;
 }
 
+// ---- BVH2 -> BVH4 collapse ----
+namespace {
+struct Cand { Box box; int ref; };
+
+int emit4(const std::vector<NtBvhNode> &n2, std::vector<NtBvhNode4> &n4, int node2, int depth, int &max_depth) {
+    max_depth = std::max(max_depth, depth);
+    std::vector<Cand> kids;
+    auto children = [&](int id, Cand out[2]) {
+        const NtBvhNode &n = n2[id];
+        for (int a = 0; a < 3; ++a) { out[0].box.lo[a] = n.lo0[a]; out[0].box.hi[a] = n.hi0[a]; out[1].box.lo[a] = n.lo1[a]; out[1].box.hi[a] = n.hi1[a]; }
+        out[0].ref = n.c0; out[1].ref = n.c1;
+    };
+    Cand two[2];
+    children(node2, two);
+    for (const Cand &c : two) if (c.ref != -1) kids.push_back(c);
+    while (kids.size() < 4) { // open the inner child with the largest box
+        int best = -1;
+        float area = -1;
+        for (size_t i = 0; i < kids.size(); ++i)
+            if (kids[i].ref >= 0 && kids[i].box.half_area() > area) { area = kids[i].box.half_area(); best = (int)i; }
+        if (best < 0) break;
+        children(kids[best].ref, two);
+        kids.erase(kids.begin() + best);
+        for (const Cand &c : two) if (c.ref != -1) kids.push_back(c);
+    }
+    const int id = (int)n4.size();
+    n4.emplace_back();
+    NtBvhNode4 node;
+    for (int k = 0; k < 4; ++k) {
+        for (int a = 0; a < 3; ++a) {
+            node.lo[a][k] = k < (int)kids.size() ? kids[k].box.lo[a] : std::numeric_limits<float>::infinity();
+            node.hi[a][k] = k < (int)kids.size() ? kids[k].box.hi[a] : -std::numeric_limits<float>::infinity();
+        }
+        node.ref[k] = -1;
+        node.pad[k] = 0;
+    }
+    for (size_t k = 0; k < kids.size(); ++k) node.ref[k] = kids[k].ref >= 0 ? emit4(n2, n4, kids[k].ref, depth + 1, max_depth) : kids[k].ref;
+    n4[id] = node;
+    return id;
+}
+
+void collapse4(NtBvhBuild &out) {
+    out.nodes4.clear();
+    out.nodes4.reserve(out.nodes.size() / 2 + 4);
+    out.depth4 = 0;
+    emit4(out.nodes, out.nodes4, 0, 1, out.depth4);
+}
+} // namespace
+
 void nt_bvh_build(const double *spheres, uint32_t ns, const double *triangles, uint32_t nt,
                   int leaf_max, NtBvhBuild &out) {
     if (leaf_max < 1) leaf_max = 1;
@@ -172,6 +221,7 @@ void nt_bvh_build(const double *spheres, uint32_t ns, const double *triangles, u
     const Ref rt = build_set(out.nodes, tb, out.tri_order, 0x100, leaf_max);
     nt_bvh_set_children(out.nodes[0], rs.box.lo, rs.box.hi, rs.c, rs.n, rt.box.lo, rt.box.hi, rt.c, rt.n);
     out.max_abs = max_abs;
+    collapse4(out);
     Box all = rs.box;
     all.grow(rt.box);
     for (int a = 0; a < 3; ++a) { out.blo[a] = all.lo[a]; out.bhi[a] = all.hi[a]; }

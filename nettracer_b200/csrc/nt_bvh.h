@@ -6,9 +6,11 @@
 #include "nt_device.h"
 
 struct NtBvhBuild {
-    std::vector<NtBvhNode> nodes;  // nodes[0] is the root
+    std::vector<NtBvhNode> nodes;  // binary tree (intermediate), nodes[0] is the root
+    std::vector<NtBvhNode4> nodes4; // collapsed 4-wide tree the device traverses, nodes4[0] is the root
     std::vector<int> sph_order;    // BVH-ordered position -> original sphere index
     std::vector<int> tri_order;    // BVH-ordered position -> original triangle index
+    int depth4 = 0;                 // depth of the 4-wide tree (bounds the traversal stack)
     float max_abs = 0;
     float blo[3] = { 0, 0, 0 }, bhi[3] = { 0, 0, 0 }; // union of all primitive boxes
 };

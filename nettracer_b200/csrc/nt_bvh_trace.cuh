@@ -32,7 +32,10 @@ template <typename R> struct BvhQuery { // scalars only: lives in registers (the
     V3<R> o, d;
     R tb;          // nearest: best t so far; any: the distance bound
     Hit best;
-    float ox, oy, oz, ix, iy, iz, m, tmaxf; // binary32 copy of the ray for the box tests, origin shifted by tshift
+    // binary32 copy of the ray for the box tests (origin shifted by tshift): t = plane*i - c, with the
+    // margin folded into c (cn*: near planes moved outward, cf*: far planes moved outward)
+    float ix, iy, iz, cnx, cny, cnz, cfx, cfy, cfz, tmaxf;
+    int nearx, neary, nearz; // float4 index of the near plane of each axis inside a node (lo: a, hi: 3 + a)
     R tshift;      // box-test frame: t' = t - tshift (0 unless the origin lies outside the scene bounds)
     int cur;       // ref being visited, NT_REF_EMPTY when the query needs a pop
     int sp;
@@ -63,16 +66,20 @@ __device__ __forceinline__ void query_start(const Ctx<R, true> &c, BvhQuery<R> &
     }
     if (s.n_nodes == 0) { q.done = true; return; }
     float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
-    q.ix = 1.0f / (float)d.x; q.iy = 1.0f / (float)d.y; q.iz = 1.0f / (float)d.z;
+    const float dx = (float)d.x, dy = (float)d.y, dz = (float)d.z;
+    // reciprocal direction, magnitude clamped so that plane*i - c never evaluates inf - inf
+    const float ix = copysignf(fminf(1.0f / fabsf(dx), 1e18f), dx), iy = copysignf(fminf(1.0f / fabsf(dy), 1e18f), dy),
+                iz = copysignf(fminf(1.0f / fabsf(dz), 1e18f), dz);
+    q.ix = ix; q.iy = iy; q.iz = iz;
     // Box margin: covers rounding the ray to binary32 (origin, direction, reciprocal, slab products).
     // It grows with |origin|, so a far origin (a camera outside the scene, a hit on an unbounded plane
     // kilometres away) is first slid along the exact ray to where it enters the scene bounds: only the
     // box tests use the shifted copy, the primitive tests keep the original ray.
     float m = 4e-6f * (fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz)) + s.max_abs);
     float tn = 0.0f, tf = CUDART_INF_F;
-    slab(s.blo[0], s.bhi[0], ox, q.ix, m, tn, tf);
-    slab(s.blo[1], s.bhi[1], oy, q.iy, m, tn, tf);
-    slab(s.blo[2], s.bhi[2], oz, q.iz, m, tn, tf);
+    slab(s.blo[0], s.bhi[0], ox, ix, m, tn, tf);
+    slab(s.blo[1], s.bhi[1], oy, iy, m, tn, tf);
+    slab(s.blo[2], s.bhi[2], oz, iz, m, tn, tf);
     if (!(tn <= tf) || tn > Math<R>::up(q.tb)) { q.done = true; return; } // misses every bounded primitive
     q.tshift = R(0);
     if (tn > 0.0f) {
@@ -82,7 +89,12 @@ __device__ __forceinline__ void query_start(const Ctx<R, true> &c, BvhQuery<R> &
         m = 4e-6f * (fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz)) + s.max_abs);
         q.tshift = ts;
     }
-    q.ox = ox; q.oy = oy; q.oz = oz; q.m = m;
+    // near plane of an axis: lo when the ray runs in +axis, hi otherwise; each moved outward by m
+    const bool px = !(dx < 0.0f), py = !(dy < 0.0f), pz = !(dz < 0.0f);
+    q.nearx = px ? 0 : 3; q.neary = py ? 1 : 4; q.nearz = pz ? 2 : 5;
+    q.cnx = (px ? ox + m : ox - m) * ix; q.cfx = (px ? ox - m : ox + m) * ix;
+    q.cny = (py ? oy + m : oy - m) * iy; q.cfy = (py ? oy - m : oy + m) * iy;
+    q.cnz = (pz ? oz + m : oz - m) * iz; q.cfz = (pz ? oz - m : oz + m) * iz;
     q.tmaxf = Math<R>::up(q.tb - q.tshift);
     q.cur = 0;
 }
@@ -96,29 +108,41 @@ template <typename R> __device__ __forceinline__ void query_pop(BvhQuery<R> &q, 
     q.done = true;
 }
 
-// One inner node: both child boxes (binary32, conservative), near child next, far child pushed.
+// One inner node of the 4-wide tree: 7 x 128-bit loads (near planes, far planes, refs), 4 slab tests as
+// 6 FMAs + max3/min3 each, then the hit children ordered by entry distance with a 4-key sorting network
+// on (t_near bits | slot): nearest visited next, the others pushed far-to-near.
 template <typename R>
 __device__ __forceinline__ void query_inner_step(const Ctx<R, true> &c, BvhQuery<R> &q, int2 *stack, Counters &k) {
     const float4 *n = (const float4 *)(c.s->nodes + q.cur);
-    const float4 q0 = __ldg(n), q1 = __ldg(n + 1), q2 = __ldg(n + 2);
-    const int4 q3 = __ldg((const int4 *)(n + 3));
-    float n0 = 0.0f, f0 = CUDART_INF_F, n1 = 0.0f, f1 = CUDART_INF_F;
-    slab(q0.x, q0.w, q.ox, q.ix, q.m, n0, f0);
-    slab(q0.y, q1.x, q.oy, q.iy, q.m, n0, f0);
-    slab(q0.z, q1.y, q.oz, q.iz, q.m, n0, f0);
-    slab(q1.z, q2.y, q.ox, q.ix, q.m, n1, f1);
-    slab(q1.w, q2.z, q.oy, q.iy, q.m, n1, f1);
-    slab(q2.x, q2.w, q.oz, q.iz, q.m, n1, f1);
-    k.box += 2;
-    const bool h0 = q3.x != NT_REF_EMPTY && n0 <= f0 && n0 <= q.tmaxf;
-    const bool h1 = q3.y != NT_REF_EMPTY && n1 <= f1 && n1 <= q.tmaxf;
-    if (h0 && h1) {
-        const bool first1 = n1 < n0;
-        q.cur = first1 ? q3.y : q3.x;
-        stack[q.sp++] = make_int2(first1 ? q3.x : q3.y, __float_as_int(first1 ? n0 : n1));
-    } else if (h0) q.cur = q3.x;
-    else if (h1) q.cur = q3.y;
-    else query_pop(q, stack);
+    const float4 nx = __ldg(n + q.nearx), ny = __ldg(n + q.neary), nz = __ldg(n + q.nearz);
+    const float4 fx = __ldg(n + (3 - q.nearx)), fy = __ldg(n + (5 - q.neary)), fz = __ldg(n + (7 - q.nearz));
+    const int4 rf = __ldg((const int4 *)(n + 6));
+    k.box += 4;
+    const float nxa[4] = { nx.x, nx.y, nx.z, nx.w }, nya[4] = { ny.x, ny.y, ny.z, ny.w }, nza[4] = { nz.x, nz.y, nz.z, nz.w };
+    const float fxa[4] = { fx.x, fx.y, fx.z, fx.w }, fya[4] = { fy.x, fy.y, fy.z, fy.w }, fza[4] = { fz.x, fz.y, fz.z, fz.w };
+    const int ra[4] = { rf.x, rf.y, rf.z, rf.w };
+    int key[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float tn = fmaxf(fmaxf(__fmaf_rn(nxa[j], q.ix, -q.cnx), __fmaf_rn(nya[j], q.iy, -q.cny)),
+                               fmaxf(__fmaf_rn(nza[j], q.iz, -q.cnz), 0.0f));
+        const float tf = fminf(fminf(__fmaf_rn(fxa[j], q.ix, -q.cfx), __fmaf_rn(fya[j], q.iy, -q.cfy)),
+                               __fmaf_rn(fza[j], q.iz, -q.cfz));
+        const bool hit = ra[j] != NT_REF_EMPTY && tn <= tf && tn <= q.tmaxf;
+        key[j] = hit ? ((__float_as_int(tn) & ~3) | j) : 0x7fffffff; // tn >= 0: integer order == float order
+    }
+#define NT_CSWAP(a, b) { const int lo_ = min(key[a], key[b]), hi_ = max(key[a], key[b]); key[a] = lo_; key[b] = hi_; }
+    NT_CSWAP(0, 1) NT_CSWAP(2, 3) NT_CSWAP(0, 2) NT_CSWAP(1, 3) NT_CSWAP(1, 2)
+#undef NT_CSWAP
+    if (key[0] == 0x7fffffff) { query_pop(q, stack); return; }
+#pragma unroll
+    for (int j = 3; j >= 1; --j)
+        if (key[j] != 0x7fffffff) {
+            const int slot = key[j] & 3;
+            stack[q.sp++] = make_int2(slot == 0 ? rf.x : slot == 1 ? rf.y : slot == 2 ? rf.z : rf.w, key[j] & ~3);
+        }
+    const int slot = key[0] & 3;
+    q.cur = slot == 0 ? rf.x : slot == 1 ? rf.y : slot == 2 ? rf.z : rf.w;
 }
 
 // One leaf: up to 4 primitives of one kind, exact tests in R.

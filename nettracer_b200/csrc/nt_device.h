@@ -12,7 +12,7 @@
 #ifndef NT_MIN_BLOCKS
 #define NT_MIN_BLOCKS 3     // resident blocks per SM the render kernels are compiled for
 #endif
-#define NT_BVH_STACK 64
+#define NT_BVH_STACK 96     // entries; a 4-wide node pushes up to 3: scene creation checks 3*depth + 4 <= this
 #ifndef NT_FILTER_BATCH
 #define NT_FILTER_BATCH 4   // filter evaluations interleaved per loop iteration
 #endif
@@ -49,6 +49,19 @@ struct NtBvhNode {
 };
 static_assert(sizeof(NtBvhNode) == 64, "node must be 64 bytes");
 
+// 128-byte BVH4 node (one cache line), the layout the kernels traverse.  The host builder collapses its
+// binary tree into it (largest-area inner child is replaced by its two children until 4 slots are used).
+// Boxes are SoA so that the near/far plane of each axis is ONE 128-bit load chosen by the ray's sign:
+//   float4 #0..2 = lo.x lo.y lo.z of the 4 children, #3..5 = hi.x hi.y hi.z, int4 #6 = child refs
+//   (same ref encoding as above; empty slots: ref -1 and an inverted box), #7 = padding.
+struct NtBvhNode4 {
+    float lo[3][4];
+    float hi[3][4];
+    int ref[4];
+    int pad[4];
+};
+static_assert(sizeof(NtBvhNode4) == 128, "node must be 128 bytes");
+
 template <typename R>
 struct NtSceneView {
     const R *sph;      // [ns][4]  cx cy cz r2
@@ -67,7 +80,7 @@ struct NtDevScene {
     float blo[3], bhi[3]; // bounds of all bounded primitives (float, rounded outward)
     const int *sph_mat, *sph_gid, *pln_mat, *tri_mat, *tri_gid;
     const unsigned *pln_code; // 2 bits per plane, 16 planes per word: 0..2 normal == +-e_k, 3 general
-    const NtBvhNode *nodes;
+    const NtBvhNode4 *nodes;
     NtSceneView<double> v64;
     NtSceneView<float> v32;
 };
