@@ -274,3 +274,32 @@ def test_two_gpu_sharded_renderer_modes():
                               os.path.join(root, "tests", "sharded_gpu_worker.py"), mode],
                              capture_output=True, text=True, timeout=600)
         assert out.returncode == 0 and "SHARDED_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_trace_rays_bvh_stress_far_and_axis_parallel():
+    """Conservative culling under stress: origins up to 1e5 away from a scene of extent ~10, directions
+    with exact zeros (axis-parallel, reciprocal clamped), grazing rays.  Every hit must equal the oracle's
+    brute-force answer bit for bit."""
+    s, cam = scenes.random_mixed(220, 1, 420, seed=13)
+    rng = np.random.default_rng(5)
+    n = 60000
+    target = rng.uniform(-6, 6, (n, 3)); target[:, 2] -= 3
+    d = rng.normal(size=(n, 3))
+    # a third of the rays axis-parallel in one or two components
+    z1 = rng.integers(0, 3, n); z2 = rng.integers(0, 3, n)
+    sel = rng.random(n) < 0.33
+    d[sel, z1[sel]] = 0.0
+    sel2 = rng.random(n) < 0.1
+    d[sel2, z2[sel2]] = 0.0
+    bad = np.linalg.norm(d, axis=1) == 0
+    d[bad] = [0.0, 0.0, -1.0]
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    dist = 10.0 ** rng.uniform(0, 5, (n, 1))
+    o = target - d * dist
+    with Renderer(s) as r:
+        assert r.info()["uses_bvh"]
+        t, prim = r.trace_rays(o, d)
+    to, po = oracle.trace_rays(s, o, d, accel=0)
+    assert np.array_equal(prim, po), int((prim != po).sum())
+    assert np.array_equal(t.view(np.uint64), to.view(np.uint64))
+    assert (prim >= 0).mean() > 0.2
