@@ -328,7 +328,8 @@ def main():
                 "e2e": {"value": e2e_val, "unit": METRIC, "ms_per_frame": e2e_ms, "h2d_bytes_per_step": C.sizeof(abi.nt_render_params),
                         "d2h_bytes_per_step": h * w * 4 + 8 * 8 * 32,
                         "api": "nt_render -> pinned host RGBA8" if world == 1 else "ShardedRenderer.render + D2H on rank 0"},
-                "gpu_launches": a.steps * (1 + (1 if sr.mode == "gather" and world > 1 else 0)),
+                "gpu_launches": a.steps * ((2 if info["uses_bvh"] else 1) + (1 if sr.mode == "gather" and world > 1 else 0)),
+                "gpu_launches_note": "per frame and rank: render kernel (+ resolve kernel on BVH scenes, + deinterleave on rank 0 in gather mode)",
                 "kernel_ms": kernel_ms, "wall_s_timed_region": wall, "clocks": clocks, "roofline": roof}
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_oracle_sample(scene, cam, w, h, spp, depth, a.cpu_seconds)
