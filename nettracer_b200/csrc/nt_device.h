@@ -9,12 +9,18 @@
 #define NT_COUNTER_SLOTS 32
 #define NT_NCOUNTERS 8     // primary secondary shadow sphere plane triangle box light
 #define NT_BLOCK_THREADS 256
-#ifndef NT_MIN_BLOCKS
-#define NT_MIN_BLOCKS 3     // resident blocks per SM the render kernels are compiled for
+#ifndef NT_MIN_BLOCKS_F64
+#define NT_MIN_BLOCKS_F64 4 // resident blocks/SM the flat render kernel is compiled for (64 registers); measured
+#endif                      // on configs[2] strict: 2 -> 1.55 ms, 3 -> 1.35 ms, 4 -> 1.30 ms, 5 -> 1.40 ms
+#ifndef NT_MIN_BLOCKS_F32
+#define NT_MIN_BLOCKS_F32 3 // fast mode: 3 -> 0.72 ms, 4 -> 0.74 ms
 #endif
 #define NT_BVH_STACK 96     // entries; a 4-wide node pushes up to 3: scene creation checks 3*depth + 4 <= this
 #ifndef NT_FILTER_BATCH
 #define NT_FILTER_BATCH 4   // filter evaluations interleaved per loop iteration
+#endif
+#ifndef NT_COUNTERS_SMEM
+#define NT_COUNTERS_SMEM 0   // flat render kernel: work counters in per-thread shared-memory slots instead of registers
 #endif
 #ifndef NT_SPHERE_FILTER
 #define NT_SPHERE_FILTER 0  // strict flat scenes: binary32 conservative pre-filter before the exact sphere test.

@@ -122,8 +122,13 @@ template <> struct Ld<float> {
     }
 };
 
-struct Counters {
+struct Counters { // per-thread work counters in registers (BVH and unit kernels)
     unsigned prim, sec, shadow, sph, pln, tri, box, light;
+};
+// Same fields backed by per-thread shared-memory slots (flat render kernel): an update costs
+// LDS + IADD + STS off the critical path instead of 8 live registers in a register-bound kernel.
+struct CountersRef {
+    unsigned &prim, &sec, &shadow, &sph, &pln, &tri, &box, &light;
 };
 
 // ---- SPEC §3 intersections ----
@@ -307,9 +312,9 @@ __device__ __forceinline__ void slab(float lo, float hi, float o, float inv, flo
 }
 
 // SPEC §3 nearest hit: smallest t; equal t -> smallest global primitive id.
-template <typename R, bool BVH>
+template <typename R, bool BVH, typename K>
 __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o, const V3<R> &d,
-                                            R &tb, Hit &best, Counters &k) {
+                                            R &tb, Hit &best, K &k) {
     const NtDevScene &s = *c.s;
     tb = Math<R>::inf();
     best.kind = -1; best.idx = -1; best.gid = 0x7fffffff;
@@ -373,9 +378,9 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
 
 // SPEC §3 occlusion: any primitive hit (t > eps) with t < dist; first found ends the query.
 // Counters follow the sequential rule (tests up to and including the first occluder).
-template <typename R, bool BVH>
+template <typename R, bool BVH, typename K>
 __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, const V3<R> &d, R dist,
-                                         Counters &k) {
+                                         K &k) {
     const NtDevScene &s = *c.s;
     R t;
     if constexpr (!BVH && sizeof(R) == 8 && NT_SPHERE_FILTER) {
@@ -435,24 +440,26 @@ __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, c
 }
 
 // SPEC §4: radiance of one sample = sum over its ray tree in depth-first pre-order of W * local.
-template <typename R, bool BVH>
-__device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R> d, R acc[3],
-                                             Counters &k) {
+// `accp` / `Wp`: the sample's running radiance sum (3 values, stride NT_BLOCK_THREADS) and path weight,
+// kept in per-thread shared-memory slots: touched once per tree node, not worth 8 registers.
+#define NT_ACC(ch) accp[(ch) * NT_BLOCK_THREADS]
+template <typename R, bool BVH, typename K>
+__device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R> d, R *accp, R *Wp, K &k) {
     const NtDevScene &s = *c.s;
     const NtSceneView<R> &v = *c.v;
     // deferred transmission children (reflection children are followed immediately)
     R st[NT_MAX_DEPTH_DEV][7];
     unsigned st_depth[NT_MAX_DEPTH_DEV];
     int sp = 0;
-    R W = R(1);
+    *Wp = R(1);
     unsigned depth = 1;
     for (;;) {
         R t;
         Hit h;
         bool descend = false;
-        if (!nearest_hit<R, BVH>(c, o, d, t, h, k)) {
+        if (!nearest_hit<R, BVH, K>(c, o, d, t, h, k)) {
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) acc[ch] = acc[ch] + W * __ldg(v.globals + 3 + ch);
+            for (int ch = 0; ch < 3; ++ch) NT_ACC(ch) = NT_ACC(ch) + *Wp * __ldg(v.globals + 3 + ch);
         } else {
             const V3<R> P = { o.x + d.x * t, o.y + d.y * t, o.z + d.z * t };
             V3<R> Ng;
@@ -473,17 +480,20 @@ __device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R
                 Ng = { __ldg(tp), __ldg(tp + 1), __ldg(tp + 2) };
                 mat = __ldg(s.tri_mat + h.idx);
             }
+            // material rows are re-read where they are used (128-bit __ldg, L1 hits) instead of being kept
+            // live across the occlusion queries: the kernel is register-bound
             const R *mp = v.mat + (size_t)mat * NT_MAT_STRIDE;
-            R mq[12];
-            Ld<R>::g4(mp, mq); Ld<R>::g4(mp + 4, mq + 4); Ld<R>::g4(mp + 8, mq + 8);
-            const R ka = mq[3], kd = mq[4], ks = mq[5], shin = mq[6], kr = mq[7], kt = mq[8];
             const R cosd = dot(d, Ng);
             const bool entering = cosd < R(0);
             V3<R> N = Ng;
             if (!entering) { N.x = -Ng.x; N.y = -Ng.y; N.z = -Ng.z; }
             R local[3];
+            {
+                R m0[4];
+                Ld<R>::g4(mp, m0); // r g b ka
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) local[ch] = __ldg(v.globals + ch) * (ka * mq[ch]);
+                for (int ch = 0; ch < 3; ++ch) local[ch] = __ldg(v.globals + ch) * (m0[3] * m0[ch]);
+            }
             for (unsigned l = 0; l < s.nl; ++l) {
                 const R *lp = v.lights + 6 * l;
                 const V3<R> Lv = { __ldg(lp) - P.x, __ldg(lp + 1) - P.y, __ldg(lp + 2) - P.z };
@@ -493,30 +503,36 @@ __device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R
                 const R ndl = dot(N, L);
                 if (!(ndl > R(0))) continue;
                 k.shadow++;
-                if (occluded<R, BVH>(c, P, L, dist, k)) continue;
+                if (occluded<R, BVH, K>(c, P, L, dist, k)) continue;
                 k.light++;
-                const R kdn = kd * ndl;
+                R m0[4], m1[4];
+                Ld<R>::g4(mp, m0);     // r g b ka
+                Ld<R>::g4(mp + 4, m1); // kd ks shininess kr
+                const R kdn = m1[0] * ndl;
                 const R lc[3] = { __ldg(lp + 3), __ldg(lp + 4), __ldg(lp + 5) };
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) local[ch] = local[ch] + lc[ch] * (mq[ch] * kdn);
+                for (int ch = 0; ch < 3; ++ch) local[ch] = local[ch] + lc[ch] * (m0[ch] * kdn);
                 const R two = R(2) * ndl;
                 const V3<R> Rv = { N.x * two - L.x, N.y * two - L.y, N.z * two - L.z };
                 const R rv = -dot(Rv, d);
-                if (ks > R(0) && rv > R(0)) {
-                    const R sterm = ks * Math<R>::pow_(rv, shin);
+                if (m1[1] > R(0) && rv > R(0)) {
+                    const R sterm = m1[1] * Math<R>::pow_(rv, m1[2]);
 #pragma unroll
                     for (int ch = 0; ch < 3; ++ch) local[ch] = local[ch] + lc[ch] * sterm;
                 }
             }
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) acc[ch] = acc[ch] + W * local[ch];
+            for (int ch = 0; ch < 3; ++ch) NT_ACC(ch) = NT_ACC(ch) + *Wp * local[ch];
 
             if (depth < c.max_depth) {
+                R m2[4];
+                Ld<R>::g4(mp + 8, m2); // kt ior inv_ior pad
+                const R kr = __ldg(mp + 7), kt = m2[0];
                 const R cosi = -dot(d, N);
                 R wr = kr, wt = R(0);
                 V3<R> T = { R(0), R(0), R(0) };
                 if (kt > R(0)) {
-                    const R eta = entering ? mq[10] : mq[9];
+                    const R eta = entering ? m2[2] : m2[1];
                     const R kk = R(1) - (eta * eta) * (R(1) - cosi * cosi);
                     if (kk < R(0)) wr = kr + kt;
                     else {
@@ -530,7 +546,7 @@ __device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R
                     if (wr > R(0)) { // defer: reflection subtree comes first in pre-order
                         st[sp][0] = P.x; st[sp][1] = P.y; st[sp][2] = P.z;
                         st[sp][3] = T.x; st[sp][4] = T.y; st[sp][5] = T.z;
-                        st[sp][6] = W * wt; st_depth[sp] = depth + 1;
+                        st[sp][6] = *Wp * wt; st_depth[sp] = depth + 1;
                         ++sp;
                     }
                 }
@@ -538,10 +554,10 @@ __device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R
                     k.sec++;
                     const R two = R(2) * cosi;
                     const V3<R> Rd = { d.x + N.x * two, d.y + N.y * two, d.z + N.z * two };
-                    o = P; d = Rd; W = W * wr; depth = depth + 1;
+                    o = P; d = Rd; *Wp = *Wp * wr; depth = depth + 1;
                     descend = true;
                 } else if (wt > R(0)) {
-                    o = P; d = T; W = W * wt; depth = depth + 1;
+                    o = P; d = T; *Wp = *Wp * wt; depth = depth + 1;
                     descend = true;
                 }
             }
@@ -551,7 +567,7 @@ __device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R
         --sp;
         o = { st[sp][0], st[sp][1], st[sp][2] };
         d = { st[sp][3], st[sp][4], st[sp][5] };
-        W = st[sp][6];
+        *Wp = st[sp][6];
         depth = st_depth[sp];
     }
 }
@@ -594,9 +610,8 @@ __device__ __forceinline__ void stage_scene(const NtDevScene &s, const NtSceneVi
 }
 
 // Per-thread counters -> one atomic per counter per block, spread over NT_COUNTER_SLOTS slots.
-__device__ __forceinline__ void flush_counters(const Counters &k, unsigned long long *counters,
-                                               unsigned long long *s_cnt) {
-    const unsigned vals[NT_NCOUNTERS] = { k.prim, k.sec, k.shadow, k.sph, k.pln, k.tri, k.box, k.light };
+__device__ __forceinline__ void flush_counter_values(const unsigned vals[NT_NCOUNTERS], unsigned long long *counters,
+                                                     unsigned long long *s_cnt) {
     if (threadIdx.x < NT_NCOUNTERS) s_cnt[threadIdx.x] = 0;
     __syncthreads();
 #pragma unroll
@@ -610,83 +625,125 @@ __device__ __forceinline__ void flush_counters(const Counters &k, unsigned long 
         atomicAdd(&counters[slot * NT_NCOUNTERS + threadIdx.x], s_cnt[threadIdx.x]);
     }
 }
+__device__ __forceinline__ void flush_counters(const Counters &k, unsigned long long *counters,
+                                               unsigned long long *s_cnt) {
+    const unsigned vals[NT_NCOUNTERS] = { k.prim, k.sec, k.shadow, k.sph, k.pln, k.tri, k.box, k.light };
+    flush_counter_values(vals, counters, s_cnt);
+}
 
 // Persistent warps: the grid is sized to fill the machine once (SM count x resident blocks); every
 // warp pulls warp-tiles (twx x twy pixels x `lanes` samples = 32 samples) from one atomic counter until
 // the image is exhausted, so no block waits at a barrier for its slowest tile and an expensive region
 // (glass, mirrors) is spread over all SMs.  The only block barriers are the scene staging at the start
 // and the counter flush at the end.
-template <typename R, bool BVH>
-__global__ void __launch_bounds__(NT_BLOCK_THREADS, NT_MIN_BLOCKS)
+//
+// Register diet (the kernel is register- and latency-bound): the work counters, the
+// sample's running sum and its path weight live in per-thread shared-memory slots; material rows are
+// re-read where used; pixel coordinates are recomputed after the trace instead of being kept live;
+// SINGLE = (spp / lanes == 1) drops the cross-round pixel sum.  With that 4 blocks/SM fit in 64
+// registers with ~220 bytes of spills (configs[2] f64: 1.39 -> 1.30 ms; f32 prefers 3 blocks: 0.80 -> 0.72 ms).
+// Putting the work counters into shared memory as well (NT_COUNTERS_SMEM) removes the remaining spills
+// but costs more instructions than it saves (1.34 ms).
+template <typename R, bool BVH, bool SINGLE>
+__global__ void __launch_bounds__(NT_BLOCK_THREADS, sizeof(R) == 8 ? NT_MIN_BLOCKS_F64 : NT_MIN_BLOCKS_F32)
 render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRenderArgs a) {
     __shared__ unsigned long long s_cnt[NT_NCOUNTERS];
+#if NT_COUNTERS_SMEM
+    __shared__ unsigned s_k[NT_NCOUNTERS][NT_BLOCK_THREADS];
+#endif
+    __shared__ R s_state[4][NT_BLOCK_THREADS]; // acc r g b, W
     const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
     Ctx<R, BVH> c;
     c.s = &s; c.v = &v; c.eps = (R)a.eps; c.max_depth = a.max_depth;
     stage_scene<R, BVH>(s, v, c);
 
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned L = a.lanes, j = lane & (L - 1), pw = lane / L;
-    const unsigned lx = pw % a.twx, ly = pw / a.twx;
+    const unsigned tid = threadIdx.x, lane = tid & 31;
+#if NT_COUNTERS_SMEM
+#pragma unroll
+    for (int i = 0; i < NT_NCOUNTERS; ++i) s_k[i][tid] = 0;
+    CountersRef k = { s_k[0][tid], s_k[1][tid], s_k[2][tid], s_k[3][tid], s_k[4][tid], s_k[5][tid], s_k[6][tid], s_k[7][tid] };
+    typedef CountersRef KT;
+#else
+    Counters k = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    typedef Counters KT;
+#endif
+    R *accp = &s_state[0][tid], *Wp = &s_state[3][tid];
     const unsigned warps_per_block = NT_BLOCK_THREADS / 32, total_warps = gridDim.x * warps_per_block;
     const unsigned n_tiles = a.tiles_x * a.tiles_y;
     unsigned long long *next_tile = a.counters + NT_COUNTER_SLOTS * NT_NCOUNTERS;
-    const V3<R> eye = { (R)a.cam[0], (R)a.cam[1], (R)a.cam[2] };
-    const R rn = (R)a.n;
-    const R inv_spp = Math<R>::rcp((R)a.spp);
-    const unsigned rounds = a.spp / L;
-    Counters k = { 0, 0, 0, 0, 0, 0, 0, 0 };
 
-    unsigned tile = blockIdx.x * warps_per_block + (threadIdx.x >> 5); // first tile: no atomic needed
+    unsigned tile = blockIdx.x * warps_per_block + (tid >> 5); // first tile: no atomic needed
     while (tile < n_tiles) {
-        const unsigned px = (tile % a.tiles_x) * a.twx + lx;
-        const unsigned vr = (tile / a.tiles_x) * a.twy + ly;
-        const bool live = px < a.width && vr < a.vrows;
-        const unsigned y = ((vr / a.band_rows) * a.shard_count + a.shard_index) * a.band_rows + vr % a.band_rows;
         R sum[3] = { R(0), R(0), R(0) };
+        const unsigned rounds = SINGLE ? 1u : a.spp / a.lanes;
         for (unsigned r = 0; r < rounds; ++r) {
-            R acc[3] = { R(0), R(0), R(0) };
-            if (live) {
-                // SPEC §2: regular n x n grid, sample s = r*L + j
-                const unsigned sidx = r * L + j;
-                const unsigned si = sidx % a.n, sj = sidx / a.n;
-                const R ox = Math<R>::div((R)si + R(0.5), rn), oy = Math<R>::div((R)sj + R(0.5), rn);
-                const R fx = (R)px + ox, fy = (R)y + oy;
-                const V3<R> D = { ((R)a.cam[3] + (R)a.cam[6] * fx) + (R)a.cam[9] * fy,
-                                  ((R)a.cam[4] + (R)a.cam[7] * fx) + (R)a.cam[10] * fy,
-                                  ((R)a.cam[5] + (R)a.cam[8] * fx) + (R)a.cam[11] * fy };
-                const V3<R> dir = scale(D, Math<R>::rcp(Math<R>::sqrt_(dot(D, D))));
-                k.prim++;
-                trace_sample<R, BVH>(c, eye, dir, acc, k);
+            {
+                const unsigned L = a.lanes, j = lane & (L - 1), pw = lane / L;
+                const unsigned px = (tile % a.tiles_x) * a.twx + pw % a.twx;
+                const unsigned vr = (tile / a.tiles_x) * a.twy + pw / a.twx;
+                NT_ACC(0) = R(0); NT_ACC(1) = R(0); NT_ACC(2) = R(0);
+                if (px < a.width && vr < a.vrows) {
+                    const unsigned y = ((vr / a.band_rows) * a.shard_count + a.shard_index) * a.band_rows + vr % a.band_rows;
+                    // SPEC §2: regular n x n grid, sample s = r*L + j
+                    const unsigned sidx = r * L + j;
+                    const unsigned si = sidx % a.n, sj = sidx / a.n;
+                    const R rn = (R)a.n;
+                    const R ox = Math<R>::div((R)si + R(0.5), rn), oy = Math<R>::div((R)sj + R(0.5), rn);
+                    const R fx = (R)px + ox, fy = (R)y + oy;
+                    const V3<R> D = { ((R)a.cam[3] + (R)a.cam[6] * fx) + (R)a.cam[9] * fy,
+                                      ((R)a.cam[4] + (R)a.cam[7] * fx) + (R)a.cam[10] * fy,
+                                      ((R)a.cam[5] + (R)a.cam[8] * fx) + (R)a.cam[11] * fy };
+                    const V3<R> dir = scale(D, Math<R>::rcp(Math<R>::sqrt_(dot(D, D))));
+                    const V3<R> eye = { (R)a.cam[0], (R)a.cam[1], (R)a.cam[2] };
+                    k.prim++;
+                    trace_sample<R, BVH, KT>(c, eye, dir, accp, Wp, k);
+                }
             }
+            asm volatile("" : "+r"(tile)); // pixel coordinates are recomputed below, not carried across the trace
             // SPEC §5: samples are added in sample order; the lanes of one pixel are adjacent
+            const unsigned L = a.lanes;
             if (L == 1) {
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) sum[ch] = sum[ch] + acc[ch];
+                for (int ch = 0; ch < 3; ++ch) sum[ch] = sum[ch] + NT_ACC(ch);
             } else {
                 const unsigned base = lane & ~(L - 1);
+                const R a0 = NT_ACC(0), a1 = NT_ACC(1), a2 = NT_ACC(2);
 #pragma unroll 1
-                for (unsigned jj = 0; jj < L; ++jj)
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) sum[ch] = sum[ch] + __shfl_sync(0xffffffffu, acc[ch], base + jj);
+                for (unsigned jj = 0; jj < L; ++jj) {
+                    sum[0] = sum[0] + __shfl_sync(0xffffffffu, a0, base + jj);
+                    sum[1] = sum[1] + __shfl_sync(0xffffffffu, a1, base + jj);
+                    sum[2] = sum[2] + __shfl_sync(0xffffffffu, a2, base + jj);
+                }
             }
         }
-        if (live && j == 0) {
-            unsigned rgba = 0xff000000u;
+        {
+            const unsigned L = a.lanes, j = lane & (L - 1), pw = lane / L;
+            const unsigned px = (tile % a.tiles_x) * a.twx + pw % a.twx;
+            const unsigned vr = (tile / a.tiles_x) * a.twy + pw / a.twx;
+            if (px < a.width && vr < a.vrows && j == 0) {
+                const unsigned y = ((vr / a.band_rows) * a.shard_count + a.shard_index) * a.band_rows + vr % a.band_rows;
+                const R inv_spp = Math<R>::rcp((R)a.spp);
+                unsigned rgba = 0xff000000u;
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-                const R cv = sum[ch] * inv_spp;
-                const unsigned q = cv <= R(0) ? 0u : cv >= R(1) ? 255u : (unsigned)(int)(cv * R(255) + R(0.5));
-                rgba |= q << (8 * ch);
+                for (int ch = 0; ch < 3; ++ch) {
+                    const R cv = sum[ch] * inv_spp;
+                    const unsigned q = cv <= R(0) ? 0u : cv >= R(1) ? 255u : (unsigned)(int)(cv * R(255) + R(0.5));
+                    rgba |= q << (8 * ch);
+                }
+                const size_t row = a.layout == 1 ? vr : y;
+                *(unsigned *)(a.out + row * a.stride + 4 * (size_t)px) = rgba;
             }
-            const size_t row = a.layout == 1 ? vr : y;
-            *(unsigned *)(a.out + row * a.stride + 4 * (size_t)px) = rgba;
         }
         unsigned long long nt = 0;
         if (lane == 0) nt = atomicAdd(next_tile, 1ull) + total_warps;
         tile = (unsigned)__shfl_sync(0xffffffffu, nt, 0);
     }
+#if NT_COUNTERS_SMEM
+    const unsigned vals[NT_NCOUNTERS] = { s_k[0][tid], s_k[1][tid], s_k[2][tid], s_k[3][tid], s_k[4][tid], s_k[5][tid], s_k[6][tid], s_k[7][tid] };
+    flush_counter_values(vals, a.counters, s_cnt);
+#else
     flush_counters(k, a.counters, s_cnt);
+#endif
 }
 
 // Unit-level entry: nearest hit of arbitrary rays (nt_trace_rays).
@@ -704,7 +761,7 @@ trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtTra
     Counters k = { 0, 0, 0, 0, 0, 0, 0, 0 };
     R t;
     Hit h;
-    if (nearest_hit<R, BVH>(c, o, d, t, h, k)) {
+    if (nearest_hit<R, BVH, Counters>(c, o, d, t, h, k)) {
         a.t_out[i] = (double)t;
         a.prim_out[i] = h.kind == 1 ? h.gid : (h.kind == 0 ? h.idx : (int)(s.ns + s.np) + h.idx);
     } else {
@@ -738,7 +795,7 @@ inline int launch_render_t(const NtDevScene &s, const NtRenderArgs &a, cudaStrea
     if (!sms[dev]) {
         cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
         if (BVH) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[dev], render_bvh_kernel<R>, NT_BLOCK_THREADS, 4096);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[dev], render_kernel<R, false>, NT_BLOCK_THREADS, 4096);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[dev], render_kernel<R, false, true>, NT_BLOCK_THREADS, 4096);
         if (blocks_per_sm[dev] < 1) blocks_per_sm[dev] = 1;
     }
     const unsigned n_tiles = a.tiles_x * a.tiles_y, wpb = NT_BLOCK_THREADS / 32;
@@ -747,7 +804,8 @@ inline int launch_render_t(const NtDevScene &s, const NtRenderArgs &a, cudaStrea
     if (BVH) {
         render_bvh_kernel<R><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
         resolve_kernel<R><<<dim3((a.width + 255) / 256, a.vrows), 256, 0, st>>>(a);
-    } else render_kernel<R, false><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
+    } else if (a.spp == a.lanes) render_kernel<R, false, true><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
+    else render_kernel<R, false, false><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
     return (int)cudaGetLastError();
 }
 
