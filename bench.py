@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--band-rows", type=int, default=8)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bvh-build", default="host", choices=["host", "gpu"],
+                    help="BVH scenes: binned-SAH build on the host (default) or LBVH build on the GPU")
     return ap.parse_args()
 
 
@@ -221,6 +223,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    if a.bvh_build == "gpu":
+        os.environ["NT_BVH_BUILD"] = "gpu"
     scene, cam, w, h, spp, depth = workload(a.workload)
     prec = abi.NT_F64_STRICT if a.precision == "f64" else abi.NT_F32_FAST
     t0 = time.perf_counter()
@@ -324,7 +328,8 @@ def main():
                            "rays_per_frame": rays_total, "sharding": f"{world} x interleaved {a.band_rows}-row bands" if world > 1 else "none",
                            "exchange": (sr.mode if world > 1 else "none"), "uses_bvh": info["uses_bvh"],
                            "l2": "256 MiB memset between timed steps (outside each step's event pair)",
-                           "scene_create_s": scene_create_s},
+                           "scene_create_s": scene_create_s, "bvh_on_gpu": info.get("bvh_on_gpu", False),
+                           "bvh_build_ms": info.get("bvh_build_ms", 0.0), "bvh_nodes": info["bvh_nodes"]},
                 "e2e": {"value": e2e_val, "unit": METRIC, "ms_per_frame": e2e_ms, "h2d_bytes_per_step": C.sizeof(abi.nt_render_params),
                         "d2h_bytes_per_step": h * w * 4 + 8 * 8 * 32,
                         "api": "nt_render -> pinned host RGBA8" if world == 1 else "ShardedRenderer.render + D2H on rank 0"},

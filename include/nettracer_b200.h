@@ -109,7 +109,8 @@ int nt_device_count(int *count);
  * primitives than fit the flat kernel, and uploads to `device`. */
 int nt_scene_create(const nt_scene_desc *desc, int device, nt_scene **out);
 void nt_scene_destroy(nt_scene *scene);
-/* info[0]=uses_bvh info[1]=bvh_nodes info[2]=device_bytes info[3]=device */
+/* info[0] = bit 0 uses_bvh | bit 1 BVH built on the GPU (NT_BVH_BUILD=gpu) | bits 8.. BVH build time in us;
+ * info[1] = 4-wide BVH nodes; info[2] = device bytes; info[3] = device */
 int nt_scene_info(const nt_scene *scene, uint64_t info[4]);
 
 /* ---- render ---- */

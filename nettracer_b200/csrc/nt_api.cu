@@ -69,6 +69,8 @@ struct nt_scene {
     unsigned long long *d_counters = nullptr, *h_counters = nullptr;
     uint8_t *d_fb = nullptr;
     size_t fb_bytes = 0;
+    bool bvh_on_gpu = false;
+    double bvh_build_ms = 0;
     void *d_samples = nullptr; // BVH scenes: per-sample radiance scratch
     size_t samples_bytes = 0;
     std::mutex mu;
@@ -152,13 +154,46 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
     std::vector<int> sph_order(ns), tri_order(nt);
     for (uint32_t i = 0; i < ns; ++i) sph_order[i] = (int)i;
     for (uint32_t i = 0; i < nt; ++i) tri_order[i] = (int)i;
+    const NtBvhNode4 *gpu_nodes = nullptr; // set when the tree was built on the device
+    uint32_t gpu_n_nodes = 0;
     if (use_bvh) {
         int leaf_max = 4;
         if (const char *e = getenv("NT_BVH_LEAF")) leaf_max = atoi(e);
-        nt_bvh_build(d->spheres, ns, d->triangles, nt, leaf_max, bvh);
-        if (3 * bvh.depth4 + 4 > NT_BVH_STACK) return fail(NT_ERR_INVALID, "BVH too deep (%d levels) for the %d-entry traversal stack", bvh.depth4, NT_BVH_STACK);
-        sph_order = bvh.sph_order;
-        tri_order = bvh.tri_order;
+        const char *bm = getenv("NT_BVH_BUILD"); // "gpu": LBVH on the device (row f3); default: binned SAH on the host
+        if (bm && !strcmp(bm, "gpu")) {
+            const auto tb0 = std::chrono::steady_clock::now();
+            double *d_s = nullptr, *d_t = nullptr;
+            cudaError_t e = cudaSuccess;
+            if (ns && (e = cudaMalloc((void **)&d_s, sizeof(double) * 4 * (size_t)ns)) == cudaSuccess)
+                e = cudaMemcpy(d_s, d->spheres, sizeof(double) * 4 * (size_t)ns, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess && nt && (e = cudaMalloc((void **)&d_t, sizeof(double) * 9 * (size_t)nt)) == cudaSuccess)
+                e = cudaMemcpy(d_t, d->triangles, sizeof(double) * 9 * (size_t)nt, cudaMemcpyHostToDevice);
+            NtBvhNode4 *nodes = nullptr;
+            int depth4 = 0, brc = (int)e;
+            if (e == cudaSuccess)
+                brc = nt_bvh_build_gpu(d_s, ns, d_t, nt, leaf_max, nullptr, &nodes, &gpu_n_nodes, sph_order, tri_order, bvh.blo, bvh.bhi,
+                                       &bvh.max_abs, &depth4);
+            cudaFree(d_s); cudaFree(d_t);
+            if (brc) return fail(NT_ERR_CUDA, "GPU BVH build: %s", cudaGetErrorString((cudaError_t)brc));
+            if (3 * depth4 + 4 > NT_BVH_STACK) { // pathological Morton tree: fall back to the host builder
+                cudaFree(nodes);
+                for (uint32_t i = 0; i < ns; ++i) sph_order[i] = (int)i;
+                for (uint32_t i = 0; i < nt; ++i) tri_order[i] = (int)i;
+            } else {
+                gpu_nodes = nodes;
+                sc->allocs.push_back(nodes);
+                sc->device_bytes += sizeof(NtBvhNode4) * (size_t)gpu_n_nodes;
+                sc->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb0).count();
+            }
+        }
+        if (!gpu_nodes) {
+            const auto tb0 = std::chrono::steady_clock::now();
+            nt_bvh_build(d->spheres, ns, d->triangles, nt, leaf_max, bvh);
+            if (3 * bvh.depth4 + 4 > NT_BVH_STACK) return fail(NT_ERR_INVALID, "BVH too deep (%d levels) for the %d-entry traversal stack", bvh.depth4, NT_BVH_STACK);
+            sph_order = bvh.sph_order;
+            tri_order = bvh.tri_order;
+            sc->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb0).count();
+        }
     }
 
     // SPEC-PROVISIONAL §1 derived quantities, in binary64; the float view is the rounded double view
@@ -209,7 +244,8 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
     NtDevScene &ds = sc->ds;
     ds.ns = ns; ds.np = np; ds.nt = nt; ds.nm = nm; ds.nl = nl;
     ds.use_bvh = use_bvh ? 1 : 0;
-    ds.n_nodes = use_bvh && ns + nt > 0 ? (uint32_t)bvh.nodes4.size() : 0;
+    ds.n_nodes = use_bvh && ns + nt > 0 ? (gpu_nodes ? gpu_n_nodes : (uint32_t)bvh.nodes4.size()) : 0;
+    sc->bvh_on_gpu = gpu_nodes != nullptr;
     ds.max_abs = bvh.max_abs;
     if (!use_bvh) { // flat scenes: extent of the bounded primitives, for the binary32 filter margin
         double mx = 0;
@@ -228,7 +264,7 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
     UP(fsph, ds.v32.sph); UP(fir, ds.v32.sph_invr); UP(fpln, ds.v32.pln); UP(ftri, ds.v32.tri);
     UP(fmat, ds.v32.mat); UP(fl, ds.v32.lights); UP(fg, ds.v32.globals);
     UP(sph_mat, ds.sph_mat); UP(sph_gid, ds.sph_gid); UP(pln_mat, ds.pln_mat); UP(pln_code, ds.pln_code); UP(tri_mat, ds.tri_mat); UP(tri_gid, ds.tri_gid);
-    UP(bvh.nodes4, ds.nodes);
+    if (gpu_nodes) ds.nodes = gpu_nodes; else UP(bvh.nodes4, ds.nodes);
 #undef UP
     CU(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&sc->ev0));
@@ -254,7 +290,8 @@ extern "C" int nt_scene_create(const nt_scene_desc *desc, int device, nt_scene *
 
 extern "C" int nt_scene_info(const nt_scene *sc, uint64_t info[4]) {
     if (!sc || !info) return fail(NT_ERR_INVALID, "NULL argument");
-    info[0] = sc->ds.use_bvh; info[1] = sc->ds.n_nodes; info[2] = sc->device_bytes; info[3] = (uint64_t)sc->device;
+    info[0] = (uint64_t)sc->ds.use_bvh | ((uint64_t)sc->bvh_on_gpu << 1) | ((uint64_t)(sc->bvh_build_ms * 1000.0) << 8);
+    info[1] = sc->ds.n_nodes; info[2] = sc->device_bytes; info[3] = (uint64_t)sc->device;
     return NT_OK;
 }
 

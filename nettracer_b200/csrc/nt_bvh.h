@@ -19,3 +19,8 @@ void nt_bvh_set_children(NtBvhNode &n, const float *lo0, const float *hi0, int c
                          const float *lo1, const float *hi1, int c1, int n1);
 void nt_bvh_build(const double *spheres, uint32_t ns, const double *triangles, uint32_t nt,
                   int leaf_max, NtBvhBuild &out);
+
+// On-GPU LBVH build straight into the 4-wide node format (nt_bvh_gpu.cu).  Returns 0 or a cudaError_t.
+int nt_bvh_build_gpu(const double *d_spheres, uint32_t ns, const double *d_triangles, uint32_t nt, int leaf_max, void *stream,
+                     NtBvhNode4 **d_nodes_out, uint32_t *n_nodes_out, std::vector<int> &sph_order, std::vector<int> &tri_order,
+                     float blo[3], float bhi[3], float *max_abs, int *depth4);

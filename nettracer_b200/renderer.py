@@ -41,7 +41,8 @@ class Renderer:
     def info(self) -> dict:
         a = (C.c_uint64 * 4)()
         check(self._lib.nt_scene_info(self._h, a))
-        return {"uses_bvh": bool(a[0]), "bvh_nodes": int(a[1]), "device_bytes": int(a[2]), "device": int(a[3])}
+        return {"uses_bvh": bool(a[0] & 1), "bvh_on_gpu": bool(a[0] & 2), "bvh_build_ms": (int(a[0]) >> 8) / 1000.0,
+                "bvh_nodes": int(a[1]), "device_bytes": int(a[2]), "device": int(a[3])}
 
     # -- host path --
     def render_params(self, params: abi.nt_render_params, out: np.ndarray | None = None):

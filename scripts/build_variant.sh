@@ -12,6 +12,7 @@ nvcc $COMMON -use_fast_math $PTXAS_V -c nt_kernels_f32.cu -o $OBJ/f32.o &
 nvcc $COMMON -c nt_api.cu -o $OBJ/api.o &
 nvcc $COMMON -c nt_peaks.cu -o $OBJ/peaks.o &
 nvcc $COMMON -c nt_bvh.cpp -o $OBJ/bvh.o &
+nvcc $COMMON -c nt_bvh_gpu.cu -o $OBJ/bvhgpu.o &
 wait
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/libnt_$NAME.so $OBJ/f64.o $OBJ/f32.o $OBJ/api.o $OBJ/peaks.o $OBJ/bvh.o -lcudart
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/libnt_$NAME.so $OBJ/f64.o $OBJ/f32.o $OBJ/api.o $OBJ/peaks.o $OBJ/bvh.o $OBJ/bvhgpu.o -lcudart
 echo built $OUT/libnt_$NAME.so

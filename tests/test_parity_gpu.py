@@ -303,3 +303,50 @@ def test_trace_rays_bvh_stress_far_and_axis_parallel():
     assert np.array_equal(prim, po), int((prim != po).sum())
     assert np.array_equal(t.view(np.uint64), to.view(np.uint64))
     assert (prim >= 0).mean() > 0.2
+
+
+# ---------------- on-GPU BVH build: same images as with the host tree ----------------
+@pytest.mark.parametrize("seed", [4, 6])
+def test_gpu_built_bvh_equals_bruteforce_oracle(monkeypatch, seed):
+    monkeypatch.setenv("NT_BVH_BUILD", "gpu")
+    s, cam = scenes.random_mixed(150, 2, 300, seed=seed)
+    img, st, ref, rst, info = render_both(s, cam, 224, 160, 4, 4)
+    assert info["uses_bvh"] and info["bvh_on_gpu"] and info["bvh_nodes"] > 10
+    assert_images_match(img, ref, f"gpu-built bvh seed={seed}")
+    for k in COUNTER_KEYS:
+        assert st[k] == rst[k], k
+
+
+def test_gpu_built_bvh_mesh_and_rays(monkeypatch):
+    monkeypatch.setenv("NT_BVH_BUILD", "gpu")
+    s, cam = scenes.spheres_and_mesh(n_spheres=2000, mesh_n=96)
+    img, st, ref, rst, info = render_both(s, cam, 256, 144, 4, 3, accel=1)
+    assert info["bvh_on_gpu"]
+    assert_images_match(img, ref, "gpu-built mesh")
+    s2, _ = scenes.random_mixed(220, 1, 420, seed=13)
+    rng = np.random.default_rng(8)
+    o = rng.uniform(-8, 8, (20000, 3)); o[:, 2] += 10
+    d = rng.normal(size=(20000, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    with Renderer(s2) as r:
+        assert r.info()["bvh_on_gpu"]
+        t, prim = r.trace_rays(o, d)
+    to, po = oracle.trace_rays(s2, o, d, accel=0)
+    assert np.array_equal(prim, po) and np.array_equal(t.view(np.uint64), to.view(np.uint64))
+
+
+def test_gpu_built_bvh_tiny_sets(monkeypatch):
+    """Degenerate set sizes: one sphere + many triangles, exactly leaf_max primitives, identical centroids."""
+    monkeypatch.setenv("NT_BVH_BUILD", "gpu")
+    monkeypatch.setenv("NT_BVH", "1")
+    from nettracer_b200.scene import Camera, Material, Scene
+    s = Scene(background=(0.1, 0.2, 0.3))
+    m = s.add_material(Material((0.8, 0.6, 0.4), kd=0.7, ks=0.3, shininess=20, kr=0.3))
+    s.add_sphere((0, 0.5, 0), 0.7, m)
+    for i in range(4):  # four coincident triangles: equal Morton keys, tie-break by id
+        s.add_triangle((-2, -0.5, -1), (2, -0.5, -1), (0, -0.5, 2), m)
+    s.add_triangle((-3, -0.6, -3), (3, -0.6, -3), (0, -0.6, 3), m)
+    s.add_light((2, 5, 3), (0.8, 0.8, 0.8))
+    cam = Camera((0, 2, 6), (0, 0, 0))
+    img, st, ref, rst, info = render_both(s, cam, 96, 64, 4, 3)
+    assert info["uses_bvh"] and info["bvh_on_gpu"]
+    assert_images_match(img, ref, "tiny sets")
