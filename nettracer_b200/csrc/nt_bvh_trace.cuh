@@ -59,7 +59,7 @@ __device__ __forceinline__ void query_start(const Ctx<R, true> &c, BvhQuery<R> &
         const int code = (int)(codes & 3u);
         codes >>= 2;
         k.pln++;
-        if (hit_plane<R>(pq, code, o, d, c.eps, q.tb, t) && t < q.tb) {
+        if (hit_plane<R>(pq, code, o, d, c.eps, plane_bound<R>(q.tb), t) && t < q.tb) {
             if (any) { q.done = true; q.found = true; return; }
             q.tb = t; q.best.kind = 1; q.best.idx = (int)i; q.best.gid = (int)(s.ns + i); q.found = true;
         }

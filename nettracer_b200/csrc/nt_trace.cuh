@@ -194,10 +194,17 @@ __device__ __forceinline__ void plane_eval(const R q[4], int code, const V3<R> &
     }
     num = q[3] - dno;
 }
+// `tm1` = tmax * (1 + 2e-15), computed once per query (and again when the bound shrinks) so that a plane
+// costs one product here.  If |num| >= fl(|dn| * tm1) then |num|/|dn| >= tmax*(1+2e-15)(1-2^-53) > tmax*(1+1.8e-15),
+// hence the correctly rounded quotient is >= tmax: the plane cannot be nearer than the bound.
 template <typename R>
-__device__ __forceinline__ bool plane_reject(R dn, R num, R tmax) {
+__device__ __forceinline__ R plane_bound(R tmax) {
+    if constexpr (sizeof(R) == 8) return tmax * (1.0 + 2e-15); else return tmax;
+}
+template <typename R>
+__device__ __forceinline__ bool plane_reject(R dn, R num, R tm1) {
     if constexpr (sizeof(R) == 8)
-        return ((__double2hiint(num) ^ __double2hiint(dn)) < 0) | (fabs(num) >= (fabs(dn) * tmax) * (1.0 + 1e-15));
+        return ((__double2hiint(num) ^ __double2hiint(dn)) < 0) | (fabs(num) >= fabs(dn) * tm1);
     else
         return false;
 }
@@ -214,14 +221,14 @@ __device__ __forceinline__ bool plane_finish(R dn, R num, R eps, R &t_out) {
 // plane is either missed or certainly not nearer than tmax.  The strict mode avoids the binary64
 // division (~15 FP64-pipe instructions) unless the quotient can matter:
 //   * num and dn of different sign            -> t < 0, a miss
-//   * |num| >= (|dn| * tmax) * (1 + 1e-15)     -> the correctly rounded quotient is >= tmax
+//   * |num| >= |dn| * (tmax * (1 + 2e-15))     -> the correctly rounded quotient is >= tmax (see plane_bound)
 // Both tests are implied by the exact rule, so the result is bit-identical to dividing always.
 template <typename R>
-__device__ __forceinline__ bool hit_plane(const R q[4], int code, const V3<R> &o, const V3<R> &d, R eps, R tmax,
+__device__ __forceinline__ bool hit_plane(const R q[4], int code, const V3<R> &o, const V3<R> &d, R eps, R tm1,
                                           R &t_out) {
     R dn, num;
     plane_eval<R>(q, code, o, d, dn, num);
-    if (plane_reject<R>(dn, num, tmax)) return false;
+    if (plane_reject<R>(dn, num, tm1)) return false;
     return plane_finish<R>(dn, num, eps, t_out);
 }
 
@@ -377,6 +384,7 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
         // current when the pair started is rejected a fortiori against a smaller one
         const unsigned np = NT_EXP_NP(s.np);
         unsigned codes = 0, i = 0;
+        R tm1 = plane_bound<R>(tb);
         // (pairs pay in binary32: 0.727 -> 0.700 ms; in binary64 the extra live values spill: 1.295 -> 1.372 ms)
         for (; sizeof(R) == 4 && i + 2 <= np; i += 2) {
             R q0[4], q1[4], dn0, num0, dn1, num1;
@@ -386,9 +394,10 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
             plane_eval<R>(q0, (int)(codes & 3u), o, d, dn0, num0);
             plane_eval<R>(q1, (int)((codes >> 2) & 3u), o, d, dn1, num1);
             codes >>= 4;
-            const bool r0 = plane_reject<R>(dn0, num0, tb), r1 = plane_reject<R>(dn1, num1, tb);
+            const bool r0 = plane_reject<R>(dn0, num0, tm1), r1 = plane_reject<R>(dn1, num1, tm1);
             if (!r0 && plane_finish<R>(dn0, num0, c.eps, t) && t < tb) { tb = t; best.kind = 1; best.idx = (int)i; best.gid = (int)(s.ns + i); }
             if (!r1 && plane_finish<R>(dn1, num1, c.eps, t) && t < tb) { tb = t; best.kind = 1; best.idx = (int)i + 1; best.gid = (int)(s.ns + i + 1); }
+            tm1 = plane_bound<R>(tb);
         }
         for (; i < np; ++i) {
             R q[4];
@@ -396,7 +405,7 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
             c.ld_pln(i, q);
             const int code = (int)(codes & 3u);
             codes >>= 2;
-            if (hit_plane<R>(q, code, o, d, c.eps, tb, t) && t < tb) { tb = t; best.kind = 1; best.idx = (int)i; best.gid = (int)(s.ns + i); }
+            if (hit_plane<R>(q, code, o, d, c.eps, tm1, t) && t < tb) { tb = t; best.kind = 1; best.idx = (int)i; best.gid = (int)(s.ns + i); tm1 = plane_bound<R>(tb); }
         }
     }
     k.pln += s.np;
@@ -456,6 +465,7 @@ __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, c
     {
         const unsigned np = NT_EXP_NP(s.np);
         unsigned codes = 0, i = 0;
+        const R dm1 = plane_bound<R>(dist);
         for (; sizeof(R) == 4 && i + 2 <= np; i += 2) {
             R q0[4], q1[4], dn0, num0, dn1, num1;
             if ((i & 15) == 0) codes = c.pln_codes(i >> 4);
@@ -464,7 +474,7 @@ __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, c
             plane_eval<R>(q0, (int)(codes & 3u), o, d, dn0, num0);
             plane_eval<R>(q1, (int)((codes >> 2) & 3u), o, d, dn1, num1);
             codes >>= 4;
-            const bool r0 = plane_reject<R>(dn0, num0, dist), r1 = plane_reject<R>(dn1, num1, dist);
+            const bool r0 = plane_reject<R>(dn0, num0, dm1), r1 = plane_reject<R>(dn1, num1, dm1);
             if (!r0 && plane_finish<R>(dn0, num0, c.eps, t) && t < dist) { k.pln += i + 1; return true; }
             if (!r1 && plane_finish<R>(dn1, num1, c.eps, t) && t < dist) { k.pln += i + 2; return true; }
         }
@@ -474,7 +484,7 @@ __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, c
             c.ld_pln(i, q);
             const int code = (int)(codes & 3u);
             codes >>= 2;
-            if (hit_plane<R>(q, code, o, d, c.eps, dist, t) && t < dist) { k.pln += i + 1; return true; }
+            if (hit_plane<R>(q, code, o, d, c.eps, dm1, t) && t < dist) { k.pln += i + 1; return true; }
         }
     }
     k.pln += s.np;
