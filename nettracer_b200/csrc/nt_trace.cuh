@@ -18,11 +18,15 @@
 // what-if timing hooks (experiments only; the shipped build defines none of them)
 #ifdef NT_EXP_NOPLANES
 #define NT_EXP_NP(x) 0u
+#elif defined(NT_EXP_FIXED_NP)
+#define NT_EXP_NP(x) ((unsigned)NT_EXP_FIXED_NP) // what-if: compile-time primitive counts (full unrolling)
 #else
 #define NT_EXP_NP(x) (x)
 #endif
 #ifdef NT_EXP_NOSPHERES
 #define NT_EXP_NS(x) 0u
+#elif defined(NT_EXP_FIXED_NS)
+#define NT_EXP_NS(x) ((unsigned)NT_EXP_FIXED_NS)
 #else
 #define NT_EXP_NS(x) (x)
 #endif
@@ -372,7 +376,7 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
             if (!(d0 < R(0)) && sphere_finish<R>(b0, d0, c.eps, t) && t < tb) { tb = t; best.kind = 0; best.idx = (int)i; }
             if (!(d1 < R(0)) && sphere_finish<R>(b1, d1, c.eps, t) && t < tb) { tb = t; best.kind = 0; best.idx = (int)i + 1; }
         }
-        if (i < s.ns) {
+        if (i < NT_EXP_NS(s.ns)) {
             R q[4];
             c.ld_sph(i, q);
             if (hit_sphere<R>(q, o, d, c.eps, t) && t < tb) { tb = t; best.kind = 0; best.idx = (int)i; }
@@ -455,7 +459,7 @@ __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, c
             if (!(d0 < R(0)) && sphere_finish<R>(b0, d0, c.eps, t) && t < dist) { k.sph += i + 1; return true; }
             if (!(d1 < R(0)) && sphere_finish<R>(b1, d1, c.eps, t) && t < dist) { k.sph += i + 2; return true; }
         }
-        if (i < s.ns) {
+        if (i < NT_EXP_NS(s.ns)) {
             R q[4];
             c.ld_sph(i, q);
             if (hit_sphere<R>(q, o, d, c.eps, t) && t < dist) { k.sph += s.ns; return true; }
