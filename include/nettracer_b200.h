@@ -109,9 +109,18 @@ int nt_device_count(int *count);
  * primitives than fit the flat kernel, and uploads to `device`. */
 int nt_scene_create(const nt_scene_desc *desc, int device, nt_scene **out);
 void nt_scene_destroy(nt_scene *scene);
-/* info[0] = bit 0 uses_bvh | bit 1 BVH built on the GPU (NT_BVH_BUILD=gpu) | bits 8.. BVH build time in us;
+/* info[0] = bit 0 uses_bvh | bit 1 BVH built on the GPU (NT_BVH_BUILD=gpu) | bit 2 flat culling tables in use
+ *           | bits 8.. BVH build time in us;
  * info[1] = 4-wide BVH nodes; info[2] = device bytes; info[3] = device */
 int nt_scene_info(const nt_scene *scene, uint64_t info[4]);
+
+/* Diagnostic, host only (no GPU needed): the conservative culling tables nt_scene_create builds for a flat
+ * scene (<= 64 bounded primitives; nettracer_b200/csrc/nt_cull.h).  Bit j of a mask = sphere j, then triangle
+ * j - n_spheres.  *k_out = cells per cube-face edge; lbuf_out[n_lights][6][k][k] light buffers (may be NULL);
+ * nbr_out[n_spheres] balls touching each sphere; bsph_out[n_spheres + n_triangles][4] bounding spheres.
+ * NT_ERR_INVALID when the scene is not eligible.  Tests use it to prove conservativeness on the CPU. */
+int nt_cull_tables(const nt_scene_desc *desc, uint32_t *k_out, uint64_t *lbuf_out, size_t lbuf_capacity,
+                   uint64_t *nbr_out, double *bsph_out);
 
 /* ---- render ---- */
 /* Host buffer (pageable or pinned), blocking.  Renders the shard named in params, copies the

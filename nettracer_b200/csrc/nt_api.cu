@@ -15,6 +15,7 @@
 
 #include "../../include/nettracer_b200.h"
 #include "nt_bvh.h"
+#include "nt_cull.h"
 #include "nt_device.h"
 
 static_assert(NT_MAX_DEPTH == NT_MAX_DEPTH_DEV, "depth limits must agree");
@@ -142,10 +143,10 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
 
     // flat (everything staged in shared memory) or BVH (bounded primitives in HBM behind a tree)
     bool use_bvh = ns + nt > kFlatMaxBounded ||
-                   ((size_t)ns * 4 + (size_t)np * 4 + (size_t)nt * NT_TRI_STRIDE) * sizeof(double) > kSmemBudget;
+                   (((size_t)ns + 1) * 4 + (size_t)np * 7 + (size_t)nt * NT_TRI_STRIDE) * sizeof(double) > kSmemBudget;
     if (const char *e = getenv("NT_BVH")) {
         if (e[0] == '1') use_bvh = true;
-        else if (e[0] == '0' && ((size_t)ns * 4 + (size_t)np * 4 + (size_t)nt * NT_TRI_STRIDE) * sizeof(double) <= kSmemBudget) use_bvh = false;
+        else if (e[0] == '0' && ns + nt <= kFlatMaxBounded && (((size_t)ns + 1) * 4 + (size_t)np * 7 + (size_t)nt * NT_TRI_STRIDE) * sizeof(double) <= kSmemBudget) use_bvh = false;
     }
     if (ns >= (1u << 26) || nt >= (1u << 26)) return fail(NT_ERR_INVALID, "more than 2^26 spheres or triangles");
     if ((size_t)np * 4 * sizeof(double) > kSmemBudget) return fail(NT_ERR_INVALID, "too many planes (%u): planes are staged in shared memory, limit %zu", np, kSmemBudget / 32);
@@ -219,6 +220,28 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
             if (std::fabs(n[k]) == 1.0 && n[(k + 1) % 3] == 0.0 && n[(k + 2) % 3] == 0.0) code = (unsigned)k;
         pln_code[i / 16] |= code << (2 * (i % 16));
     }
+    // flat kernels: axis-aligned planes by axis as (p = n_k * d, index) pairs, everything else in a general list
+    std::vector<double> axl64;
+    std::vector<float> axl32;
+    std::vector<int> pgen;
+    uint32_t nax[3] = { 0, 0, 0 };
+    for (int k = 0; k < 3; ++k)
+        for (uint32_t i = 0; i < np; ++i)
+            if (((pln_code[i / 16] >> (2 * (i % 16))) & 3u) == (unsigned)k) {
+                const double *n = d->planes + 4 * (size_t)i;
+                const double pk = n[k] * n[3]; // exact: n[k] = +-1
+                double bits64 = 0;
+                float bits32 = 0;
+                const long long i64 = (long long)i;
+                const int i32 = (int)i;
+                memcpy(&bits64, &i64, 8);
+                memcpy(&bits32, &i32, 4);
+                axl64.push_back(pk); axl64.push_back(bits64);
+                axl32.push_back((float)pk); axl32.push_back(bits32);
+                ++nax[k];
+            }
+    for (uint32_t i = 0; i < np; ++i)
+        if (((pln_code[i / 16] >> (2 * (i % 16))) & 3u) == 3u) pgen.push_back((int)i);
     for (uint32_t k = 0; k < nt; ++k) {
         const int i = tri_order[k];
         const double *t = d->triangles + 9 * (size_t)i;
@@ -265,6 +288,26 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
     UP(fmat, ds.v32.mat); UP(fl, ds.v32.lights); UP(fg, ds.v32.globals);
     UP(sph_mat, ds.sph_mat); UP(sph_gid, ds.sph_gid); UP(pln_mat, ds.pln_mat); UP(pln_code, ds.pln_code); UP(tri_mat, ds.tri_mat); UP(tri_gid, ds.tri_gid);
     if (gpu_nodes) ds.nodes = gpu_nodes; else UP(bvh.nodes4, ds.nodes);
+    for (int k = 0; k < 3; ++k) ds.nax[k] = nax[k];
+    ds.ngen = (uint32_t)pgen.size();
+    UP(axl64, ds.axl64); UP(axl32, ds.axl32); UP(pgen, ds.pgen);
+    // flat scenes: conservative culling tables (nt_cull.h); NT_CULL=0 renders by brute force (A/B, tests)
+    ds.cull = 0; ds.lbuf_k = NT_LBUF_K;
+    NtCullTables ct;
+    const char *ce = getenv("NT_CULL");
+    if (!use_bvh && !(ce && ce[0] == '0') && nt_cull_build(d->spheres, ns, d->triangles, nt, d->lights, nl, ct)) {
+        ds.cull = 1; ds.lbuf_k = ct.k;
+    }
+    {
+        std::vector<float4> b32(ct.bsph.size() / 4);
+        for (size_t j = 0; j < b32.size(); ++j) {
+            const double *b = ct.bsph.data() + 4 * j;
+            float r = (float)b[3];
+            if ((double)r < b[3]) r = std::nextafter(r, INFINITY);
+            b32[j] = make_float4((float)b[0], (float)b[1], (float)b[2], r);
+        }
+        UP(b32, ds.bsph32); UP(ct.lbuf, ds.lbuf); UP(ct.nbr, ds.nbr); // 16-byte placeholders when culling is off
+    }
 #undef UP
     CU(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&sc->ev0));
@@ -288,9 +331,26 @@ extern "C" int nt_scene_create(const nt_scene_desc *desc, int device, nt_scene *
     return NT_OK;
 }
 
+extern "C" int nt_cull_tables(const nt_scene_desc *desc, uint32_t *k_out, uint64_t *lbuf_out, size_t lbuf_capacity,
+                              uint64_t *nbr_out, double *bsph_out) {
+    int rc = validate_desc(desc);
+    if (rc) return rc;
+    NtCullTables ct;
+    if (!nt_cull_build(desc->spheres, desc->n_spheres, desc->triangles, desc->n_triangles, desc->lights, desc->n_lights, ct))
+        return fail(NT_ERR_INVALID, "scene is not eligible for the flat culling tables (0 or > 64 bounded primitives, or > %d lights)", NT_CULL_MAX_LIGHTS);
+    if (k_out) *k_out = ct.k;
+    if (lbuf_out) {
+        if (lbuf_capacity < ct.lbuf.size()) return fail(NT_ERR_INVALID, "lbuf_out holds %zu masks, %zu needed", lbuf_capacity, ct.lbuf.size());
+        for (size_t i = 0; i < ct.lbuf.size(); ++i) lbuf_out[i] = ct.lbuf[i];
+    }
+    if (nbr_out) for (size_t i = 0; i < ct.nbr.size(); ++i) nbr_out[i] = ct.nbr[i];
+    if (bsph_out) for (size_t i = 0; i < ct.bsph.size(); ++i) bsph_out[i] = ct.bsph[i];
+    return NT_OK;
+}
+
 extern "C" int nt_scene_info(const nt_scene *sc, uint64_t info[4]) {
     if (!sc || !info) return fail(NT_ERR_INVALID, "NULL argument");
-    info[0] = (uint64_t)sc->ds.use_bvh | ((uint64_t)sc->bvh_on_gpu << 1) | ((uint64_t)(sc->bvh_build_ms * 1000.0) << 8);
+    info[0] = (uint64_t)sc->ds.use_bvh | ((uint64_t)sc->bvh_on_gpu << 1) | ((uint64_t)sc->ds.cull << 2) | ((uint64_t)(sc->bvh_build_ms * 1000.0) << 8);
     info[1] = sc->ds.n_nodes; info[2] = sc->device_bytes; info[3] = (uint64_t)sc->device;
     return NT_OK;
 }
@@ -341,6 +401,15 @@ static int make_args(const nt_render_params *p, size_t stride, NtRenderArgs *a) 
         a->cam[6 + k] = p->camera.dx[k]; a->cam[9 + k] = p->camera.dy[k];
     }
     a->stride = stride;
+    // binary32 copy of the camera for the primary-ray culling cone (nt_trace.cuh tile_mask); lengths rounded up
+    double len[2] = { 0, 0 }, eye_inf = 0;
+    for (int k = 0; k < 12; ++k) a->camf[k] = (float)a->cam[k];
+    for (int k = 0; k < 3; ++k) {
+        len[0] += p->camera.dx[k] * p->camera.dx[k]; len[1] += p->camera.dy[k] * p->camera.dy[k];
+        eye_inf = std::max(eye_inf, std::fabs(p->camera.eye[k]));
+    }
+    a->dxlen = (float)(std::sqrt(len[0]) * 1.000001); a->dylen = (float)(std::sqrt(len[1]) * 1.000001);
+    a->cull_margin = (float)eye_inf; // the scene extent is added by launch()
     return NT_OK;
 }
 
@@ -356,6 +425,7 @@ static int launch(nt_scene *sc, NtRenderArgs &a, uint32_t precision, cudaStream_
         sc->samples_bytes = need;
     }
     a.samples = sc->d_samples;
+    a.cull_margin = 1e-5f * (a.cull_margin + sc->ds.max_abs);
     const int e = precision == NT_F64_STRICT ? nt_launch_render_f64(sc->ds, a, st) : nt_launch_render_f32(sc->ds, a, st);
     if (e) return fail(NT_ERR_CUDA, "render kernel launch: %s", cudaGetErrorString((cudaError_t)e));
     return NT_OK;

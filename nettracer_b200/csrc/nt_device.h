@@ -4,6 +4,8 @@
 #include <cstddef>
 #include <cstdint>
 
+#include <vector_types.h>
+
 #define NT_TRI_STRIDE 12   // v0[3] e1[3] e2[3] ng[3]  (R units; 16-byte aligned rows)
 #define NT_MAT_STRIDE 12   // r g b ka kd ks shininess kr kt ior inv_ior pad
 #define NT_COUNTER_SLOTS 32
@@ -16,18 +18,12 @@
 #define NT_MIN_BLOCKS_F32 3 // fast mode: 3 -> 0.72 ms, 4 -> 0.74 ms
 #endif
 #define NT_BVH_STACK 96     // entries; a 4-wide node pushes up to 3: scene creation checks 3*depth + 4 <= this
-#ifndef NT_FILTER_BATCH
-#define NT_FILTER_BATCH 4   // filter evaluations interleaved per loop iteration
-#endif
 #ifndef NT_COUNTERS_SMEM
 #define NT_COUNTERS_SMEM 0   // flat render kernel: work counters in per-thread shared-memory slots instead of registers
 #endif
-#ifndef NT_SPHERE_FILTER
-#define NT_SPHERE_FILTER 0  // strict flat scenes: binary32 conservative pre-filter before the exact sphere test.
-                           // Bit-exact (tests pass with it on) but SLOWER on configs[2]: 1.49 ms (one at a time), 1.90 ms
-                           // (batch 4), 2.27 ms (batch 8) vs 1.39 ms without -- the kernel is register-bound at 80
-                           // registers and the extra live state spills; kept for the next round's register diet
-#endif
+#ifndef NT_CULL_PAIR
+#define NT_CULL_PAIR 0      // flat scenes: candidate spheres two per iteration (the second one a never-hit dummy row when
+#endif                      // a lane has an odd number left) instead of one
 #ifndef NT_MIN_BLOCKS_BVH
 #define NT_MIN_BLOCKS_BVH 4 // measured best on configs[3] (2: 93.7 ms, 3: 78.2 ms, 4: 75.2 ms) despite spills
 #endif
@@ -85,8 +81,19 @@ struct NtDevScene {
     float max_abs; // largest |coordinate| of any bounded primitive (box-test margin)
     float blo[3], bhi[3]; // bounds of all bounded primitives (float, rounded outward)
     const int *sph_mat, *sph_gid, *pln_mat, *tri_mat, *tri_gid;
-    const unsigned *pln_code; // 2 bits per plane, 16 planes per word: 0..2 normal == +-e_k, 3 general
+    const unsigned *pln_code; // 2 bits per plane, 16 planes per word: 0..2 normal == +-e_k, 3 general (BVH scenes)
+    // flat scenes: planes with a normal of exactly +-e_k, grouped by axis k: nax[k] (position p = +-d, index bits)
+    // pairs in axl64 / axl32; pgen[ngen] = indices of all other planes
+    uint32_t nax[3], ngen;
+    const double *axl64;
+    const float *axl32;
+    const int *pgen;
     const NtBvhNode4 *nodes;
+    // flat scenes: conservative culling tables (nt_cull.h); cull == 0 -> every query tests every primitive
+    uint32_t cull, lbuf_k;
+    const float4 *bsph32;           // [ns+nt] bounding spheres of the bounded primitives (bit order; radius rounded up)
+    const unsigned long long *lbuf; // [nl][6][lbuf_k][lbuf_k] light buffers
+    const unsigned long long *nbr;  // [ns] balls touching ball i
     NtSceneView<double> v64;
     NtSceneView<float> v32;
 };
@@ -99,6 +106,8 @@ struct NtRenderArgs {
     uint32_t tiles_x, tiles_y; // warp tiles over the virtual image (owned rows only)
     double eps;
     double cam[12];    // eye p00 dx dy
+    float camf[12];    // the same in binary32 (primary-ray culling cone only)
+    float dxlen, dylen, cull_margin; // |dx|, |dy| rounded up; 1e-5 * (scene extent + |eye|)
     uint8_t *out;
     size_t stride;
     unsigned long long *counters; // [NT_COUNTER_SLOTS][NT_NCOUNTERS] + 1 (next warp tile / next sample id)

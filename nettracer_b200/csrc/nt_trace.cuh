@@ -83,6 +83,11 @@ template <> struct Ld<double> {
         asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "r"(addr));
         asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+16];" : "=d"(o[2]), "=d"(o[3]) : "r"(addr));
     }
+    static __device__ __forceinline__ void s2(unsigned addr, double &p, int &idx) { // axis-plane entry: position, index bits
+        double b;
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(p), "=d"(b) : "r"(addr));
+        idx = __double2loint(b);
+    }
     static __device__ __forceinline__ void g9(const double *p, double *o) {
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
@@ -108,6 +113,11 @@ template <> struct Ld<float> {
     }
     static __device__ __forceinline__ void s4(unsigned addr, float *o) {
         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "r"(addr));
+    }
+    static __device__ __forceinline__ void s2(unsigned addr, float &p, int &idx) {
+        float b;
+        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(p), "=f"(b) : "r"(addr));
+        idx = __float_as_int(b);
     }
     static __device__ __forceinline__ void g9(const float *p, float *o) {
 #pragma unroll
@@ -255,42 +265,75 @@ __device__ __forceinline__ bool hit_triangle(const R q[9], const V3<R> &o, const
     return true;
 }
 
-// ---- binary32 pre-filter for the strict sphere test (flat scenes) ----
-// The strict mode must return exactly what the binary64 rule of SPEC §3 returns, but it does not have
-// to evaluate that rule for a sphere that provably cannot matter.  The filter works on a binary32 copy
-// of the ray and of the sphere (centre rounded to nearest, radius rounded up) and answers one question
-// conservatively: could this sphere have a hit with t in (0, tmax]?  It reports "no" only if
-//   * the centre is farther from the ray's line than r + m            (clear miss), or
-//   * the whole chord lies behind the origin, t_far + m < 0            (both roots negative), or
-//   * the chord starts beyond the bound, t_near - m > tmax.
-// m = 4e-5 * (|origin|_inf + scene extent) is ~20x the worst-case binary32 error of the quantities
-// involved (conversions 2^-24 relative, then <= ~12 roundings on values bounded by 2*(|o|+extent)); the
-// comparisons are written so that NaN/overflow answers "maybe".  Every "maybe" gets the exact test, in
-// the original order, so results are bit-identical (tests/test_parity_gpu.py compares against the
-// oracle, which has no filter).  Counters still count every sphere as tested.
-struct SphFilterRay {
-    float ox, oy, oz, dx, dy, dz, m;
-};
-__device__ __forceinline__ bool sphere_maybe(const SphFilterRay &r, float4 s /*cx cy cz r_up*/, float tmaxf) {
-    // branch-free on purpose: NT_FILTER_BATCH of these are evaluated back to back so that their
-    // (4-cycle-latency) dependency chains interleave; the kernel is latency-, not throughput-bound
-    const float x = r.ox - s.x, y = r.oy - s.y, z = r.oz - s.z;
-    const float b = __fmaf_rn(z, r.dz, __fmaf_rn(y, r.dy, x * r.dx));
-    const float lx = __fmaf_rn(-b, r.dx, x), ly = __fmaf_rn(-b, r.dy, y), lz = __fmaf_rn(-b, r.dz, z);
-    const float l2 = __fmaf_rn(lz, lz, __fmaf_rn(ly, ly, lx * lx));
-    const float rm = s.w + r.m, rm2 = rm * rm * 1.000001f;
-    const float h = sqrtf(fmaxf(rm2 - l2, 0.0f)) * 1.000001f;
-    const bool no = (l2 > rm2) | (-b + h + r.m < 0.0f) | (-b - h - r.m > tmaxf);
-    return !no;
+// ---- conservative culling for flat scenes (nt_cull.h; SPEC §3 "conservative culling only") ----
+// Bit j of a mask = bounded primitive j (spheres 0..ns-1, then triangles).  A primitive that is absent from
+// the mask a query uses provably cannot be hit by that query, so skipping it leaves every result bit-identical
+// to the brute-force rule (the oracle has no culling; tests compare images, counters and t bit for bit).
+// Work counters keep the brute-force meaning: they count the tests the sequential rule would have done.
+__device__ __forceinline__ unsigned long long low_bits(unsigned n) { return n >= 64 ? ~0ull : (1ull << n) - 1ull; }
+
+// Light buffer look-up for a shadow query.  Lv = light - P, so the direction light -> P is -Lv.  Cube face =
+// major axis and sign; (a, b) = the two other components in increasing axis order, divided by |major|.
+// Approximate binary32 arithmetic is fine: the host dilated every footprint by 2e-3 rad (nt_cull.cpp), the cell
+// index is clamped, and a NaN direction reads cell 0 (such a query has no defined answer anyway).
+template <typename R>
+__device__ __forceinline__ unsigned long long lbuf_mask(const NtDevScene &s, unsigned l, const V3<R> &Lv) {
+    const float x = -(float)Lv.x, y = -(float)Lv.y, z = -(float)Lv.z;
+    const float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
+    const bool fx = ax >= ay && ax >= az, fy = !fx && ay >= az;
+    const float m = fx ? ax : (fy ? ay : az), comp = fx ? x : (fy ? y : z);
+    const float a = fx ? y : x, b = (fx || fy) ? z : y;
+    const unsigned face = (fx ? 0u : (fy ? 2u : 4u)) + (comp < 0.0f ? 1u : 0u);
+    const int K = (int)s.lbuf_k;
+    const float half = 0.5f * (float)K, sc = __fdividef(half, m);
+    int iu = (int)(a * sc + half), iv = (int)(b * sc + half);
+    iu = min(max(iu, 0), K - 1);
+    iv = min(max(iv, 0), K - 1);
+    return __ldg(s.lbuf + ((size_t)(l * 6u + face) * (unsigned)K + (unsigned)iv) * (unsigned)K + (unsigned)iu);
 }
 
-template <typename R>
-__device__ __forceinline__ SphFilterRay make_filter_ray(const V3<R> &o, const V3<R> &d, float scene_max_abs) {
-    SphFilterRay r;
-    r.ox = (float)o.x; r.oy = (float)o.y; r.oz = (float)o.z;
-    r.dx = (float)d.x; r.dy = (float)d.y; r.dz = (float)d.z;
-    r.m = 4e-5f * (fmaxf(fmaxf(fabsf(r.ox), fabsf(r.oy)), fabsf(r.oz)) + scene_max_abs);
-    return r;
+// Primary rays: the bounded primitives whose (dilated) bounding sphere meets a cone around one warp tile's
+// pixel frustum.  Every lane tests primitive `lane` (and `lane + 32`); a ballot makes the warp-uniform mask.
+// Binary32 on purpose (it runs once per 32 samples, a binary64 version cost 15 % of the kernel); everything is
+// dilated far beyond the rounding errors involved:
+//   cone     axis u = D(tile centre) / |D|, sin(half-angle) <= |e| / |D| with |e| <= hx*|dx| + hy*|dy| the largest
+//            offset of a sample direction from the centre direction (both lengths rounded up on the host); x 1.001
+//   sphere   r * 1.001 + 1e-3 * |c - eye| + cull_margin   (cull_margin = 1e-5 * (scene extent + |eye|), host)
+// A sphere is kept unless its centre is farther than that from the cone: perp*cos - along*sin > r, with
+// perp taken from v - along*u (no cancellation).  NaN compares keep the primitive.
+// Pixel area: x in [px0, px0 + twx], y in [ymin, ymax1].
+static __device__ __forceinline__ unsigned long long tile_mask(const NtDevScene &s, const NtRenderArgs &a, unsigned px0, unsigned ymin,
+                                                               unsigned ymax1, unsigned lane) {
+    const unsigned nb = s.ns + s.nt;
+    const unsigned long long all = low_bits(nb);
+    const float hx = 0.5f * (float)a.twx, hy = 0.5f * (float)(ymax1 - ymin);
+    const float fxc = (float)px0 + hx, fyc = (float)ymin + hy;
+    const float Dx = __fmaf_rn(a.camf[9], fyc, __fmaf_rn(a.camf[6], fxc, a.camf[3]));
+    const float Dy = __fmaf_rn(a.camf[10], fyc, __fmaf_rn(a.camf[7], fxc, a.camf[4]));
+    const float Dz = __fmaf_rn(a.camf[11], fyc, __fmaf_rn(a.camf[8], fxc, a.camf[5]));
+    const float inv = rsqrtf(__fmaf_rn(Dz, Dz, __fmaf_rn(Dy, Dy, Dx * Dx)));
+    const float ux = Dx * inv, uy = Dy * inv, uz = Dz * inv;
+    const float sn = __fmaf_rn(hx, a.dxlen, hy * a.dylen) * inv * 1.001f + 1e-6f;
+    if (!(sn < 0.7f)) return all; // very wide tile (or NaN): no culling
+    const float cs = sqrtf(1.0f - sn * sn);
+    unsigned long long mask = 0;
+#pragma unroll 1
+    for (unsigned base = 0; base < nb; base += 32) {
+        const unsigned j = base + lane;
+        bool in = false;
+        if (j < nb) {
+            const float4 b = __ldg(s.bsph32 + j);
+            const float vx = b.x - a.camf[0], vy = b.y - a.camf[1], vz = b.z - a.camf[2];
+            const float along = __fmaf_rn(vz, uz, __fmaf_rn(vy, uy, vx * ux));
+            const float lx = __fmaf_rn(-along, ux, vx), ly = __fmaf_rn(-along, uy, vy), lz = __fmaf_rn(-along, uz, vz);
+            const float perp = sqrtf(__fmaf_rn(lz, lz, __fmaf_rn(ly, ly, lx * lx)));
+            const float vlen = sqrtf(__fmaf_rn(vz, vz, __fmaf_rn(vy, vy, vx * vx)));
+            const float r = __fmaf_rn(b.w, 1.001f, __fmaf_rn(1e-3f, vlen, a.cull_margin));
+            in = !(__fmaf_rn(perp, cs, -along * sn) > r);
+        }
+        mask |= (unsigned long long)__ballot_sync(0xffffffffu, in) << base;
+    }
+    return mask;
 }
 
 // ---- scene context of one block ----
@@ -302,18 +345,14 @@ extern __shared__ __align__(16) unsigned char nt_smem[];
 template <typename R, bool BVH> struct Ctx {
     const NtDevScene *s;
     const NtSceneView<R> *v;
-    unsigned sph_addr, pln_addr, tri_addr, code_addr, fsph_addr; // 32-bit shared-memory byte addresses of the staged arrays
+    unsigned sph_addr, pln_addr, tri_addr, code_addr; // 32-bit shared-memory byte addresses of the staged arrays
+    unsigned axl_addr, gen_addr;                      // flat scenes: axis-aligned plane lists, general-plane index list
     R eps;
     unsigned max_depth;
     __device__ __forceinline__ void ld_sph(unsigned i, R *q) const {
         if constexpr (BVH) Ld<R>::g4(v->sph + 4 * (size_t)i, q); else Ld<R>::s4(sph_addr + i * (4 * (unsigned)sizeof(R)), q);
     }
     __device__ __forceinline__ void ld_pln(unsigned i, R *q) const { Ld<R>::s4(pln_addr + i * (4 * (unsigned)sizeof(R)), q); }
-    __device__ __forceinline__ float4 ld_fsph(unsigned i) const {
-        float4 v;
-        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(fsph_addr + 16 * i));
-        return v;
-    }
     // plane classes, 2 bits per plane, 16 planes per word
     __device__ __forceinline__ unsigned pln_codes(unsigned word) const {
         unsigned v;
@@ -339,166 +378,222 @@ __device__ __forceinline__ void slab(float lo, float hi, float o, float inv, flo
     tf = fminf(tf, fmaxf(a, b));
 }
 
+// ---- planes of a flat scene ----
+// The host splits the planes into three lists of axis-aligned ones (normal exactly +-e_k) and a list of general
+// ones (NtDevScene::nax / axl / pgen).  For n = s*e_k, s = +-1, SPEC §3 reduces EXACTLY (products with +-1 and 0
+// are exact, negation commutes with rounding) to
+//     t = fl( fl(p - o_k) / d_k ),   p = s * d_plane      (entry of the axis list: p and the plane index)
+// i.e. one subtraction per plane, no per-plane switch.  The lists are not in index order, so ties are broken
+// explicitly (smallest global id, SPEC §3); the conservative bound test only rejects quotients that are
+// STRICTLY larger than the bound (see plane_bound), so a tie is never rejected.
+// Strict mode: can the quotient num / dk lie in (0, bound)?  bk = |dk| * plane_bound(bound).  "No" when the
+// signs differ (t < 0) or |num| >= bk (t > bound, strictly); NaN anywhere answers "no", and the exact rule then
+// misses as well (a NaN quotient fails t > eps; dk == 0 is a miss).
+template <typename R>
+__device__ __forceinline__ bool axis_candidate(R dk, R num, R bk) {
+    if constexpr (sizeof(R) == 8) return (__double2hiint(num) ^ __double2hiint(dk)) >= 0 && fabs(num) < bk;
+    else return true;
+}
+template <typename R>
+__device__ __forceinline__ void planes_nearest(const Ctx<R, false> &c, const V3<R> &o, const V3<R> &d, R &tb, Hit &best) {
+    const NtDevScene &s = *c.s;
+    R tm1 = plane_bound<R>(tb);
+    unsigned addr = c.axl_addr;
+#pragma unroll 1
+    for (int k = 0; k < 3; ++k) { // one copy of the body: the kernel has to stay inside the instruction cache
+        const unsigned n = s.nax[k];
+        const R ok = k == 0 ? o.x : (k == 1 ? o.y : o.z), dk = k == 0 ? d.x : (k == 1 ? d.y : d.z);
+        R bk = fabs(dk) * tm1;
+#pragma unroll 1
+        for (unsigned j = 0; j < n; ++j, addr += 2u * (unsigned)sizeof(R)) {
+            R p, t;
+            int idx;
+            Ld<R>::s2(addr, p, idx);
+            const R num = p - ok;
+            if (!axis_candidate<R>(dk, num, bk)) continue;
+            if (!plane_finish<R>(dk, num, c.eps, t)) continue;
+            const int gid = (int)s.ns + idx;
+            if (t < tb || (t == tb && gid < best.gid)) {
+                tb = t; best.kind = 1; best.idx = idx; best.gid = gid;
+                tm1 = plane_bound<R>(tb); bk = fabs(dk) * tm1;
+            }
+        }
+    }
+#pragma unroll 1
+    for (unsigned j = 0; j < s.ngen; ++j) {
+        int idx;
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(idx) : "r"(c.gen_addr + 4u * j));
+        R q[4], dn, num, t;
+        c.ld_pln((unsigned)idx, q);
+        plane_eval<R>(q, 3, o, d, dn, num);
+        if (plane_reject<R>(dn, num, tm1)) continue;
+        if (!plane_finish<R>(dn, num, c.eps, t)) continue;
+        const int gid = (int)s.ns + idx;
+        if (t < tb || (t == tb && gid < best.gid)) { tb = t; best.kind = 1; best.idx = idx; best.gid = gid; tm1 = plane_bound<R>(tb); }
+    }
+}
+// Any plane with eps < t < dist?
+template <typename R>
+__device__ __forceinline__ bool planes_occluded(const Ctx<R, false> &c, const V3<R> &o, const V3<R> &d, R dist) {
+    const NtDevScene &s = *c.s;
+    const R dm1 = plane_bound<R>(dist);
+    unsigned addr = c.axl_addr;
+#pragma unroll 1
+    for (int k = 0; k < 3; ++k) {
+        const unsigned n = s.nax[k];
+        const R ok = k == 0 ? o.x : (k == 1 ? o.y : o.z), dk = k == 0 ? d.x : (k == 1 ? d.y : d.z), bk = fabs(dk) * dm1;
+#pragma unroll 1
+        for (unsigned j = 0; j < n; ++j, addr += 2u * (unsigned)sizeof(R)) {
+            R p, t;
+            int idx;
+            Ld<R>::s2(addr, p, idx);
+            const R num = p - ok;
+            if (!axis_candidate<R>(dk, num, bk)) continue;
+            if (plane_finish<R>(dk, num, c.eps, t) && t < dist) return true;
+        }
+    }
+#pragma unroll 1
+    for (unsigned j = 0; j < s.ngen; ++j) {
+        int idx;
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(idx) : "r"(c.gen_addr + 4u * j));
+        R q[4], dn, num, t;
+        c.ld_pln((unsigned)idx, q);
+        plane_eval<R>(q, 3, o, d, dn, num);
+        if (plane_reject<R>(dn, num, dm1)) continue;
+        if (plane_finish<R>(dn, num, c.eps, t) && t < dist) return true;
+    }
+    return false;
+}
+// Rare path (a plane occludes the light): index of the FIRST occluding plane in index order, for the work
+// counters' sequential rule.  Plain SPEC §3 formula; gives the same t as the list forms above, bit for bit.
+template <typename R>
+__device__ __noinline__ unsigned first_occluding_plane(const Ctx<R, false> &c, const V3<R> &o, const V3<R> &d, R dist) {
+    const NtDevScene &s = *c.s;
+#pragma unroll 1
+    for (unsigned i = 0; i < s.np; ++i) {
+        R q[4], dn, num, t;
+        c.ld_pln(i, q);
+        plane_eval<R>(q, 3, o, d, dn, num);
+        if (plane_finish<R>(dn, num, c.eps, t) && t < dist) return i;
+    }
+    return s.np - 1;
+}
+
 // SPEC §3 nearest hit: smallest t; equal t -> smallest global primitive id.
+// Flat scenes: `mask` = the bounded primitives this ray can possibly hit (per lane).  `own` >= 0: the ray
+// starts on sphere `own` (a reflection / refraction child): that sphere is tested first, and when it is hit
+// the segment up to that hit is a chord of its ball, so only the balls touching it (nbr[own]) can stop the
+// ray earlier.  Bounded primitives come in index order; the only out-of-order test is `own`, hence the
+// explicit tie rule in the sphere loop.
 template <typename R, bool BVH, typename K>
-__device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o, const V3<R> &d,
-                                            R &tb, Hit &best, K &k) {
+__device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o, const V3<R> &d, unsigned long long mask,
+                                            int own, R &tb, Hit &best, K &k) {
     const NtDevScene &s = *c.s;
     tb = Math<R>::inf();
     best.kind = -1; best.idx = -1; best.gid = 0x7fffffff;
     R t;
-    if constexpr (!BVH && sizeof(R) == 8 && NT_SPHERE_FILTER) {
-        const SphFilterRay fr = make_filter_ray(o, d, s.max_abs);
-        float tbf = CUDART_INF_F;
-        for (unsigned i0 = 0; i0 < NT_EXP_NS(s.ns); i0 += NT_FILTER_BATCH) {
-            unsigned mask = 0;
-#pragma unroll
-            for (int u = 0; u < NT_FILTER_BATCH; ++u)
-                if (i0 + u < s.ns && sphere_maybe(fr, c.ld_fsph(i0 + u), tbf)) mask |= 1u << u;
-            while (mask) { // exact tests of the survivors, in index order
-                const unsigned i = i0 + (unsigned)__ffs((int)mask) - 1;
-                mask &= mask - 1;
-                R q[4];
-                c.ld_sph(i, q);
-                if (hit_sphere<R>(q, o, d, c.eps, t) && t < tb) { tb = t; best.kind = 0; best.idx = (int)i; tbf = Math<R>::up(tb); }
-            }
+    if constexpr (!BVH) {
+        if (own >= 0) {
+            R q[4];
+            c.ld_sph((unsigned)own, q);
+            if (hit_sphere<R>(q, o, d, c.eps, t)) { tb = t; best.kind = 0; best.idx = own; best.gid = own; mask = __ldg(s.nbr + own); }
+            else mask &= ~(1ull << own);
         }
-        k.sph += s.ns;
-    } else if constexpr (!BVH) {
-        // two spheres per iteration: the two discriminant chains are independent and interleave
-        unsigned i = 0;
-        for (; i + 2 <= NT_EXP_NS(s.ns); i += 2) {
+        unsigned long long m = mask & low_bits(s.ns);
+#if NT_CULL_PAIR
+        while (m) { // two candidates per iteration (independent chains interleave); row ns is a never-hit dummy
+            const unsigned i0 = (unsigned)__ffsll((long long)m) - 1u;
+            m &= m - 1;
+            const unsigned i1 = m ? (unsigned)__ffsll((long long)m) - 1u : s.ns;
+            m &= m - 1;
             R q0[4], q1[4], b0, b1, d0, d1;
-            c.ld_sph(i, q0);
-            c.ld_sph(i + 1, q1);
+            c.ld_sph(i0, q0);
+            c.ld_sph(i1, q1);
             sphere_eval<R>(q0, o, d, b0, d0);
             sphere_eval<R>(q1, o, d, b1, d1);
-            if (!(d0 < R(0)) && sphere_finish<R>(b0, d0, c.eps, t) && t < tb) { tb = t; best.kind = 0; best.idx = (int)i; }
-            if (!(d1 < R(0)) && sphere_finish<R>(b1, d1, c.eps, t) && t < tb) { tb = t; best.kind = 0; best.idx = (int)i + 1; }
+            if (!(d0 < R(0)) && sphere_finish<R>(b0, d0, c.eps, t) && (t < tb || (t == tb && (int)i0 < best.gid))) { tb = t; best.kind = 0; best.idx = (int)i0; best.gid = (int)i0; }
+            if (!(d1 < R(0)) && sphere_finish<R>(b1, d1, c.eps, t) && (t < tb || (t == tb && (int)i1 < best.gid))) { tb = t; best.kind = 0; best.idx = (int)i1; best.gid = (int)i1; }
         }
-        if (i < NT_EXP_NS(s.ns)) {
+#else
+        while (m) {
+            const unsigned i = (unsigned)__ffsll((long long)m) - 1u;
+            m &= m - 1;
             R q[4];
             c.ld_sph(i, q);
-            if (hit_sphere<R>(q, o, d, c.eps, t) && t < tb) { tb = t; best.kind = 0; best.idx = (int)i; }
+            if (hit_sphere<R>(q, o, d, c.eps, t) && (t < tb || (t == tb && (int)i < best.gid))) { tb = t; best.kind = 0; best.idx = (int)i; best.gid = (int)i; }
         }
+#endif
         k.sph += s.ns;
     }
-    {
-        // two planes per iteration (their chains interleave); a plane rejected against the bound that was
-        // current when the pair started is rejected a fortiori against a smaller one
-        const unsigned np = NT_EXP_NP(s.np);
-        unsigned codes = 0, i = 0;
-        R tm1 = plane_bound<R>(tb);
-        // (pairs pay in binary32: 0.727 -> 0.700 ms; in binary64 the extra live values spill: 1.295 -> 1.372 ms)
-        for (; sizeof(R) == 4 && i + 2 <= np; i += 2) {
-            R q0[4], q1[4], dn0, num0, dn1, num1;
-            if ((i & 15) == 0) codes = c.pln_codes(i >> 4);
-            c.ld_pln(i, q0);
-            c.ld_pln(i + 1, q1);
-            plane_eval<R>(q0, (int)(codes & 3u), o, d, dn0, num0);
-            plane_eval<R>(q1, (int)((codes >> 2) & 3u), o, d, dn1, num1);
-            codes >>= 4;
-            const bool r0 = plane_reject<R>(dn0, num0, tm1), r1 = plane_reject<R>(dn1, num1, tm1);
-            if (!r0 && plane_finish<R>(dn0, num0, c.eps, t) && t < tb) { tb = t; best.kind = 1; best.idx = (int)i; best.gid = (int)(s.ns + i); }
-            if (!r1 && plane_finish<R>(dn1, num1, c.eps, t) && t < tb) { tb = t; best.kind = 1; best.idx = (int)i + 1; best.gid = (int)(s.ns + i + 1); }
-            tm1 = plane_bound<R>(tb);
-        }
-        for (; i < np; ++i) {
-            R q[4];
-            if ((i & 15) == 0) codes = c.pln_codes(i >> 4);
-            c.ld_pln(i, q);
-            const int code = (int)(codes & 3u);
-            codes >>= 2;
-            if (hit_plane<R>(q, code, o, d, c.eps, tm1, t) && t < tb) { tb = t; best.kind = 1; best.idx = (int)i; best.gid = (int)(s.ns + i); tm1 = plane_bound<R>(tb); }
-        }
-    }
+    if constexpr (!BVH) planes_nearest<R>(c, o, d, tb, best);
     k.pln += s.np;
     if constexpr (!BVH) {
-        for (unsigned i = 0; i < s.nt; ++i) {
-            R q[9];
-            c.ld_tri(i, q);
-            if (hit_triangle<R>(q, o, d, c.eps, t) && t < tb) { tb = t; best.kind = 2; best.idx = (int)i; }
+        if (s.nt) { // uniform
+            unsigned long long m = s.ns >= 64 ? 0ull : mask >> s.ns;
+            while (m) {
+                const unsigned i = (unsigned)__ffsll((long long)m) - 1u;
+                m &= m - 1;
+                R q[9];
+                c.ld_tri(i, q);
+                if (hit_triangle<R>(q, o, d, c.eps, t) && t < tb) { tb = t; best.kind = 2; best.idx = (int)i; best.gid = (int)(s.ns + s.np + i); }
+            }
+            k.tri += s.nt;
         }
-        k.tri += s.nt;
     }
     return best.kind >= 0;
 }
 
 // SPEC §3 occlusion: any primitive hit (t > eps) with t < dist; first found ends the query.
-// Counters follow the sequential rule (tests up to and including the first occluder).
+// Counters follow the sequential rule (tests up to and including the first occluder); a culled primitive is
+// a certain miss, so the first occluder found in mask order is the first one in index order.
 template <typename R, bool BVH, typename K>
-__device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, const V3<R> &d, R dist,
+__device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, const V3<R> &d, R dist, unsigned long long mask,
                                          K &k) {
     const NtDevScene &s = *c.s;
     R t;
-    if constexpr (!BVH && sizeof(R) == 8 && NT_SPHERE_FILTER) {
-        const SphFilterRay fr = make_filter_ray(o, d, s.max_abs);
-        const float distf = Math<R>::up(dist);
-        for (unsigned i0 = 0; i0 < NT_EXP_NS(s.ns); i0 += NT_FILTER_BATCH) {
-            unsigned mask = 0;
-#pragma unroll
-            for (int u = 0; u < NT_FILTER_BATCH; ++u)
-                if (i0 + u < s.ns && sphere_maybe(fr, c.ld_fsph(i0 + u), distf)) mask |= 1u << u;
-            while (mask) {
-                const unsigned i = i0 + (unsigned)__ffs((int)mask) - 1;
-                mask &= mask - 1;
-                R q[4];
-                c.ld_sph(i, q);
-                if (hit_sphere<R>(q, o, d, c.eps, t) && t < dist) { k.sph += i + 1; return true; }
-            }
-        }
-        k.sph += s.ns;
-    } else if constexpr (!BVH) {
-        unsigned i = 0;
-        for (; i + 2 <= NT_EXP_NS(s.ns); i += 2) {
+    if constexpr (!BVH) {
+        unsigned long long m = mask & low_bits(s.ns);
+#if NT_CULL_PAIR
+        while (m) {
+            const unsigned i0 = (unsigned)__ffsll((long long)m) - 1u;
+            m &= m - 1;
+            const unsigned i1 = m ? (unsigned)__ffsll((long long)m) - 1u : s.ns;
+            m &= m - 1;
             R q0[4], q1[4], b0, b1, d0, d1;
-            c.ld_sph(i, q0);
-            c.ld_sph(i + 1, q1);
+            c.ld_sph(i0, q0);
+            c.ld_sph(i1, q1);
             sphere_eval<R>(q0, o, d, b0, d0);
             sphere_eval<R>(q1, o, d, b1, d1);
-            if (!(d0 < R(0)) && sphere_finish<R>(b0, d0, c.eps, t) && t < dist) { k.sph += i + 1; return true; }
-            if (!(d1 < R(0)) && sphere_finish<R>(b1, d1, c.eps, t) && t < dist) { k.sph += i + 2; return true; }
+            if (!(d0 < R(0)) && sphere_finish<R>(b0, d0, c.eps, t) && t < dist) { k.sph += i0 + 1; return true; }
+            if (!(d1 < R(0)) && sphere_finish<R>(b1, d1, c.eps, t) && t < dist) { k.sph += i1 + 1; return true; }
         }
-        if (i < NT_EXP_NS(s.ns)) {
+#else
+        while (m) {
+            const unsigned i = (unsigned)__ffsll((long long)m) - 1u;
+            m &= m - 1;
             R q[4];
             c.ld_sph(i, q);
-            if (hit_sphere<R>(q, o, d, c.eps, t) && t < dist) { k.sph += s.ns; return true; }
+            if (hit_sphere<R>(q, o, d, c.eps, t) && t < dist) { k.sph += i + 1; return true; }
         }
+#endif
         k.sph += s.ns;
     }
-    {
-        const unsigned np = NT_EXP_NP(s.np);
-        unsigned codes = 0, i = 0;
-        const R dm1 = plane_bound<R>(dist);
-        for (; sizeof(R) == 4 && i + 2 <= np; i += 2) {
-            R q0[4], q1[4], dn0, num0, dn1, num1;
-            if ((i & 15) == 0) codes = c.pln_codes(i >> 4);
-            c.ld_pln(i, q0);
-            c.ld_pln(i + 1, q1);
-            plane_eval<R>(q0, (int)(codes & 3u), o, d, dn0, num0);
-            plane_eval<R>(q1, (int)((codes >> 2) & 3u), o, d, dn1, num1);
-            codes >>= 4;
-            const bool r0 = plane_reject<R>(dn0, num0, dm1), r1 = plane_reject<R>(dn1, num1, dm1);
-            if (!r0 && plane_finish<R>(dn0, num0, c.eps, t) && t < dist) { k.pln += i + 1; return true; }
-            if (!r1 && plane_finish<R>(dn1, num1, c.eps, t) && t < dist) { k.pln += i + 2; return true; }
-        }
-        for (; i < np; ++i) {
-            R q[4];
-            if ((i & 15) == 0) codes = c.pln_codes(i >> 4);
-            c.ld_pln(i, q);
-            const int code = (int)(codes & 3u);
-            codes >>= 2;
-            if (hit_plane<R>(q, code, o, d, c.eps, dm1, t) && t < dist) { k.pln += i + 1; return true; }
-        }
+    if constexpr (!BVH) {
+        if (planes_occluded<R>(c, o, d, dist)) { k.pln += first_occluding_plane<R>(c, o, d, dist) + 1; return true; }
     }
     k.pln += s.np;
     if constexpr (!BVH) {
-        for (unsigned i = 0; i < s.nt; ++i) {
-            R q[9];
-            c.ld_tri(i, q);
-            if (hit_triangle<R>(q, o, d, c.eps, t) && t < dist) { k.tri += i + 1; return true; }
+        if (s.nt) { // uniform
+            unsigned long long m = s.ns >= 64 ? 0ull : mask >> s.ns;
+            while (m) {
+                const unsigned i = (unsigned)__ffsll((long long)m) - 1u;
+                m &= m - 1;
+                R q[9];
+                c.ld_tri(i, q);
+                if (hit_triangle<R>(q, o, d, c.eps, t) && t < dist) { k.tri += i + 1; return true; }
+            }
+            k.tri += s.nt;
         }
-        k.tri += s.nt;
     }
     return false;
 }
@@ -507,21 +602,27 @@ __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, c
 // `accp` / `Wp`: the sample's running radiance sum (3 values, stride NT_BLOCK_THREADS) and path weight,
 // kept in per-thread shared-memory slots: touched once per tree node, not worth 8 registers.
 #define NT_ACC(ch) accp[(ch) * NT_BLOCK_THREADS]
+// `pmask`: address of the warp's primary-ray mask (tile_mask) in shared memory.  `own` of the current ray:
+// -2 primary ray (mask = *pmask), -1 no culling information (all bounded primitives), >= 0 the ray starts on
+// that sphere (see nearest_hit).  Kept as ONE register instead of a live 64-bit mask: the kernel is register-bound.
 template <typename R, bool BVH, typename K>
-__device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R> d, R *accp, R *Wp, K &k) {
+__device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R> d, R *accp, R *Wp, const unsigned long long *pmask,
+                                             K &k) {
     const NtDevScene &s = *c.s;
     const NtSceneView<R> &v = *c.v;
     // deferred transmission children (reflection children are followed immediately)
     R st[NT_MAX_DEPTH_DEV][7];
-    unsigned st_depth[NT_MAX_DEPTH_DEV];
+    unsigned st_depth[NT_MAX_DEPTH_DEV]; // depth | (own + 1) << 8
     int sp = 0;
     *Wp = R(1);
     unsigned depth = 1;
+    int own = -2;
     for (;;) {
         R t;
         Hit h;
         bool descend = false;
-        if (!nearest_hit<R, BVH, K>(c, o, d, t, h, k)) {
+        const unsigned long long qmask = own == -2 ? *pmask : low_bits(s.ns + s.nt);
+        if (!nearest_hit<R, BVH, K>(c, o, d, qmask, own, t, h, k)) {
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) NT_ACC(ch) = NT_ACC(ch) + *Wp * __ldg(v.globals + 3 + ch);
         } else {
@@ -567,7 +668,8 @@ __device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R
                 const R ndl = dot(N, L);
                 if (!(ndl > R(0))) continue;
                 k.shadow++;
-                if (occluded<R, BVH, K>(c, P, L, dist, k)) continue;
+                const unsigned long long lmask = s.cull ? lbuf_mask<R>(s, l, Lv) : low_bits(s.ns + s.nt);
+                if (occluded<R, BVH, K>(c, P, L, dist, lmask, k)) continue;
                 k.light++;
                 R m0[4], m1[4];
                 Ld<R>::g4(mp, m0);     // r g b ka
@@ -610,7 +712,7 @@ __device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R
                     if (wr > R(0)) { // defer: reflection subtree comes first in pre-order
                         st[sp][0] = P.x; st[sp][1] = P.y; st[sp][2] = P.z;
                         st[sp][3] = T.x; st[sp][4] = T.y; st[sp][5] = T.z;
-                        st[sp][6] = *Wp * wt; st_depth[sp] = depth + 1;
+                        st[sp][6] = *Wp * wt; st_depth[sp] = (depth + 1) | (unsigned)((s.cull && h.kind == 0 ? h.idx : -1) + 1) << 8;
                         ++sp;
                     }
                 }
@@ -624,6 +726,7 @@ __device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R
                     o = P; d = T; *Wp = *Wp * wt; depth = depth + 1;
                     descend = true;
                 }
+                own = s.cull && h.kind == 0 ? h.idx : -1;
             }
         }
         if (descend) continue;
@@ -632,7 +735,8 @@ __device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R
         o = { st[sp][0], st[sp][1], st[sp][2] };
         d = { st[sp][3], st[sp][4], st[sp][5] };
         *Wp = st[sp][6];
-        depth = st_depth[sp];
+        depth = st_depth[sp] & 0xffu;
+        own = (int)(st_depth[sp] >> 8) - 1;
     }
 }
 
@@ -641,27 +745,33 @@ __device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R
 // Stage the flat intersection data in shared memory with 128-bit loads.
 template <typename R, bool BVH>
 __device__ __forceinline__ void stage_scene(const NtDevScene &s, const NtSceneView<R> &v, Ctx<R, BVH> &c) {
-    const unsigned n_sph = BVH ? 0u : s.ns * 4, n_pln = s.np * 4, n_tri = BVH ? 0u : s.nt * NT_TRI_STRIDE;
+    // flat scenes: sphere row ns is a dummy that no ray can hit (r2 = -inf): the partner of an odd candidate
+    const unsigned n_sph = BVH ? 0u : (s.ns + 1) * 4, n_pln = s.np * 4, n_tri = BVH ? 0u : s.nt * NT_TRI_STRIDE;
     R *smem = (R *)nt_smem;
     constexpr int VEC = 16 / sizeof(R);
     typedef typename std::conditional<sizeof(R) == 8, double2, float4>::type VT;
-    if constexpr (!BVH)
+    if constexpr (!BVH) {
 #pragma unroll 1
-        for (unsigned i = threadIdx.x; i < n_sph / VEC; i += blockDim.x) ((VT *)smem)[i] = __ldg((const VT *)v.sph + i);
-#pragma unroll 1
-    for (unsigned i = threadIdx.x; i < n_pln / VEC; i += blockDim.x) ((VT *)(smem + n_sph))[i] = __ldg((const VT *)v.pln + i);
-    if constexpr (!BVH)
-#pragma unroll 1
-        for (unsigned i = threadIdx.x; i < n_tri / VEC; i += blockDim.x) ((VT *)(smem + n_sph + n_pln))[i] = __ldg((const VT *)v.tri + i);
-    unsigned *codes = (unsigned *)(smem + n_sph + n_pln + n_tri);
-    for (unsigned i = threadIdx.x; i < (s.np + 15) / 16; i += blockDim.x) codes[i] = __ldg(s.pln_code + i);
-    const unsigned code_words = (s.np + 15) / 16, fs_off = (code_words + 3) & ~3u; // float4-aligned
-    if constexpr (!BVH && sizeof(R) == 8) {
-        float4 *fs = (float4 *)(codes + fs_off);
-        for (unsigned i = threadIdx.x; i < s.ns; i += blockDim.x) {
-            const double2 a = __ldg((const double2 *)v.sph + 2 * i), b2 = __ldg((const double2 *)v.sph + 2 * i + 1);
-            fs[i] = make_float4((float)a.x, (float)a.y, (float)b2.x, __double2float_ru(sqrt(b2.y)));
+        for (unsigned i = threadIdx.x; i < n_sph / VEC; i += blockDim.x) {
+            if (i < s.ns * 4 / VEC) ((VT *)smem)[i] = __ldg((const VT *)v.sph + i);
+            else { R *row = smem + i * VEC; for (int e = 0; e < VEC; ++e) row[e] = ((i * VEC + e) & 3u) == 3u ? -Math<R>::inf() : R(0); }
         }
+    }
+#pragma unroll 1
+    for (unsigned i = threadIdx.x; i < n_pln / VEC; i += blockDim.x) { ((VT *)(smem + n_sph))[i] = __ldg((const VT *)v.pln + i); }
+    if constexpr (!BVH) {
+#pragma unroll 1
+        for (unsigned i = threadIdx.x; i < n_tri / VEC; i += blockDim.x) { ((VT *)(smem + n_sph + n_pln))[i] = __ldg((const VT *)v.tri + i); }
+    }
+    const unsigned n_ax = BVH ? 0u : 2u * (s.nax[0] + s.nax[1] + s.nax[2]); // R units: (position, index bits) pairs
+    if constexpr (BVH) {
+        unsigned *codes = (unsigned *)(smem + n_sph + n_pln + n_tri);
+        for (unsigned i = threadIdx.x; i < (s.np + 15) / 16; i += blockDim.x) codes[i] = __ldg(s.pln_code + i);
+    } else {
+        const R *axl = (const R *)(sizeof(R) == 8 ? (const void *)s.axl64 : (const void *)s.axl32);
+        for (unsigned i = threadIdx.x; i < n_ax; i += blockDim.x) smem[n_sph + n_pln + n_tri + i] = __ldg(axl + i);
+        int *gen = (int *)(smem + n_sph + n_pln + n_tri + n_ax);
+        for (unsigned i = threadIdx.x; i < s.ngen; i += blockDim.x) gen[i] = __ldg(s.pgen + i);
     }
     __syncthreads();
     unsigned base = (unsigned)__cvta_generic_to_shared(nt_smem);
@@ -670,7 +780,8 @@ __device__ __forceinline__ void stage_scene(const NtDevScene &s, const NtSceneVi
     c.pln_addr = base + n_sph * (unsigned)sizeof(R);
     c.tri_addr = base + (n_sph + n_pln) * (unsigned)sizeof(R);
     c.code_addr = base + (n_sph + n_pln + n_tri) * (unsigned)sizeof(R);
-    c.fsph_addr = c.code_addr + 4 * fs_off;
+    c.axl_addr = c.code_addr;
+    c.gen_addr = c.axl_addr + n_ax * (unsigned)sizeof(R);
 }
 
 // Per-thread counters -> one atomic per counter per block, spread over NT_COUNTER_SLOTS slots.
@@ -716,6 +827,7 @@ render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRe
     __shared__ unsigned s_k[NT_NCOUNTERS][NT_BLOCK_THREADS];
 #endif
     __shared__ R s_state[4][NT_BLOCK_THREADS]; // acc r g b, W
+    __shared__ unsigned long long s_pmask[NT_BLOCK_THREADS / 32]; // per warp: primary-ray candidates of its tile
     const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
     Ctx<R, BVH> c;
     c.s = &s; c.v = &v; c.eps = (R)a.eps; c.max_depth = a.max_depth;
@@ -740,6 +852,19 @@ render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRe
     while (tile < n_tiles) {
         R sum[3] = { R(0), R(0), R(0) };
         const unsigned rounds = SINGLE ? 1u : a.spp / a.lanes;
+        if constexpr (!BVH) {
+            unsigned long long pm = low_bits(s.ns + s.nt);
+            if (s.cull) {
+                const unsigned px0 = (tile % a.tiles_x) * a.twx, vr0 = (tile / a.tiles_x) * a.twy;
+                const unsigned vr1 = min(vr0 + a.twy, a.vrows) - 1; // first / last owned row of the tile -> image rows
+                const unsigned y0 = ((vr0 / a.band_rows) * a.shard_count + a.shard_index) * a.band_rows + vr0 % a.band_rows;
+                const unsigned y1 = ((vr1 / a.band_rows) * a.shard_count + a.shard_index) * a.band_rows + vr1 % a.band_rows;
+                pm = tile_mask(s, a, px0, y0, y1 + 1, lane);
+            }
+            __syncwarp();
+            if (lane == 0) s_pmask[tid >> 5] = pm;
+            __syncwarp();
+        }
         for (unsigned r = 0; r < rounds; ++r) {
             {
                 const unsigned L = a.lanes, j = lane & (L - 1), pw = lane / L;
@@ -760,7 +885,7 @@ render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRe
                     const V3<R> dir = scale(D, Math<R>::rcp(Math<R>::sqrt_(dot(D, D))));
                     const V3<R> eye = { (R)a.cam[0], (R)a.cam[1], (R)a.cam[2] };
                     k.prim++;
-                    trace_sample<R, BVH, KT>(c, eye, dir, accp, Wp, k);
+                    trace_sample<R, BVH, KT>(c, eye, dir, accp, Wp, &s_pmask[tid >> 5], k);
                 }
             }
             asm volatile("" : "+r"(tile)); // pixel coordinates are recomputed below, not carried across the trace
@@ -825,9 +950,9 @@ trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtTra
     Counters k = { 0, 0, 0, 0, 0, 0, 0, 0 };
     R t;
     Hit h;
-    if (nearest_hit<R, BVH, Counters>(c, o, d, t, h, k)) {
+    if (nearest_hit<R, BVH, Counters>(c, o, d, low_bits(s.ns + s.nt), -1, t, h, k)) {
         a.t_out[i] = (double)t;
-        a.prim_out[i] = h.kind == 1 ? h.gid : (h.kind == 0 ? h.idx : (int)(s.ns + s.np) + h.idx);
+        a.prim_out[i] = h.gid;
     } else {
         a.t_out[i] = -1.0;
         a.prim_out[i] = -1;
@@ -837,10 +962,10 @@ trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtTra
 template <typename R>
 inline size_t flat_smem_bytes(const NtDevScene &s, bool bvh) {
     size_t n = (size_t)s.np * 4;
-    if (!bvh) n += (size_t)s.ns * 4 + (size_t)s.nt * NT_TRI_STRIDE;
-    size_t bytes = n * sizeof(R) + (size_t)((((s.np + 15) / 16) + 3) & ~3u) * sizeof(unsigned);
-    if (!bvh && sizeof(R) == 8) bytes += (size_t)s.ns * sizeof(float4); // binary32 filter spheres
-    return bytes;
+    if (bvh) return n * sizeof(R) + (size_t)((((s.np + 15) / 16) + 3) & ~3u) * sizeof(unsigned);
+    n += ((size_t)s.ns + 1) * 4 + (size_t)s.nt * NT_TRI_STRIDE; // + the dummy sphere row
+    n += 2 * ((size_t)s.nax[0] + s.nax[1] + s.nax[2]);          // axis-aligned plane lists
+    return n * sizeof(R) + (((size_t)s.ngen + 3) & ~(size_t)3) * sizeof(int);
 }
 
 } // namespace nt

@@ -45,9 +45,14 @@ def load():
         "nt_ipc_open": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
         "nt_ipc_close": (C.c_int, [vp, C.c_int]),
         "nt_measure_peaks": (C.c_int, [C.c_int, C.POINTER(abi.nt_peaks)]),
+        "nt_cull_tables": (C.c_int, [C.POINTER(abi.nt_scene_desc), C.POINTER(u32), vp, C.c_size_t, vp, vp]),
     }
     for name, (res, args) in sig.items():
-        fn = getattr(L, name)
+        fn = getattr(L, name, None)
+        if fn is None:
+            if os.environ.get("NT_LIB_PATH"):  # an older experiment build: tolerate a missing newer entry point
+                continue
+            raise ImportError(f"{LIB_PATH} does not export {name}: rebuild it (make -C nettracer_b200/csrc)")
         fn.restype, fn.argtypes = res, args
     if L.nt_abi_version() != abi.NT_ABI_VERSION:
         raise ImportError("libnettracer_b200.so ABI version mismatch")

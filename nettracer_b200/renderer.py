@@ -41,7 +41,8 @@ class Renderer:
     def info(self) -> dict:
         a = (C.c_uint64 * 4)()
         check(self._lib.nt_scene_info(self._h, a))
-        return {"uses_bvh": bool(a[0] & 1), "bvh_on_gpu": bool(a[0] & 2), "bvh_build_ms": (int(a[0]) >> 8) / 1000.0,
+        return {"uses_bvh": bool(a[0] & 1), "bvh_on_gpu": bool(a[0] & 2), "culling": bool(a[0] & 4),
+                "bvh_build_ms": (int(a[0]) >> 8) / 1000.0,
                 "bvh_nodes": int(a[1]), "device_bytes": int(a[2]), "device": int(a[3])}
 
     # -- host path --
@@ -81,6 +82,22 @@ class Renderer:
         check(self._lib.nt_trace_rays(self._h, len(o), o.ctypes.data, d.ctypes.data, int(precision),
                                       float(ray_epsilon), t.ctypes.data, prim.ctypes.data))
         return t, prim
+
+
+def cull_tables(scene: Scene) -> dict:
+    """The conservative culling tables nt_scene_create builds for a flat scene (nt_cull_tables: host only,
+    no GPU needed).  Returns k, lbuf [n_lights, 6, k, k] uint64, nbr [n_spheres] uint64, bsph [nb, 4]."""
+    lib = load()
+    desc, keep = scene.to_desc()
+    k = C.c_uint32()
+    check(lib.nt_cull_tables(C.byref(desc), C.byref(k), None, 0, None, None))
+    nb = desc.n_spheres + desc.n_triangles
+    lbuf = np.zeros((desc.n_lights, 6, k.value, k.value), dtype=np.uint64)
+    nbr = np.zeros(desc.n_spheres, dtype=np.uint64)
+    bsph = np.zeros((nb, 4), dtype=np.float64)
+    check(lib.nt_cull_tables(C.byref(desc), C.byref(k), lbuf.ctypes.data, lbuf.size, nbr.ctypes.data, bsph.ctypes.data))
+    del keep
+    return {"k": int(k.value), "lbuf": lbuf, "nbr": nbr, "bsph": bsph}
 
 
 def measure_peaks(device=0) -> dict:

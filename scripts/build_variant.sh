@@ -13,6 +13,7 @@ nvcc $COMMON -c nt_api.cu -o $OBJ/api.o &
 nvcc $COMMON -c nt_peaks.cu -o $OBJ/peaks.o &
 nvcc $COMMON -c nt_bvh.cpp -o $OBJ/bvh.o &
 nvcc $COMMON -c nt_bvh_gpu.cu -o $OBJ/bvhgpu.o &
+nvcc $COMMON -c nt_cull.cpp -o $OBJ/cull.o &
 wait
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/libnt_$NAME.so $OBJ/f64.o $OBJ/f32.o $OBJ/api.o $OBJ/peaks.o $OBJ/bvh.o $OBJ/bvhgpu.o -lcudart
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/libnt_$NAME.so $OBJ/f64.o $OBJ/f32.o $OBJ/api.o $OBJ/peaks.o $OBJ/bvh.o $OBJ/bvhgpu.o $OBJ/cull.o -lcudart
 echo built $OUT/libnt_$NAME.so

@@ -1,0 +1,138 @@
+"""CPU tests of the flat-scene culling tables (nettracer_b200/csrc/nt_cull.cpp, exported for inspection as
+nt_cull_tables): every table must be CONSERVATIVE — a primitive a query can hit is always in the mask the
+query would look up.  Checked here by brute force in numpy float64 against the exact SPEC-PROVISIONAL §3
+tests, with the light-buffer cell picked in emulated binary32 exactly as the device does (lbuf_mask in
+nt_trace.cuh).  The bit-exact GPU parity tests (test_parity_gpu.py, culling on and off) are the end-to-end proof."""
+import numpy as np
+import pytest
+
+from nettracer_b200 import scenes
+from nettracer_b200.renderer import cull_tables
+
+EPS = 1e-6
+
+
+def lbuf_cell(Lv, k):
+    """Mirror of lbuf_mask(): direction light -> P = -Lv, binary32."""
+    v = (-Lv).astype(np.float32)
+    x, y, z = v[:, 0], v[:, 1], v[:, 2]
+    ax, ay, az = np.abs(x), np.abs(y), np.abs(z)
+    fx = (ax >= ay) & (ax >= az)
+    fy = ~fx & (ay >= az)
+    m = np.where(fx, ax, np.where(fy, ay, az))
+    comp = np.where(fx, x, np.where(fy, y, z))
+    a = np.where(fx, y, x)
+    b = np.where(fx | fy, z, y)
+    face = np.where(fx, 0, np.where(fy, 2, 4)) + (comp < 0)
+    half = np.float32(0.5 * k)
+    sc = half / m
+    iu = np.clip((a * sc + half).astype(np.int64), 0, k - 1)
+    iv = np.clip((b * sc + half).astype(np.int64), 0, k - 1)
+    return face, iv, iu
+
+
+def sphere_hits(o, d, sph, tmax):
+    """SPEC §3 sphere rule, vectorised: hit with eps < t < tmax."""
+    oc = o - sph[:3]
+    b = (oc * d).sum(-1)
+    cc = (oc * oc).sum(-1) - sph[3] * sph[3]
+    disc = b * b - cc
+    sq = np.sqrt(np.maximum(disc, 0))
+    t = -b - sq
+    t = np.where(t > EPS, t, -b + sq)
+    return (disc >= 0) & (t > EPS) & (t < tmax), t
+
+
+def tri_hits(o, d, tri, tmax):
+    v0, e1, e2 = tri[0:3], tri[3:6] - tri[0:3], tri[6:9] - tri[0:3]
+    p = np.cross(d, e2)
+    det = (e1 * p).sum(-1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv = 1.0 / det
+        tv = o - v0
+        u = (tv * p).sum(-1) * inv
+        q = np.cross(tv, e1)
+        v = (d * q).sum(-1) * inv
+        t = (q * e2).sum(-1) * inv
+    return (det != 0) & (u >= 0) & (u <= 1) & (v >= 0) & (u + v <= 1) & (t > EPS) & (t < tmax), t
+
+
+def surface_points(scene, rng, n):
+    """Points where shadow queries start: on spheres, on triangles, on the planes' region, and free space."""
+    a = scene.arrays()
+    pts = [rng.uniform(-12, 12, (n, 3))]
+    for s in a["spheres"]:
+        v = rng.normal(size=(n // 4, 3))
+        v /= np.linalg.norm(v, axis=1, keepdims=True)
+        pts.append(s[:3] + s[3] * v)
+    for t in a["triangles"]:
+        w = rng.dirichlet((1, 1, 1), n // 8)
+        pts.append(w @ t.reshape(3, 3))
+    return np.concatenate(pts)
+
+
+@pytest.mark.parametrize("which", ["cornell", "mixed1", "mixed2"])
+def test_light_buffer_is_conservative(which):
+    scene = scenes.cornell_box()[0] if which == "cornell" else scenes.random_mixed(12, 3, 20, seed=1 if which == "mixed1" else 2)[0]
+    a = scene.arrays()
+    tab = cull_tables(scene)
+    k, ns = tab["k"], len(a["spheres"])
+    rng = np.random.default_rng(7)
+    P = surface_points(scene, rng, 4000)
+    culled = total = 0
+    for l, light in enumerate(a["lights"]):
+        Lv = light[:3] - P
+        dist = np.sqrt((Lv * Lv).sum(-1))
+        L = Lv / dist[:, None]
+        face, iv, iu = lbuf_cell(Lv, k)
+        masks = tab["lbuf"][l, face, iv, iu]
+        for j in range(ns + len(a["triangles"])):
+            hit, _ = (sphere_hits(P, L, a["spheres"][j], dist) if j < ns else tri_hits(P, L, a["triangles"][j - ns], dist))
+            inmask = ((masks >> np.uint64(j)) & np.uint64(1)).astype(bool)
+            assert not (hit & ~inmask).any(), f"light {l} primitive {j}: occluder missing from the light buffer"
+            culled += int((~inmask).sum())
+            total += len(P)
+    assert culled > 0.5 * total, "the light buffer should cull most candidates on these scenes"
+
+
+@pytest.mark.parametrize("which", ["cornell", "mixed1"])
+def test_neighbour_masks_are_conservative(which):
+    scene = scenes.cornell_box()[0] if which == "cornell" else scenes.random_mixed(12, 3, 20, seed=1)[0]
+    a = scene.arrays()
+    tab = cull_tables(scene)
+    ns = len(a["spheres"])
+    rng = np.random.default_rng(11)
+    n = 3000
+    for i, s in enumerate(a["spheres"]):
+        assert not (int(tab["nbr"][i]) >> i) & 1, "own bit must be excluded"
+        v = rng.normal(size=(n, 3))
+        v /= np.linalg.norm(v, axis=1, keepdims=True)
+        o = s[:3] + s[3] * v                       # on sphere i
+        d = rng.normal(size=(n, 3))
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        own, t_own = sphere_hits(o, d, s, np.inf)  # rays that hit sphere i again: chords
+        for j in range(ns + len(a["triangles"])):
+            if j == i:
+                continue
+            hit, t = (sphere_hits(o, d, a["spheres"][j], np.inf) if j < ns else tri_hits(o, d, a["triangles"][j - ns], np.inf))
+            nearer = own & hit & (t <= t_own)
+            if nearer.any():
+                assert (int(tab["nbr"][i]) >> j) & 1, f"sphere {i}: primitive {j} stops a chord but is not a neighbour"
+
+
+def test_bounding_spheres_contain_primitives():
+    scene = scenes.random_mixed(12, 3, 20, seed=3)[0]
+    a = scene.arrays()
+    tab = cull_tables(scene)
+    ns = len(a["spheres"])
+    assert np.array_equal(tab["bsph"][:ns], a["spheres"])
+    for j, t in enumerate(a["triangles"]):
+        c, r = tab["bsph"][ns + j, :3], tab["bsph"][ns + j, 3]
+        assert (np.linalg.norm(t.reshape(3, 3) - c, axis=1) <= r).all()
+
+
+def test_not_eligible_is_an_error():
+    from nettracer_b200.lib import NetTracerError
+    scene = scenes.random_mixed(150, 2, 300, seed=4)[0]  # > 64 bounded primitives -> BVH scene
+    with pytest.raises(NetTracerError):
+        cull_tables(scene)
