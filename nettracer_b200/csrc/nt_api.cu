@@ -293,6 +293,8 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
     UP(axl64, ds.axl64); UP(axl32, ds.axl32); UP(pgen, ds.pgen);
     // flat scenes: conservative culling tables (nt_cull.h); NT_CULL=0 renders by brute force (A/B, tests)
     ds.cull = 0; ds.lbuf_k = NT_LBUF_K;
+    ds.sph_bits = ns >= 64 ? ~0ull : (1ull << ns) - 1ull;
+    ds.all_bits = ns + nt >= 64 ? ~0ull : (1ull << (ns + nt)) - 1ull;
     NtCullTables ct;
     const char *ce = getenv("NT_CULL");
     if (!use_bvh && !(ce && ce[0] == '0') && nt_cull_build(d->spheres, ns, d->triangles, nt, d->lights, nl, ct)) {
@@ -378,7 +380,8 @@ static int make_args(const nt_render_params *p, size_t stride, NtRenderArgs *a) 
     if (p->max_depth < 1 || p->max_depth > NT_MAX_DEPTH) return fail(NT_ERR_INVALID, "max_depth %u not in 1..%d", p->max_depth, NT_MAX_DEPTH);
     if (p->precision != NT_F64_STRICT && p->precision != NT_F32_FAST) return fail(NT_ERR_INVALID, "unknown precision %u", p->precision);
     if (p->layout != NT_LAYOUT_FULL && p->layout != NT_LAYOUT_COMPACT) return fail(NT_ERR_INVALID, "unknown layout %u", p->layout);
-    const uint32_t scount = p->shard_count ? p->shard_count : 1, band = p->band_rows ? p->band_rows : 1;
+    const uint32_t scount = p->shard_count ? p->shard_count : 1;
+    const uint32_t band = p->band_rows ? (p->band_rows > 65536 ? 65536 : p->band_rows) : 1; // height <= 65536: same partition
     if (p->shard_index >= scount) return fail(NT_ERR_INVALID, "shard_index %u >= shard_count %u", p->shard_index, scount);
     if (stride < (size_t)p->width * 4 || stride % 4) return fail(NT_ERR_INVALID, "row stride %zu must be >= 4*width and a multiple of 4", stride);
     memset(a, 0, sizeof *a);
@@ -394,6 +397,12 @@ static int make_args(const nt_render_params *p, size_t stride, NtRenderArgs *a) 
     a->twx = tw[li][0]; a->twy = tw[li][1];
     a->tiles_x = (p->width + a->twx - 1) / a->twx;
     a->tiles_y = (a->vrows + a->twy - 1) / a->twy;
+    a->log2_lanes = (uint32_t)li;
+    for (a->log2_twx = 0; (1u << a->log2_twx) < a->twx; ++a->log2_twx) {}
+    for (a->log2_twy = 0; (1u << a->log2_twy) < a->twy; ++a->log2_twy) {}
+    a->band_magic = band > 1 ? (uint32_t)(((1ull << 32) + band - 1) / band) : 0u;
+    a->n_mul = (65536u + n - 1) / n;
+    a->inv_tiles_x = 1.0f / (float)a->tiles_x;
     a->eps = p->ray_epsilon > 0 ? p->ray_epsilon : 1e-6;
     if (p->precision == NT_F32_FAST && a->eps < 1e-4) a->eps = 1e-4; // SPEC-PROVISIONAL §7
     for (int k = 0; k < 3; ++k) {

@@ -91,6 +91,7 @@ struct NtDevScene {
     const NtBvhNode4 *nodes;
     // flat scenes: conservative culling tables (nt_cull.h); cull == 0 -> every query tests every primitive
     uint32_t cull, lbuf_k;
+    unsigned long long sph_bits, all_bits; // masks of the sphere bits / of all bounded primitives (flat scenes)
     const float4 *bsph32;           // [ns+nt] bounding spheres of the bounded primitives (bit order; radius rounded up)
     const unsigned long long *lbuf; // [nl][6][lbuf_k][lbuf_k] light buffers
     const unsigned long long *nbr;  // [ns] balls touching ball i
@@ -108,6 +109,11 @@ struct NtRenderArgs {
     double cam[12];    // eye p00 dx dy
     float camf[12];    // the same in binary32 (primary-ray culling cone only)
     float dxlen, dylen, cull_margin; // |dx|, |dy| rounded up; 1e-5 * (scene extent + |eye|)
+    // division-free tile arithmetic (nt_trace.cuh tile_origin / row_to_y): twx, twy, lanes are powers of two
+    uint32_t log2_twx, log2_twy, log2_lanes;
+    uint32_t band_magic; // ceil(2^32 / band_rows) (band_rows > 1)
+    uint32_t n_mul;      // ceil(65536 / n)
+    float inv_tiles_x;
     uint8_t *out;
     size_t stride;
     unsigned long long *counters; // [NT_COUNTER_SLOTS][NT_NCOUNTERS] + 1 (next warp tile / next sample id)

@@ -292,6 +292,25 @@ __device__ __forceinline__ unsigned long long lbuf_mask(const NtDevScene &s, uns
     return __ldg(s.lbuf + ((size_t)(l * 6u + face) * (unsigned)K + (unsigned)iv) * (unsigned)K + (unsigned)iu);
 }
 
+// ---- warp-tile coordinates without integer division (they are recomputed around every trace instead of
+// being kept live, and a 32-bit division is ~20 instructions) ----
+// tile -> (first pixel column, first owned row).  tile / tiles_x from a binary32 estimate + one fix-up step:
+// the quotient is a tile row < 2^16, so the estimate is off by at most one.
+__device__ __forceinline__ void tile_origin(const NtRenderArgs &a, unsigned tile, unsigned &px0, unsigned &vr0) {
+    unsigned ty = __float2uint_rz(__uint2float_rz(tile) * a.inv_tiles_x);
+    int r = (int)(tile - ty * a.tiles_x);
+    if (r < 0) { --ty; r += (int)a.tiles_x; }
+    else if (r >= (int)a.tiles_x) { ++ty; r -= (int)a.tiles_x; }
+    px0 = (unsigned)r << a.log2_twx;
+    vr0 = ty << a.log2_twy;
+}
+// owned (virtual) row -> image row.  vr < 2^16, so __umulhi(vr, ceil(2^32 / band_rows)) == vr / band_rows exactly.
+__device__ __forceinline__ unsigned row_to_y(const NtRenderArgs &a, unsigned vr) {
+    if (a.shard_count == 1) return vr;
+    const unsigned b = a.band_rows == 1 ? vr : __umulhi(vr, a.band_magic);
+    return (b * a.shard_count + a.shard_index) * a.band_rows + (vr - b * a.band_rows);
+}
+
 // Primary rays: the bounded primitives whose (dilated) bounding sphere meets a cone around one warp tile's
 // pixel frustum.  Every lane tests primitive `lane` (and `lane + 32`); a ballot makes the warp-uniform mask.
 // Binary32 on purpose (it runs once per 32 samples, a binary64 version cost 15 % of the kernel); everything is
@@ -305,7 +324,7 @@ __device__ __forceinline__ unsigned long long lbuf_mask(const NtDevScene &s, uns
 static __device__ __forceinline__ unsigned long long tile_mask(const NtDevScene &s, const NtRenderArgs &a, unsigned px0, unsigned ymin,
                                                                unsigned ymax1, unsigned lane) {
     const unsigned nb = s.ns + s.nt;
-    const unsigned long long all = low_bits(nb);
+    const unsigned long long all = s.all_bits;
     const float hx = 0.5f * (float)a.twx, hy = 0.5f * (float)(ymax1 - ymin);
     const float fxc = (float)px0 + hx, fyc = (float)ymin + hy;
     const float Dx = __fmaf_rn(a.camf[9], fyc, __fmaf_rn(a.camf[6], fxc, a.camf[3]));
@@ -499,7 +518,7 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
             if (hit_sphere<R>(q, o, d, c.eps, t)) { tb = t; best.kind = 0; best.idx = own; best.gid = own; mask = __ldg(s.nbr + own); }
             else mask &= ~(1ull << own);
         }
-        unsigned long long m = mask & low_bits(s.ns);
+        unsigned long long m = mask & s.sph_bits;
 #if NT_CULL_PAIR
         while (m) { // two candidates per iteration (independent chains interleave); row ns is a never-hit dummy
             const unsigned i0 = (unsigned)__ffsll((long long)m) - 1u;
@@ -552,7 +571,7 @@ __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, c
     const NtDevScene &s = *c.s;
     R t;
     if constexpr (!BVH) {
-        unsigned long long m = mask & low_bits(s.ns);
+        unsigned long long m = mask & s.sph_bits;
 #if NT_CULL_PAIR
         while (m) {
             const unsigned i0 = (unsigned)__ffsll((long long)m) - 1u;
@@ -621,7 +640,7 @@ __device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R
         R t;
         Hit h;
         bool descend = false;
-        const unsigned long long qmask = own == -2 ? *pmask : low_bits(s.ns + s.nt);
+        const unsigned long long qmask = own == -2 ? *pmask : s.all_bits;
         if (!nearest_hit<R, BVH, K>(c, o, d, qmask, own, t, h, k)) {
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) NT_ACC(ch) = NT_ACC(ch) + *Wp * __ldg(v.globals + 3 + ch);
@@ -668,7 +687,7 @@ __device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R
                 const R ndl = dot(N, L);
                 if (!(ndl > R(0))) continue;
                 k.shadow++;
-                const unsigned long long lmask = s.cull ? lbuf_mask<R>(s, l, Lv) : low_bits(s.ns + s.nt);
+                const unsigned long long lmask = s.cull ? lbuf_mask<R>(s, l, Lv) : s.all_bits;
                 if (occluded<R, BVH, K>(c, P, L, dist, lmask, k)) continue;
                 k.light++;
                 R m0[4], m1[4];
@@ -853,13 +872,12 @@ render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRe
         R sum[3] = { R(0), R(0), R(0) };
         const unsigned rounds = SINGLE ? 1u : a.spp / a.lanes;
         if constexpr (!BVH) {
-            unsigned long long pm = low_bits(s.ns + s.nt);
+            unsigned long long pm = s.all_bits;
             if (s.cull) {
-                const unsigned px0 = (tile % a.tiles_x) * a.twx, vr0 = (tile / a.tiles_x) * a.twy;
+                unsigned px0, vr0;
+                tile_origin(a, tile, px0, vr0);
                 const unsigned vr1 = min(vr0 + a.twy, a.vrows) - 1; // first / last owned row of the tile -> image rows
-                const unsigned y0 = ((vr0 / a.band_rows) * a.shard_count + a.shard_index) * a.band_rows + vr0 % a.band_rows;
-                const unsigned y1 = ((vr1 / a.band_rows) * a.shard_count + a.shard_index) * a.band_rows + vr1 % a.band_rows;
-                pm = tile_mask(s, a, px0, y0, y1 + 1, lane);
+                pm = tile_mask(s, a, px0, row_to_y(a, vr0), row_to_y(a, vr1) + 1, lane);
             }
             __syncwarp();
             if (lane == 0) s_pmask[tid >> 5] = pm;
@@ -867,15 +885,17 @@ render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRe
         }
         for (unsigned r = 0; r < rounds; ++r) {
             {
-                const unsigned L = a.lanes, j = lane & (L - 1), pw = lane / L;
-                const unsigned px = (tile % a.tiles_x) * a.twx + pw % a.twx;
-                const unsigned vr = (tile / a.tiles_x) * a.twy + pw / a.twx;
+                const unsigned L = a.lanes, j = lane & (L - 1), pw = lane >> a.log2_lanes;
+                unsigned px, vr;
+                tile_origin(a, tile, px, vr);
+                px += pw & (a.twx - 1);
+                vr += pw >> a.log2_twx;
                 NT_ACC(0) = R(0); NT_ACC(1) = R(0); NT_ACC(2) = R(0);
                 if (px < a.width && vr < a.vrows) {
-                    const unsigned y = ((vr / a.band_rows) * a.shard_count + a.shard_index) * a.band_rows + vr % a.band_rows;
+                    const unsigned y = row_to_y(a, vr);
                     // SPEC §2: regular n x n grid, sample s = r*L + j
                     const unsigned sidx = r * L + j;
-                    const unsigned si = sidx % a.n, sj = sidx / a.n;
+                    const unsigned sj = (sidx * a.n_mul) >> 16, si = sidx - sj * a.n; // sidx / n, sidx % n (sidx < 64, n <= 8)
                     const R rn = (R)a.n;
                     const R ox = Math<R>::div((R)si + R(0.5), rn), oy = Math<R>::div((R)sj + R(0.5), rn);
                     const R fx = (R)px + ox, fy = (R)y + oy;
@@ -906,11 +926,13 @@ render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRe
             }
         }
         {
-            const unsigned L = a.lanes, j = lane & (L - 1), pw = lane / L;
-            const unsigned px = (tile % a.tiles_x) * a.twx + pw % a.twx;
-            const unsigned vr = (tile / a.tiles_x) * a.twy + pw / a.twx;
+            const unsigned L = a.lanes, j = lane & (L - 1), pw = lane >> a.log2_lanes;
+            unsigned px, vr;
+            tile_origin(a, tile, px, vr);
+            px += pw & (a.twx - 1);
+            vr += pw >> a.log2_twx;
             if (px < a.width && vr < a.vrows && j == 0) {
-                const unsigned y = ((vr / a.band_rows) * a.shard_count + a.shard_index) * a.band_rows + vr % a.band_rows;
+                const unsigned y = row_to_y(a, vr);
                 const R inv_spp = Math<R>::rcp((R)a.spp);
                 unsigned rgba = 0xff000000u;
 #pragma unroll
@@ -950,7 +972,7 @@ trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtTra
     Counters k = { 0, 0, 0, 0, 0, 0, 0, 0 };
     R t;
     Hit h;
-    if (nearest_hit<R, BVH, Counters>(c, o, d, low_bits(s.ns + s.nt), -1, t, h, k)) {
+    if (nearest_hit<R, BVH, Counters>(c, o, d, s.all_bits, -1, t, h, k)) {
         a.t_out[i] = (double)t;
         a.prim_out[i] = h.gid;
     } else {
