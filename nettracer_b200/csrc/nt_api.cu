@@ -74,6 +74,8 @@ struct nt_scene {
     double bvh_build_ms = 0;
     void *d_samples = nullptr; // BVH scenes: per-sample radiance scratch
     size_t samples_bytes = 0;
+    void *d_wf = nullptr;      // BVH scenes: wavefront workspace (level records of one chunk of samples)
+    size_t wf_bytes = 0;
     std::mutex mu;
 };
 
@@ -128,6 +130,7 @@ extern "C" void nt_scene_destroy(nt_scene *sc) {
     for (void *p : sc->allocs) cudaFree(p);
     if (sc->d_fb) cudaFree(sc->d_fb);
     if (sc->d_samples) cudaFree(sc->d_samples);
+    if (sc->d_wf) cudaFree(sc->d_wf);
     if (sc->d_counters) cudaFree(sc->d_counters);
     if (sc->h_counters) cudaFreeHost(sc->h_counters);
     if (sc->ev0) cudaEventDestroy(sc->ev0);
@@ -434,6 +437,27 @@ static int launch(nt_scene *sc, NtRenderArgs &a, uint32_t precision, cudaStream_
         sc->samples_bytes = need;
     }
     a.samples = sc->d_samples;
+    // BVH scenes render through the wavefront pipeline (nt_wavefront.cuh) unless NT_WAVEFRONT=0, the trees are deeper
+    // than NT_WF_MAX_DEPTH or the scene has more than 32 lights; the frame is cut into chunks that fit the workspace
+    // (NT_WF_MB megabytes at most, default 16384)
+    a.wf = nullptr; a.wf_bytes = 0;
+    {
+        const char *e_on = getenv("NT_WAVEFRONT"), *e_mb = getenv("NT_WF_MB"); // read per launch: tests toggle them
+        const bool on = !(e_on && e_on[0] == '0');
+        const size_t budget = (size_t)(e_mb && atoll(e_mb) > 0 ? atoll(e_mb) : 16384) << 20;
+        size_t want = on ? nt_wavefront_bytes(sc->ds, a, (int)precision) : 0;
+        if (want) {
+            if (want > budget) want = budget;
+            if (want > sc->wf_bytes) {
+                if (sc->d_wf) cudaFree(sc->d_wf);
+                sc->d_wf = nullptr; sc->wf_bytes = 0;
+                cudaError_t e = cudaMalloc(&sc->d_wf, want);
+                if (e != cudaSuccess) return fail(NT_ERR_NOMEM, "wavefront workspace cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+                sc->wf_bytes = want;
+            }
+            a.wf = sc->d_wf; a.wf_bytes = want;
+        }
+    }
     a.cull_margin = 1e-5f * (a.cull_margin + sc->ds.max_abs);
     const int e = precision == NT_F64_STRICT ? nt_launch_render_f64(sc->ds, a, st) : nt_launch_render_f32(sc->ds, a, st);
     if (e) return fail(NT_ERR_CUDA, "render kernel launch: %s", cudaGetErrorString((cudaError_t)e));

@@ -15,7 +15,7 @@
 #define NT_MIN_BLOCKS_F64 4 // resident blocks/SM the flat render kernel is compiled for (64 registers); measured
 #endif                      // on configs[2] strict: 2 -> 1.55 ms, 3 -> 1.35 ms, 4 -> 1.30 ms, 5 -> 1.40 ms
 #ifndef NT_MIN_BLOCKS_F32
-#define NT_MIN_BLOCKS_F32 3 // fast mode: 3 -> 0.72 ms, 4 -> 0.74 ms
+#define NT_MIN_BLOCKS_F32 4 // fast mode with culling: 3 -> 0.68 ms, 4 -> 0.61 ms (before culling: 3 -> 0.72, 4 -> 0.74)
 #endif
 #define NT_BVH_STACK 96     // entries; a 4-wide node pushes up to 3: scene creation checks 3*depth + 4 <= this
 #ifndef NT_COUNTERS_SMEM
@@ -118,6 +118,8 @@ struct NtRenderArgs {
     size_t stride;
     unsigned long long *counters; // [NT_COUNTER_SLOTS][NT_NCOUNTERS] + 1 (next warp tile / next sample id)
     void *samples;                // BVH scenes: per-sample radiance, R[3] each (see nt_bvh_trace.cuh)
+    void *wf;                     // BVH scenes: wavefront workspace (nt_wavefront.cuh); NULL = per-lane state machine
+    size_t wf_bytes;
 };
 
 struct NtTraceArgs {
@@ -135,3 +137,5 @@ int nt_launch_trace_f64(const NtDevScene &s, const NtTraceArgs &a, void *stream)
 int nt_launch_trace_f32(const NtDevScene &s, const NtTraceArgs &a, void *stream);
 size_t nt_flat_smem_bytes(const NtDevScene &s, int precision);
 size_t nt_sample_buffer_bytes(const NtDevScene &s, const NtRenderArgs &a, int precision); // 0 for flat scenes
+// Wavefront workspace that holds the whole frame in one chunk (0: the scene / parameters do not use the wavefront path)
+size_t nt_wavefront_bytes(const NtDevScene &s, const NtRenderArgs &a, int precision);

@@ -16,3 +16,6 @@ size_t nt_sample_buffer_bytes(const NtDevScene &s, const NtRenderArgs &a, int pr
     const size_t n = (size_t)a.tiles_x * a.tiles_y * (a.spp / a.lanes) * 32;
     return n * 3 * (precision == 0 ? sizeof(double) : sizeof(float));
 }
+size_t nt_wavefront_bytes(const NtDevScene &s, const NtRenderArgs &a, int precision) {
+    return precision == 0 ? nt::wavefront_bytes<double>(s, a) : nt::wavefront_bytes<float>(s, a);
+}

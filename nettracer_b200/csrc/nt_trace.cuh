@@ -544,7 +544,27 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
 #endif
         k.sph += s.ns;
     }
-    if constexpr (!BVH) planes_nearest<R>(c, o, d, tb, best);
+    if constexpr (!BVH && sizeof(R) == 8) planes_nearest<R>(c, o, d, tb, best);
+    if constexpr (!BVH && sizeof(R) == 4) {
+        // fast mode: the quotient is two instructions, so the plain SPEC §3 form in index order, two planes per
+        // iteration and without branches around the division, beats the axis lists
+        unsigned i = 0;
+        for (; i + 2 <= s.np; i += 2) {
+            R q0[4], q1[4], dn0, num0, dn1, num1;
+            c.ld_pln(i, q0);
+            c.ld_pln(i + 1, q1);
+            plane_eval<R>(q0, 3, o, d, dn0, num0);
+            plane_eval<R>(q1, 3, o, d, dn1, num1);
+            if (plane_finish<R>(dn0, num0, c.eps, t) && t < tb) { tb = t; best.kind = 1; best.idx = (int)i; best.gid = (int)(s.ns + i); }
+            if (plane_finish<R>(dn1, num1, c.eps, t) && t < tb) { tb = t; best.kind = 1; best.idx = (int)i + 1; best.gid = (int)(s.ns + i + 1); }
+        }
+        if (i < s.np) {
+            R q[4], dn, num;
+            c.ld_pln(i, q);
+            plane_eval<R>(q, 3, o, d, dn, num);
+            if (plane_finish<R>(dn, num, c.eps, t) && t < tb) { tb = t; best.kind = 1; best.idx = (int)i; best.gid = (int)(s.ns + i); }
+        }
+    }
     k.pln += s.np;
     if constexpr (!BVH) {
         if (s.nt) { // uniform
@@ -597,8 +617,26 @@ __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, c
 #endif
         k.sph += s.ns;
     }
-    if constexpr (!BVH) {
+    if constexpr (!BVH && sizeof(R) == 8) {
         if (planes_occluded<R>(c, o, d, dist)) { k.pln += first_occluding_plane<R>(c, o, d, dist) + 1; return true; }
+    }
+    if constexpr (!BVH && sizeof(R) == 4) {
+        unsigned i = 0;
+        for (; i + 2 <= s.np; i += 2) {
+            R q0[4], q1[4], dn0, num0, dn1, num1;
+            c.ld_pln(i, q0);
+            c.ld_pln(i + 1, q1);
+            plane_eval<R>(q0, 3, o, d, dn0, num0);
+            plane_eval<R>(q1, 3, o, d, dn1, num1);
+            if (plane_finish<R>(dn0, num0, c.eps, t) && t < dist) { k.pln += i + 1; return true; }
+            if (plane_finish<R>(dn1, num1, c.eps, t) && t < dist) { k.pln += i + 2; return true; }
+        }
+        if (i < s.np) {
+            R q[4], dn, num;
+            c.ld_pln(i, q);
+            plane_eval<R>(q, 3, o, d, dn, num);
+            if (plane_finish<R>(dn, num, c.eps, t) && t < dist) { k.pln += i + 1; return true; }
+        }
     }
     k.pln += s.np;
     if constexpr (!BVH) {
@@ -993,6 +1031,7 @@ inline size_t flat_smem_bytes(const NtDevScene &s, bool bvh) {
 } // namespace nt
 
 #include "nt_bvh_trace.cuh"
+#include "nt_wavefront.cuh"
 
 namespace nt {
 
@@ -1013,11 +1052,20 @@ inline int launch_render_t(const NtDevScene &s, const NtRenderArgs &a, cudaStrea
     unsigned grid = (unsigned)(sms[dev] * blocks_per_sm[dev]);
     if (grid > (n_tiles + wpb - 1) / wpb) grid = (n_tiles + wpb - 1) / wpb;
     if (BVH) {
+        if (a.wf) return launch_wavefront<R>(s, a, st, sms[dev], blocks_per_sm[dev]);
         render_bvh_kernel<R><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
         resolve_kernel<R><<<dim3((a.width + 255) / 256, a.vrows), 256, 0, st>>>(a);
     } else if (a.spp == a.lanes) render_kernel<R, false, true><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
     else render_kernel<R, false, false><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
     return (int)cudaGetLastError();
+}
+
+// Whole-frame wavefront workspace; 0 when the wavefront path does not apply (flat scene, deep trees, > 32 lights).
+template <typename R>
+inline size_t wavefront_bytes(const NtDevScene &s, const NtRenderArgs &a) {
+    if (!s.use_bvh || a.max_depth > NT_WF_MAX_DEPTH || s.nl > 32) return 0;
+    const size_t n = (size_t)a.tiles_x * a.tiles_y * (a.spp / a.lanes) * 32;
+    return 256 + 256 * 8 * (size_t)a.max_depth + n * wf_bytes_per_sample<R>(a.max_depth);
 }
 
 template <typename R>

@@ -1,0 +1,454 @@
+// nt_wavefront.cuh — wavefront renderer for BVH scenes (BASELINE.json configs[3], [4]): the render loop as
+// per-bounce ray queues.  Same arithmetic as nt_bvh_trace.cuh / nt_trace.cuh (SPEC-PROVISIONAL §2-§5, same
+// operation order, so the strict mode stays bit-exact against the oracle), different schedule:
+//
+//   A frame is cut into chunks of S samples.  Tree level l = 1..max_depth of a chunk is a record array in heap
+//   layout: the node of sample i reached by the reflection/transmission choices `path` (l-1 bits, first choice
+//   in the top bit) is record (i << (l-1)) | path; its reflection child is record 2r, its transmission
+//   child 2r+1 of level l+1.  So no pointers are stored and the final sum can walk the tree in pre-order.
+//
+//   per level:  wf_trace<nearest>  persistent warps pull ray records from the level's task list (one atomicAdd
+//                                  per warp, ballot + popc prefix), traverse, write (t, primitive).  A lane that
+//                                  finishes pulls the next ray: no lane waits for another lane's shading.
+//               wf_trace<shadow>   tasks = (record, light): the lane rebuilds the hit point and the shadow ray,
+//                                  runs the any-hit query and sets the light's bit in the record when visible.
+//               wf_shade           one thread per record: Phong with the visibility bits, term = W * local,
+//                                  children written to level l+1 and appended to its task list (compacted with
+//                                  ballot/popc, one atomicAdd per warp).
+//   per chunk:  wf_sum             one thread per sample: adds the terms of its tree in depth-first pre-order
+//                                  (SPEC §4), writes the per-sample radiance the resolve kernel consumes.
+//
+// In the per-lane state machine of nt_bvh_trace.cuh a warp's traversal runs at ~13 of 32 lanes (lanes park
+// while others finish, and shading interleaves with traversal); here traversal, shadow and shading are
+// separate coherent passes.  The price is the record traffic (~100 B per tree node), a few percent of HBM
+// bandwidth at the ray rates this path reaches.
+#pragma once
+#include "nt_bvh_trace.cuh"
+
+#define NT_WF_MAX_DEPTH 6  // deeper trees use the per-lane state machine (heap layout: 2^depth - 1 records per sample)
+#ifndef NT_WF_REFILL
+#define NT_WF_REFILL 8     // idle lanes before a warp pulls new tasks
+#endif
+
+struct NtWfLevel {
+    void *ray;            // R[7][cap]: ox oy oz dx dy dz W   (levels >= 2; level 1 rays come from the camera)
+    void *hit_t;          // R[cap]
+    int *prim;            // kind << 28 | idx, -1 miss, -2 no ray
+    unsigned *vis;        // bit l: light l faces the surface and is not occluded
+    void *term;           // R[3][cap]: W * local (or W * background)
+    unsigned char *kids;  // bit 0 reflection child, bit 1 transmission child
+    unsigned *tasks;      // record indices with a ray at this level (level >= 2)
+    unsigned cap;
+};
+struct NtWfArgs {
+    NtWfLevel lv[NT_WF_MAX_DEPTH];
+    unsigned *counts;             // [NT_WF_MAX_DEPTH + 1] tasks per level (level 1: samples of the chunk)
+    unsigned long long *fetch;    // [2 * NT_WF_MAX_DEPTH] task-fetch cursors (nearest, shadow) per level
+    unsigned sid0, n_samples;     // this chunk: first sample id, sample count
+    unsigned level;               // 1-based
+};
+
+namespace nt {
+
+template <typename R> struct WfHit {
+    V3<R> P, Ng;
+    int mat;
+};
+// Hit point and geometric normal of a record (SPEC §4), exactly as lane_advance computes them.
+template <typename R>
+__device__ __forceinline__ WfHit<R> wf_hit(const Ctx<R, true> &c, const V3<R> &o, const V3<R> &d, R t, int prim) {
+    const NtDevScene &s = *c.s;
+    const NtSceneView<R> &v = *c.v;
+    WfHit<R> h;
+    h.P = { o.x + d.x * t, o.y + d.y * t, o.z + d.z * t };
+    const int kind = prim >> 28, idx = prim & 0x0fffffff;
+    if (kind == 0) {
+        R p[4];
+        c.ld_sph(idx, p);
+        const R ir = __ldg(v.sph_invr + idx);
+        h.Ng = { (h.P.x - p[0]) * ir, (h.P.y - p[1]) * ir, (h.P.z - p[2]) * ir };
+        h.mat = __ldg(s.sph_mat + idx);
+    } else if (kind == 1) {
+        R p[4];
+        c.ld_pln(idx, p);
+        h.Ng = { p[0], p[1], p[2] };
+        h.mat = __ldg(s.pln_mat + idx);
+    } else {
+        const R *tp = v.tri + (size_t)idx * NT_TRI_STRIDE + 9;
+        h.Ng = { __ldg(tp), __ldg(tp + 1), __ldg(tp + 2) };
+        h.mat = __ldg(s.tri_mat + idx);
+    }
+    return h;
+}
+
+// The ray of a record: level 1 from the camera (SPEC §2), deeper levels from the record array.
+template <typename R>
+__device__ __forceinline__ bool wf_ray(const NtRenderArgs &a, const NtWfArgs &w, unsigned rec, V3<R> &o, V3<R> &d, R &W) {
+    const NtWfLevel &L = w.lv[w.level - 1];
+    if (w.level == 1) {
+        const SampleMap m = map_sample(a, w.sid0 + rec);
+        if (!m.live) return false;
+        const R rn = (R)a.n;
+        const unsigned si = m.sidx % a.n, sj = m.sidx / a.n;
+        const R ox = Math<R>::div((R)si + R(0.5), rn), oy = Math<R>::div((R)sj + R(0.5), rn);
+        const R fx = (R)m.px + ox, fy = (R)m.y + oy;
+        const V3<R> D = { ((R)a.cam[3] + (R)a.cam[6] * fx) + (R)a.cam[9] * fy,
+                          ((R)a.cam[4] + (R)a.cam[7] * fx) + (R)a.cam[10] * fy,
+                          ((R)a.cam[5] + (R)a.cam[8] * fx) + (R)a.cam[11] * fy };
+        o = { (R)a.cam[0], (R)a.cam[1], (R)a.cam[2] };
+        d = scale(D, Math<R>::rcp(Math<R>::sqrt_(dot(D, D))));
+        W = R(1);
+        return true;
+    }
+    const R *ray = (const R *)L.ray;
+    const size_t cap = L.cap;
+    o = { ray[rec], ray[cap + rec], ray[2 * cap + rec] };
+    d = { ray[3 * cap + rec], ray[4 * cap + rec], ray[5 * cap + rec] };
+    W = ray[6 * cap + rec];
+    return true;
+}
+
+// Persistent traversal kernel.  SHADOW == false: one task = one record, nearest hit.  SHADOW == true: one task =
+// (record, light), any hit between the hit point and the light.
+template <typename R, bool SHADOW>
+__global__ void __launch_bounds__(NT_BLOCK_THREADS, NT_MIN_BLOCKS_BVH)
+wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRenderArgs a, const __grid_constant__ NtWfArgs w) {
+    __shared__ unsigned long long s_cnt[NT_NCOUNTERS];
+    const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
+    Ctx<R, true> c;
+    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.max_depth = a.max_depth;
+    stage_scene<R, true>(s, v, c);
+    const unsigned lane = threadIdx.x & 31;
+    const NtWfLevel &L = w.lv[w.level - 1];
+    const unsigned n_rec = w.level == 1 ? w.n_samples : w.counts[w.level];
+    const unsigned long long n_tasks = SHADOW ? (unsigned long long)n_rec * s.nl : n_rec;
+    unsigned long long *cursor = w.fetch + 2 * (w.level - 1) + (SHADOW ? 1 : 0);
+    Counters k = { 0, 0, 0, 0, 0, 0, 0, 0 };
+
+    BvhQuery<R> q;
+    int2 bstack[NT_BVH_STACK];
+    q.done = true; q.cur = NT_REF_EMPTY; q.sp = 0; q.found = false; q.any = SHADOW;
+    bool active = false, exhausted = false;
+    unsigned rec = 0, light = 0;
+
+    for (;;) {
+        // ---- refill: idle lanes pull tasks, one atomic per warp ----
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (!exhausted && (__popc(idle) >= NT_WF_REFILL || idle == 0xffffffffu)) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(cursor, (unsigned long long)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + __popc(idle) >= n_tasks) exhausted = true;
+            if (!active) {
+                const unsigned long long ti = base + __popc(idle & ((1u << lane) - 1));
+                if (ti < n_tasks) {
+                    if constexpr (!SHADOW) {
+                        rec = w.level == 1 ? (unsigned)ti : L.tasks[ti];
+                        V3<R> o, d;
+                        R W;
+                        if (wf_ray<R>(a, w, rec, o, d, W)) {
+                            if (w.level == 1) k.prim++;
+                            query_start<R>(c, q, o, d, Math<R>::inf(), false, k);
+                            active = true;
+                        } else {
+                            L.prim[rec] = -2;
+                        }
+                    } else {
+                        const unsigned ri = (unsigned)(ti / s.nl);
+                        light = (unsigned)(ti - (unsigned long long)ri * s.nl);
+                        rec = w.level == 1 ? ri : L.tasks[ri];
+                        const int prim = L.prim[rec];
+                        if (prim >= 0) {
+                            V3<R> o, d;
+                            R W;
+                            wf_ray<R>(a, w, rec, o, d, W);
+                            const WfHit<R> h = wf_hit<R>(c, o, d, ((const R *)L.hit_t)[rec], prim);
+                            const bool entering = dot(d, h.Ng) < R(0);
+                            const V3<R> N = entering ? h.Ng : V3<R>{ -h.Ng.x, -h.Ng.y, -h.Ng.z };
+                            const R *lp = v.lights + 6 * light;
+                            const V3<R> Lv = { __ldg(lp) - h.P.x, __ldg(lp + 1) - h.P.y, __ldg(lp + 2) - h.P.z };
+                            const R d2 = dot(Lv, Lv);
+                            const R dist = Math<R>::sqrt_(d2);
+                            const V3<R> Ld = scale(Lv, Math<R>::rcp(dist));
+                            const R ndl = dot(N, Ld);
+                            if (ndl > R(0)) {
+                                k.shadow++;
+                                query_start<R>(c, q, h.P, Ld, dist, true, k);
+                                active = true;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- traversal rounds (as in render_bvh_kernel) until enough lanes have finished ----
+        for (;;) {
+            for (;;) {
+                const bool inner = active && !q.done && q.cur >= 0;
+                const unsigned im = __ballot_sync(0xffffffffu, inner);
+                if (im == 0) break;
+                if (inner) query_inner_step<R>(c, q, bstack, k);
+                if (__popc(im) < NT_DESCEND_MIN &&
+                    __ballot_sync(0xffffffffu, active && !q.done && ref_is_leaf(q.cur)) != 0) break;
+            }
+            const bool leaf = active && !q.done && ref_is_leaf(q.cur);
+            if (leaf) query_leaf_step<R>(c, q, bstack, k);
+            const unsigned parked = __ballot_sync(0xffffffffu, !active || q.done);
+            if (parked == 0xffffffffu || (!exhausted && __popc(parked) >= NT_WF_REFILL)) break;
+        }
+        // ---- retire finished queries ----
+        if (active && q.done) {
+            if constexpr (!SHADOW) {
+                ((R *)L.hit_t)[rec] = q.tb;
+                L.prim[rec] = q.best.kind >= 0 ? (q.best.kind << 28) | q.best.idx : -1;
+                L.vis[rec] = 0u;
+            } else {
+                if (!q.found) atomicOr(L.vis + rec, 1u << light);
+            }
+            active = false;
+        }
+    }
+    flush_counters(k, a.counters, s_cnt);
+}
+
+// Shade one level: term = W * local (SPEC §4) and the children of every record that has a ray.
+template <typename R>
+__global__ void __launch_bounds__(NT_BLOCK_THREADS)
+wf_shade_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRenderArgs a, const __grid_constant__ NtWfArgs w) {
+    __shared__ unsigned long long s_cnt[NT_NCOUNTERS];
+    const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
+    Ctx<R, true> c;
+    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.max_depth = a.max_depth;
+    stage_scene<R, true>(s, v, c);
+    const NtWfLevel &L = w.lv[w.level - 1];
+    const unsigned n_rec = w.level == 1 ? w.n_samples : w.counts[w.level];
+    Counters k = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned stride = gridDim.x * blockDim.x;
+    // whole warps iterate together (the child append uses warp ballots)
+    for (unsigned base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_rec; base += stride) {
+        const unsigned i = base + lane;
+        bool refl = false, trans = false;
+        V3<R> P = { R(0), R(0), R(0) }, Rd = P, T = P;
+        R Wr = R(0), Wt = R(0);
+        unsigned rec = 0;
+        if (i < n_rec) {
+            rec = w.level == 1 ? i : L.tasks[i];
+            const int prim = L.prim[rec];
+            R *term = (R *)L.term;
+            const size_t cap = L.cap;
+            unsigned char kids = 0;
+            if (prim != -2) {
+                V3<R> o, d;
+                R W;
+                wf_ray<R>(a, w, rec, o, d, W);
+                if (prim < 0) {
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) term[ch * cap + rec] = W * __ldg(v.globals + 3 + ch);
+                } else {
+                    const WfHit<R> h = wf_hit<R>(c, o, d, ((const R *)L.hit_t)[rec], prim);
+                    P = h.P;
+                    const R *mp = v.mat + (size_t)h.mat * NT_MAT_STRIDE;
+                    R m0[4], m1[4];
+                    Ld<R>::g4(mp, m0);     // r g b ka
+                    Ld<R>::g4(mp + 4, m1); // kd ks shininess kr
+                    const bool entering = dot(d, h.Ng) < R(0);
+                    const V3<R> N = entering ? h.Ng : V3<R>{ -h.Ng.x, -h.Ng.y, -h.Ng.z };
+                    R local[3];
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) local[ch] = __ldg(v.globals + ch) * (m0[3] * m0[ch]);
+                    const unsigned vis = L.vis[rec];
+                    for (unsigned l = 0; l < s.nl; ++l) {
+                        if (!((vis >> l) & 1u)) continue;
+                        k.light++;
+                        const R *lp = v.lights + 6 * l;
+                        const V3<R> Lv = { __ldg(lp) - P.x, __ldg(lp + 1) - P.y, __ldg(lp + 2) - P.z };
+                        const R d2 = dot(Lv, Lv);
+                        const R dist = Math<R>::sqrt_(d2);
+                        const V3<R> Ld_ = scale(Lv, Math<R>::rcp(dist));
+                        const R ndl = dot(N, Ld_);
+                        const R lc[3] = { __ldg(lp + 3), __ldg(lp + 4), __ldg(lp + 5) };
+                        const R kdn = m1[0] * ndl;
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) local[ch] = local[ch] + lc[ch] * (m0[ch] * kdn);
+                        const R two = R(2) * ndl;
+                        const V3<R> Rv = { N.x * two - Ld_.x, N.y * two - Ld_.y, N.z * two - Ld_.z };
+                        const R rv = -dot(Rv, d);
+                        if (m1[1] > R(0) && rv > R(0)) {
+                            const R sterm = m1[1] * Math<R>::pow_(rv, m1[2]);
+#pragma unroll
+                            for (int ch = 0; ch < 3; ++ch) local[ch] = local[ch] + lc[ch] * sterm;
+                        }
+                    }
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) term[ch * cap + rec] = W * local[ch];
+                    if (w.level < a.max_depth) {
+                        R m2[4];
+                        Ld<R>::g4(mp + 8, m2); // kt ior inv_ior pad
+                        const R kr = m1[3], kt = m2[0];
+                        const R cosi = -dot(d, N);
+                        R wr = kr, wt = R(0);
+                        if (kt > R(0)) {
+                            const R eta = entering ? m2[2] : m2[1];
+                            const R kk = R(1) - (eta * eta) * (R(1) - cosi * cosi);
+                            if (kk < R(0)) wr = kr + kt;
+                            else {
+                                wt = kt;
+                                const R sterm = eta * cosi - Math<R>::sqrt_(kk);
+                                T = { d.x * eta + N.x * sterm, d.y * eta + N.y * sterm, d.z * eta + N.z * sterm };
+                            }
+                        }
+                        if (wt > R(0)) { k.sec++; trans = true; Wt = W * wt; }
+                        if (wr > R(0)) {
+                            k.sec++;
+                            refl = true; Wr = W * wr;
+                            const R two = R(2) * cosi;
+                            Rd = { d.x + N.x * two, d.y + N.y * two, d.z + N.z * two };
+                        }
+                        kids = (unsigned char)((refl ? 1 : 0) | (trans ? 2 : 0));
+                    }
+                }
+            }
+            L.kids[rec] = kids;
+        }
+        // ---- children -> level + 1 records (heap layout) and its compacted task list ----
+        if (w.level < a.max_depth) { // uniform
+            const NtWfLevel &C = w.lv[w.level];
+            const unsigned mr = __ballot_sync(0xffffffffu, refl), mt = __ballot_sync(0xffffffffu, trans);
+            const unsigned total = __popc(mr) + __popc(mt);
+            if (total) {
+                unsigned pos = 0;
+                if (lane == 0) pos = atomicAdd(w.counts + w.level + 1, total);
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                R *ray = (R *)C.ray;
+                const size_t cap = C.cap;
+                const unsigned below = (1u << lane) - 1;
+                if (refl) {
+                    const unsigned cr = 2 * rec;
+                    ray[cr] = P.x; ray[cap + cr] = P.y; ray[2 * cap + cr] = P.z;
+                    ray[3 * cap + cr] = Rd.x; ray[4 * cap + cr] = Rd.y; ray[5 * cap + cr] = Rd.z;
+                    ray[6 * cap + cr] = Wr;
+                    C.tasks[pos + __popc(mr & below)] = cr;
+                }
+                if (trans) {
+                    const unsigned cr = 2 * rec + 1;
+                    ray[cr] = P.x; ray[cap + cr] = P.y; ray[2 * cap + cr] = P.z;
+                    ray[3 * cap + cr] = T.x; ray[4 * cap + cr] = T.y; ray[5 * cap + cr] = T.z;
+                    ray[6 * cap + cr] = Wt;
+                    C.tasks[pos + __popc(mr) + __popc(mt & below)] = cr;
+                }
+            }
+        }
+    }
+    flush_counters(k, a.counters, s_cnt);
+}
+
+// Per sample: the terms of its ray tree added in depth-first pre-order, reflection subtree before transmission
+// subtree (SPEC §4), into a running sum that starts at 0.
+template <typename R>
+__global__ void __launch_bounds__(256)
+wf_sum_kernel(const __grid_constant__ NtRenderArgs a, const __grid_constant__ NtWfArgs w) {
+    R *samples = (R *)a.samples;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < w.n_samples; i += gridDim.x * blockDim.x) {
+        R acc[3] = { R(0), R(0), R(0) };
+        unsigned level = 1, path = 0;
+        unsigned pend[NT_WF_MAX_DEPTH]; // deferred transmission children: level << 16 | path  (path < 2^5)
+        int sp = 0;
+        if (w.lv[0].prim[i] != -2) {
+            for (;;) {
+                const NtWfLevel &L = w.lv[level - 1];
+                const unsigned rec = (i << (level - 1)) | path;
+                const R *term = (const R *)L.term;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) acc[ch] = acc[ch] + term[(size_t)ch * L.cap + rec];
+                const unsigned kids = L.kids[rec];
+                if ((kids & 3u) == 3u) pend[sp++] = (level + 1) << 16 | (2 * path + 1);
+                if (kids & 1u) { ++level; path = 2 * path; continue; }
+                if (kids & 2u) { ++level; path = 2 * path + 1; continue; }
+                if (sp == 0) break;
+                const unsigned e = pend[--sp];
+                level = e >> 16; path = e & 0xffffu;
+            }
+        }
+        R *dst = samples + 3 * (size_t)(w.sid0 + i);
+        dst[0] = acc[0]; dst[1] = acc[1]; dst[2] = acc[2];
+    }
+}
+
+// Bytes of workspace per sample for trees of depth D, and the layout of one chunk inside the workspace.
+template <typename R>
+inline size_t wf_bytes_per_sample(unsigned depth) {
+    size_t b = 0;
+    for (unsigned l = 1; l <= depth; ++l) {
+        const size_t per = (l >= 2 ? 7 * sizeof(R) : 0) + sizeof(R) + 4 + 4 + 3 * sizeof(R) + 1 + (l >= 2 ? 4 : 0);
+        b += per << (l - 1);
+    }
+    return b + 16; // slack for alignment
+}
+
+template <typename R>
+inline int launch_wavefront(const NtDevScene &s, const NtRenderArgs &a, cudaStream_t st, int sms, int blocks_per_sm) {
+    const unsigned depth = a.max_depth;
+    const unsigned n_sids = a.tiles_x * a.tiles_y * (a.spp / a.lanes) * 32;
+    const size_t header = 256;
+    if (a.wf_bytes <= header + 4096) return (int)cudaErrorInvalidValue;
+    size_t S = (a.wf_bytes - header - 256 * 8 * depth) / wf_bytes_per_sample<R>(depth);
+    S &= ~(size_t)31;
+    if (S > n_sids) S = n_sids;
+    const size_t max_s = ((size_t)1 << 31) >> (depth - 1); // record indices must fit 32 bits
+    if (S > max_s) S = max_s & ~(size_t)31;
+    if (S < 32) return (int)cudaErrorInvalidValue;
+
+    NtWfArgs w;
+    memset(&w, 0, sizeof w);
+    unsigned char *p = (unsigned char *)a.wf;
+    w.counts = (unsigned *)p;                                  // [NT_WF_MAX_DEPTH + 2]
+    w.fetch = (unsigned long long *)(p + 64);                  // [2 * NT_WF_MAX_DEPTH]
+    p += header;
+    auto take = [&](size_t bytes) { void *r = p; p += (bytes + 255) & ~(size_t)255; return r; };
+    for (unsigned l = 1; l <= depth; ++l) {
+        NtWfLevel &L = w.lv[l - 1];
+        const size_t cap = S << (l - 1);
+        L.cap = (unsigned)cap;
+        L.ray = l >= 2 ? take(7 * sizeof(R) * cap) : nullptr;
+        L.hit_t = take(sizeof(R) * cap);
+        L.term = take(3 * sizeof(R) * cap);
+        L.prim = (int *)take(4 * cap);
+        L.vis = (unsigned *)take(4 * cap);
+        L.tasks = l >= 2 ? (unsigned *)take(4 * cap) : nullptr;
+        L.kids = (unsigned char *)take(cap);
+    }
+    if ((size_t)(p - (unsigned char *)a.wf) > a.wf_bytes) return (int)cudaErrorInvalidValue;
+
+    const size_t smem = flat_smem_bytes<R>(s, true);
+    const unsigned grid_full = (unsigned)(sms * blocks_per_sm);
+    for (unsigned sid0 = 0; sid0 < n_sids; sid0 += (unsigned)S) {
+        w.sid0 = sid0;
+        w.n_samples = (unsigned)(n_sids - sid0 < S ? n_sids - sid0 : S);
+        cudaMemsetAsync(a.wf, 0, header, st);
+        for (unsigned l = 1; l <= depth; ++l) {
+            w.level = l;
+            // an upper bound of the level's records (the exact count lives on the device)
+            const size_t bound = (size_t)w.n_samples << (l - 1);
+            unsigned grid = grid_full;
+            const size_t warps_needed = (bound + 31) / 32, wpb = NT_BLOCK_THREADS / 32;
+            if (grid > (warps_needed + wpb - 1) / wpb) grid = (unsigned)((warps_needed + wpb - 1) / wpb);
+            wf_trace_kernel<R, false><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a, w);
+            if (s.nl) wf_trace_kernel<R, true><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a, w);
+            unsigned sgrid = (unsigned)(sms * 8);
+            if (sgrid > (bound + NT_BLOCK_THREADS - 1) / NT_BLOCK_THREADS) sgrid = (unsigned)((bound + NT_BLOCK_THREADS - 1) / NT_BLOCK_THREADS);
+            wf_shade_kernel<R><<<sgrid, NT_BLOCK_THREADS, smem, st>>>(s, a, w);
+        }
+        unsigned ggrid = (unsigned)(sms * 8);
+        if (ggrid > (w.n_samples + 255) / 256) ggrid = (w.n_samples + 255) / 256;
+        wf_sum_kernel<R><<<ggrid, 256, 0, st>>>(a, w);
+    }
+    resolve_kernel<R><<<dim3((a.width + 255) / 256, a.vrows), 256, 0, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+} // namespace nt

@@ -69,6 +69,42 @@ def test_bvh_equals_bruteforce_oracle(seed):
         assert st[k] == rst[k], k
 
 
+@pytest.mark.parametrize("mode", ["wavefront_chunked", "state_machine", "deep_trees"])
+def test_bvh_render_paths_agree(mode, monkeypatch):
+    """BVH scenes have two schedules of the same arithmetic: the wavefront pipeline (nt_wavefront.cuh; default,
+    here also with a workspace so small that the frame is cut into many chunks) and the per-lane state machine
+    (nt_bvh_trace.cuh; NT_WAVEFRONT=0, and always for trees deeper than 6).  All must equal the oracle bit for bit."""
+    depth = 4
+    if mode == "wavefront_chunked":
+        monkeypatch.setenv("NT_WF_MB", "3")
+    elif mode == "state_machine":
+        monkeypatch.setenv("NT_WAVEFRONT", "0")
+    else:
+        depth = 8
+    s, cam = scenes.random_mixed(150, 2, 300, seed=6)
+    img, st, ref, rst, info = render_both(s, cam, 200, 144, 4, depth)
+    assert info["uses_bvh"]
+    assert_images_match(img, ref, f"bvh {mode}")
+    for k in COUNTER_KEYS:
+        assert st[k] == rst[k], k
+
+
+def test_flat_culling_off_equals_on(monkeypatch):
+    """NT_CULL=0 renders flat scenes by brute force; the culled default must give the same image and counters."""
+    s, cam = scenes.random_mixed(12, 3, 20, seed=8)
+    p = make_params(200, 150, 4, 5, cam.resolve(200, 150), abi.NT_F64_STRICT)
+    with Renderer(s) as r:
+        assert r.info()["culling"]
+        img, st = r.render_params(p)
+    monkeypatch.setenv("NT_CULL", "0")
+    with Renderer(s) as r:
+        assert not r.info()["culling"]
+        img0, st0 = r.render_params(p)
+    assert np.array_equal(img, img0)
+    for k in COUNTER_KEYS + FLAT_TEST_KEYS:
+        assert st[k] == st0[k], k
+
+
 def test_mesh_scene_reduced_bvh():
     s, cam = scenes.spheres_and_mesh(n_spheres=2000, mesh_n=96)
     img, st, ref, rst, info = render_both(s, cam, 256, 144, 4, 3, accel=1)
