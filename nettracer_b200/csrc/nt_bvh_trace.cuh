@@ -109,8 +109,8 @@ template <typename R> __device__ __forceinline__ void query_pop(BvhQuery<R> &q, 
 }
 
 // One inner node of the 4-wide tree: 7 x 128-bit loads (near planes, far planes, refs), 4 slab tests as
-// 6 FMAs + max3/min3 each, then the hit children ordered by entry distance with a 4-key sorting network
-// on (t_near bits | slot): nearest visited next, the others pushed far-to-near.
+// 6 FMAs + max3/min3 each, then the nearest hit child (min over four (t_near bits | slot) keys) is visited next
+// and the other hit children are pushed with their entry distance.
 template <typename R>
 __device__ __forceinline__ void query_inner_step(const Ctx<R, true> &c, BvhQuery<R> &q, int2 *stack, Counters &k) {
     const float4 *n = (const float4 *)(c.s->nodes + q.cur);
@@ -131,17 +131,16 @@ __device__ __forceinline__ void query_inner_step(const Ctx<R, true> &c, BvhQuery
         const bool hit = ra[j] != NT_REF_EMPTY && tn <= tf && tn <= q.tmaxf;
         key[j] = hit ? ((__float_as_int(tn) & ~3) | j) : 0x7fffffff; // tn >= 0: integer order == float order
     }
-#define NT_CSWAP(a, b) { const int lo_ = min(key[a], key[b]), hi_ = max(key[a], key[b]); key[a] = lo_; key[b] = hi_; }
-    NT_CSWAP(0, 1) NT_CSWAP(2, 3) NT_CSWAP(0, 2) NT_CSWAP(1, 3) NT_CSWAP(1, 2)
-#undef NT_CSWAP
-    if (key[0] == 0x7fffffff) { query_pop(q, stack); return; }
+    // Next = the nearest hit child; the other hit children are pushed in slot order with their entry distance
+    // (a pop discards entries that start beyond the current bound).  A full sort of the four keys (the first
+    // version, a 5-exchange network) cost a third of this routine and saved only 1.4 % of the node visits on
+    // configs[3] (66.6 -> 63.1 ms without it); occlusion queries do not care about the order at all.
+    const int best = min(min(key[0], key[1]), min(key[2], key[3]));
+    if (best == 0x7fffffff) { query_pop(q, stack); return; }
+    const int slot = best & 3;
 #pragma unroll
-    for (int j = 3; j >= 1; --j)
-        if (key[j] != 0x7fffffff) {
-            const int slot = key[j] & 3;
-            stack[q.sp++] = make_int2(slot == 0 ? rf.x : slot == 1 ? rf.y : slot == 2 ? rf.z : rf.w, key[j] & ~3);
-        }
-    const int slot = key[0] & 3;
+    for (int j = 0; j < 4; ++j)
+        if (key[j] != 0x7fffffff && j != slot) stack[q.sp++] = make_int2(ra[j], key[j] & ~3);
     q.cur = slot == 0 ? rf.x : slot == 1 ? rf.y : slot == 2 ? rf.z : rf.w;
 }
 
