@@ -27,7 +27,7 @@
 
 #define NT_WF_MAX_DEPTH 6  // deeper trees use the per-lane state machine (heap layout: 2^depth - 1 records per sample)
 #ifndef NT_WF_REFILL
-#define NT_WF_REFILL 8     // idle lanes before a warp pulls new tasks
+#define NT_WF_REFILL 16    // idle lanes before a warp pulls new tasks (configs[3] f64: 4 -> 70.0 ms, 8 -> 69.8, 16 -> 62.5, 24 -> 62.7)
 #endif
 
 struct NtWfLevel {
@@ -121,7 +121,7 @@ wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
     const unsigned lane = threadIdx.x & 31;
     const NtWfLevel &L = w.lv[w.level - 1];
     const unsigned n_rec = w.level == 1 ? w.n_samples : w.counts[w.level];
-    const unsigned long long n_tasks = SHADOW ? (unsigned long long)n_rec * s.nl : n_rec;
+    const unsigned long long n_tasks = SHADOW ? (((unsigned long long)n_rec + 31) / 32) * 32 * s.nl : n_rec;
     unsigned long long *cursor = w.fetch + 2 * (w.level - 1) + (SHADOW ? 1 : 0);
     Counters k = { 0, 0, 0, 0, 0, 0, 0, 0 };
 
@@ -154,10 +154,17 @@ wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
                             L.prim[rec] = -2;
                         }
                     } else {
-                        const unsigned ri = (unsigned)(ti / s.nl);
-                        light = (unsigned)(ti - (unsigned long long)ri * s.nl);
+                        bool continue_task = true;
+                        // light-major inside groups of 32 records: the lanes of a warp get consecutive records and
+                        // the same light, i.e. coherent shadow rays
+                        const unsigned long long grp = ti / (32ull * s.nl);
+                        const unsigned within = (unsigned)(ti - grp * 32ull * s.nl);
+                        light = within >> 5;
+                        const unsigned long long ri64 = grp * 32ull + (within & 31u);
+                        if (ri64 >= n_rec) continue_task = false;
+                        const unsigned ri = (unsigned)(ri64 < n_rec ? ri64 : 0);
                         rec = w.level == 1 ? ri : L.tasks[ri];
-                        const int prim = L.prim[rec];
+                        const int prim = continue_task ? L.prim[rec] : -2;
                         if (prim >= 0) {
                             V3<R> o, d;
                             R W;
