@@ -306,15 +306,17 @@ def main():
 
     if rank == 0:
         strict = a.precision == "f64"
+        per_frame_launches = backend.renderer.info()["last_launches"]
         peak_gf = peaks["f64_nofma_gflops"] if strict else peaks["f32_fma_gflops"]
         achieved_tf = flops_local / (kernel_ms_local * 1e-3) / 1e12
         roof = {"bound": "fp64" if strict else "fp32", "achieved": achieved_tf, "peak": peak_gf / 1e3, "unit": "TFLOP/s",
                 "frac": achieved_tf / (peak_gf / 1e3),
-                "traffic": ({"cfg3_cornell_1080p_4spp_d5": 5.38e7}.get(a.workload) if strict else None),
-                "traffic_note": "dram read+write bytes of one render launch inside this bench (ncu --set full, "
-                                "profiles/r01_c_cfg3_f64_final.md): 1.2 MB read + 52.6 MB written, of which 8.3 MB is the "
-                                "frame and the rest dirty L2 lines of the 256 MiB flush; the kernel is not HBM bound (0.3 %)",
-                "kernel": "render_kernel<%s,%s>" % ("double" if strict else "float", "bvh" if info["uses_bvh"] else "flat"),
+                "traffic": ({"cfg3_cornell_1080p_4spp_d5": 9.215e7}.get(a.workload) if strict else None),
+                "traffic_note": "dram read+write bytes of one render launch (ncu --set full, profiles/r01c_cfg3_f64_final.md): "
+                                "2.5 MB read + 89.7 MB written, of which 8.3 MB is the frame and the rest evicted local-memory "
+                                "(spill) lines; 0.2 % of HBM bandwidth - the kernel is FP-issue bound, not HBM bound",
+                "kernel": ("wf_trace_kernel + wf_shade_kernel (wavefront pipeline, all kernels of a frame)" if info["uses_bvh"] and per_frame_launches > 2
+                           else "render_%skernel<%s>" % ("bvh_" if info["uses_bvh"] else "", "double" if strict else "float")),
                 "kernel_ms": kernel_ms_local, "algorithmic_flops_per_launch": flops_local,
                 "peak_source": "nt_measure_peaks in this process: " + ("FP64 mul/add issue rate without FMA (strict mode may not fuse)"
                                                                         if strict else "FP32 FMA issue rate"),
@@ -333,8 +335,10 @@ def main():
                 "e2e": {"value": e2e_val, "unit": METRIC, "ms_per_frame": e2e_ms, "h2d_bytes_per_step": C.sizeof(abi.nt_render_params),
                         "d2h_bytes_per_step": h * w * 4 + 8 * 8 * 32,
                         "api": "nt_render -> pinned host RGBA8" if world == 1 else "ShardedRenderer.render + D2H on rank 0"},
-                "gpu_launches": a.steps * ((2 if info["uses_bvh"] else 1) + (1 if sr.mode == "gather" and world > 1 else 0)),
-                "gpu_launches_note": "per frame and rank: render kernel (+ resolve kernel on BVH scenes, + deinterleave on rank 0 in gather mode)",
+                "gpu_launches": a.steps * (per_frame_launches + (1 if sr.mode == "gather" and world > 1 else 0)),
+                "gpu_launches_note": "per frame and rank, counted by the library (nt_scene_info): flat scenes 1 render kernel; BVH scenes "
+                                     "the wavefront pipeline's trace/shadow/shade kernels per level and chunk + sum + resolve "
+                                     "(or 2 with NT_WAVEFRONT=0); + deinterleave on rank 0 in gather mode",
                 "kernel_ms": kernel_ms, "wall_s_timed_region": wall, "clocks": clocks, "roofline": roof}
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_oracle_sample(scene, cam, w, h, spp, depth, a.cpu_seconds)

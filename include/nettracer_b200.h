@@ -111,7 +111,7 @@ int nt_scene_create(const nt_scene_desc *desc, int device, nt_scene **out);
 void nt_scene_destroy(nt_scene *scene);
 /* info[0] = bit 0 uses_bvh | bit 1 BVH built on the GPU (NT_BVH_BUILD=gpu) | bit 2 flat culling tables in use
  *           | bits 8.. BVH build time in us;
- * info[1] = 4-wide BVH nodes; info[2] = device bytes; info[3] = device */
+ * info[1] = 4-wide BVH nodes; info[2] = device bytes; info[3] = device | kernels launched by the last render call << 32 */
 int nt_scene_info(const nt_scene *scene, uint64_t info[4]);
 
 /* Diagnostic, host only (no GPU needed): the conservative culling tables nt_scene_create builds for a flat

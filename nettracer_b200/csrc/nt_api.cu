@@ -74,6 +74,7 @@ struct nt_scene {
     double bvh_build_ms = 0;
     void *d_samples = nullptr; // BVH scenes: per-sample radiance scratch
     size_t samples_bytes = 0;
+    unsigned last_launches = 0; // kernels launched by the last render call
     void *d_wf = nullptr;      // BVH scenes: wavefront workspace (level records of one chunk of samples)
     size_t wf_bytes = 0;
     std::mutex mu;
@@ -356,7 +357,7 @@ extern "C" int nt_cull_tables(const nt_scene_desc *desc, uint32_t *k_out, uint64
 extern "C" int nt_scene_info(const nt_scene *sc, uint64_t info[4]) {
     if (!sc || !info) return fail(NT_ERR_INVALID, "NULL argument");
     info[0] = (uint64_t)sc->ds.use_bvh | ((uint64_t)sc->bvh_on_gpu << 1) | ((uint64_t)sc->ds.cull << 2) | ((uint64_t)(sc->bvh_build_ms * 1000.0) << 8);
-    info[1] = sc->ds.n_nodes; info[2] = sc->device_bytes; info[3] = (uint64_t)sc->device;
+    info[1] = sc->ds.n_nodes; info[2] = sc->device_bytes; info[3] = (uint64_t)sc->device | ((uint64_t)sc->last_launches << 32);
     return NT_OK;
 }
 
@@ -437,6 +438,8 @@ static int launch(nt_scene *sc, NtRenderArgs &a, uint32_t precision, cudaStream_
         sc->samples_bytes = need;
     }
     a.samples = sc->d_samples;
+    sc->last_launches = 0;
+    a.n_launches = &sc->last_launches;
     // BVH scenes render through the wavefront pipeline (nt_wavefront.cuh) unless NT_WAVEFRONT=0, the trees are deeper
     // than NT_WF_MAX_DEPTH or the scene has more than 32 lights; the frame is cut into chunks that fit the workspace
     // (NT_WF_MB megabytes at most, default 16384)

@@ -118,6 +118,7 @@ struct NtRenderArgs {
     size_t stride;
     unsigned long long *counters; // [NT_COUNTER_SLOTS][NT_NCOUNTERS] + 1 (next warp tile / next sample id)
     void *samples;                // BVH scenes: per-sample radiance, R[3] each (see nt_bvh_trace.cuh)
+    unsigned *n_launches;         // host counter: kernels launched for this frame (may be NULL)
     void *wf;                     // BVH scenes: wavefront workspace (nt_wavefront.cuh); NULL = per-lane state machine
     size_t wf_bytes;
 };

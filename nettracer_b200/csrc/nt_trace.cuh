@@ -1055,8 +1055,11 @@ inline int launch_render_t(const NtDevScene &s, const NtRenderArgs &a, cudaStrea
         if (a.wf) return launch_wavefront<R>(s, a, st, sms[dev], blocks_per_sm[dev]);
         render_bvh_kernel<R><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
         resolve_kernel<R><<<dim3((a.width + 255) / 256, a.vrows), 256, 0, st>>>(a);
+        if (a.n_launches) *a.n_launches += 2;
+        return (int)cudaGetLastError();
     } else if (a.spp == a.lanes) render_kernel<R, false, true><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
     else render_kernel<R, false, false><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
+    if (a.n_launches) *a.n_launches += 1;
     return (int)cudaGetLastError();
 }
 

@@ -446,6 +446,7 @@ inline int launch_wavefront(const NtDevScene &s, const NtRenderArgs &a, cudaStre
             if (grid > (warps_needed + wpb - 1) / wpb) grid = (unsigned)((warps_needed + wpb - 1) / wpb);
             wf_trace_kernel<R, false><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a, w);
             if (s.nl) wf_trace_kernel<R, true><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a, w);
+            if (a.n_launches) *a.n_launches += s.nl ? 3 : 2;
             unsigned sgrid = (unsigned)(sms * 8);
             if (sgrid > (bound + NT_BLOCK_THREADS - 1) / NT_BLOCK_THREADS) sgrid = (unsigned)((bound + NT_BLOCK_THREADS - 1) / NT_BLOCK_THREADS);
             wf_shade_kernel<R><<<sgrid, NT_BLOCK_THREADS, smem, st>>>(s, a, w);
@@ -453,8 +454,10 @@ inline int launch_wavefront(const NtDevScene &s, const NtRenderArgs &a, cudaStre
         unsigned ggrid = (unsigned)(sms * 8);
         if (ggrid > (w.n_samples + 255) / 256) ggrid = (w.n_samples + 255) / 256;
         wf_sum_kernel<R><<<ggrid, 256, 0, st>>>(a, w);
+        if (a.n_launches) *a.n_launches += 1;
     }
     resolve_kernel<R><<<dim3((a.width + 255) / 256, a.vrows), 256, 0, st>>>(a);
+    if (a.n_launches) *a.n_launches += 1;
     return (int)cudaGetLastError();
 }
 

@@ -43,7 +43,8 @@ class Renderer:
         check(self._lib.nt_scene_info(self._h, a))
         return {"uses_bvh": bool(a[0] & 1), "bvh_on_gpu": bool(a[0] & 2), "culling": bool(a[0] & 4),
                 "bvh_build_ms": (int(a[0]) >> 8) / 1000.0,
-                "bvh_nodes": int(a[1]), "device_bytes": int(a[2]), "device": int(a[3])}
+                "bvh_nodes": int(a[1]), "device_bytes": int(a[2]), "device": int(a[3]) & 0xffffffff,
+                "last_launches": int(a[3]) >> 32}
 
     # -- host path --
     def render_params(self, params: abi.nt_render_params, out: np.ndarray | None = None):
