@@ -414,6 +414,8 @@ static int make_args(const nt_render_params *p, size_t stride, NtRenderArgs *a) 
         a->cam[6 + k] = p->camera.dx[k]; a->cam[9 + k] = p->camera.dy[k];
     }
     a->stride = stride;
+    for (uint32_t i = 0; i < n; ++i) a->samp_off[i] = ((double)i + 0.5) / (double)n;
+    a->inv_spp = 1.0 / (double)p->spp;
     // binary32 copy of the camera for the primary-ray culling cone (nt_trace.cuh tile_mask); lengths rounded up
     double len[2] = { 0, 0 }, eye_inf = 0;
     for (int k = 0; k < 12; ++k) a->camf[k] = (float)a->cam[k];

@@ -107,6 +107,8 @@ struct NtRenderArgs {
     uint32_t tiles_x, tiles_y; // warp tiles over the virtual image (owned rows only)
     double eps;
     double cam[12];    // eye p00 dx dy
+    double samp_off[8]; // SPEC §2 sample offsets (i + 0.5) / n, i < n
+    double inv_spp;     // 1 / spp
     float camf[12];    // the same in binary32 (primary-ray culling cone only)
     float dxlen, dylen, cull_margin; // |dx|, |dy| rounded up; 1e-5 * (scene extent + |eye|)
     // division-free tile arithmetic (nt_trace.cuh tile_origin / row_to_y): twx, twy, lanes are powers of two

@@ -934,8 +934,7 @@ render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRe
                     // SPEC §2: regular n x n grid, sample s = r*L + j
                     const unsigned sidx = r * L + j;
                     const unsigned sj = (sidx * a.n_mul) >> 16, si = sidx - sj * a.n; // sidx / n, sidx % n (sidx < 64, n <= 8)
-                    const R rn = (R)a.n;
-                    const R ox = Math<R>::div((R)si + R(0.5), rn), oy = Math<R>::div((R)sj + R(0.5), rn);
+                    const R ox = (R)a.samp_off[si], oy = (R)a.samp_off[sj]; // (i + 0.5) / n, divided on the host (IEEE, same value)
                     const R fx = (R)px + ox, fy = (R)y + oy;
                     const V3<R> D = { ((R)a.cam[3] + (R)a.cam[6] * fx) + (R)a.cam[9] * fy,
                                       ((R)a.cam[4] + (R)a.cam[7] * fx) + (R)a.cam[10] * fy,
@@ -971,7 +970,7 @@ render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRe
             vr += pw >> a.log2_twx;
             if (px < a.width && vr < a.vrows && j == 0) {
                 const unsigned y = row_to_y(a, vr);
-                const R inv_spp = Math<R>::rcp((R)a.spp);
+                const R inv_spp = (R)a.inv_spp; // 1 / spp, divided on the host
                 unsigned rgba = 0xff000000u;
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
