@@ -56,7 +56,23 @@ template <> struct Math<double> {
 #ifdef NT_EXP_NOPOW
     static __device__ __forceinline__ double pow_(double a, double b) { return a * b; }
 #else
-    static __device__ __forceinline__ double pow_(double a, double b) { return pow(a, b); }
+    // SPEC §0: `pow` is the one operation that may differ from the oracle's libm in the last bits.  Integer
+    // exponents (every shininess of the benchmark scenes) go through square-and-multiply: <= 20 roundings,
+    // relative error < 3e-15, ~30 instructions executed instead of libdevice pow's ~150 (which also was 2.4 KB of
+    // the strict kernel's hot code); anything else takes libdevice's pow.
+    static __device__ __forceinline__ double pow_(double a, double b) {
+        const int n = (int)b;
+        if ((double)n == b && n >= 1 && n <= 1024) {
+            double r = (n & 1) ? a : 1.0, x = a;
+#pragma unroll 1
+            for (int e = n >> 1; e; e >>= 1) {
+                x = x * x;
+                if (e & 1) r = r * x;
+            }
+            return r;
+        }
+        return pow(a, b);
+    }
 #endif
     static __device__ __forceinline__ float up(double x) { return __double2float_ru(x); }
     static __device__ __forceinline__ double inf() { return CUDART_INF; }
@@ -418,10 +434,11 @@ __device__ __forceinline__ void planes_nearest(const Ctx<R, false> &c, const V3<
     const NtDevScene &s = *c.s;
     R tm1 = plane_bound<R>(tb);
     unsigned addr = c.axl_addr;
-#pragma unroll 1
-    for (int k = 0; k < 3; ++k) { // one copy of the body: the kernel has to stay inside the instruction cache
+    const R oo[3] = { o.x, o.y, o.z }, dd[3] = { d.x, d.y, d.z };
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { // unrolled over the axes (no selects, list lengths straight from the constant bank)
         const unsigned n = s.nax[k];
-        const R ok = k == 0 ? o.x : (k == 1 ? o.y : o.z), dk = k == 0 ? d.x : (k == 1 ? d.y : d.z);
+        const R ok = oo[k], dk = dd[k];
         R bk = fabs(dk) * tm1;
 #pragma unroll 1
         for (unsigned j = 0; j < n; ++j, addr += 2u * (unsigned)sizeof(R)) {
@@ -457,10 +474,11 @@ __device__ __forceinline__ bool planes_occluded(const Ctx<R, false> &c, const V3
     const NtDevScene &s = *c.s;
     const R dm1 = plane_bound<R>(dist);
     unsigned addr = c.axl_addr;
-#pragma unroll 1
+    const R oo[3] = { o.x, o.y, o.z }, dd[3] = { d.x, d.y, d.z };
+#pragma unroll
     for (int k = 0; k < 3; ++k) {
         const unsigned n = s.nax[k];
-        const R ok = k == 0 ? o.x : (k == 1 ? o.y : o.z), dk = k == 0 ? d.x : (k == 1 ? d.y : d.z), bk = fabs(dk) * dm1;
+        const R ok = oo[k], dk = dd[k], bk = fabs(dk) * dm1;
 #pragma unroll 1
         for (unsigned j = 0; j < n; ++j, addr += 2u * (unsigned)sizeof(R)) {
             R p, t;
@@ -846,7 +864,7 @@ __device__ __forceinline__ void flush_counter_values(const unsigned vals[NT_NCOU
                                                      unsigned long long *s_cnt) {
     if (threadIdx.x < NT_NCOUNTERS) s_cnt[threadIdx.x] = 0;
     __syncthreads();
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < NT_NCOUNTERS; ++i) {
         const unsigned w = __reduce_add_sync(0xffffffffu, vals[i]);
         if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_cnt[i], (unsigned long long)w);
