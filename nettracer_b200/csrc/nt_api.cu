@@ -147,10 +147,10 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
 
     // flat (everything staged in shared memory) or BVH (bounded primitives in HBM behind a tree)
     bool use_bvh = ns + nt > kFlatMaxBounded ||
-                   (((size_t)ns + 1) * 4 + (size_t)np * 7 + (size_t)nt * NT_TRI_STRIDE) * sizeof(double) > kSmemBudget;
+                   ((size_t)ns * 4 + (size_t)np * 7 + (size_t)nt * NT_TRI_STRIDE) * sizeof(double) > kSmemBudget;
     if (const char *e = getenv("NT_BVH")) {
         if (e[0] == '1') use_bvh = true;
-        else if (e[0] == '0' && ns + nt <= kFlatMaxBounded && (((size_t)ns + 1) * 4 + (size_t)np * 7 + (size_t)nt * NT_TRI_STRIDE) * sizeof(double) <= kSmemBudget) use_bvh = false;
+        else if (e[0] == '0' && ns + nt <= kFlatMaxBounded && ((size_t)ns * 4 + (size_t)np * 7 + (size_t)nt * NT_TRI_STRIDE) * sizeof(double) <= kSmemBudget) use_bvh = false;
     }
     if (ns >= (1u << 26) || nt >= (1u << 26)) return fail(NT_ERR_INVALID, "more than 2^26 spheres or triangles");
     if ((size_t)np * 4 * sizeof(double) > kSmemBudget) return fail(NT_ERR_INVALID, "too many planes (%u): planes are staged in shared memory, limit %zu", np, kSmemBudget / 32);

@@ -21,9 +21,6 @@
 #ifndef NT_COUNTERS_SMEM
 #define NT_COUNTERS_SMEM 0   // flat render kernel: work counters in per-thread shared-memory slots instead of registers
 #endif
-#ifndef NT_CULL_PAIR
-#define NT_CULL_PAIR 0      // flat scenes: candidate spheres two per iteration (the second one a never-hit dummy row when
-#endif                      // a lane has an odd number left) instead of one
 #ifndef NT_MIN_BLOCKS_BVH
 #define NT_MIN_BLOCKS_BVH 4 // measured best on configs[3] (2: 93.7 ms, 3: 78.2 ms, 4: 75.2 ms) despite spills
 #endif

@@ -537,21 +537,6 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
             else mask &= ~(1ull << own);
         }
         unsigned long long m = mask & s.sph_bits;
-#if NT_CULL_PAIR
-        while (m) { // two candidates per iteration (independent chains interleave); row ns is a never-hit dummy
-            const unsigned i0 = (unsigned)__ffsll((long long)m) - 1u;
-            m &= m - 1;
-            const unsigned i1 = m ? (unsigned)__ffsll((long long)m) - 1u : s.ns;
-            m &= m - 1;
-            R q0[4], q1[4], b0, b1, d0, d1;
-            c.ld_sph(i0, q0);
-            c.ld_sph(i1, q1);
-            sphere_eval<R>(q0, o, d, b0, d0);
-            sphere_eval<R>(q1, o, d, b1, d1);
-            if (!(d0 < R(0)) && sphere_finish<R>(b0, d0, c.eps, t) && (t < tb || (t == tb && (int)i0 < best.gid))) { tb = t; best.kind = 0; best.idx = (int)i0; best.gid = (int)i0; }
-            if (!(d1 < R(0)) && sphere_finish<R>(b1, d1, c.eps, t) && (t < tb || (t == tb && (int)i1 < best.gid))) { tb = t; best.kind = 0; best.idx = (int)i1; best.gid = (int)i1; }
-        }
-#else
         while (m) {
             const unsigned i = (unsigned)__ffsll((long long)m) - 1u;
             m &= m - 1;
@@ -559,7 +544,6 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
             c.ld_sph(i, q);
             if (hit_sphere<R>(q, o, d, c.eps, t) && (t < tb || (t == tb && (int)i < best.gid))) { tb = t; best.kind = 0; best.idx = (int)i; best.gid = (int)i; }
         }
-#endif
         k.sph += s.ns;
     }
     if constexpr (!BVH && sizeof(R) == 8) planes_nearest<R>(c, o, d, tb, best);
@@ -610,21 +594,6 @@ __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, c
     R t;
     if constexpr (!BVH) {
         unsigned long long m = mask & s.sph_bits;
-#if NT_CULL_PAIR
-        while (m) {
-            const unsigned i0 = (unsigned)__ffsll((long long)m) - 1u;
-            m &= m - 1;
-            const unsigned i1 = m ? (unsigned)__ffsll((long long)m) - 1u : s.ns;
-            m &= m - 1;
-            R q0[4], q1[4], b0, b1, d0, d1;
-            c.ld_sph(i0, q0);
-            c.ld_sph(i1, q1);
-            sphere_eval<R>(q0, o, d, b0, d0);
-            sphere_eval<R>(q1, o, d, b1, d1);
-            if (!(d0 < R(0)) && sphere_finish<R>(b0, d0, c.eps, t) && t < dist) { k.sph += i0 + 1; return true; }
-            if (!(d1 < R(0)) && sphere_finish<R>(b1, d1, c.eps, t) && t < dist) { k.sph += i1 + 1; return true; }
-        }
-#else
         while (m) {
             const unsigned i = (unsigned)__ffsll((long long)m) - 1u;
             m &= m - 1;
@@ -632,7 +601,6 @@ __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, c
             c.ld_sph(i, q);
             if (hit_sphere<R>(q, o, d, c.eps, t) && t < dist) { k.sph += i + 1; return true; }
         }
-#endif
         k.sph += s.ns;
     }
     if constexpr (!BVH && sizeof(R) == 8) {
@@ -820,17 +788,13 @@ __device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R
 // Stage the flat intersection data in shared memory with 128-bit loads.
 template <typename R, bool BVH>
 __device__ __forceinline__ void stage_scene(const NtDevScene &s, const NtSceneView<R> &v, Ctx<R, BVH> &c) {
-    // flat scenes: sphere row ns is a dummy that no ray can hit (r2 = -inf): the partner of an odd candidate
-    const unsigned n_sph = BVH ? 0u : (s.ns + 1) * 4, n_pln = s.np * 4, n_tri = BVH ? 0u : s.nt * NT_TRI_STRIDE;
+    const unsigned n_sph = BVH ? 0u : s.ns * 4, n_pln = s.np * 4, n_tri = BVH ? 0u : s.nt * NT_TRI_STRIDE;
     R *smem = (R *)nt_smem;
     constexpr int VEC = 16 / sizeof(R);
     typedef typename std::conditional<sizeof(R) == 8, double2, float4>::type VT;
     if constexpr (!BVH) {
 #pragma unroll 1
-        for (unsigned i = threadIdx.x; i < n_sph / VEC; i += blockDim.x) {
-            if (i < s.ns * 4 / VEC) ((VT *)smem)[i] = __ldg((const VT *)v.sph + i);
-            else { R *row = smem + i * VEC; for (int e = 0; e < VEC; ++e) row[e] = ((i * VEC + e) & 3u) == 3u ? -Math<R>::inf() : R(0); }
-        }
+        for (unsigned i = threadIdx.x; i < n_sph / VEC; i += blockDim.x) { ((VT *)smem)[i] = __ldg((const VT *)v.sph + i); }
     }
 #pragma unroll 1
     for (unsigned i = threadIdx.x; i < n_pln / VEC; i += blockDim.x) { ((VT *)(smem + n_sph))[i] = __ldg((const VT *)v.pln + i); }
@@ -1040,7 +1004,7 @@ template <typename R>
 inline size_t flat_smem_bytes(const NtDevScene &s, bool bvh) {
     size_t n = (size_t)s.np * 4;
     if (bvh) return n * sizeof(R) + (size_t)((((s.np + 15) / 16) + 3) & ~3u) * sizeof(unsigned);
-    n += ((size_t)s.ns + 1) * 4 + (size_t)s.nt * NT_TRI_STRIDE; // + the dummy sphere row
+    n += (size_t)s.ns * 4 + (size_t)s.nt * NT_TRI_STRIDE;
     n += 2 * ((size_t)s.nax[0] + s.nax[1] + s.nax[2]);          // axis-aligned plane lists
     return n * sizeof(R) + (((size_t)s.ngen + 3) & ~(size_t)3) * sizeof(int);
 }
