@@ -118,6 +118,16 @@ static int validate_desc(const nt_scene_desc *d) {
         for (int k = 0; k < 9; ++k) sum += t[k];
         if (!std::isfinite(sum)) return fail(NT_ERR_INVALID, "triangle %u: non-finite value", i);
     }
+    for (uint32_t i = 0; i < d->n_lights; ++i) {
+        double sum = 0;
+        for (int k = 0; k < 6; ++k) sum += d->lights[6 * (size_t)i + k];
+        if (!std::isfinite(sum)) return fail(NT_ERR_INVALID, "light %u: non-finite value", i);
+    }
+    for (uint32_t i = 0; i < d->n_materials; ++i) {
+        double sum = 0;
+        for (int k = 0; k < 10; ++k) sum += d->materials[10 * (size_t)i + k];
+        if (!std::isfinite(sum)) return fail(NT_ERR_INVALID, "material %u: non-finite value", i);
+    }
     return NT_OK;
 }
 
@@ -451,8 +461,9 @@ static int launch(nt_scene *sc, NtRenderArgs &a, uint32_t precision, cudaStream_
         const bool on = !(e_on && e_on[0] == '0');
         const size_t budget = (size_t)(e_mb && atoll(e_mb) > 0 ? atoll(e_mb) : 16384) << 20;
         size_t want = on ? nt_wavefront_bytes(sc->ds, a, (int)precision) : 0;
+        if (want > budget) want = budget;
+        if (want && want < nt_wavefront_min_bytes(a, (int)precision)) want = 0; // not even one warp of samples fits: state machine
         if (want) {
-            if (want > budget) want = budget;
             if (want > sc->wf_bytes) {
                 if (sc->d_wf) cudaFree(sc->d_wf);
                 sc->d_wf = nullptr; sc->wf_bytes = 0;

@@ -139,3 +139,4 @@ size_t nt_flat_smem_bytes(const NtDevScene &s, int precision);
 size_t nt_sample_buffer_bytes(const NtDevScene &s, const NtRenderArgs &a, int precision); // 0 for flat scenes
 // Wavefront workspace that holds the whole frame in one chunk (0: the scene / parameters do not use the wavefront path)
 size_t nt_wavefront_bytes(const NtDevScene &s, const NtRenderArgs &a, int precision);
+size_t nt_wavefront_min_bytes(const NtRenderArgs &a, int precision); // workspace for a chunk of 32 samples

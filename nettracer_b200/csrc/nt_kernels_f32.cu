@@ -16,6 +16,10 @@ size_t nt_sample_buffer_bytes(const NtDevScene &s, const NtRenderArgs &a, int pr
     const size_t n = (size_t)a.tiles_x * a.tiles_y * (a.spp / a.lanes) * 32;
     return n * 3 * (precision == 0 ? sizeof(double) : sizeof(float));
 }
+size_t nt_wavefront_min_bytes(const NtRenderArgs &a, int precision) {
+    const size_t per = precision == 0 ? nt::wf_bytes_per_sample<double>(a.max_depth) : nt::wf_bytes_per_sample<float>(a.max_depth);
+    return 256 + 256 * 8 * (size_t)a.max_depth + 32 * per + 4096;
+}
 size_t nt_wavefront_bytes(const NtDevScene &s, const NtRenderArgs &a, int precision) {
     return precision == 0 ? nt::wavefront_bytes<double>(s, a) : nt::wavefront_bytes<float>(s, a);
 }

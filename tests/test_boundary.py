@@ -88,6 +88,17 @@ def test_invalid_scene_rejected_before_device_work():
     d, keep = s.to_desc()
     assert L.nt_scene_create(C.byref(d), 0, C.byref(h)) == abi.NT_ERR_INVALID
     assert L.nt_scene_create(None, 0, C.byref(h)) == abi.NT_ERR_INVALID
+    # non-finite lights / materials are refused too (they would poison the culling tables and every pixel)
+    s, cam = scenes.cornell_box()
+    s.lights[0] = (float("nan"), 9.0, 4.0, 1.0, 1.0, 1.0)
+    d, keep = s.to_desc()
+    assert L.nt_scene_create(C.byref(d), 0, C.byref(h)) == abi.NT_ERR_INVALID
+    assert b"light 0" in L.nt_last_error()
+    s, cam = scenes.cornell_box()
+    s.materials[1].kd = float("inf")
+    d, keep = s.to_desc()
+    assert L.nt_scene_create(C.byref(d), 0, C.byref(h)) == abi.NT_ERR_INVALID
+    assert b"material 1" in L.nt_last_error()
 
 
 def test_product_never_touches_the_oracle():

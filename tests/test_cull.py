@@ -136,3 +136,25 @@ def test_not_eligible_is_an_error():
     scene = scenes.random_mixed(150, 2, 300, seed=4)[0]  # > 64 bounded primitives -> BVH scene
     with pytest.raises(NetTracerError):
         cull_tables(scene)
+
+
+def test_light_inside_a_sphere_sees_it_everywhere():
+    """A light inside a primitive's (dilated) ball: every direction cell must carry that primitive."""
+    scene = scenes.cornell_box()[0]
+    c = scene.spheres[2]
+    scene.add_light((c[0], c[1] + 0.1 * c[3], c[2]), (1.0, 1.0, 1.0))
+    tab = cull_tables(scene)
+    l = len(scene.lights) - 1
+    assert ((tab["lbuf"][l] >> np.uint64(2)) & np.uint64(1)).all()
+    # and the other lights' tables are unchanged by it
+    ref = cull_tables(scenes.cornell_box()[0])
+    assert np.array_equal(tab["lbuf"][:l], ref["lbuf"])
+
+
+def test_too_many_lights_disables_the_tables():
+    from nettracer_b200.lib import NetTracerError
+    scene = scenes.cornell_box()[0]
+    for i in range(20):
+        scene.add_light((0.1 * i, 9.0, 1.0), (0.1, 0.1, 0.1))
+    with pytest.raises(NetTracerError):
+        cull_tables(scene)  # > NT_CULL_MAX_LIGHTS: nt_scene_create then simply renders without culling

@@ -140,6 +140,71 @@ def test_trace_rays_bvh_matches_bruteforce():
     assert np.array_equal(t.view(np.uint64), to.view(np.uint64))
 
 
+def test_flat_plane_lists_ties_and_many_lights():
+    """Flat-scene corner cases of the second half of round 1: axis-aligned and general planes mixed, two
+    coincident axis-aligned planes with different materials (SPEC §3 tie: the smaller global id must win even
+    though the axis lists are not in index order), a duplicate sphere, planes as occluders (rare counter path),
+    and so many lights that the culling tables are not built."""
+    from nettracer_b200.scene import Camera, Material, Scene
+    s = Scene(ambient=(1.0, 1.0, 1.0), background=(0.05, 0.05, 0.1))
+    a = s.add_material(Material((0.8, 0.3, 0.2), ka=0.1, kd=0.8, ks=0.3, shininess=25.0, kr=0.3))
+    b = s.add_material(Material((0.2, 0.8, 0.3), ka=0.1, kd=0.8))
+    g = s.add_material(Material((0.9, 0.95, 1.0), ka=0.0, kd=0.1, ks=0.4, shininess=7.5, kr=0.1, kt=0.8, ior=1.4))
+    s.add_plane((0, 0, 1), -6.0, b)          # z = -6, general id order: this one first ...
+    s.add_plane((0.2, 1.0, 0.1), -2.0, a)    # general plane between the axis-aligned ones
+    s.add_plane((0, 0, -1), 6.0, a)          # ... and the SAME plane z = -6 again (normal flipped), larger id: must lose ties
+    s.add_plane((0, 1, 0), -2.5, b)
+    s.add_plane((1, 0, 0), 1.5, a)           # a wall between the scene and the second light: planes occlude
+    s.add_sphere((0.0, 0.0, -2.0), 1.2, g)
+    s.add_sphere((0.0, 0.0, -2.0), 1.2, a)   # duplicate sphere: the smaller index wins every tie
+    s.add_sphere((-2.5, -0.5, -3.0), 0.9, a)
+    s.add_triangle((-3, -1, -4), (3, -1, -4.5), (0, 3, -5), b)
+    s.add_light((-4.0, 6.0, 5.0), (0.6, 0.6, 0.6))
+    s.add_light((6.0, 3.0, 0.0), (0.5, 0.5, 0.5))
+    cam = Camera((0.0, 1.0, 7.0), (0.0, 0.0, -2.0), vfov_deg=50.0)
+    img, st, ref, rst, info = render_both(s, cam, 240, 160, 4, 5)
+    assert info["culling"] and not info["uses_bvh"]
+    assert_images_match(img, ref, "plane lists / ties")
+    for k in COUNTER_KEYS + FLAT_TEST_KEYS:
+        assert st[k] == rst[k], k
+    for i in range(18):                       # > NT_CULL_MAX_LIGHTS: no tables, brute force
+        s.add_light((-5.0 + 0.6 * i, 7.0, 4.0), (0.05, 0.05, 0.05))
+    img, st, ref, rst, info = render_both(s, cam, 120, 80, 1, 3)
+    assert not info["culling"]
+    assert_images_match(img, ref, "many lights")
+    for k in COUNTER_KEYS + FLAT_TEST_KEYS:
+        assert st[k] == rst[k], k
+    # planes only: no bounded primitive, nothing to cull
+    p = Scene(background=(0.1, 0.1, 0.1))
+    m = p.add_material(Material((0.7, 0.7, 0.7), kd=0.8, kr=0.4))
+    p.add_plane((0, 1, 0), -1.0, m)
+    p.add_plane((0, 0, 1), -8.0, m)
+    p.add_light((0.0, 5.0, 2.0))
+    img, st, ref, rst, info = render_both(p, cam, 96, 64, 4, 4)
+    assert_images_match(img, ref, "planes only")
+    for k in COUNTER_KEYS + FLAT_TEST_KEYS:
+        assert st[k] == rst[k], k
+
+
+@pytest.mark.parametrize("band,shards", [(1, 3), (5, 2), (7, 4), (100000, 2)])
+def test_sharded_tile_arithmetic_odd_bands(band, shards):
+    """Band sizes that are no power of two and do not divide the tile height or the image height: every shard's
+    owned rows, rendered compactly, must equal the same rows of the oracle's full frame (division-free tile /
+    row arithmetic, culling cones of tiles that straddle bands)."""
+    s, cam = scenes.cornell_box()
+    w, h = 150, 101
+    full_ref, _ = oracle.render(s, make_params(w, h, 4, 3, cam.resolve(w, h)))
+    from nettracer_b200.scene import owned_rows
+    with Renderer(s) as r:
+        for i in range(shards):
+            p = make_params(w, h, 4, 3, cam.resolve(w, h), shard_index=i, shard_count=shards, band_rows=band,
+                            layout=abi.NT_LAYOUT_COMPACT)
+            img, _ = r.render_params(p)
+            rows = owned_rows(h, band, i, shards)
+            assert img.shape[0] == len(rows)
+            assert np.array_equal(img, full_ref[rows]), f"shard {i} of {shards}, band {band}"
+
+
 @pytest.mark.parametrize("layout", [abi.NT_LAYOUT_COMPACT, abi.NT_LAYOUT_FULL])
 def test_sharded_render_reassembles(layout):
     s, cam = scenes.cornell_box()
