@@ -238,9 +238,27 @@ __device__ __forceinline__ bool plane_reject(R dn, R num, R tm1) {
     else
         return false;
 }
+// Strict mode: is the correctly rounded quotient num / dn certainly <= eps (a miss by the exact rule)?
+//   lo = fl(|dn| * fl(eps * k)), k = 1 - 2^-50.  When lo is a normal number, |num| <= lo implies
+//   |num| / |dn| <= eps * k * (1 + 2^-53)^2 < eps, and rounding is monotonic, so |fl(num / dn)| <= eps.
+// This is every ray that starts ON a plane (a shadow, reflection or refraction ray leaving a wall: num is 0 or
+// a few ulps): 44 % of all plane quotients of configs[2], and a zero numerator takes the ~100-instruction
+// special-operand path of the binary64 division (ncu: 4 % of the kernel's instructions, profiles/r01g_*).
+template <typename R>
+__device__ __forceinline__ bool plane_below_eps(R dn, R num, R eps) {
+    if constexpr (sizeof(R) == 8) {
+        const double lo = fabs(dn) * (eps * (1.0 - 8.8817841970012523e-16));
+        return fabs(num) <= lo && lo >= 2.2250738585072014e-308 && eps >= 1e-290;
+    } else {
+        return false;
+    }
+}
 template <typename R>
 __device__ __forceinline__ bool plane_finish(R dn, R num, R eps, R &t_out) {
     if (dn == R(0)) return false;
+#ifndef NT_EXP_NO_LOWREJECT
+    if (plane_below_eps<R>(dn, num, eps)) return false;
+#endif
     R t;
     if constexpr (sizeof(R) == 8) t = plane_quotient<R>(num, dn); else t = Math<R>::div(num, dn);
     if (!(t > eps)) return false;
