@@ -131,7 +131,7 @@ static int validate_desc(const nt_scene_desc *d) {
     return NT_OK;
 }
 
-static const size_t kSmemBudget = 40 * 1024;
+static const size_t kSmemBudget = 39 * 1024; // + 8.3 KB of static shared memory + list padding stays under the 48 KB default limit
 static const size_t kCounterBytes = sizeof(unsigned long long) * (NT_COUNTER_SLOTS * NT_NCOUNTERS + 1);
 static const uint32_t kFlatMaxBounded = 64;
 
@@ -239,7 +239,7 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
     std::vector<float> axl32;
     std::vector<int> pgen;
     uint32_t nax[3] = { 0, 0, 0 };
-    for (int k = 0; k < 3; ++k)
+    for (int k = 0; k < 3; ++k) {
         for (uint32_t i = 0; i < np; ++i)
             if (((pln_code[i / 16] >> (2 * (i % 16))) & 3u) == (unsigned)k) {
                 const double *n = d->planes + 4 * (size_t)i;
@@ -254,6 +254,7 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
                 axl32.push_back((float)pk); axl32.push_back(bits32);
                 ++nax[k];
             }
+    }
     for (uint32_t i = 0; i < np; ++i)
         if (((pln_code[i / 16] >> (2 * (i % 16))) & 3u) == 3u) pgen.push_back((int)i);
     for (uint32_t k = 0; k < nt; ++k) {
@@ -384,6 +385,8 @@ extern "C" uint32_t nt_shard_rows(uint32_t height, uint32_t band_rows, uint32_t 
 }
 
 // ---------------- render ----------------
+// nt_trace.cuh plane_below_eps: eps * (1 - 2^-50), rounded; 0 switches the shortcut off for absurdly small epsilons
+static double eps_low_bound(double eps) { return eps >= 1e-290 ? eps * (1.0 - 8.8817841970012523e-16) : 0.0; }
 static int make_args(const nt_render_params *p, size_t stride, NtRenderArgs *a) {
     if (!p) return fail(NT_ERR_INVALID, "params is NULL");
     if (p->struct_size != sizeof(nt_render_params)) return fail(NT_ERR_INVALID, "nt_render_params.struct_size %u != %zu", p->struct_size, sizeof(nt_render_params));
@@ -419,6 +422,7 @@ static int make_args(const nt_render_params *p, size_t stride, NtRenderArgs *a) 
     a->inv_tiles_x = 1.0f / (float)a->tiles_x;
     a->eps = p->ray_epsilon > 0 ? p->ray_epsilon : 1e-6;
     if (p->precision == NT_F32_FAST && a->eps < 1e-4) a->eps = 1e-4; // SPEC-PROVISIONAL §7
+    a->eps_lo = eps_low_bound(a->eps);
     for (int k = 0; k < 3; ++k) {
         a->cam[k] = p->camera.eye[k]; a->cam[3 + k] = p->camera.p00[k];
         a->cam[6 + k] = p->camera.dx[k]; a->cam[9 + k] = p->camera.dy[k];
@@ -607,6 +611,7 @@ extern "C" int nt_trace_rays(nt_scene *sc, uint32_t n, const double *origins, co
         a.n = n;
         a.eps = ray_epsilon > 0 ? ray_epsilon : 1e-6;
         if (precision == NT_F32_FAST && a.eps < 1e-4) a.eps = 1e-4;
+        a.eps_lo = eps_low_bound(a.eps);
         a.origins = d_o; a.dirs = d_d; a.t_out = d_t; a.prim_out = d_p;
         const int le = precision == NT_F64_STRICT ? nt_launch_trace_f64(sc->ds, a, sc->stream) : nt_launch_trace_f32(sc->ds, a, sc->stream);
         if (le) { rc = fail(NT_ERR_CUDA, "trace kernel launch: %s", cudaGetErrorString((cudaError_t)le)); break; }

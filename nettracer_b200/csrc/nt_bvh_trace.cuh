@@ -59,7 +59,7 @@ __device__ __forceinline__ void query_start(const Ctx<R, true> &c, BvhQuery<R> &
         const int code = (int)(codes & 3u);
         codes >>= 2;
         k.pln++;
-        if (hit_plane<R>(pq, code, o, d, c.eps, plane_bound<R>(q.tb), t) && t < q.tb) {
+        if (hit_plane<R>(pq, code, o, d, c.eps, c.eps_lo, plane_bound<R>(q.tb), t) && t < q.tb) {
             if (any) { q.done = true; q.found = true; return; }
             q.tb = t; q.best.kind = 1; q.best.idx = (int)i; q.best.gid = (int)(s.ns + i); q.found = true;
         }
@@ -381,7 +381,7 @@ render_bvh_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ 
     __shared__ unsigned long long s_cnt[NT_NCOUNTERS];
     const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
     Ctx<R, true> c;
-    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.max_depth = a.max_depth;
+    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.eps_lo = (R)a.eps_lo; c.max_depth = a.max_depth;
     stage_scene<R, true>(s, v, c);
 
     const unsigned lane = threadIdx.x & 31;
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(NT_BLOCK_THREADS)
 trace_bvh_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtTraceArgs a) {
     const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
     Ctx<R, true> c;
-    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.max_depth = 1;
+    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.eps_lo = (R)a.eps_lo; c.max_depth = 1;
     stage_scene<R, true>(s, v, c);
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;

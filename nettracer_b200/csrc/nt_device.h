@@ -103,6 +103,7 @@ struct NtRenderArgs {
     uint32_t twx, twy; // warp tile in pixels, twx*twy*lanes == 32
     uint32_t tiles_x, tiles_y; // warp tiles over the virtual image (owned rows only)
     double eps;
+    double eps_lo;     // fl(eps * (1 - 2^-50)), 0 when eps < 1e-290: quotients provably <= eps skip the division (plane_below_eps)
     double cam[12];    // eye p00 dx dy
     double samp_off[8]; // SPEC §2 sample offsets (i + 0.5) / n, i < n
     double inv_spp;     // 1 / spp
@@ -124,7 +125,7 @@ struct NtRenderArgs {
 
 struct NtTraceArgs {
     uint32_t n;
-    double eps;
+    double eps, eps_lo;
     const double *origins, *dirs;
     double *t_out;
     int *prim_out;

@@ -239,26 +239,26 @@ __device__ __forceinline__ bool plane_reject(R dn, R num, R tm1) {
         return false;
 }
 // Strict mode: is the correctly rounded quotient num / dn certainly <= eps (a miss by the exact rule)?
-//   lo = fl(|dn| * fl(eps * k)), k = 1 - 2^-50.  When lo is a normal number, |num| <= lo implies
-//   |num| / |dn| <= eps * k * (1 + 2^-53)^2 < eps, and rounding is monotonic, so |fl(num / dn)| <= eps.
+//   eps_lo = fl(eps * k), k = 1 - 2^-50 (made on the host; 0 when eps < 1e-290), lo = fl(|dn| * eps_lo).  When lo is a
+//   normal number, |num| <= lo implies |num| / |dn| <= eps * k * (1 + 2^-53)^2 < eps, and rounding is monotonic,
+//   so |fl(num / dn)| <= eps.
 // This is every ray that starts ON a plane (a shadow, reflection or refraction ray leaving a wall: num is 0 or
 // a few ulps): 44 % of all plane quotients of configs[2], and a zero numerator takes the ~100-instruction
-// special-operand path of the binary64 division (ncu: 4 % of the kernel's instructions, profiles/r01g_*).
+// special-operand path of the binary64 division (ncu: 4 % of the kernel's instructions and most of its
+// instruction-cache misses, profiles/r01g_cfg3_f64_before_lowreject.md).
 template <typename R>
-__device__ __forceinline__ bool plane_below_eps(R dn, R num, R eps) {
+__device__ __forceinline__ bool plane_below_eps(R dn, R num, R eps_lo) {
     if constexpr (sizeof(R) == 8) {
-        const double lo = fabs(dn) * (eps * (1.0 - 8.8817841970012523e-16));
-        return fabs(num) <= lo && lo >= 2.2250738585072014e-308 && eps >= 1e-290;
+        const double lo = fabs(dn) * eps_lo;
+        return fabs(num) <= lo && lo >= 2.2250738585072014e-308;
     } else {
         return false;
     }
 }
 template <typename R>
-__device__ __forceinline__ bool plane_finish(R dn, R num, R eps, R &t_out) {
+__device__ __forceinline__ bool plane_finish(R dn, R num, R eps, R eps_lo, R &t_out) {
     if (dn == R(0)) return false;
-#ifndef NT_EXP_NO_LOWREJECT
-    if (plane_below_eps<R>(dn, num, eps)) return false;
-#endif
+    if (plane_below_eps<R>(dn, num, eps_lo)) return false;
     R t;
     if constexpr (sizeof(R) == 8) t = plane_quotient<R>(num, dn); else t = Math<R>::div(num, dn);
     if (!(t > eps)) return false;
@@ -272,12 +272,12 @@ __device__ __forceinline__ bool plane_finish(R dn, R num, R eps, R &t_out) {
 //   * |num| >= |dn| * (tmax * (1 + 2e-15))     -> the correctly rounded quotient is >= tmax (see plane_bound)
 // Both tests are implied by the exact rule, so the result is bit-identical to dividing always.
 template <typename R>
-__device__ __forceinline__ bool hit_plane(const R q[4], int code, const V3<R> &o, const V3<R> &d, R eps, R tm1,
+__device__ __forceinline__ bool hit_plane(const R q[4], int code, const V3<R> &o, const V3<R> &d, R eps, R eps_lo, R tm1,
                                           R &t_out) {
     R dn, num;
     plane_eval<R>(q, code, o, d, dn, num);
     if (plane_reject<R>(dn, num, tm1)) return false;
-    return plane_finish<R>(dn, num, eps, t_out);
+    return plane_finish<R>(dn, num, eps, eps_lo, t_out);
 }
 
 template <typename R>
@@ -400,7 +400,7 @@ template <typename R, bool BVH> struct Ctx {
     const NtSceneView<R> *v;
     unsigned sph_addr, pln_addr, tri_addr, code_addr; // 32-bit shared-memory byte addresses of the staged arrays
     unsigned axl_addr, gen_addr;                      // flat scenes: axis-aligned plane lists, general-plane index list
-    R eps;
+    R eps, eps_lo; // eps_lo: see plane_below_eps
     unsigned max_depth;
     __device__ __forceinline__ void ld_sph(unsigned i, R *q) const {
         if constexpr (BVH) Ld<R>::g4(v->sph + 4 * (size_t)i, q); else Ld<R>::s4(sph_addr + i * (4 * (unsigned)sizeof(R)), q);
@@ -465,7 +465,7 @@ __device__ __forceinline__ void planes_nearest(const Ctx<R, false> &c, const V3<
             Ld<R>::s2(addr, p, idx);
             const R num = p - ok;
             if (!axis_candidate<R>(dk, num, bk)) continue;
-            if (!plane_finish<R>(dk, num, c.eps, t)) continue;
+            if (!plane_finish<R>(dk, num, c.eps, c.eps_lo, t)) continue;
             const int gid = (int)s.ns + idx;
             if (t < tb || (t == tb && gid < best.gid)) {
                 tb = t; best.kind = 1; best.idx = idx; best.gid = gid;
@@ -481,7 +481,7 @@ __device__ __forceinline__ void planes_nearest(const Ctx<R, false> &c, const V3<
         c.ld_pln((unsigned)idx, q);
         plane_eval<R>(q, 3, o, d, dn, num);
         if (plane_reject<R>(dn, num, tm1)) continue;
-        if (!plane_finish<R>(dn, num, c.eps, t)) continue;
+        if (!plane_finish<R>(dn, num, c.eps, c.eps_lo, t)) continue;
         const int gid = (int)s.ns + idx;
         if (t < tb || (t == tb && gid < best.gid)) { tb = t; best.kind = 1; best.idx = idx; best.gid = gid; tm1 = plane_bound<R>(tb); }
     }
@@ -504,7 +504,7 @@ __device__ __forceinline__ bool planes_occluded(const Ctx<R, false> &c, const V3
             Ld<R>::s2(addr, p, idx);
             const R num = p - ok;
             if (!axis_candidate<R>(dk, num, bk)) continue;
-            if (plane_finish<R>(dk, num, c.eps, t) && t < dist) return true;
+            if (plane_finish<R>(dk, num, c.eps, c.eps_lo, t) && t < dist) return true;
         }
     }
 #pragma unroll 1
@@ -515,7 +515,7 @@ __device__ __forceinline__ bool planes_occluded(const Ctx<R, false> &c, const V3
         c.ld_pln((unsigned)idx, q);
         plane_eval<R>(q, 3, o, d, dn, num);
         if (plane_reject<R>(dn, num, dm1)) continue;
-        if (plane_finish<R>(dn, num, c.eps, t) && t < dist) return true;
+        if (plane_finish<R>(dn, num, c.eps, c.eps_lo, t) && t < dist) return true;
     }
     return false;
 }
@@ -529,7 +529,7 @@ __device__ __noinline__ unsigned first_occluding_plane(const Ctx<R, false> &c, c
         R q[4], dn, num, t;
         c.ld_pln(i, q);
         plane_eval<R>(q, 3, o, d, dn, num);
-        if (plane_finish<R>(dn, num, c.eps, t) && t < dist) return i;
+        if (plane_finish<R>(dn, num, c.eps, c.eps_lo, t) && t < dist) return i;
     }
     return s.np - 1;
 }
@@ -575,14 +575,14 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
             c.ld_pln(i + 1, q1);
             plane_eval<R>(q0, 3, o, d, dn0, num0);
             plane_eval<R>(q1, 3, o, d, dn1, num1);
-            if (plane_finish<R>(dn0, num0, c.eps, t) && t < tb) { tb = t; best.kind = 1; best.idx = (int)i; best.gid = (int)(s.ns + i); }
-            if (plane_finish<R>(dn1, num1, c.eps, t) && t < tb) { tb = t; best.kind = 1; best.idx = (int)i + 1; best.gid = (int)(s.ns + i + 1); }
+            if (plane_finish<R>(dn0, num0, c.eps, c.eps_lo, t) && t < tb) { tb = t; best.kind = 1; best.idx = (int)i; best.gid = (int)(s.ns + i); }
+            if (plane_finish<R>(dn1, num1, c.eps, c.eps_lo, t) && t < tb) { tb = t; best.kind = 1; best.idx = (int)i + 1; best.gid = (int)(s.ns + i + 1); }
         }
         if (i < s.np) {
             R q[4], dn, num;
             c.ld_pln(i, q);
             plane_eval<R>(q, 3, o, d, dn, num);
-            if (plane_finish<R>(dn, num, c.eps, t) && t < tb) { tb = t; best.kind = 1; best.idx = (int)i; best.gid = (int)(s.ns + i); }
+            if (plane_finish<R>(dn, num, c.eps, c.eps_lo, t) && t < tb) { tb = t; best.kind = 1; best.idx = (int)i; best.gid = (int)(s.ns + i); }
         }
     }
     k.pln += s.np;
@@ -632,14 +632,14 @@ __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, c
             c.ld_pln(i + 1, q1);
             plane_eval<R>(q0, 3, o, d, dn0, num0);
             plane_eval<R>(q1, 3, o, d, dn1, num1);
-            if (plane_finish<R>(dn0, num0, c.eps, t) && t < dist) { k.pln += i + 1; return true; }
-            if (plane_finish<R>(dn1, num1, c.eps, t) && t < dist) { k.pln += i + 2; return true; }
+            if (plane_finish<R>(dn0, num0, c.eps, c.eps_lo, t) && t < dist) { k.pln += i + 1; return true; }
+            if (plane_finish<R>(dn1, num1, c.eps, c.eps_lo, t) && t < dist) { k.pln += i + 2; return true; }
         }
         if (i < s.np) {
             R q[4], dn, num;
             c.ld_pln(i, q);
             plane_eval<R>(q, 3, o, d, dn, num);
-            if (plane_finish<R>(dn, num, c.eps, t) && t < dist) { k.pln += i + 1; return true; }
+            if (plane_finish<R>(dn, num, c.eps, c.eps_lo, t) && t < dist) { k.pln += i + 1; return true; }
         }
     }
     k.pln += s.np;
@@ -887,7 +887,7 @@ render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRe
     __shared__ unsigned long long s_pmask[NT_BLOCK_THREADS / 32]; // per warp: primary-ray candidates of its tile
     const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
     Ctx<R, BVH> c;
-    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.max_depth = a.max_depth;
+    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.eps_lo = (R)a.eps_lo; c.max_depth = a.max_depth;
     stage_scene<R, BVH>(s, v, c);
 
     const unsigned tid = threadIdx.x, lane = tid & 31;
@@ -1000,7 +1000,7 @@ __global__ void __launch_bounds__(NT_BLOCK_THREADS)
 trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtTraceArgs a) {
     const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
     Ctx<R, BVH> c;
-    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.max_depth = 1;
+    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.eps_lo = (R)a.eps_lo; c.max_depth = 1;
     stage_scene<R, BVH>(s, v, c);
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;

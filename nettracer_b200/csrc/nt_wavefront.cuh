@@ -116,7 +116,7 @@ wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
     __shared__ unsigned long long s_cnt[NT_NCOUNTERS];
     const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
     Ctx<R, true> c;
-    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.max_depth = a.max_depth;
+    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.eps_lo = (R)a.eps_lo; c.max_depth = a.max_depth;
     stage_scene<R, true>(s, v, c);
     const unsigned lane = threadIdx.x & 31;
     const NtWfLevel &L = w.lv[w.level - 1];
@@ -229,7 +229,7 @@ wf_shade_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
     __shared__ unsigned long long s_cnt[NT_NCOUNTERS];
     const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
     Ctx<R, true> c;
-    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.max_depth = a.max_depth;
+    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.eps_lo = (R)a.eps_lo; c.max_depth = a.max_depth;
     stage_scene<R, true>(s, v, c);
     const NtWfLevel &L = w.lv[w.level - 1];
     const unsigned n_rec = w.level == 1 ? w.n_samples : w.counts[w.level];
