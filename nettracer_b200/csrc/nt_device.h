@@ -18,9 +18,6 @@
 #define NT_MIN_BLOCKS_F32 4 // fast mode with culling: 3 -> 0.68 ms, 4 -> 0.61 ms (before culling: 3 -> 0.72, 4 -> 0.74)
 #endif
 #define NT_BVH_STACK 96     // entries; a 4-wide node pushes up to 3: scene creation checks 3*depth + 4 <= this
-#ifndef NT_COUNTERS_SMEM
-#define NT_COUNTERS_SMEM 0   // flat render kernel: work counters in per-thread shared-memory slots instead of registers
-#endif
 #ifndef NT_MIN_BLOCKS_BVH
 #define NT_MIN_BLOCKS_BVH 4 // measured best on configs[3] (2: 93.7 ms, 3: 78.2 ms, 4: 75.2 ms) despite spills
 #endif

@@ -155,12 +155,6 @@ template <> struct Ld<float> {
 struct Counters { // per-thread work counters in registers (BVH and unit kernels)
     unsigned prim, sec, shadow, sph, pln, tri, box, light;
 };
-// Same fields backed by per-thread shared-memory slots (flat render kernel): an update costs
-// LDS + IADD + STS off the critical path instead of 8 live registers in a register-bound kernel.
-struct CountersRef {
-    unsigned &prim, &sec, &shadow, &sph, &pln, &tri, &box, &light;
-};
-
 // ---- SPEC §3 intersections ----
 // Sphere, part 1 (branch-free, so two spheres can be interleaved): b and the discriminant.
 template <typename R>
@@ -323,7 +317,8 @@ __device__ __forceinline__ unsigned long long lbuf_mask(const NtDevScene &s, uns
     int iu = (int)(a * sc + half), iv = (int)(b * sc + half);
     iu = min(max(iu, 0), K - 1);
     iv = min(max(iv, 0), K - 1);
-    return __ldg(s.lbuf + ((size_t)(l * 6u + face) * (unsigned)K + (unsigned)iv) * (unsigned)K + (unsigned)iu);
+    const unsigned cell = ((l * 6u + face) * (unsigned)K + (unsigned)iv) * (unsigned)K + (unsigned)iu; // < 2^32: <= 32 lights (nt_cull.h)
+    return __ldg(s.lbuf + cell);
 }
 
 // ---- warp-tile coordinates without integer division (they are recomputed around every trace instead of
@@ -562,7 +557,6 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
             c.ld_sph(i, q);
             if (hit_sphere<R>(q, o, d, c.eps, t) && (t < tb || (t == tb && (int)i < best.gid))) { tb = t; best.kind = 0; best.idx = (int)i; best.gid = (int)i; }
         }
-        k.sph += s.ns;
     }
     if constexpr (!BVH && sizeof(R) == 8) planes_nearest<R>(c, o, d, tb, best);
     if constexpr (!BVH && sizeof(R) == 4) {
@@ -585,7 +579,7 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
             if (plane_finish<R>(dn, num, c.eps, c.eps_lo, t) && t < tb) { tb = t; best.kind = 1; best.idx = (int)i; best.gid = (int)(s.ns + i); }
         }
     }
-    k.pln += s.np;
+    if constexpr (BVH) k.pln += s.np;
     if constexpr (!BVH) {
         if (s.nt) { // uniform
             unsigned long long m = s.ns >= 64 ? 0ull : mask >> s.ns;
@@ -596,7 +590,6 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
                 c.ld_tri(i, q);
                 if (hit_triangle<R>(q, o, d, c.eps, t) && t < tb) { tb = t; best.kind = 2; best.idx = (int)i; best.gid = (int)(s.ns + s.np + i); }
             }
-            k.tri += s.nt;
         }
     }
     return best.kind >= 0;
@@ -605,6 +598,9 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
 // SPEC §3 occlusion: any primitive hit (t > eps) with t < dist; first found ends the query.
 // Counters follow the sequential rule (tests up to and including the first occluder); a culled primitive is
 // a certain miss, so the first occluder found in mask order is the first one in index order.
+// Flat scenes count the tests NOT made: k.sph / k.pln / k.tri are deficits against "every query tests every
+// primitive" and are touched only when a query ends early (the kernel's flush turns them into test counts:
+// queries * n - deficit); an update per query was a spilled load-add-store on the common path.
 template <typename R, bool BVH, typename K>
 __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, const V3<R> &d, R dist, unsigned long long mask,
                                          K &k) {
@@ -617,12 +613,11 @@ __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, c
             m &= m - 1;
             R q[4];
             c.ld_sph(i, q);
-            if (hit_sphere<R>(q, o, d, c.eps, t) && t < dist) { k.sph += i + 1; return true; }
+            if (hit_sphere<R>(q, o, d, c.eps, t) && t < dist) { k.sph += s.ns - (i + 1); k.pln += s.np; k.tri += s.nt; return true; }
         }
-        k.sph += s.ns;
     }
     if constexpr (!BVH && sizeof(R) == 8) {
-        if (planes_occluded<R>(c, o, d, dist)) { k.pln += first_occluding_plane<R>(c, o, d, dist) + 1; return true; }
+        if (planes_occluded<R>(c, o, d, dist)) { k.pln += s.np - (first_occluding_plane<R>(c, o, d, dist) + 1); k.tri += s.nt; return true; }
     }
     if constexpr (!BVH && sizeof(R) == 4) {
         unsigned i = 0;
@@ -632,17 +627,17 @@ __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, c
             c.ld_pln(i + 1, q1);
             plane_eval<R>(q0, 3, o, d, dn0, num0);
             plane_eval<R>(q1, 3, o, d, dn1, num1);
-            if (plane_finish<R>(dn0, num0, c.eps, c.eps_lo, t) && t < dist) { k.pln += i + 1; return true; }
-            if (plane_finish<R>(dn1, num1, c.eps, c.eps_lo, t) && t < dist) { k.pln += i + 2; return true; }
+            if (plane_finish<R>(dn0, num0, c.eps, c.eps_lo, t) && t < dist) { k.pln += s.np - (i + 1); k.tri += s.nt; return true; }
+            if (plane_finish<R>(dn1, num1, c.eps, c.eps_lo, t) && t < dist) { k.pln += s.np - (i + 2); k.tri += s.nt; return true; }
         }
         if (i < s.np) {
             R q[4], dn, num;
             c.ld_pln(i, q);
             plane_eval<R>(q, 3, o, d, dn, num);
-            if (plane_finish<R>(dn, num, c.eps, c.eps_lo, t) && t < dist) { k.pln += i + 1; return true; }
+            if (plane_finish<R>(dn, num, c.eps, c.eps_lo, t) && t < dist) { k.pln += s.np - (i + 1); k.tri += s.nt; return true; }
         }
     }
-    k.pln += s.np;
+    if constexpr (BVH) k.pln += s.np;
     if constexpr (!BVH) {
         if (s.nt) { // uniform
             unsigned long long m = s.ns >= 64 ? 0ull : mask >> s.ns;
@@ -651,9 +646,8 @@ __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, c
                 m &= m - 1;
                 R q[9];
                 c.ld_tri(i, q);
-                if (hit_triangle<R>(q, o, d, c.eps, t) && t < dist) { k.tri += i + 1; return true; }
+                if (hit_triangle<R>(q, o, d, c.eps, t) && t < dist) { k.tri += s.nt - (i + 1); return true; }
             }
-            k.tri += s.nt;
         }
     }
     return false;
@@ -874,15 +868,12 @@ __device__ __forceinline__ void flush_counters(const Counters &k, unsigned long 
 // re-read where used; pixel coordinates are recomputed after the trace instead of being kept live;
 // SINGLE = (spp / lanes == 1) drops the cross-round pixel sum.  With that 4 blocks/SM fit in 64
 // registers with ~220 bytes of spills (configs[2] f64: 1.39 -> 1.30 ms; f32 prefers 3 blocks: 0.80 -> 0.72 ms).
-// Putting the work counters into shared memory as well (NT_COUNTERS_SMEM) removes the remaining spills
-// but costs more instructions than it saves (1.34 ms).
+// (Work counters in shared memory as well removed the remaining spills but cost more instructions than it
+// saved: 1.34 ms against 1.30.)
 template <typename R, bool BVH, bool SINGLE>
 __global__ void __launch_bounds__(NT_BLOCK_THREADS, sizeof(R) == 8 ? NT_MIN_BLOCKS_F64 : NT_MIN_BLOCKS_F32)
 render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRenderArgs a) {
     __shared__ unsigned long long s_cnt[NT_NCOUNTERS];
-#if NT_COUNTERS_SMEM
-    __shared__ unsigned s_k[NT_NCOUNTERS][NT_BLOCK_THREADS];
-#endif
     __shared__ R s_state[4][NT_BLOCK_THREADS]; // acc r g b, W
     __shared__ unsigned long long s_pmask[NT_BLOCK_THREADS / 32]; // per warp: primary-ray candidates of its tile
     const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
@@ -891,15 +882,8 @@ render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRe
     stage_scene<R, BVH>(s, v, c);
 
     const unsigned tid = threadIdx.x, lane = tid & 31;
-#if NT_COUNTERS_SMEM
-#pragma unroll
-    for (int i = 0; i < NT_NCOUNTERS; ++i) s_k[i][tid] = 0;
-    CountersRef k = { s_k[0][tid], s_k[1][tid], s_k[2][tid], s_k[3][tid], s_k[4][tid], s_k[5][tid], s_k[6][tid], s_k[7][tid] };
-    typedef CountersRef KT;
-#else
     Counters k = { 0, 0, 0, 0, 0, 0, 0, 0 };
     typedef Counters KT;
-#endif
     R *accp = &s_state[0][tid], *Wp = &s_state[3][tid];
     const unsigned warps_per_block = NT_BLOCK_THREADS / 32, total_warps = gridDim.x * warps_per_block;
     const unsigned n_tiles = a.tiles_x * a.tiles_y;
@@ -952,13 +936,15 @@ render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRe
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) sum[ch] = sum[ch] + NT_ACC(ch);
             } else {
-                const unsigned base = lane & ~(L - 1);
+                // only the pixel's first lane (which stores the pixel) needs the sum: its own sample, then the
+                // samples of the L - 1 lanes above it in sample order; the other lanes' sums are never used
                 const R a0 = NT_ACC(0), a1 = NT_ACC(1), a2 = NT_ACC(2);
+                sum[0] = sum[0] + a0; sum[1] = sum[1] + a1; sum[2] = sum[2] + a2;
 #pragma unroll 1
-                for (unsigned jj = 0; jj < L; ++jj) {
-                    sum[0] = sum[0] + __shfl_sync(0xffffffffu, a0, base + jj);
-                    sum[1] = sum[1] + __shfl_sync(0xffffffffu, a1, base + jj);
-                    sum[2] = sum[2] + __shfl_sync(0xffffffffu, a2, base + jj);
+                for (unsigned jj = 1; jj < L; ++jj) {
+                    sum[0] = sum[0] + __shfl_down_sync(0xffffffffu, a0, jj);
+                    sum[1] = sum[1] + __shfl_down_sync(0xffffffffu, a1, jj);
+                    sum[2] = sum[2] + __shfl_down_sync(0xffffffffu, a2, jj);
                 }
             }
         }
@@ -986,12 +972,13 @@ render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRe
         if (lane == 0) nt = atomicAdd(next_tile, 1ull) + total_warps;
         tile = (unsigned)__shfl_sync(0xffffffffu, nt, 0);
     }
-#if NT_COUNTERS_SMEM
-    const unsigned vals[NT_NCOUNTERS] = { s_k[0][tid], s_k[1][tid], s_k[2][tid], s_k[3][tid], s_k[4][tid], s_k[5][tid], s_k[6][tid], s_k[7][tid] };
-    flush_counter_values(vals, a.counters, s_cnt);
-#else
+    if constexpr (!BVH) { // deficits -> test counts (see occluded())
+        const unsigned queries = k.prim + k.sec + k.shadow;
+        k.sph = queries * s.ns - k.sph;
+        k.pln = queries * s.np - k.pln;
+        k.tri = queries * s.nt - k.tri;
+    }
     flush_counters(k, a.counters, s_cnt);
-#endif
 }
 
 // Unit-level entry: nearest hit of arbitrary rays (nt_trace_rays).
