@@ -122,6 +122,11 @@ int nt_scene_info(const nt_scene *scene, uint64_t info[4]);
 int nt_cull_tables(const nt_scene_desc *desc, uint32_t *k_out, uint64_t *lbuf_out, size_t lbuf_capacity,
                    uint64_t *nbr_out, double *bsph_out);
 
+/* Diagnostic, host only: the pixel rectangles { x0, x1, y0, y1 } (inclusive; empty when x0 > x1) that nt_render
+ * derives from the camera for the primary rays of a flat scene - no primary ray of a pixel outside rectangle j can
+ * touch bounded primitive j.  rects_out[n_spheres + n_triangles][4].  Same eligibility as nt_cull_tables. */
+int nt_primary_rects(const nt_scene_desc *desc, const nt_render_params *params, uint16_t *rects_out);
+
 /* ---- render ---- */
 /* Host buffer (pageable or pinned), blocking.  Renders the shard named in params, copies the
  * result to rgba_out.  stats may be NULL. */

@@ -75,6 +75,7 @@ struct nt_scene {
     void *d_samples = nullptr; // BVH scenes: per-sample radiance scratch
     size_t samples_bytes = 0;
     unsigned last_launches = 0; // kernels launched by the last render call
+    std::vector<double> h_bsph; // flat scenes with culling: bounding spheres (host copy, for the per-camera pixel rectangles)
     void *d_wf = nullptr;      // BVH scenes: wavefront workspace (level records of one chunk of samples)
     size_t wf_bytes = 0;
     std::mutex mu;
@@ -314,6 +315,7 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
     const char *ce = getenv("NT_CULL");
     if (!use_bvh && !(ce && ce[0] == '0') && nt_cull_build(d->spheres, ns, d->triangles, nt, d->lights, nl, ct)) {
         ds.cull = 1; ds.lbuf_k = ct.k;
+        sc->h_bsph = ct.bsph;
     }
     {
         std::vector<float4> b32(ct.bsph.size() / 4);
@@ -362,6 +364,26 @@ extern "C" int nt_cull_tables(const nt_scene_desc *desc, uint32_t *k_out, uint64
     }
     if (nbr_out) for (size_t i = 0; i < ct.nbr.size(); ++i) nbr_out[i] = ct.nbr[i];
     if (bsph_out) for (size_t i = 0; i < ct.bsph.size(); ++i) bsph_out[i] = ct.bsph[i];
+    return NT_OK;
+}
+
+extern "C" int nt_primary_rects(const nt_scene_desc *desc, const nt_render_params *p, uint16_t *rects_out) {
+    int rc = validate_desc(desc);
+    if (rc) return rc;
+    if (!p || !rects_out) return fail(NT_ERR_INVALID, "NULL argument");
+    if (p->width == 0 || p->height == 0 || p->width > 65536 || p->height > 65536) return fail(NT_ERR_INVALID, "bad image size %ux%u", p->width, p->height);
+    NtCullTables ct;
+    if (!nt_cull_build(desc->spheres, desc->n_spheres, desc->triangles, desc->n_triangles, desc->lights, desc->n_lights, ct))
+        return fail(NT_ERR_INVALID, "scene is not eligible for the flat culling tables");
+    double cam[12], eye_inf = 0, mx = 0;
+    for (int k = 0; k < 3; ++k) {
+        cam[k] = p->camera.eye[k]; cam[3 + k] = p->camera.p00[k]; cam[6 + k] = p->camera.dx[k]; cam[9 + k] = p->camera.dy[k];
+        eye_inf = std::max(eye_inf, std::fabs(cam[k]));
+    }
+    for (uint32_t i = 0; i < desc->n_spheres; ++i)
+        for (int a = 0; a < 3; ++a) mx = std::max(mx, std::fabs(desc->spheres[4 * (size_t)i + a]) + desc->spheres[4 * (size_t)i + 3]);
+    for (size_t i = 0; i < 9 * (size_t)desc->n_triangles; ++i) mx = std::max(mx, std::fabs(desc->triangles[i]));
+    nt_cull_primary_rects(ct.bsph.data(), desc->n_spheres + desc->n_triangles, cam, p->width, p->height, 1e-5 * (eye_inf + mx), rects_out);
     return NT_OK;
 }
 
@@ -430,15 +452,6 @@ static int make_args(const nt_render_params *p, size_t stride, NtRenderArgs *a) 
     a->stride = stride;
     for (uint32_t i = 0; i < n; ++i) a->samp_off[i] = ((double)i + 0.5) / (double)n;
     a->inv_spp = 1.0 / (double)p->spp;
-    // binary32 copy of the camera for the primary-ray culling cone (nt_trace.cuh tile_mask); lengths rounded up
-    double len[2] = { 0, 0 }, eye_inf = 0;
-    for (int k = 0; k < 12; ++k) a->camf[k] = (float)a->cam[k];
-    for (int k = 0; k < 3; ++k) {
-        len[0] += p->camera.dx[k] * p->camera.dx[k]; len[1] += p->camera.dy[k] * p->camera.dy[k];
-        eye_inf = std::max(eye_inf, std::fabs(p->camera.eye[k]));
-    }
-    a->dxlen = (float)(std::sqrt(len[0]) * 1.000001); a->dylen = (float)(std::sqrt(len[1]) * 1.000001);
-    a->cull_margin = (float)eye_inf; // the scene extent is added by launch()
     return NT_OK;
 }
 
@@ -478,7 +491,11 @@ static int launch(nt_scene *sc, NtRenderArgs &a, uint32_t precision, cudaStream_
             a.wf = sc->d_wf; a.wf_bytes = want;
         }
     }
-    a.cull_margin = 1e-5f * (a.cull_margin + sc->ds.max_abs);
+    if (!sc->ds.use_bvh && sc->ds.cull) { // primary rays: per-primitive pixel rectangles for this camera (nt_cull.h)
+        double eye_inf = 0;
+        for (int k = 0; k < 3; ++k) eye_inf = std::max(eye_inf, std::fabs(a.cam[k]));
+        nt_cull_primary_rects(sc->h_bsph.data(), sc->ds.ns + sc->ds.nt, a.cam, a.width, a.height, 1e-5 * (eye_inf + (double)sc->ds.max_abs), &a.prect[0][0]);
+    }
     const int e = precision == NT_F64_STRICT ? nt_launch_render_f64(sc->ds, a, st) : nt_launch_render_f32(sc->ds, a, st);
     if (e) return fail(NT_ERR_CUDA, "render kernel launch: %s", cudaGetErrorString((cudaError_t)e));
     return NT_OK;

@@ -144,3 +144,40 @@ bool nt_cull_build(const double *spheres, uint32_t ns, const double *triangles, 
     }
     return true;
 }
+
+// The lines through the eye that touch the ball (centre C, radius rho) satisfy (V.D)^2 >= k |D|^2 with V = C - eye,
+// k = |V|^2 - rho^2 > 0.  With D = p00 + x dx + y dy this is F(x, y) = a x^2 + 2 b x y + c y^2 + 2 d x + 2 e y + f >= 0,
+// M = g g^T - k G (g = A^T V, G = A^T A, A = [dx dy p00]).  When the quadratic part is negative definite the set
+// is the inside of an ellipse; for a fixed x, F has a real root in y iff (b x + e)^2 - c (a x^2 + 2 d x + f) >= 0,
+// i.e. -D2 x^2 + 2 q x + r >= 0 (D2 = a c - b^2 > 0, q = b e - c d, r = e^2 - c f): x between (q -+ sqrt(q^2 + D2 r)) / D2.
+// Lines, not half-lines: a ball behind the eye keeps its rectangle (a superset is all that is needed).
+void nt_cull_primary_rects(const double *bsph, uint32_t nb, const double cam[12], uint32_t width, uint32_t height,
+                           double margin, uint16_t *rects) {
+    const double *E = cam, *P0 = cam + 3, *DX = cam + 6, *DY = cam + 9;
+    auto dot3 = [](const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+    const double gxx = dot3(DX, DX), gxy = dot3(DX, DY), gx0 = dot3(DX, P0), gyy = dot3(DY, DY), gy0 = dot3(DY, P0), g00 = dot3(P0, P0);
+    const uint16_t xmax = (uint16_t)std::min<uint32_t>(width - 1, 65535u), ymax = (uint16_t)std::min<uint32_t>(height - 1, 65535u);
+    for (uint32_t j = 0; j < nb; ++j) {
+        uint16_t *o = rects + 4 * (size_t)j;
+        o[0] = 0; o[1] = xmax; o[2] = 0; o[3] = ymax; // the whole image unless proven smaller
+        const double *bs = bsph + 4 * (size_t)j;
+        const double V[3] = { bs[0] - E[0], bs[1] - E[1], bs[2] - E[2] };
+        const double v2 = dot3(V, V), rho = bs[3] * 1.001 + 1e-3 * std::sqrt(v2) + margin;
+        const double k = v2 - rho * rho;
+        if (!(k > 0) || !std::isfinite(k)) continue;
+        const double vx = dot3(V, DX), vy = dot3(V, DY), v0 = dot3(V, P0);
+        const double a = vx * vx - k * gxx, b = vx * vy - k * gxy, c = vy * vy - k * gyy;
+        const double d = vx * v0 - k * gx0, e = vy * v0 - k * gy0, f = v0 * v0 - k * g00;
+        const double D2 = a * c - b * b;
+        if (!(a < 0 && c < 0 && D2 > 1e-9 * (a * c))) continue; // not (safely) an ellipse
+        const double qx = b * e - c * d, rx = e * e - c * f, qy = b * d - a * e, ry = d * d - a * f;
+        const double sx = std::sqrt(std::max(0.0, qx * qx + D2 * rx)), sy = std::sqrt(std::max(0.0, qy * qy + D2 * ry));
+        const double x_lo = (qx - sx) / D2, x_hi = (qx + sx) / D2, y_lo = (qy - sy) / D2, y_hi = (qy + sy) / D2;
+        if (!std::isfinite(x_lo + x_hi + y_lo + y_hi)) continue;
+        // pixel px holds x in (px, px + 1); two pixels of slack on every side
+        const double px_lo = std::floor(x_lo) - 2, px_hi = std::floor(x_hi) + 2, py_lo = std::floor(y_lo) - 2, py_hi = std::floor(y_hi) + 2;
+        if (px_hi < 0 || py_hi < 0 || px_lo > xmax || py_lo > ymax) { o[0] = 1; o[1] = 0; o[2] = 1; o[3] = 0; continue; } // off the image
+        o[0] = (uint16_t)std::max(0.0, px_lo); o[1] = (uint16_t)std::min((double)xmax, px_hi);
+        o[2] = (uint16_t)std::max(0.0, py_lo); o[3] = (uint16_t)std::min((double)ymax, py_hi);
+    }
+}

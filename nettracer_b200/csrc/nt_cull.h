@@ -8,8 +8,9 @@
 //   nbr   per sphere i: the primitives whose bounding ball touches ball i.  A secondary ray that starts on
 //         sphere i and hits sphere i again (a chord: refraction, internal reflection) can only be stopped
 //         earlier by one of those.
-// The primary-ray mask (primitives whose bounding sphere meets the frustum of one warp tile) is computed
-// inside the render kernel from bsph.
+//   prect per render call (it depends on the camera): for every bounded primitive the rectangle of pixels outside
+//         which no primary ray can touch its bounding sphere (nt_cull_primary_rects).  A warp tile keeps the
+//         primitives whose rectangle it overlaps.
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -28,3 +29,11 @@ struct NtCullTables {
 // Returns false when the scene is not eligible (no bounded primitive, more than 64, too many lights).
 bool nt_cull_build(const double *spheres, uint32_t ns, const double *triangles, uint32_t nt, const double *lights,
                    uint32_t nl, NtCullTables &out);
+
+// Primary rays D(x, y) = p00 + x dx + y dy from `eye` (cam = eye p00 dx dy, SPEC-PROVISIONAL §2; pixel px holds
+// the sample positions x in (px, px + 1)).  rects[j] = { x0, x1, y0, y1 }: every pixel whose samples can touch
+// the ball j (radius dilated to r * 1.001 + 1e-3 |c - eye| + margin) lies in [x0, x1] x [y0, y1]; an empty
+// rectangle has x0 > x1.  Exact conic bounds in binary64, widened by two pixels; the whole image whenever the
+// ball's outline on the image plane is not an ellipse (eye inside the ball, ball crossing the eye's plane).
+void nt_cull_primary_rects(const double *bsph, uint32_t nb, const double cam[12], uint32_t width, uint32_t height,
+                           double margin, uint16_t *rects);

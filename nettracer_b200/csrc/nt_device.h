@@ -104,8 +104,7 @@ struct NtRenderArgs {
     double cam[12];    // eye p00 dx dy
     double samp_off[8]; // SPEC §2 sample offsets (i + 0.5) / n, i < n
     double inv_spp;     // 1 / spp
-    float camf[12];    // the same in binary32 (primary-ray culling cone only)
-    float dxlen, dylen, cull_margin; // |dx|, |dy| rounded up; 1e-5 * (scene extent + |eye|)
+    alignas(8) uint16_t prect[64][4]; // flat scenes with culling: pixel rectangle x0 x1 y0 y1 of every bounded primitive (nt_cull.h)
     // division-free tile arithmetic (nt_trace.cuh tile_origin / row_to_y): twx, twy, lanes are powers of two
     uint32_t log2_twx, log2_twy, log2_lanes;
     uint32_t band_magic; // ceil(2^32 / band_rows) (band_rows > 1)

@@ -340,44 +340,23 @@ __device__ __forceinline__ unsigned row_to_y(const NtRenderArgs &a, unsigned vr)
     return (b * a.shard_count + a.shard_index) * a.band_rows + (vr - b * a.band_rows);
 }
 
-// Primary rays: the bounded primitives whose (dilated) bounding sphere meets a cone around one warp tile's
-// pixel frustum.  Every lane tests primitive `lane` (and `lane + 32`); a ballot makes the warp-uniform mask.
-// Binary32 on purpose (it runs once per 32 samples, a binary64 version cost 15 % of the kernel); everything is
-// dilated far beyond the rounding errors involved:
-//   cone     axis u = D(tile centre) / |D|, sin(half-angle) <= |e| / |D| with |e| <= hx*|dx| + hy*|dy| the largest
-//            offset of a sample direction from the centre direction (both lengths rounded up on the host); x 1.001
-//   sphere   r * 1.001 + 1e-3 * |c - eye| + cull_margin   (cull_margin = 1e-5 * (scene extent + |eye|), host)
-// A sphere is kept unless its centre is farther than that from the cone: perp*cos - along*sin > r, with
-// perp taken from v - along*u (no cancellation).  NaN compares keep the primitive.
-// Pixel area: x in [px0, px0 + twx], y in [ymin, ymax1].
+// Primary rays: the bounded primitives whose pixel rectangle (made on the host for this camera from the dilated
+// bounding spheres, nt_cull.h nt_cull_primary_rects) overlaps the warp tile's pixel area x in [px0, px0 + twx),
+// y in [ymin, ymax1).  Every lane tests primitive `lane` (and `lane + 32`); a ballot makes the warp-uniform mask.
+// (The first version tested the ball against a cone around the tile in binary32 inside the kernel: 130 warp
+// instructions per tile, 4.8 % of the kernel; the rectangles cost ~15.)
 static __device__ __forceinline__ unsigned long long tile_mask(const NtDevScene &s, const NtRenderArgs &a, unsigned px0, unsigned ymin,
                                                                unsigned ymax1, unsigned lane) {
     const unsigned nb = s.ns + s.nt;
-    const unsigned long long all = s.all_bits;
-    const float hx = 0.5f * (float)a.twx, hy = 0.5f * (float)(ymax1 - ymin);
-    const float fxc = (float)px0 + hx, fyc = (float)ymin + hy;
-    const float Dx = __fmaf_rn(a.camf[9], fyc, __fmaf_rn(a.camf[6], fxc, a.camf[3]));
-    const float Dy = __fmaf_rn(a.camf[10], fyc, __fmaf_rn(a.camf[7], fxc, a.camf[4]));
-    const float Dz = __fmaf_rn(a.camf[11], fyc, __fmaf_rn(a.camf[8], fxc, a.camf[5]));
-    const float inv = rsqrtf(__fmaf_rn(Dz, Dz, __fmaf_rn(Dy, Dy, Dx * Dx)));
-    const float ux = Dx * inv, uy = Dy * inv, uz = Dz * inv;
-    const float sn = __fmaf_rn(hx, a.dxlen, hy * a.dylen) * inv * 1.001f + 1e-6f;
-    if (!(sn < 0.7f)) return all; // very wide tile (or NaN): no culling
-    const float cs = sqrtf(1.0f - sn * sn);
+    const unsigned x1 = px0 + a.twx - 1u, y1 = ymax1 - 1u;
     unsigned long long mask = 0;
 #pragma unroll 1
     for (unsigned base = 0; base < nb; base += 32) {
         const unsigned j = base + lane;
         bool in = false;
         if (j < nb) {
-            const float4 b = __ldg(s.bsph32 + j);
-            const float vx = b.x - a.camf[0], vy = b.y - a.camf[1], vz = b.z - a.camf[2];
-            const float along = __fmaf_rn(vz, uz, __fmaf_rn(vy, uy, vx * ux));
-            const float lx = __fmaf_rn(-along, ux, vx), ly = __fmaf_rn(-along, uy, vy), lz = __fmaf_rn(-along, uz, vz);
-            const float perp = sqrtf(__fmaf_rn(lz, lz, __fmaf_rn(ly, ly, lx * lx)));
-            const float vlen = sqrtf(__fmaf_rn(vz, vz, __fmaf_rn(vy, vy, vx * vx)));
-            const float r = __fmaf_rn(b.w, 1.001f, __fmaf_rn(1e-3f, vlen, a.cull_margin));
-            in = !(__fmaf_rn(perp, cs, -along * sn) > r);
+            const uint2 r = *(const uint2 *)a.prect[j]; // x0 | x1 << 16, y0 | y1 << 16
+            in = (r.x & 0xffffu) <= x1 && (r.x >> 16) >= px0 && (r.y & 0xffffu) <= y1 && (r.y >> 16) >= ymin;
         }
         mask |= (unsigned long long)__ballot_sync(0xffffffffu, in) << base;
     }

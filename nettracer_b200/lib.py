@@ -46,6 +46,7 @@ def load():
         "nt_ipc_close": (C.c_int, [vp, C.c_int]),
         "nt_measure_peaks": (C.c_int, [C.c_int, C.POINTER(abi.nt_peaks)]),
         "nt_cull_tables": (C.c_int, [C.POINTER(abi.nt_scene_desc), C.POINTER(u32), vp, C.c_size_t, vp, vp]),
+        "nt_primary_rects": (C.c_int, [C.POINTER(abi.nt_scene_desc), C.POINTER(abi.nt_render_params), vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name, None)

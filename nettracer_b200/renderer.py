@@ -101,6 +101,16 @@ def cull_tables(scene: Scene) -> dict:
     return {"k": int(k.value), "lbuf": lbuf, "nbr": nbr, "bsph": bsph}
 
 
+def primary_rects(scene: Scene, params) -> np.ndarray:
+    """Per bounded primitive the pixel rectangle [x0, x1, y0, y1] (inclusive; x0 > x1 = empty) outside which no
+    primary ray of `params`' camera can touch it (nt_primary_rects: host only).  uint16 [n_spheres + n_triangles, 4]."""
+    desc, keep = scene.to_desc()
+    out = np.zeros((desc.n_spheres + desc.n_triangles, 4), dtype=np.uint16)
+    check(load().nt_primary_rects(C.byref(desc), C.byref(params), out.ctypes.data))
+    del keep
+    return out
+
+
 def measure_peaks(device=0) -> dict:
     p = abi.nt_peaks()
     check(load().nt_measure_peaks(int(device), C.byref(p)))

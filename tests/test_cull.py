@@ -7,7 +7,8 @@ import numpy as np
 import pytest
 
 from nettracer_b200 import scenes
-from nettracer_b200.renderer import cull_tables
+from nettracer_b200.renderer import cull_tables, primary_rects
+from nettracer_b200.scene import Camera, make_params
 
 EPS = 1e-6
 
@@ -158,3 +159,71 @@ def test_too_many_lights_disables_the_tables():
         scene.add_light((0.1 * i, 9.0, 1.0), (0.1, 0.1, 0.1))
     with pytest.raises(NetTracerError):
         cull_tables(scene)  # > NT_CULL_MAX_LIGHTS: nt_scene_create then simply renders without culling
+
+
+# ---- primary rays: per-primitive pixel rectangles (nt_cull_primary_rects) ----
+def _primary_dirs(cam, w, h, n):
+    """Directions of all n x n samples of every pixel: D = p00 + (px + (i + .5) / n) dx + (py + (j + .5) / n) dy, plus
+    the pixel corners (a superset of the sample positions)."""
+    c = cam.resolve(w, h)
+    eye, p00, dx, dy = (np.array(list(getattr(c, k))) for k in ("eye", "p00", "dx", "dy"))
+    offs = np.concatenate([(np.arange(n) + 0.5) / n, [0.0, 1.0]])
+    fx = (np.arange(w)[:, None] + offs[None, :]).reshape(-1)          # [w * (n + 2)]
+    fy = (np.arange(h)[:, None] + offs[None, :]).reshape(-1)
+    D = p00[None, None, :] + fx[None, :, None] * dx[None, None, :] + fy[:, None, None] * dy[None, None, :]
+    px = np.repeat(np.arange(w), len(offs))
+    py = np.repeat(np.arange(h), len(offs))
+    return eye, D, px, py
+
+
+def _line_touches_ball(eye, D, ball):
+    """Does the forward half-line eye + t D, t > 0, touch the ball?  Exact rule in float64 with a tiny slack."""
+    V = ball[:3] - eye
+    dd = (D * D).sum(-1)
+    vd = (D * V).sum(-1)
+    dist2 = (V * V).sum() - vd * vd / dd
+    return (dist2 <= ball[3] * ball[3] * (1 + 1e-9)) & ((vd > 0) | ((V * V).sum() <= ball[3] * ball[3]))
+
+
+CAMERAS = {
+    "cornell": None,  # the scene's own camera
+    "close": Camera(eye=(0.3, 0.2, 3.0), at=(0.0, 0.0, 0.0), vfov_deg=70.0),          # big outlines, some partly off-screen
+    "side": Camera(eye=(9.0, 4.0, 2.0), at=(0.0, 0.0, -3.0), up=(0.1, 1, 0), vfov_deg=35.0),
+    "inside": Camera(eye=(0.0, 0.0, 0.0), at=(0.0, 0.0, -1.0), vfov_deg=100.0),        # may sit inside a ball; balls behind the eye
+}
+
+
+@pytest.mark.parametrize("which,camname", [("cornell", "cornell"), ("cornell", "close"), ("mixed1", "cornell"),
+                                           ("mixed1", "side"), ("mixed2", "inside"), ("mixed2", "close")])
+def test_primary_rects_are_conservative(which, camname):
+    scene, cam = scenes.cornell_box() if which == "cornell" else scenes.random_mixed(12, 3, 20, seed=1 if which == "mixed1" else 2)
+    cam = CAMERAS[camname] or cam
+    w, h, n = 224, 128, 2
+    rects = primary_rects(scene, make_params(w, h, n * n, 1, cam.resolve(w, h))).astype(np.int64)
+    balls = cull_tables(scene)["bsph"]
+    eye, D, px, py = _primary_dirs(cam, w, h, n)
+    kept = 0
+    for j, ball in enumerate(balls):
+        touch = _line_touches_ball(eye, D, ball)                      # [rows, cols] of sample positions
+        x0, x1, y0, y1 = rects[j]
+        inside = ((py >= y0) & (py <= y1))[:, None] & ((px >= x0) & (px <= x1))[None, :]
+        assert not (touch & ~inside).any(), f"primitive {j}: a primary ray touches its ball outside its rectangle {rects[j]}"
+        kept += int(inside.sum())
+    assert kept < 0.6 * len(balls) * D.shape[0] * D.shape[1] or camname == "inside", "the rectangles should cull most of the image"
+
+
+def test_primary_rects_are_tight_enough():
+    """A ball in the middle of the view: its rectangle is its outline plus a few pixels, not the whole image."""
+    scene, cam = scenes.cornell_box()
+    w, h = 320, 180
+    rects = primary_rects(scene, make_params(w, h, 1, 1, cam.resolve(w, h))).astype(np.int64)
+    balls = cull_tables(scene)["bsph"]
+    eye, D, px, py = _primary_dirs(cam, w, h, 1)
+    for j, ball in enumerate(balls):
+        touch = _line_touches_ball(eye, D, ball)
+        if not touch.any():
+            continue
+        ys, xs = np.nonzero(touch)
+        x0, x1, y0, y1 = rects[j]
+        assert x0 >= max(px[xs].min() - 6, 0) - 1 and x1 <= min(px[xs].max() + 6, w - 1) + 1
+        assert y0 >= max(py[ys].min() - 6, 0) - 1 and y1 <= min(py[ys].max() + 6, h - 1) + 1
