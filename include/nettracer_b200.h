@@ -127,6 +127,11 @@ int nt_cull_tables(const nt_scene_desc *desc, uint32_t *k_out, uint64_t *lbuf_ou
  * touch bounded primitive j.  rects_out[n_spheres + n_triangles][4].  Same eligibility as nt_cull_tables. */
 int nt_primary_rects(const nt_scene_desc *desc, const nt_render_params *params, uint16_t *rects_out);
 
+/* Diagnostic, host only: bit l of *mask_out is set when nt_scene_create proved that no plane of a flat scene can lie
+ * between light l and any point of a bounded primitive (shadow queries from spheres / triangles towards that light
+ * then skip the planes).  Same eligibility as nt_cull_tables. */
+int nt_plane_free_lights(const nt_scene_desc *desc, uint32_t *mask_out);
+
 /* ---- render ---- */
 /* Host buffer (pageable or pinned), blocking.  Renders the shard named in params, copies the
  * result to rgba_out.  stats may be NULL. */

@@ -71,7 +71,7 @@ EXPORTS = [
     "nt_render", "nt_render_device", "nt_render_device_stats", "nt_trace_rays",
     "nt_shard_rows", "nt_deinterleave_device",
     "nt_device_malloc", "nt_device_free", "nt_ipc_export", "nt_ipc_open", "nt_ipc_close",
-    "nt_measure_peaks", "nt_cull_tables", "nt_primary_rects",
+    "nt_measure_peaks", "nt_cull_tables", "nt_primary_rects", "nt_plane_free_lights",
 ]
 
 # Flop-counting convention fixed in SURVEY.md §8(d) (FMA = 2, div/sqrt = 1).

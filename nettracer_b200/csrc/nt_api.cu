@@ -75,6 +75,7 @@ struct nt_scene {
     void *d_samples = nullptr; // BVH scenes: per-sample radiance scratch
     size_t samples_bytes = 0;
     unsigned last_launches = 0; // kernels launched by the last render call
+    uint32_t lfree = 0;         // flat scenes with culling: lights no plane can hide from a bounded primitive (nt_cull.h)
     std::vector<double> h_bsph; // flat scenes with culling: bounding spheres (host copy, for the per-camera pixel rectangles)
     void *d_wf = nullptr;      // BVH scenes: wavefront workspace (level records of one chunk of samples)
     size_t wf_bytes = 0;
@@ -130,6 +131,13 @@ static int validate_desc(const nt_scene_desc *d) {
         if (!std::isfinite(sum)) return fail(NT_ERR_INVALID, "material %u: non-finite value", i);
     }
     return NT_OK;
+}
+
+// nt_cull.h: lights towards which a strict-mode shadow query from a bounded primitive cannot be stopped by any
+// plane, for ray epsilons >= kPlaneFreeEps (launch() clears the bits for smaller ones)
+static const double kPlaneFreeEps = 1e-7;
+static uint32_t plane_free_lights(const nt_scene_desc *d) {
+    return nt_cull_plane_free_lights(d->spheres, d->n_spheres, d->triangles, d->n_triangles, d->planes, d->n_planes, d->lights, d->n_lights, kPlaneFreeEps);
 }
 
 static const size_t kSmemBudget = 39 * 1024; // + 8.3 KB of static shared memory + list padding stays under the 48 KB default limit
@@ -316,6 +324,8 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
     if (!use_bvh && !(ce && ce[0] == '0') && nt_cull_build(d->spheres, ns, d->triangles, nt, d->lights, nl, ct)) {
         ds.cull = 1; ds.lbuf_k = ct.k;
         sc->h_bsph = ct.bsph;
+        const char *pe = getenv("NT_PLANE_FREE"); // 0: always run the plane loops of a shadow query (A/B, tests)
+        if (!(pe && pe[0] == '0')) sc->lfree = plane_free_lights(d);
     }
     {
         std::vector<float4> b32(ct.bsph.size() / 4);
@@ -384,6 +394,17 @@ extern "C" int nt_primary_rects(const nt_scene_desc *desc, const nt_render_param
         for (int a = 0; a < 3; ++a) mx = std::max(mx, std::fabs(desc->spheres[4 * (size_t)i + a]) + desc->spheres[4 * (size_t)i + 3]);
     for (size_t i = 0; i < 9 * (size_t)desc->n_triangles; ++i) mx = std::max(mx, std::fabs(desc->triangles[i]));
     nt_cull_primary_rects(ct.bsph.data(), desc->n_spheres + desc->n_triangles, cam, p->width, p->height, 1e-5 * (eye_inf + mx), rects_out);
+    return NT_OK;
+}
+
+extern "C" int nt_plane_free_lights(const nt_scene_desc *desc, uint32_t *mask_out) {
+    int rc = validate_desc(desc);
+    if (rc) return rc;
+    if (!mask_out) return fail(NT_ERR_INVALID, "NULL argument");
+    NtCullTables ct;
+    if (!nt_cull_build(desc->spheres, desc->n_spheres, desc->triangles, desc->n_triangles, desc->lights, desc->n_lights, ct))
+        return fail(NT_ERR_INVALID, "scene is not eligible for the flat culling tables");
+    *mask_out = plane_free_lights(desc);
     return NT_OK;
 }
 
@@ -496,6 +517,7 @@ static int launch(nt_scene *sc, NtRenderArgs &a, uint32_t precision, cudaStream_
         for (int k = 0; k < 3; ++k) eye_inf = std::max(eye_inf, std::fabs(a.cam[k]));
         nt_cull_primary_rects(sc->h_bsph.data(), sc->ds.ns + sc->ds.nt, a.cam, a.width, a.height, 1e-5 * (eye_inf + (double)sc->ds.max_abs), &a.prect[0][0]);
     }
+    sc->ds.lfree = a.eps >= kPlaneFreeEps ? sc->lfree : 0u; // the proof behind the bits assumes this epsilon at least
     const int e = precision == NT_F64_STRICT ? nt_launch_render_f64(sc->ds, a, st) : nt_launch_render_f32(sc->ds, a, st);
     if (e) return fail(NT_ERR_CUDA, "render kernel launch: %s", cudaGetErrorString((cudaError_t)e));
     return NT_OK;

@@ -181,3 +181,50 @@ void nt_cull_primary_rects(const double *bsph, uint32_t nb, const double cam[12]
         o[2] = (uint16_t)std::max(0.0, py_lo); o[3] = (uint16_t)std::min((double)ymax, py_hi);
     }
 }
+
+uint32_t nt_cull_plane_free_lights(const double *spheres, uint32_t ns, const double *triangles, uint32_t nt, const double *planes,
+                                   uint32_t np, const double *lights, uint32_t nl, double eps_min) {
+    if (ns + nt == 0 || nl == 0 || nl > 32) return 0;
+    // exact bounding box of the bounded primitives (c -+ r is one rounding; triangle vertices are exact)
+    double lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY }, ext = 0;
+    for (uint32_t j = 0; j < ns; ++j)
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = std::min(lo[a], spheres[4 * (size_t)j + a] - spheres[4 * (size_t)j + 3]);
+            hi[a] = std::max(hi[a], spheres[4 * (size_t)j + a] + spheres[4 * (size_t)j + 3]);
+        }
+    for (size_t i = 0; i < 9 * (size_t)nt; ++i) {
+        lo[i % 3] = std::min(lo[i % 3], triangles[i]);
+        hi[i % 3] = std::max(hi[i % 3], triangles[i]);
+    }
+    for (int a = 0; a < 3; ++a) ext = std::max(ext, std::max(std::fabs(lo[a]), std::fabs(hi[a])));
+    uint32_t out = 0;
+    for (uint32_t l = 0; l < nl; ++l) {
+        const double *L = lights + 6 * (size_t)l;
+        double dmax2 = 0, lext = ext;
+        for (int a = 0; a < 3; ++a) {
+            const double m = std::max(std::fabs(L[a] - lo[a]), std::fabs(L[a] - hi[a]));
+            dmax2 += m * m;
+            lext = std::max(lext, std::fabs(L[a]));
+        }
+        const double dist_max = std::sqrt(dmax2);
+        bool free_ = std::isfinite(dist_max) && dist_max > 0;
+        for (uint32_t i = 0; i < np && free_; ++i) {
+            const double *p = planes + 4 * (size_t)i;
+            const double len = std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+            double sl = (p[0] * L[0] + p[1] * L[1] + p[2] * L[2]) - p[3];
+            double smin = -p[3], smax = -p[3]; // range of n.x - d over the box
+            for (int a = 0; a < 3; ++a) {
+                smin += std::min(p[a] * lo[a], p[a] * hi[a]);
+                smax += std::max(p[a] * lo[a], p[a] * hi[a]);
+            }
+            if (sl < 0) { sl = -sl; const double t = -smin; smin = -smax; smax = t; } // light below: mirror
+            const double round = 1e-12 * len * (lext + std::fabs(p[3]) / (len > 0 ? len : 1.0)); // >> rounding of hit points and of n.P - d
+            const double allowed = 1e-3 * eps_min * sl / dist_max - 2.0 * round;
+            // light clearly off the plane; no point of the box farther than `allowed` on the other side
+            free_ = len > 0 && sl > 1e-6 * (std::fabs(smax) + std::fabs(smin) + len * lext) &&
+                    (smin >= 2.0 * round || (allowed > 2.0 * round && smin >= -allowed));
+        }
+        if (free_) out |= 1u << l;
+    }
+    return out;
+}

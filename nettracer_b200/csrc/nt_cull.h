@@ -37,3 +37,14 @@ bool nt_cull_build(const double *spheres, uint32_t ns, const double *triangles, 
 // ball's outline on the image plane is not an ellipse (eye inside the ball, ball crossing the eye's plane).
 void nt_cull_primary_rects(const double *bsph, uint32_t nb, const double cam[12], uint32_t width, uint32_t height,
                            double margin, uint16_t *rects);
+
+// Bit l of the result: no plane can stop a strict-mode shadow query (ray epsilon >= eps_min) that starts on a
+// bounded primitive and aims at light l.  Per plane: the light is clearly off the plane (s_L = n.L - d), and no point
+// of the primitives' exact bounding box is farther than `allowed` on the other side, allowed = 1e-3 eps_min s_L /
+// dist_max (dist_max = largest distance from the light to the box).  A point P on the light's side gives a crossing
+// parameter t < 0 or t >= dist (1 + 1e-6); a point within `allowed` beyond the plane (a sphere resting on the floor:
+// its lowest point, give or take rounding) gives t = dist (-s_P) / (s_L - s_P) <= 1e-3 eps_min: a miss by t > eps.
+// All margins are many orders above the rounding errors of the exact rule.  planes [np][4] = nx ny nz d with
+// n.x = d on the plane (SPEC-PROVISIONAL §1).  At most 32 lights.
+uint32_t nt_cull_plane_free_lights(const double *spheres, uint32_t ns, const double *triangles, uint32_t nt, const double *planes,
+                                   uint32_t np, const double *lights, uint32_t nl, double eps_min);

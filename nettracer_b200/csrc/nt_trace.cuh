@@ -580,9 +580,11 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
 // Flat scenes count the tests NOT made: k.sph / k.pln / k.tri are deficits against "every query tests every
 // primitive" and are touched only when a query ends early (the kernel's flush turns them into test counts:
 // queries * n - deficit); an update per query was a spilled load-add-store on the common path.
+// `planes`: false when the host proved that no plane can lie between this query's origin and its light (the
+// origin is on a bounded primitive and the light's bit of NtDevScene::lfree is set, nt_cull.h).
 template <typename R, bool BVH, typename K>
 __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, const V3<R> &d, R dist, unsigned long long mask,
-                                         K &k) {
+                                         bool planes, K &k) {
     const NtDevScene &s = *c.s;
     R t;
     if constexpr (!BVH) {
@@ -596,7 +598,7 @@ __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, c
         }
     }
     if constexpr (!BVH && sizeof(R) == 8) {
-        if (planes_occluded<R>(c, o, d, dist)) { k.pln += s.np - (first_occluding_plane<R>(c, o, d, dist) + 1); k.tri += s.nt; return true; }
+        if (planes && planes_occluded<R>(c, o, d, dist)) { k.pln += s.np - (first_occluding_plane<R>(c, o, d, dist) + 1); k.tri += s.nt; return true; }
     }
     if constexpr (!BVH && sizeof(R) == 4) {
         unsigned i = 0;
@@ -703,7 +705,8 @@ __device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R
                 if (!(ndl > R(0))) continue;
                 k.shadow++;
                 const unsigned long long lmask = s.cull ? lbuf_mask<R>(s, l, Lv) : s.all_bits;
-                if (occluded<R, BVH, K>(c, P, L, dist, lmask, k)) continue;
+                const bool planes = sizeof(R) == 4 || h.kind == 1 || !((s.lfree >> l) & 1u); // strict mode only: see nt_cull.h
+                if (occluded<R, BVH, K>(c, P, L, dist, lmask, planes, k)) continue;
                 k.light++;
                 R m0[4], m1[4];
                 Ld<R>::g4(mp, m0);     // r g b ka

@@ -47,6 +47,7 @@ def load():
         "nt_measure_peaks": (C.c_int, [C.c_int, C.POINTER(abi.nt_peaks)]),
         "nt_cull_tables": (C.c_int, [C.POINTER(abi.nt_scene_desc), C.POINTER(u32), vp, C.c_size_t, vp, vp]),
         "nt_primary_rects": (C.c_int, [C.POINTER(abi.nt_scene_desc), C.POINTER(abi.nt_render_params), vp]),
+        "nt_plane_free_lights": (C.c_int, [C.POINTER(abi.nt_scene_desc), C.POINTER(u32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name, None)

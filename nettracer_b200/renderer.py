@@ -111,6 +111,16 @@ def primary_rects(scene: Scene, params) -> np.ndarray:
     return out
 
 
+def plane_free_lights(scene: Scene) -> int:
+    """Bit mask of the lights towards which a shadow query from a bounded primitive cannot be stopped by a plane
+    (nt_plane_free_lights: host only)."""
+    desc, keep = scene.to_desc()
+    m = C.c_uint32()
+    check(load().nt_plane_free_lights(C.byref(desc), C.byref(m)))
+    del keep
+    return int(m.value)
+
+
 def measure_peaks(device=0) -> dict:
     p = abi.nt_peaks()
     check(load().nt_measure_peaks(int(device), C.byref(p)))

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from nettracer_b200 import scenes
-from nettracer_b200.renderer import cull_tables, primary_rects
+from nettracer_b200.renderer import cull_tables, plane_free_lights, primary_rects
 from nettracer_b200.scene import Camera, make_params
 
 EPS = 1e-6
@@ -227,3 +227,64 @@ def test_primary_rects_are_tight_enough():
         x0, x1, y0, y1 = rects[j]
         assert x0 >= max(px[xs].min() - 6, 0) - 1 and x1 <= min(px[xs].max() + 6, w - 1) + 1
         assert y0 >= max(py[ys].min() - 6, 0) - 1 and y1 <= min(py[ys].max() + 6, h - 1) + 1
+
+
+# ---- shadow queries from bounded primitives: lights no plane can hide (nt_cull_plane_free_lights) ----
+def _plane_occludes(P, light, planes):
+    """SPEC §3 plane rule for the segment P -> light: eps < t < dist for any plane."""
+    Lv = light[:3] - P
+    dist = np.sqrt((Lv * Lv).sum(-1))
+    L = Lv / dist[:, None]
+    occ = np.zeros(len(P), dtype=bool)
+    for pl in planes:
+        dn = (L * pl[:3]).sum(-1)
+        num = pl[3] - (P * pl[:3]).sum(-1)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t = num / dn
+        occ |= (dn != 0) & (t > EPS) & (t < dist)
+    return occ
+
+
+def _points_on_bounded(scene, rng, n):
+    a = scene.arrays()
+    pts = []
+    for s in a["spheres"]:
+        v = rng.normal(size=(n, 3))
+        v /= np.linalg.norm(v, axis=1, keepdims=True)
+        pts.append(s[:3] + s[3] * v)
+    for t in a["triangles"]:
+        pts.append(rng.dirichlet((1, 1, 1), n) @ t.reshape(3, 3))
+    return np.concatenate(pts)
+
+
+def test_plane_free_lights_cornell():
+    scene = scenes.cornell_box()[0]
+    a = scene.arrays()
+    mask = plane_free_lights(scene)
+    assert mask == (1 << len(a["lights"])) - 1, "both lights of the box sit inside the room with all spheres"
+    P = _points_on_bounded(scene, np.random.default_rng(3), 2000)
+    for light in a["lights"]:
+        assert not _plane_occludes(P, light, a["planes"]).any()
+
+
+def test_plane_free_lights_is_conservative():
+    """Random scenes and a box with one light moved behind a wall: a set bit must mean that the exact rule never finds
+    an occluding plane from any point of a bounded primitive; an unset bit is always allowed."""
+    rng = np.random.default_rng(11)
+    cases = [scenes.random_mixed(12, 3, 20, seed=sd)[0] for sd in (1, 2, 3)]
+    box = scenes.cornell_box()[0]
+    l0 = box.lights[0]
+    box.lights[0] = (l0[0], l0[1] + 100.0, l0[2], l0[3], l0[4], l0[5])  # far above the ceiling
+    cases.append(box)
+    seen_clear = False
+    for scene in cases:
+        a = scene.arrays()
+        mask = plane_free_lights(scene)
+        P = _points_on_bounded(scene, rng, 500)
+        for l, light in enumerate(a["lights"]):
+            occ = _plane_occludes(P, light, a["planes"])
+            if (mask >> l) & 1:
+                assert not occ.any(), f"light {l} is flagged plane-free but a plane hides it from {int(occ.sum())} points"
+            else:
+                seen_clear = True
+    assert seen_clear, "at least one light of the random scenes should have a plane in the way"

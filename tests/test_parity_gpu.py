@@ -105,6 +105,28 @@ def test_flat_culling_off_equals_on(monkeypatch):
         assert st[k] == st0[k], k
 
 
+def test_plane_free_lights_off_equals_on(monkeypatch):
+    """Shadow queries from spheres skip the planes when the host proved no plane can hide the light (both lights of the
+    box; spheres resting on the floor).  NT_PLANE_FREE=0 runs the plane loops always: same image, same counters, also
+    with a ray epsilon below the proof's assumption (the bits are then cleared per launch)."""
+    from nettracer_b200.renderer import plane_free_lights
+    s, cam = scenes.cornell_box()
+    assert plane_free_lights(s) == 3
+    outs = []
+    for env in (None, "0"):
+        if env is not None:
+            monkeypatch.setenv("NT_PLANE_FREE", env)
+        with Renderer(s) as r:
+            outs.append([r.render_params(make_params(320, 180, 4, 5, cam.resolve(320, 180), abi.NT_F64_STRICT, ray_epsilon=e))
+                         for e in (0.0, 1e-9)])
+    for (img, st), (img0, st0) in zip(outs[0], outs[1]):
+        assert np.array_equal(img, img0)
+        for k in COUNTER_KEYS + FLAT_TEST_KEYS:
+            assert st[k] == st0[k], k
+    ref, rst = oracle.render(s, make_params(320, 180, 4, 5, cam.resolve(320, 180), abi.NT_F64_STRICT, ray_epsilon=1e-9))
+    assert_images_match(outs[0][1][0], ref, "eps 1e-9")
+
+
 def test_mesh_scene_reduced_bvh():
     s, cam = scenes.spheres_and_mesh(n_spheres=2000, mesh_n=96)
     img, st, ref, rst, info = render_both(s, cam, 256, 144, 4, 3, accel=1)
