@@ -75,6 +75,7 @@ struct nt_scene {
     void *d_samples = nullptr; // BVH scenes: per-sample radiance scratch
     size_t samples_bytes = 0;
     unsigned last_launches = 0; // kernels launched by the last render call
+    unsigned long long heavy_bits = 0; // flat scenes: bounded primitives whose material both reflects and transmits (branching ray trees)
     uint32_t lfree = 0;         // flat scenes with culling: lights no plane can hide from a bounded primitive (nt_cull.h)
     std::vector<double> h_bsph; // flat scenes with culling: bounding spheres (host copy, for the per-camera pixel rectangles)
     void *d_wf = nullptr;      // BVH scenes: wavefront workspace (level records of one chunk of samples)
@@ -324,6 +325,8 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
     if (!use_bvh && !(ce && ce[0] == '0') && nt_cull_build(d->spheres, ns, d->triangles, nt, d->lights, nl, ct)) {
         ds.cull = 1; ds.lbuf_k = ct.k;
         sc->h_bsph = ct.bsph;
+        for (uint32_t j = 0; j < ns; ++j) { const double *m = d->materials + 10 * (size_t)d->sphere_mat[j]; if (m[7] > 0 && m[8] > 0) sc->heavy_bits |= 1ull << j; }
+        for (uint32_t j = 0; j < nt; ++j) { const double *m = d->materials + 10 * (size_t)d->triangle_mat[j]; if (m[7] > 0 && m[8] > 0) sc->heavy_bits |= 1ull << (ns + j); }
         const char *pe = getenv("NT_PLANE_FREE"); // 0: always run the plane loops of a shadow query (A/B, tests)
         if (!(pe && pe[0] == '0')) sc->lfree = plane_free_lights(d);
     }
@@ -457,6 +460,8 @@ static int make_args(const nt_render_params *p, size_t stride, NtRenderArgs *a) 
     a->twx = tw[li][0]; a->twy = tw[li][1];
     a->tiles_x = (p->width + a->twx - 1) / a->twx;
     a->tiles_y = (a->vrows + a->twy - 1) / a->twy;
+    a->n_tiles = a->tiles_x * a->tiles_y;
+    a->tile_rot = 0;
     a->log2_lanes = (uint32_t)li;
     for (a->log2_twx = 0; (1u << a->log2_twx) < a->twx; ++a->log2_twx) {}
     for (a->log2_twy = 0; (1u << a->log2_twy) < a->twy; ++a->log2_twy) {}
@@ -516,6 +521,16 @@ static int launch(nt_scene *sc, NtRenderArgs &a, uint32_t precision, cudaStream_
         double eye_inf = 0;
         for (int k = 0; k < 3; ++k) eye_inf = std::max(eye_inf, std::fabs(a.cam[k]));
         nt_cull_primary_rects(sc->h_bsph.data(), sc->ds.ns + sc->ds.nt, a.cam, a.width, a.height, 1e-5 * (eye_inf + (double)sc->ds.max_abs), &a.prect[0][0]);
+        // start the tile sequence at the first row that shows a branching primitive (any primitive when there is none)
+        const char *re = getenv("NT_TILE_ROT");
+        uint32_t y0 = a.height;
+        for (int pass = 0; pass < 2 && y0 == a.height; ++pass)
+            for (uint32_t j = 0; j < sc->ds.ns + sc->ds.nt; ++j)
+                if ((pass == 1 || ((sc->heavy_bits >> j) & 1ull)) && a.prect[j][0] <= a.prect[j][1]) y0 = std::min<uint32_t>(y0, a.prect[j][2]);
+        if (y0 < a.height && a.max_depth > 1 && !(re && re[0] == '0')) {
+            const uint32_t vr = (uint32_t)((uint64_t)y0 * a.vrows / a.height); // owned rows are spread evenly over the image
+            a.tile_rot = std::min(vr / a.twy, a.tiles_y - 1) * a.tiles_x;
+        }
     }
     sc->ds.lfree = a.eps >= kPlaneFreeEps ? sc->lfree : 0u; // the proof behind the bits assumes this epsilon at least
     const int e = precision == NT_F64_STRICT ? nt_launch_render_f64(sc->ds, a, st) : nt_launch_render_f32(sc->ds, a, st);

@@ -100,6 +100,7 @@ struct NtRenderArgs {
     uint32_t lanes;    // lanes per pixel (power of two dividing spp, <= 32)
     uint32_t twx, twy; // warp tile in pixels, twx*twy*lanes == 32
     uint32_t tiles_x, tiles_y; // warp tiles over the virtual image (owned rows only)
+    uint32_t n_tiles, tile_rot; // tiles_x * tiles_y; the tile sequence starts at tile tile_rot and wraps (nt_trace.cuh tile_origin)
     double eps;
     double eps_lo;     // fl(eps * (1 - 2^-50)), 0 when eps < 1e-290: quotients provably <= eps skip the division (plane_below_eps)
     double cam[12];    // eye p00 dx dy
