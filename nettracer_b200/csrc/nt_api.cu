@@ -433,6 +433,18 @@ extern "C" uint32_t nt_shard_rows(uint32_t height, uint32_t band_rows, uint32_t 
 // ---------------- render ----------------
 // nt_trace.cuh plane_below_eps: eps * (1 - 2^-50), rounded; 0 switches the shortcut off for absurdly small epsilons
 static double eps_low_bound(double eps) { return eps >= 1e-290 ? eps * (1.0 - 8.8817841970012523e-16) : 0.0; }
+// Warp tile = twx x (32 / lanes / twx) pixels; everything derived from the shape (a->lanes, vrows, width must be set)
+static void set_tile_shape(NtRenderArgs *a, uint32_t twx) {
+    a->twx = twx; a->twy = 32u / a->lanes / twx;
+    a->tiles_x = (a->width + a->twx - 1) / a->twx;
+    a->tiles_y = (a->vrows + a->twy - 1) / a->twy;
+    a->n_tiles = a->tiles_x * a->tiles_y;
+    a->tile_rot = 0;
+    for (a->log2_twx = 0; (1u << a->log2_twx) < a->twx; ++a->log2_twx) {}
+    for (a->log2_twy = 0; (1u << a->log2_twy) < a->twy; ++a->log2_twy) {}
+    a->inv_tiles_x = 1.0f / (float)a->tiles_x;
+}
+
 static int make_args(const nt_render_params *p, size_t stride, NtRenderArgs *a) {
     if (!p) return fail(NT_ERR_INVALID, "params is NULL");
     if (p->struct_size != sizeof(nt_render_params)) return fail(NT_ERR_INVALID, "nt_render_params.struct_size %u != %zu", p->struct_size, sizeof(nt_render_params));
@@ -454,20 +466,18 @@ static int make_args(const nt_render_params *p, size_t stride, NtRenderArgs *a) 
     uint32_t L = 1;
     while (L < 32 && p->spp % (L * 2) == 0) L *= 2;
     a->lanes = L;
-    static const uint32_t tw[6][2] = { { 8, 4 }, { 4, 4 }, { 4, 2 }, { 2, 2 }, { 2, 1 }, { 1, 1 } }; // L = 1,2,4,8,16,32
     int li = 0;
     while ((1u << li) < L) ++li;
-    a->twx = tw[li][0]; a->twy = tw[li][1];
-    a->tiles_x = (p->width + a->twx - 1) / a->twx;
-    a->tiles_y = (a->vrows + a->twy - 1) / a->twy;
-    a->n_tiles = a->tiles_x * a->tiles_y;
-    a->tile_rot = 0;
     a->log2_lanes = (uint32_t)li;
-    for (a->log2_twx = 0; (1u << a->log2_twx) < a->twx; ++a->log2_twx) {}
-    for (a->log2_twy = 0; (1u << a->log2_twy) < a->twy; ++a->log2_twy) {}
+    static const uint32_t tw[6] = { 8, 4, 4, 2, 2, 1 }; // L = 1,2,4,8,16,32: near-square warp tiles (best culling / coherence)
+    uint32_t twx = tw[li];
+    if (const char *e = getenv("NT_TILE_W")) { // experiment: warp tile width in pixels (power of two <= 32 / lanes)
+        const uint32_t wreq = (uint32_t)atoi(e);
+        if (wreq >= 1 && wreq <= 32u / L && (wreq & (wreq - 1)) == 0) twx = wreq;
+    }
+    set_tile_shape(a, twx);
     a->band_magic = band > 1 ? (uint32_t)(((1ull << 32) + band - 1) / band) : 0u;
     a->n_mul = (65536u + n - 1) / n;
-    a->inv_tiles_x = 1.0f / (float)a->tiles_x;
     a->eps = p->ray_epsilon > 0 ? p->ray_epsilon : 1e-6;
     if (p->precision == NT_F32_FAST && a->eps < 1e-4) a->eps = 1e-4; // SPEC-PROVISIONAL §7
     a->eps_lo = eps_low_bound(a->eps);
@@ -573,6 +583,9 @@ extern "C" int nt_render(nt_scene *sc, const nt_render_params *p, uint8_t *rgba_
     if (mapped) {
         a.out = mapped;
         a.stride = stride;
+        // stores cross PCIe: one row of 32 / lanes pixels per warp tile makes the widest contiguous write (configs[2]:
+        // 4x2 tiles 0.852 ms per frame end to end, 8x1 0.783; configs[1]: 8x4 0.372, 32x1 0.206)
+        if (!getenv("NT_TILE_W")) set_tile_shape(&a, 32u / a.lanes);
     } else {
         const size_t need = pitch * out_rows;
         if (need > sc->fb_bytes) {
