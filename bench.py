@@ -311,10 +311,10 @@ def main():
         achieved_tf = flops_local / (kernel_ms_local * 1e-3) / 1e12
         roof = {"bound": "fp64" if strict else "fp32", "achieved": achieved_tf, "peak": peak_gf / 1e3, "unit": "TFLOP/s",
                 "frac": achieved_tf / (peak_gf / 1e3),
-                "traffic": ({"cfg3_cornell_1080p_4spp_d5": 9.215e7}.get(a.workload) if strict else None),
-                "traffic_note": "dram read+write bytes of one render launch (ncu --set full, profiles/r01c_cfg3_f64_final.md): "
-                                "2.5 MB read + 89.7 MB written, of which 8.3 MB is the frame and the rest evicted local-memory "
-                                "(spill) lines; 0.2 % of HBM bandwidth - the kernel is FP-issue bound, not HBM bound",
+                "traffic": ({"cfg3_cornell_1080p_4spp_d5": 7.423e7}.get(a.workload) if strict else None),
+                "traffic_note": "dram read+write bytes of one render launch (ncu --set full, profiles/r01j_cfg3_f64_final.md): "
+                                "2.3 MB read + 71.9 MB written, of which 8.3 MB is the frame and the rest evicted local-memory "
+                                "(ray-tree stack and spill) lines; 1.5 % of HBM bandwidth - the kernel is FP-issue bound, not HBM bound",
                 "kernel": ("wf_trace_kernel + wf_shade_kernel (wavefront pipeline, all kernels of a frame)" if info["uses_bvh"] and per_frame_launches > 2
                            else "render_%skernel<%s>" % ("bvh_" if info["uses_bvh"] else "", "double" if strict else "float")),
                 "kernel_ms": kernel_ms_local, "algorithmic_flops_per_launch": flops_local,

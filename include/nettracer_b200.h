@@ -61,7 +61,7 @@ typedef struct nt_scene_desc {
     const int32_t *plane_mat;     /* [n_planes] */
     const double *triangles;      /* [n_triangles][9] v0 v1 v2 */
     const int32_t *triangle_mat;  /* [n_triangles] */
-    const double *materials;      /* [n_materials][10] r g b ka kd ks shininess kr kt ior */
+    const double *materials;      /* [n_materials][10] r g b ka kd ks shininess kr kt ior (ior > 0) */
     const double *lights;         /* [n_lights][6]    px py pz r g b */
     double ambient[3];
     double background[3];

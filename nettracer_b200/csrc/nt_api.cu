@@ -130,6 +130,7 @@ static int validate_desc(const nt_scene_desc *d) {
         double sum = 0;
         for (int k = 0; k < 10; ++k) sum += d->materials[10 * (size_t)i + k];
         if (!std::isfinite(sum)) return fail(NT_ERR_INVALID, "material %u: non-finite value", i);
+        if (!(d->materials[10 * (size_t)i + 9] > 0)) return fail(NT_ERR_INVALID, "material %u: index of refraction must be > 0", i);
     }
     return NT_OK;
 }
@@ -330,16 +331,7 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
         const char *pe = getenv("NT_PLANE_FREE"); // 0: always run the plane loops of a shadow query (A/B, tests)
         if (!(pe && pe[0] == '0')) sc->lfree = plane_free_lights(d);
     }
-    {
-        std::vector<float4> b32(ct.bsph.size() / 4);
-        for (size_t j = 0; j < b32.size(); ++j) {
-            const double *b = ct.bsph.data() + 4 * j;
-            float r = (float)b[3];
-            if ((double)r < b[3]) r = std::nextafter(r, INFINITY);
-            b32[j] = make_float4((float)b[0], (float)b[1], (float)b[2], r);
-        }
-        UP(b32, ds.bsph32); UP(ct.lbuf, ds.lbuf); UP(ct.nbr, ds.nbr); // 16-byte placeholders when culling is off
-    }
+    UP(ct.lbuf, ds.lbuf); UP(ct.nbr, ds.nbr); // 16-byte placeholders when culling is off
 #undef UP
     CU(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&sc->ev0));

@@ -87,7 +87,6 @@ struct NtDevScene {
     uint32_t cull, lbuf_k;
     uint32_t lfree; // bit l: no plane can lie between a point of a bounded primitive and light l (nt_cull_plane_free_lights)
     unsigned long long sph_bits, all_bits; // masks of the sphere bits / of all bounded primitives (flat scenes)
-    const float4 *bsph32;           // [ns+nt] bounding spheres of the bounded primitives (bit order; radius rounded up)
     const unsigned long long *lbuf; // [nl][6][lbuf_k][lbuf_k] light buffers
     const unsigned long long *nbr;  // [ns] balls touching ball i
     NtSceneView<double> v64;

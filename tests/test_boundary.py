@@ -99,6 +99,11 @@ def test_invalid_scene_rejected_before_device_work():
     d, keep = s.to_desc()
     assert L.nt_scene_create(C.byref(d), 0, C.byref(h)) == abi.NT_ERR_INVALID
     assert b"material 1" in L.nt_last_error()
+    s, cam = scenes.cornell_box()
+    s.materials[2].ior = 0.0  # 1 / ior is a derived value of every material (SPEC-PROVISIONAL §1)
+    d, keep = s.to_desc()
+    assert L.nt_scene_create(C.byref(d), 0, C.byref(h)) == abi.NT_ERR_INVALID
+    assert b"index of refraction" in L.nt_last_error()
 
 
 def test_product_never_touches_the_oracle():
