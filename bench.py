@@ -101,6 +101,25 @@ class ClockSampler(threading.Thread):
         return out
 
 
+_json_out = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: everything else a library prints there (NCCL's version banner on the
+    first communicator) is sent to stderr by pointing fd 1 at fd 2; the line itself goes to a private copy of fd 1."""
+    global _json_out
+    if _json_out is None:
+        sys.stdout.flush()
+        _json_out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _json_out or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def workload(name):
     from nettracer_b200 import scenes
     factory, w, h, spp, depth = scenes.CONFIGS[name]
@@ -174,11 +193,12 @@ def run_reference(a):
                              "note": "no NetTracer source or JVM exists here; this is the SPEC-PROVISIONAL oracle"},
             "e2e": {"value": val, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
     a = parse()
+    claim_stdout()
     if a.impl == "reference":
         run_reference(a)
         return
@@ -342,7 +362,7 @@ def main():
                 "kernel_ms": kernel_ms, "wall_s_timed_region": wall, "clocks": clocks, "roofline": roof}
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_oracle_sample(scene, cam, w, h, spp, depth, a.cpu_seconds)
-        print(json.dumps(line))
+        emit(line)
     barrier()
     sr.close()
     if world > 1:
