@@ -8,7 +8,7 @@ import pytest
 
 from nettracer_b200 import scenes
 from nettracer_b200.renderer import cull_tables, plane_free_lights, primary_rects
-from nettracer_b200.scene import Camera, make_params
+from nettracer_b200.scene import Camera, Material, Scene, make_params
 
 EPS = 1e-6
 
@@ -288,3 +288,87 @@ def test_plane_free_lights_is_conservative():
             else:
                 seen_clear = True
     assert seen_clear, "at least one light of the random scenes should have a plane in the way"
+
+
+def test_primary_rects_fuzz():
+    """Random balls (radius 3e-5 ... 300, any distance, also around or behind the eye), random cameras (5 ... 150 degrees,
+    tilted), small odd images: no sample position may see a ball outside its rectangle."""
+    rng = np.random.default_rng(2024)
+    checked = 0
+    for _ in range(150):
+        s = Scene()
+        m = s.add_material(Material())
+        for _j in range(int(rng.integers(1, 6))):
+            scale = 10.0 ** rng.uniform(-2, 2)
+            s.add_sphere(tuple(rng.normal(size=3) * scale * 3), float(10.0 ** rng.uniform(-2.5, 0.5) * scale), m)
+        s.add_light((0, 50, 0))
+        cam = Camera(tuple(rng.normal(size=3) * 10.0 ** rng.uniform(-1, 1.5)), tuple(rng.normal(size=3) * 3),
+                     up=tuple(rng.normal(size=3)), vfov_deg=float(rng.uniform(5, 150)))
+        w, h = int(rng.integers(8, 90)), int(rng.integers(8, 70))
+        rects = primary_rects(s, make_params(w, h, 4, 1, cam.resolve(w, h))).astype(np.int64)
+        eye, D, px, py = _primary_dirs(cam, w, h, 2)
+        for j, ball in enumerate(cull_tables(s)["bsph"]):
+            touch = _line_touches_ball(eye, D, ball)
+            x0, x1, y0, y1 = rects[j]
+            inside = ((py >= y0) & (py <= y1))[:, None] & ((px >= x0) & (px <= x1))[None, :]
+            assert not (touch & ~inside).any(), (j, rects[j], ball, w, h)
+            checked += 1
+    assert checked > 300
+
+
+def test_plane_free_lights_fuzz():
+    """Spheres resting on, hovering over or sunk into a floor (by 1e-13 ... 2), walls, lights on either side: a flagged
+    light must never be hidden by a plane from any point of a sphere - checked with the exact rule at the smallest
+    ray epsilon the proof covers (1e-7), densely around the points nearest to every plane."""
+    rng = np.random.default_rng(77)
+    eps = 1e-7
+    flagged = 0
+    for _ in range(250):
+        s = Scene()
+        m = s.add_material(Material())
+        n = np.array([0.0, 1.0, 0.0])
+        if rng.random() < 0.4:
+            n = rng.normal(size=3)
+            n /= np.linalg.norm(n)
+        d0 = float(rng.uniform(-3, 3))
+        s.add_plane(tuple(n), d0, m)
+        if rng.random() < 0.5:
+            s.add_plane((1, 0, 0), -8.0, m)
+            s.add_plane((-1, 0, 0), -8.0, m)
+        for _j in range(int(rng.integers(1, 5))):
+            r = float(10 ** rng.uniform(-1, 0.5))
+            sink = float(rng.choice([0, 0, 1e-13, 1e-10, 1e-8, 1e-6, 1e-3, -1e-9, -0.5, -2]))
+            base = rng.normal(size=3) * 3
+            base -= n * (base @ n - d0)
+            s.add_sphere(tuple(base + n * (r - sink)), r, m)
+        for _l in range(2):
+            lp = rng.normal(size=3) * 6
+            lp = lp - n * ((lp @ n) - d0) + n * (rng.uniform(0.5, 9) if rng.random() < 0.8 else rng.uniform(-3, 0.01))
+            s.add_light(tuple(lp))
+        a = s.arrays()
+        mask = plane_free_lights(s)
+        pts = []
+        for sp in a["spheres"]:
+            v = rng.normal(size=(200, 3))
+            pts.append(sp[:3] + sp[3] * v / np.linalg.norm(v, axis=1, keepdims=True))
+            for pl in a["planes"]:
+                nn = pl[:3] / np.linalg.norm(pl[:3])
+                for sg in (-1.0, 1.0):
+                    vv = sg * nn[None, :] + rng.normal(size=(40, 3)) * 10 ** rng.uniform(-9, -1)
+                    pts.append(sp[:3] + sp[3] * vv / np.linalg.norm(vv, axis=1, keepdims=True))
+                    pts.append((sp[:3] + sg * sp[3] * nn)[None, :])
+        P = np.concatenate(pts)
+        for l, light in enumerate(a["lights"]):
+            if not (mask >> l) & 1:
+                continue
+            flagged += 1
+            Lv = light[:3] - P
+            dist = np.sqrt((Lv * Lv).sum(-1))
+            L = Lv / dist[:, None]
+            for pl in a["planes"]:
+                dn = (L * pl[:3]).sum(-1)
+                num = pl[3] - (P * pl[:3]).sum(-1)
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    t = num / dn
+                assert not ((dn != 0) & (t > eps) & (t < dist)).any(), (a["spheres"], pl, light)
+    assert flagged >= 10

@@ -127,6 +127,33 @@ def test_plane_free_lights_off_equals_on(monkeypatch):
     assert_images_match(outs[0][1][0], ref, "eps 1e-9")
 
 
+@pytest.mark.parametrize("w,h,spp", [(33, 17, 1), (200, 75, 1), (37, 19, 4), (320, 180, 4), (50, 30, 16), (21, 13, 64)])
+def test_pinned_host_buffer_equals_pageable(w, h, spp):
+    """nt_render stores straight into a PINNED caller buffer (zero copy over PCIe) with one-row warp tiles (32 / lanes
+    pixels wide); a pageable buffer goes through a device frame with near-square tiles.  Same image, same counters -
+    ragged widths included - sharded compact layout too, and the oracle agrees."""
+    import torch
+    s, cam = scenes.cornell_box()
+    with Renderer(s) as r:
+        for kw in ({}, {"shard_index": 1, "shard_count": 3, "band_rows": 4, "layout": abi.NT_LAYOUT_COMPACT}):
+            p = make_params(w, h, spp, 4, cam.resolve(w, h), abi.NT_F64_STRICT, **kw)
+            img, st = r.render_params(p)
+            pinned = torch.zeros(img.shape, dtype=torch.uint8).pin_memory()
+            img2, st2 = r.render_params(p, pinned.numpy())
+            assert np.array_equal(img, img2)
+            for k in COUNTER_KEYS + FLAT_TEST_KEYS:
+                assert st[k] == st2[k], k
+    if spp <= 4:
+        ref, rst = oracle.render(s, make_params(w, h, spp, 4, cam.resolve(w, h), abi.NT_F64_STRICT))
+        full, stf = None, None
+        with Renderer(s) as r:
+            pinned = torch.zeros((h, w, 4), dtype=torch.uint8).pin_memory()
+            full, stf = r.render_params(make_params(w, h, spp, 4, cam.resolve(w, h), abi.NT_F64_STRICT), pinned.numpy())
+        assert_images_match(full, ref, "pinned")
+        for k in COUNTER_KEYS:
+            assert stf[k] == rst[k], k
+
+
 def test_mesh_scene_reduced_bvh():
     s, cam = scenes.spheres_and_mesh(n_spheres=2000, mesh_n=96)
     img, st, ref, rst, info = render_both(s, cam, 256, 144, 4, 3, accel=1)
