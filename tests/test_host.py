@@ -64,3 +64,29 @@ def test_material_row_order():
     s = Scene()
     assert s.add_material(m) == 0 and s.arrays()["materials"].shape == (1, 10)
     assert abi.FLOPS["sphere_tests"] == 17
+
+
+def test_plane_quotient_shortcut_never_rejects_a_hit():
+    """nt_trace.cuh plane_below_eps, restated in numpy binary64 (same IEEE operations): with eps_lo = fl(eps (1 - 2^-50))
+    made as nt_api.cu makes it, `|num| <= fl(|dn| eps_lo)` with a normal product must imply that the correctly rounded
+    quotient fails `t > eps` - probed where it matters, numerators within +-40 ulps of |dn| * eps, over the whole
+    exponent range, for ordinary, huge and absurdly small epsilons (the shortcut is switched off below 1e-290)."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    k = 1.0 - 8.8817841970012523e-16
+    rejected = 0
+    for eps in (1e-6, 1e-4, 1e-7, 1e-9, 3.3e-12, 1e-290, 5e-291, 0.5, 7.0, 1e-300):
+        eps_lo = eps * k if eps >= 1e-290 else 0.0
+        for _ in range(4):
+            n = 200000
+            dn = rng.normal(size=n) * 10.0 ** rng.uniform(-300, 300, size=n)
+            f = 1.0 + rng.integers(-40, 40, size=n) * 2.0 ** -53
+            num = np.abs(dn) * eps * f * np.where(rng.random(n) < 0.5, 1, -1)
+            num = np.where(rng.random(n) < 0.1, np.nextafter(num, np.inf), num)
+            with np.errstate(all="ignore"):
+                lo = np.abs(dn) * eps_lo
+                reject = (np.abs(num) <= lo) & (lo >= 2.2250738585072014e-308)
+                hit = num / dn > eps
+            assert not (reject & hit).any()
+            rejected += int(reject.sum())
+    assert rejected > 1_000_000  # the probe does sit on the boundary
