@@ -372,3 +372,31 @@ def test_plane_free_lights_fuzz():
                     t = num / dn
                 assert not ((dn != 0) & (t > eps) & (t < dist)).any(), (a["spheres"], pl, light)
     assert flagged >= 10
+
+
+def test_diagnostic_entry_points_refuse_ineligible_scenes_and_bad_arguments():
+    """nt_primary_rects / nt_plane_free_lights follow nt_cull_tables: NT_ERR_INVALID for scenes without culling tables
+    (no bounded primitive, > 64 of them), for a bad image size and for NULL outputs - never a crash."""
+    import ctypes as C
+    from nettracer_b200 import abi
+    from nettracer_b200.lib import NetTracerError, load
+    scene, cam = scenes.cornell_box()
+    p = make_params(64, 48, 1, 1, cam.resolve(64, 48))
+    L = load()
+    desc, keep = scene.to_desc()
+    assert L.nt_primary_rects(C.byref(desc), C.byref(p), None) == abi.NT_ERR_INVALID
+    assert L.nt_primary_rects(C.byref(desc), None, None) == abi.NT_ERR_INVALID
+    assert L.nt_plane_free_lights(C.byref(desc), None) == abi.NT_ERR_INVALID
+    bad = make_params(0, 48, 1, 1, cam.resolve(64, 48))
+    with pytest.raises(NetTracerError):
+        primary_rects(scene, bad)
+    planes_only = Scene()
+    m = planes_only.add_material(Material())
+    planes_only.add_plane((0, 1, 0), 0.0, m)
+    planes_only.add_light((0, 5, 0))
+    big = scenes.random_mixed(60, 1, 30, seed=3)[0]  # 90 bounded primitives: a BVH scene
+    for sc in (planes_only, big):
+        with pytest.raises(NetTracerError):
+            primary_rects(sc, p)
+        with pytest.raises(NetTracerError):
+            plane_free_lights(sc)
