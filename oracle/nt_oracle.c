@@ -433,6 +433,7 @@ typedef struct {
     uint8_t *rgba_out;
     size_t stride;
     double *radiance_out;
+    uint16_t *cost_out; /* optional: rays and ray-tree nodes per sample, [h][w][spp][2] (analysis only) */
     uint32_t vrows, row_step, band, scount;
     int n;
     atomic_long next; /* next virtual row to take (dynamic schedule, one row at a time) */
@@ -459,8 +460,14 @@ static void render_row(const ojob *jb, uint32_t vr, ocount *k) {
                      (cam->p00[2] + cam->dx[2] * fx) + cam->dy[2] * fy };
             v3 dir = scale3(D, 1 / sqrt(dot3(D, D)));
             double acc[3] = { 0, 0, 0 };
+            const unsigned long long r0 = k->prim + k->sec + k->shadow, n0 = k->prim + k->sec;
             k->prim++;
             trace(jb->c, ld3(cam->eye), dir, 1.0, 1, acc, k);
+            if (jb->cost_out) {
+                uint16_t *co = jb->cost_out + (((size_t)y * p->width + x) * p->spp + s) * 2;
+                const unsigned long long r = k->prim + k->sec + k->shadow - r0, nn = k->prim + k->sec - n0;
+                co[0] = (uint16_t)(r > 65535 ? 65535 : r); co[1] = (uint16_t)(nn > 65535 ? 65535 : nn);
+            }
             for (int ch = 0; ch < 3; ++ch) sum[ch] = sum[ch] + acc[ch];
         }
         uint8_t *px = jb->rgba_out
@@ -490,9 +497,9 @@ static void *worker(void *arg) {
     return NULL;
 }
 
-int nto_render_radiance(const nt_scene_desc *desc, const nt_render_params *p, uint8_t *rgba_out,
-                        size_t stride, double *radiance_out, nt_render_stats *stats, int accel,
-                        int n_threads, uint32_t row_step) {
+static int render_impl(const nt_scene_desc *desc, const nt_render_params *p, uint8_t *rgba_out,
+                       size_t stride, double *radiance_out, uint16_t *cost_out, nt_render_stats *stats, int accel,
+                       int n_threads, uint32_t row_step) {
     if (!p || p->struct_size != sizeof(nt_render_params)) return NT_ERR_INVALID;
     int n = isqrt_exact(p->spp);
     if (!n || p->width == 0 || p->height == 0 || p->max_depth < 1 || p->max_depth > NT_MAX_DEPTH)
@@ -506,6 +513,7 @@ int nto_render_radiance(const nt_scene_desc *desc, const nt_render_params *p, ui
     ojob jb;
     memset(&jb, 0, sizeof jb);
     jb.c = &c; jb.p = p; jb.rgba_out = rgba_out; jb.stride = stride; jb.radiance_out = radiance_out;
+    jb.cost_out = cost_out;
     jb.vrows = shard_rows(p->height, band, p->shard_index, scount);
     jb.row_step = row_step ? row_step : 1;
     jb.band = band; jb.scount = scount; jb.n = n;
@@ -533,6 +541,18 @@ int nto_render_radiance(const nt_scene_desc *desc, const nt_render_params *p, ui
     }
     ctx_free(&c);
     return NT_OK;
+}
+
+int nto_render_radiance(const nt_scene_desc *desc, const nt_render_params *p, uint8_t *rgba_out,
+                        size_t stride, double *radiance_out, nt_render_stats *stats, int accel,
+                        int n_threads, uint32_t row_step) {
+    return render_impl(desc, p, rgba_out, stride, radiance_out, NULL, stats, accel, n_threads, row_step);
+}
+
+int nto_sample_costs(const nt_scene_desc *desc, const nt_render_params *p, uint16_t *cost_out,
+                     nt_render_stats *stats, int accel, int n_threads) {
+    if (!cost_out) return NT_ERR_INVALID;
+    return render_impl(desc, p, NULL, 0, NULL, cost_out, stats, accel, n_threads, 1);
 }
 
 int nto_render(const nt_scene_desc *desc, const nt_render_params *p, uint8_t *rgba_out, size_t stride,

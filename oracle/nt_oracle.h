@@ -35,6 +35,11 @@ int nto_render_radiance(const nt_scene_desc *desc, const nt_render_params *param
                         uint8_t *rgba_out, size_t row_stride_bytes, double *radiance_out,
                         nt_render_stats *stats, int accel, int n_threads, uint32_t row_step);
 
+/* Analysis aid (scripts/sim_tile_schedule.py): per sample the rays cast and the ray-tree nodes visited,
+ * cost_out[h][w][spp][2] (uint16, saturating).  No image is written. */
+int nto_sample_costs(const nt_scene_desc *desc, const nt_render_params *params, uint16_t *cost_out,
+                     nt_render_stats *stats, int accel, int n_threads);
+
 /* Nearest hit of n rays, SPEC-PROVISIONAL §3. */
 int nto_trace_rays(const nt_scene_desc *desc, uint32_t n, const double *origins,
                    const double *dirs, double ray_epsilon, int accel, double *t_out,

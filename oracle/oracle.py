@@ -59,6 +59,22 @@ def render(scene, params, accel=0, n_threads=0, row_step=1, radiance=False, comp
     return (img, st.as_dict(), rad) if radiance else (img, st.as_dict())
 
 
+def sample_costs(scene, params, accel=0, n_threads=0):
+    """Rays cast and ray-tree nodes visited by every sample: uint16 [h, w, spp, 2] (analysis aid)."""
+    desc, keep = scene.to_desc()
+    out = np.zeros((params.height, params.width, params.spp, 2), dtype=np.uint16)
+    st = abi.nt_render_stats()
+    L = lib()
+    L.nto_sample_costs.restype = C.c_int
+    L.nto_sample_costs.argtypes = [C.POINTER(abi.nt_scene_desc), C.POINTER(abi.nt_render_params), C.c_void_p,
+                                   C.POINTER(abi.nt_render_stats), C.c_int, C.c_int]
+    rc = L.nto_sample_costs(C.byref(desc), C.byref(params), out.ctypes.data, C.byref(st), int(accel), int(n_threads))
+    if rc != 0:
+        raise RuntimeError(f"oracle sample_costs failed: {rc}")
+    del keep
+    return out, st.as_dict()
+
+
 def trace_rays(scene, origins, dirs, ray_epsilon=0.0, accel=0):
     desc, keep = scene.to_desc()
     o = np.ascontiguousarray(origins, dtype=np.float64).reshape(-1, 3)

@@ -136,3 +136,15 @@ def test_flop_convention():
     st = {"sphere_tests": 1, "plane_tests": 1, "triangle_tests": 1, "box_tests": 1, "light_evals": 1}
     assert abi.algorithmic_flops(st) == 17 + 11 + 39 + 18 + 40
     assert math.isclose(1.0, 1.0)
+
+
+def test_sample_costs_add_up():
+    """nto_sample_costs (analysis aid behind scripts/sim_tile_schedule.py): per-sample rays and tree nodes sum to the frame's counters."""
+    s, cam = scenes.cornell_box()
+    p = make_params(96, 54, 4, 5, cam.resolve(96, 54))
+    cost, st = oracle.sample_costs(s, p)
+    _, ref = oracle.render(s, p)
+    assert cost.shape == (54, 96, 4, 2)
+    assert int(cost[..., 0].sum()) == ref["rays"] == st["rays"]
+    assert int(cost[..., 1].sum()) == ref["rays_primary"] + ref["rays_secondary"]
+    assert cost[..., 1].min() == 1 and cost[..., 1].max() <= 2 ** 5 - 1
