@@ -115,6 +115,39 @@ class Renderer {
     nt_scene *h_ = nullptr;
 };
 
+// The same scene on several GPUs of this process (nt_multi_*): interleaved row bands, every GPU stores its bands
+// straight into the host frame.  Pass a page-locked buffer (PinnedFrame) to avoid the staging copy.
+class MultiRenderer {
+  public:
+    MultiRenderer(const Scene &scene, const std::vector<int> &devices) {
+        const nt_scene_desc d = scene.desc();
+        check(nt_multi_create(&d, devices.data(), (int)devices.size(), &h_));
+    }
+    ~MultiRenderer() { nt_multi_destroy(h_); }
+    MultiRenderer(const MultiRenderer &) = delete;
+    MultiRenderer &operator=(const MultiRenderer &) = delete;
+    int devices() const { return nt_multi_device_count(h_); }
+
+    void render_into(uint8_t *rgba, size_t stride, const Camera &cam, uint32_t w, uint32_t h, uint32_t spp, uint32_t max_depth,
+                     nt_precision precision = NT_F64_STRICT, nt_render_stats *stats = nullptr, uint32_t band_rows = 8) {
+        nt_render_params p{};
+        p.struct_size = sizeof p;
+        p.width = w; p.height = h; p.spp = spp; p.max_depth = max_depth; p.precision = precision;
+        p.camera = cam.resolve(w, h);
+        p.shard_index = 0; p.shard_count = 1; p.band_rows = band_rows; p.layout = NT_LAYOUT_FULL;
+        check(nt_multi_render(h_, &p, rgba, stride, stats));
+    }
+    std::vector<uint8_t> render(const Camera &cam, uint32_t w, uint32_t h, uint32_t spp, uint32_t max_depth,
+                                nt_precision precision = NT_F64_STRICT, nt_render_stats *stats = nullptr) {
+        std::vector<uint8_t> rgba((size_t)w * h * 4);
+        render_into(rgba.data(), (size_t)w * 4, cam, w, h, spp, max_depth, precision, stats);
+        return rgba;
+    }
+
+  private:
+    nt_multi *h_ = nullptr;
+};
+
 inline void write_ppm(const std::string &path, const std::vector<uint8_t> &rgba, uint32_t w, uint32_t h) {
     FILE *f = std::fopen(path.c_str(), "wb");
     if (!f) throw std::runtime_error("cannot open " + path);

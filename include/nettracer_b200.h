@@ -23,14 +23,16 @@
 extern "C" {
 #endif
 
-#define NT_ABI_VERSION 1
+#define NT_ABI_VERSION 2
 
 enum nt_status {
     NT_OK = 0,
     NT_ERR_INVALID = -1,   /* bad argument / malformed scene */
     NT_ERR_NO_DEVICE = -2, /* no usable sm_100 device */
     NT_ERR_CUDA = -3,      /* CUDA runtime error, text in nt_last_error() */
-    NT_ERR_NOMEM = -4
+    NT_ERR_NOMEM = -4,
+    NT_ERR_TIMEOUT = -5,   /* a frame-synchronisation flag was not reached in time (a peer is gone) */
+    NT_ERR_SYSTEM = -6     /* shm_open / mmap / thread creation failed, errno text in nt_last_error() */
 };
 
 enum nt_precision {
@@ -140,11 +142,57 @@ int nt_render(nt_scene *scene, const nt_render_params *params, uint8_t *rgba_out
 
 /* Device buffer on the scene's device, asynchronous on `cuda_stream` (a cudaStream_t, may be
  * NULL for the default stream).  rgba_out_dev may be a peer-mapped pointer of another GPU
- * (NVLink): with NT_LAYOUT_FULL every shard can store straight into one remote framebuffer. */
+ * (NVLink): with NT_LAYOUT_FULL every shard can store straight into one remote framebuffer.
+ * Concurrency: calls on one scene may be in flight on DIFFERENT streams.  Flat scenes (<= 64 bounded
+ * primitives) then really overlap - each call takes its own block of work counters from a small ring;
+ * BVH scenes share per-scene scratch buffers, so the library orders a call after the previous one with
+ * an event (no overlap, no corruption).  nt_render (host buffer) is blocking and serialised per scene. */
 int nt_render_device(nt_scene *scene, const nt_render_params *params, void *rgba_out_dev,
                      size_t row_stride_bytes, void *cuda_stream);
-/* Synchronises `cuda_stream` and returns the counters of the last nt_render_device call. */
+/* Synchronises `cuda_stream` and returns the counters of the last nt_render_device[_sync] call on
+ * the scene.  NT_ERR_TIMEOUT when that frame gave up waiting on a nt_frame_sync flag. */
 int nt_render_device_stats(nt_scene *scene, void *cuda_stream, nt_render_stats *stats);
+
+/* ---- frame synchronisation of a sharded render (the exchange step of SURVEY.md section 8(e)) ----
+ * 32-bit sequence-numbered flags in memory every participant can reach: device memory of the gathering
+ * GPU (opened by the other processes with nt_ipc_open) or pinned host memory.  They order the frame
+ * exchange on the device, without a collective: each shard's last kernel release-stores "frame f is
+ * written" next to the pixels it stored over NVLink, the gathering GPU spins on those flags
+ * (nt_flags_wait_device), and its own next frame acknowledges, when it starts, that it has consumed
+ * the earlier ones so that a peer may overwrite the buffer of two frames ago.  Flags are compared by
+ * signed difference (they may wrap); a wait gives up after ~2 s (NT_ERR_TIMEOUT from the stats call). */
+typedef struct nt_frame_sync {
+    uint32_t struct_size;           /* sizeof(nt_frame_sync) */
+    uint32_t post_at_start_value;
+    uint32_t wait_value;
+    uint32_t post_when_done_value;
+    uint32_t *post_at_start;        /* may be NULL: stored when this frame's first kernel starts, i.e. after all
+                                       earlier work of the stream has completed */
+    const uint32_t *wait_before_store; /* may be NULL: no pixel is stored before *flag has reached wait_value */
+    uint32_t *post_when_done;       /* may be NULL: release-stored after this frame's last pixel store */
+} nt_frame_sync;
+/* nt_render_device with the three optional flag operations fused into the frame's kernels. */
+int nt_render_device_sync(nt_scene *scene, const nt_render_params *params, void *rgba_out_dev,
+                          size_t row_stride_bytes, void *cuda_stream, const nt_frame_sync *sync);
+/* Enqueues a wait on `cuda_stream` (of the scene's device) until flags[0..n-1] have all reached `value`:
+ * one tiny kernel; work enqueued after it sees everything the posters stored before posting.  A wait
+ * that gives up is reported by the scene's next nt_render_device_stats as NT_ERR_TIMEOUT. */
+int nt_flags_wait_device(nt_scene *scene, const uint32_t *flags, uint32_t n, uint32_t value, void *cuda_stream);
+
+/* ---- several GPUs behind one call (one host process; a Java host binds exactly this) ----
+ * The scene is replicated on every listed device; a frame is cut into interleaved row bands
+ * (params->band_rows, 0 = 8; shard_index / shard_count / layout of params are ignored), every GPU
+ * renders its bands on its own stream, driven by its own host thread, and stores the RGBA8 words
+ * straight into the caller's buffer when that is pinned host memory (cudaHostAlloc / cudaHostRegister:
+ * every GPU writes over its own PCIe link, no gather, no copy), otherwise into a pinned staging frame
+ * of the library that is copied out band by band.  Blocking.  stats: counters summed over the GPUs,
+ * kernel_ms = the slowest GPU's kernel. */
+typedef struct nt_multi nt_multi;
+int nt_multi_create(const nt_scene_desc *desc, const int *devices, int n_devices, nt_multi **out);
+void nt_multi_destroy(nt_multi *multi);
+int nt_multi_device_count(const nt_multi *multi);
+int nt_multi_render(nt_multi *multi, const nt_render_params *params, uint8_t *rgba_out,
+                    size_t row_stride_bytes, nt_render_stats *stats);
 
 /* ---- unit-level entry point (parity tests of the intersectors) ---- */
 /* Nearest hit of n rays (host arrays origins[n][3], dirs[n][3], used as given — not normalised)
@@ -174,13 +222,32 @@ int nt_ipc_export(const void *dev_ptr, int device, uint8_t handle_out[64]);
 int nt_ipc_open(const uint8_t handle[64], int device, void **dev_ptr_out);
 int nt_ipc_close(void *dev_ptr, int device);
 
+/* ---- one host frame shared by several processes (one process per GPU: torchrun, MPI, ...) ----
+ * A POSIX shared-memory segment holding an RGBA8 frame and one flag line per rank, mapped by every
+ * rank and page-locked for its GPU, so that nt_render (host pointer = nt_host_frame_pixels) stores
+ * each rank's bands straight into the one frame that rank 0's host reads: the end-to-end path of a
+ * sharded render without a gather and without a device-to-host copy.  Protocol per frame `seq`
+ * (1, 2, ...): every rank: nt_host_frame_wait_ack(seq - 1); nt_render(...); nt_host_frame_post(rank, seq);
+ * rank 0: nt_host_frame_wait_all(seq), reads the pixels, nt_host_frame_ack(seq). */
+typedef struct nt_host_frame nt_host_frame;
+/* create != 0: make the segment (rank 0); 0: attach to an existing one.  device: the GPU of the calling
+ * process that will store into it.  name: "/something", as for shm_open. */
+int nt_host_frame_open(const char *name, size_t frame_bytes, uint32_t n_ranks, int create, int device,
+                       nt_host_frame **out);
+uint8_t *nt_host_frame_pixels(nt_host_frame *frame);
+int nt_host_frame_post(nt_host_frame *frame, uint32_t rank, uint32_t seq);
+int nt_host_frame_wait_all(nt_host_frame *frame, uint32_t seq, uint32_t timeout_ms);
+int nt_host_frame_ack(nt_host_frame *frame, uint32_t seq);
+int nt_host_frame_wait_ack(nt_host_frame *frame, uint32_t seq, uint32_t timeout_ms);
+void nt_host_frame_close(nt_host_frame *frame, int unlink_segment);
+
 /* ---- roofline denominators ---- */
 typedef struct nt_peaks {
     double f64_fma_gflops;   /* DFMA chain, 2 flops per instruction */
     double f64_nofma_gflops; /* alternating DMUL / DADD, 1 flop per instruction */
     double f32_fma_gflops;   /* FFMA chain */
     double f32_nofma_gflops;
-    double sm_clock_mhz_est; /* clock64 ticks / elapsed time during the DFMA run */
+    double sm_clock_mhz_est; /* clock64 ticks / %globaltimer nanoseconds of one block of the DFMA run */
     int sm_count;
 } nt_peaks;
 /* Issue-rate micro-benchmark on all SMs of `device`: ~50 ms per figure. */

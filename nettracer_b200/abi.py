@@ -5,8 +5,8 @@ The same structs are consumed by the CUDA library and by the test-only CPU oracl
 """
 import ctypes as C
 
-NT_ABI_VERSION = 1
-NT_OK, NT_ERR_INVALID, NT_ERR_NO_DEVICE, NT_ERR_CUDA, NT_ERR_NOMEM = 0, -1, -2, -3, -4
+NT_ABI_VERSION = 2
+NT_OK, NT_ERR_INVALID, NT_ERR_NO_DEVICE, NT_ERR_CUDA, NT_ERR_NOMEM, NT_ERR_TIMEOUT, NT_ERR_SYSTEM = 0, -1, -2, -3, -4, -5, -6
 NT_F64_STRICT, NT_F32_FAST = 0, 1
 NT_LAYOUT_FULL, NT_LAYOUT_COMPACT = 0, 1
 NT_MAX_DEPTH = 16
@@ -55,6 +55,12 @@ class nt_render_stats(C.Structure):
         return d
 
 
+class nt_frame_sync(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("post_at_start_value", C.c_uint32), ("wait_value", C.c_uint32),
+                ("post_when_done_value", C.c_uint32),
+                ("post_at_start", C.c_void_p), ("wait_before_store", C.c_void_p), ("post_when_done", C.c_void_p)]
+
+
 class nt_peaks(C.Structure):
     _fields_ = [("f64_fma_gflops", C.c_double), ("f64_nofma_gflops", C.c_double),
                 ("f32_fma_gflops", C.c_double), ("f32_nofma_gflops", C.c_double),
@@ -72,6 +78,10 @@ EXPORTS = [
     "nt_shard_rows", "nt_deinterleave_device",
     "nt_device_malloc", "nt_device_free", "nt_ipc_export", "nt_ipc_open", "nt_ipc_close",
     "nt_measure_peaks", "nt_cull_tables", "nt_primary_rects", "nt_plane_free_lights",
+    "nt_render_device_sync", "nt_flags_wait_device",
+    "nt_multi_create", "nt_multi_destroy", "nt_multi_device_count", "nt_multi_render",
+    "nt_host_frame_open", "nt_host_frame_pixels", "nt_host_frame_post", "nt_host_frame_wait_all",
+    "nt_host_frame_ack", "nt_host_frame_wait_ack", "nt_host_frame_close",
 ]
 
 # Flop-counting convention fixed in SURVEY.md §8(d) (FMA = 2, div/sqrt = 1).

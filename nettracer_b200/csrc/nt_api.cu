@@ -17,6 +17,7 @@
 #include "nt_bvh.h"
 #include "nt_cull.h"
 #include "nt_device.h"
+#include "nt_sync.cuh"
 
 static_assert(NT_MAX_DEPTH == NT_MAX_DEPTH_DEV, "depth limits must agree");
 
@@ -24,6 +25,14 @@ static_assert(NT_MAX_DEPTH == NT_MAX_DEPTH_DEV, "depth limits must agree");
 static thread_local char g_err[512] = "";
 
 static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+// for the host-only translation units of the library (nt_multi.cpp, nt_hostframe.cpp)
+int nt_fail_public(int code, const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof g_err, fmt, ap);
@@ -67,7 +76,13 @@ struct nt_scene {
     size_t device_bytes = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    unsigned long long *d_counters = nullptr, *h_counters = nullptr;
+    // Work counters: one block per call in flight, taken round-robin from a small ring, so that flat-scene renders on
+    // different streams do not share the tile counter (each block remembers the stream and an event of its last use)
+    struct CounterBlock { unsigned long long *d = nullptr; cudaEvent_t ev = nullptr; cudaStream_t st = nullptr; bool used = false; };
+    static const int kRing = 4;
+    CounterBlock ring[kRing];
+    int ring_next = 0, ring_last = -1;
+    unsigned long long *h_counters = nullptr;
     uint8_t *d_fb = nullptr;
     size_t fb_bytes = 0;
     bool bvh_on_gpu = false;
@@ -79,7 +94,7 @@ struct nt_scene {
     uint32_t lfree = 0;         // flat scenes with culling: lights no plane can hide from a bounded primitive (nt_cull.h)
     std::vector<double> h_bsph; // flat scenes with culling: bounding spheres (host copy, for the per-camera pixel rectangles)
     void *d_wf = nullptr;      // BVH scenes: wavefront workspace (level records of one chunk of samples)
-    size_t wf_bytes = 0;
+    size_t wf_bytes = 0, wf_limit = (size_t)-1;
     std::mutex mu;
 };
 
@@ -143,7 +158,7 @@ static uint32_t plane_free_lights(const nt_scene_desc *d) {
 }
 
 static const size_t kSmemBudget = 39 * 1024; // + 8.3 KB of static shared memory + list padding stays under the 48 KB default limit
-static const size_t kCounterBytes = sizeof(unsigned long long) * (NT_COUNTER_SLOTS * NT_NCOUNTERS + 1);
+static const size_t kCounterBytes = sizeof(unsigned long long) * (NT_COUNTER_SLOTS * NT_NCOUNTERS + NT_COUNTER_EXTRA);
 static const uint32_t kFlatMaxBounded = 64;
 
 extern "C" void nt_scene_destroy(nt_scene *sc) {
@@ -153,7 +168,10 @@ extern "C" void nt_scene_destroy(nt_scene *sc) {
     if (sc->d_fb) cudaFree(sc->d_fb);
     if (sc->d_samples) cudaFree(sc->d_samples);
     if (sc->d_wf) cudaFree(sc->d_wf);
-    if (sc->d_counters) cudaFree(sc->d_counters);
+    for (auto &cb : sc->ring) {
+        if (cb.d) cudaFree(cb.d);
+        if (cb.ev) cudaEventDestroy(cb.ev);
+    }
     if (sc->h_counters) cudaFreeHost(sc->h_counters);
     if (sc->ev0) cudaEventDestroy(sc->ev0);
     if (sc->ev1) cudaEventDestroy(sc->ev1);
@@ -184,7 +202,7 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
     uint32_t gpu_n_nodes = 0;
     if (use_bvh) {
         int leaf_max = 4;
-        if (const char *e = getenv("NT_BVH_LEAF")) leaf_max = atoi(e);
+        if (const char *e = getenv("NT_BVH_LEAF")) leaf_max = std::min(std::max(atoi(e), 1), NT_LEAF_MAX);
         const char *bm = getenv("NT_BVH_BUILD"); // "gpu": LBVH on the device (row f3); default: binned SAH on the host
         if (bm && !strcmp(bm, "gpu")) {
             const auto tb0 = std::chrono::steady_clock::now();
@@ -336,7 +354,10 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
     CU(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&sc->ev0));
     CU(cudaEventCreate(&sc->ev1));
-    CU(cudaMalloc(&sc->d_counters, kCounterBytes));
+    for (auto &cb : sc->ring) {
+        CU(cudaMalloc(&cb.d, kCounterBytes));
+        CU(cudaEventCreateWithFlags(&cb.ev, cudaEventDisableTiming));
+    }
     CU(cudaMallocHost(&sc->h_counters, kCounterBytes));
     return NT_OK;
 }
@@ -440,11 +461,13 @@ static void set_tile_shape(NtRenderArgs *a, uint32_t twx) {
 static int make_args(const nt_render_params *p, size_t stride, NtRenderArgs *a) {
     if (!p) return fail(NT_ERR_INVALID, "params is NULL");
     if (p->struct_size != sizeof(nt_render_params)) return fail(NT_ERR_INVALID, "nt_render_params.struct_size %u != %zu", p->struct_size, sizeof(nt_render_params));
-    if (p->width == 0 || p->height == 0 || p->width > 65536 || p->height > 65536) return fail(NT_ERR_INVALID, "bad image size %ux%u", p->width, p->height);
+    if (p->width == 0 || p->height == 0 || p->width > 65536 || p->height > 65535) return fail(NT_ERR_INVALID, "bad image size %ux%u (at most 65536 x 65535)", p->width, p->height);
     uint32_t n = 0;
     for (uint32_t k = 1; k <= 8; ++k) if (k * k == p->spp) n = k;
     if (!n) return fail(NT_ERR_INVALID, "spp %u is not a perfect square in 1..64", p->spp);
     if (p->max_depth < 1 || p->max_depth > NT_MAX_DEPTH) return fail(NT_ERR_INVALID, "max_depth %u not in 1..%d", p->max_depth, NT_MAX_DEPTH);
+    if ((uint64_t)(p->width + 31) * (uint64_t)(p->height + 31) * p->spp >= (1ull << 31))
+        return fail(NT_ERR_INVALID, "%ux%u at %u spp has 2^31 samples or more: sample and tile indices are 32-bit; render it in shards", p->width, p->height, p->spp);
     if (p->precision != NT_F64_STRICT && p->precision != NT_F32_FAST) return fail(NT_ERR_INVALID, "unknown precision %u", p->precision);
     if (p->layout != NT_LAYOUT_FULL && p->layout != NT_LAYOUT_COMPACT) return fail(NT_ERR_INVALID, "unknown layout %u", p->layout);
     const uint32_t scount = p->shard_count ? p->shard_count : 1;
@@ -483,9 +506,31 @@ static int make_args(const nt_render_params *p, size_t stride, NtRenderArgs *a) 
     return NT_OK;
 }
 
-static int launch(nt_scene *sc, NtRenderArgs &a, uint32_t precision, cudaStream_t st) {
-    if (a.vrows == 0) return NT_OK;
-    if (a.vrows > 65535) return fail(NT_ERR_INVALID, "more than 65535 owned rows in one launch");
+// Flags of the multi-GPU exchange for a shard that owns no row: nothing to render, but the protocol goes on.
+static int sync_only(const NtRenderArgs &a, cudaStream_t st);
+
+static int launch(nt_scene *sc, NtRenderArgs &a, uint32_t precision, cudaStream_t st, const nt_frame_sync *sync = nullptr) {
+    a.sync_post_ptr = nullptr; a.sync_wait_ptr = nullptr; a.sync_done_ptr = nullptr;
+    if (sync) {
+        if (sync->struct_size != sizeof(nt_frame_sync)) return fail(NT_ERR_INVALID, "nt_frame_sync.struct_size %u != %zu", sync->struct_size, sizeof(nt_frame_sync));
+        if (((uintptr_t)sync->post_at_start | (uintptr_t)sync->wait_before_store | (uintptr_t)sync->post_when_done) % 4) return fail(NT_ERR_INVALID, "flag pointers must be 4-byte aligned");
+        a.sync_post_ptr = sync->post_at_start; a.sync_post_val = sync->post_at_start_value;
+        a.sync_wait_ptr = sync->wait_before_store; a.sync_wait_val = sync->wait_value;
+        a.sync_done_ptr = sync->post_when_done; a.sync_done_val = sync->post_when_done_value;
+    }
+    // this call's block of work counters; calls on other streams that used it (or, for BVH scenes, the scene's shared
+    // scratch buffers) are ordered before this one
+    nt_scene::CounterBlock &cb = sc->ring[sc->ring_next];
+    if (cb.used && cb.st != st) CU(cudaStreamWaitEvent(st, cb.ev, 0));
+    if (sc->ds.use_bvh && sc->ring_last >= 0 && sc->ring[sc->ring_last].st != st) CU(cudaStreamWaitEvent(st, sc->ring[sc->ring_last].ev, 0));
+    CU(cudaMemsetAsync(cb.d, 0, kCounterBytes, st));
+    a.counters = cb.d;
+    sc->ring_last = sc->ring_next;
+    sc->ring_next = (sc->ring_next + 1) % nt_scene::kRing;
+    cb.st = st; cb.used = true;
+    struct Mark { nt_scene::CounterBlock &cb; cudaStream_t st; ~Mark() { cudaEventRecord(cb.ev, st); } } mark{ cb, st };
+    sc->last_launches = 0;
+    if (a.vrows == 0) return sync_only(a, st);
     const size_t need = nt_sample_buffer_bytes(sc->ds, a, (int)precision);
     if (need > sc->samples_bytes) { // grows on demand; cudaFree waits for kernels still using the old one
         if (sc->d_samples) cudaFree(sc->d_samples);
@@ -495,7 +540,6 @@ static int launch(nt_scene *sc, NtRenderArgs &a, uint32_t precision, cudaStream_
         sc->samples_bytes = need;
     }
     a.samples = sc->d_samples;
-    sc->last_launches = 0;
     a.n_launches = &sc->last_launches;
     // BVH scenes render through the wavefront pipeline (nt_wavefront.cuh) unless NT_WAVEFRONT=0, the trees are deeper
     // than NT_WF_MAX_DEPTH or the scene has more than 32 lights; the frame is cut into chunks that fit the workspace
@@ -507,16 +551,23 @@ static int launch(nt_scene *sc, NtRenderArgs &a, uint32_t precision, cudaStream_
         const size_t budget = (size_t)(e_mb && atoll(e_mb) > 0 ? atoll(e_mb) : 16384) << 20;
         size_t want = on ? nt_wavefront_bytes(sc->ds, a, (int)precision) : 0;
         if (want > budget) want = budget;
+        if (want > sc->wf_limit) want = sc->wf_limit; // what the device could give last time
         if (want && want < nt_wavefront_min_bytes(a, (int)precision)) want = 0; // not even one warp of samples fits: state machine
         if (want) {
             if (want > sc->wf_bytes) {
                 if (sc->d_wf) cudaFree(sc->d_wf);
                 sc->d_wf = nullptr; sc->wf_bytes = 0;
                 cudaError_t e = cudaMalloc(&sc->d_wf, want);
-                if (e != cudaSuccess) return fail(NT_ERR_NOMEM, "wavefront workspace cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+                while (e == cudaErrorMemoryAllocation && want / 2 >= nt_wavefront_min_bytes(a, (int)precision)) { // smaller chunks, more launches
+                    cudaGetLastError();
+                    want /= 2;
+                    e = cudaMalloc(&sc->d_wf, want);
+                }
+                if (e != cudaSuccess) { cudaGetLastError(); sc->d_wf = nullptr; want = 0; } // not even that: the per-lane state machine needs no workspace
+                if (e != cudaSuccess || want < sc->wf_limit) sc->wf_limit = want;
                 sc->wf_bytes = want;
             }
-            a.wf = sc->d_wf; a.wf_bytes = want;
+            if (want) { a.wf = sc->d_wf; a.wf_bytes = want; }
         }
     }
     if (!sc->ds.use_bvh && sc->ds.cull) { // primary rays: per-primitive pixel rectangles for this camera (nt_cull.h)
@@ -589,9 +640,7 @@ extern "C" int nt_render(nt_scene *sc, const nt_render_params *p, uint8_t *rgba_
         }
         a.out = sc->d_fb;
     }
-    a.counters = sc->d_counters;
     const size_t cbytes = kCounterBytes;
-    CU(cudaMemsetAsync(sc->d_counters, 0, cbytes, sc->stream));
     CU(cudaEventRecord(sc->ev0, sc->stream));
     if ((rc = launch(sc, a, p->precision, sc->stream)) != NT_OK) return rc;
     CU(cudaEventRecord(sc->ev1, sc->stream));
@@ -606,7 +655,7 @@ extern "C" int nt_render(nt_scene *sc, const nt_render_params *p, uint8_t *rgba_
             }
         }
     }
-    CU(cudaMemcpyAsync(sc->h_counters, sc->d_counters, cbytes, cudaMemcpyDeviceToHost, sc->stream));
+    CU(cudaMemcpyAsync(sc->h_counters, a.counters, cbytes, cudaMemcpyDeviceToHost, sc->stream));
     CU(cudaStreamSynchronize(sc->stream));
     if (stats) {
         memset(stats, 0, sizeof *stats);
@@ -619,8 +668,8 @@ extern "C" int nt_render(nt_scene *sc, const nt_render_params *p, uint8_t *rgba_
     return NT_OK;
 }
 
-extern "C" int nt_render_device(nt_scene *sc, const nt_render_params *p, void *rgba_out_dev, size_t stride,
-                                void *cuda_stream) {
+extern "C" int nt_render_device_sync(nt_scene *sc, const nt_render_params *p, void *rgba_out_dev, size_t stride,
+                                     void *cuda_stream, const nt_frame_sync *sync) {
     if (!sc || !rgba_out_dev) return fail(NT_ERR_INVALID, "NULL argument");
     std::lock_guard<std::mutex> lock(sc->mu);
     NtRenderArgs a;
@@ -628,11 +677,13 @@ extern "C" int nt_render_device(nt_scene *sc, const nt_render_params *p, void *r
     if (rc) return rc;
     if (((uintptr_t)rgba_out_dev) % 4) return fail(NT_ERR_INVALID, "output pointer must be 4-byte aligned");
     CU(cudaSetDevice(sc->device));
-    cudaStream_t st = (cudaStream_t)cuda_stream;
     a.out = (uint8_t *)rgba_out_dev;
-    a.counters = sc->d_counters;
-    CU(cudaMemsetAsync(sc->d_counters, 0, kCounterBytes, st));
-    return launch(sc, a, p->precision, st);
+    return launch(sc, a, p->precision, (cudaStream_t)cuda_stream, sync);
+}
+
+extern "C" int nt_render_device(nt_scene *sc, const nt_render_params *p, void *rgba_out_dev, size_t stride,
+                                void *cuda_stream) {
+    return nt_render_device_sync(sc, p, rgba_out_dev, stride, cuda_stream, nullptr);
 }
 
 extern "C" int nt_render_device_stats(nt_scene *sc, void *cuda_stream, nt_render_stats *stats) {
@@ -640,10 +691,15 @@ extern "C" int nt_render_device_stats(nt_scene *sc, void *cuda_stream, nt_render
     std::lock_guard<std::mutex> lock(sc->mu);
     CU(cudaSetDevice(sc->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    CU(cudaMemcpyAsync(sc->h_counters, sc->d_counters, kCounterBytes, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
     memset(stats, 0, sizeof *stats);
+    if (sc->ring_last < 0) return NT_OK; // nothing rendered yet
+    const nt_scene::CounterBlock &cb = sc->ring[sc->ring_last];
+    if (cb.st != st) CU(cudaStreamWaitEvent(st, cb.ev, 0));
+    CU(cudaMemcpyAsync(sc->h_counters, cb.d, kCounterBytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     sum_counters(sc->h_counters, stats);
+    if (sc->h_counters[NT_COUNTER_SLOTS * NT_NCOUNTERS + 2])
+        return fail(NT_ERR_TIMEOUT, "the frame gave up waiting for a synchronisation flag (%llu waits timed out)", sc->h_counters[NT_COUNTER_SLOTS * NT_NCOUNTERS + 2]);
     return NT_OK;
 }
 
@@ -705,6 +761,26 @@ extern "C" int nt_deinterleave_device(const void *compact_all, size_t shard_stri
     dim3 grid((width + 255) / 256 > 8 ? 8 : (width + 255) / 256, height), block(256);
     deinterleave_kernel<<<grid, block, 0, (cudaStream_t)cuda_stream>>>((const uint32_t *)compact_all, shard_stride_bytes / 4, (uint32_t *)full_out,
                                                                        row_stride_bytes / 4, width, height, band_rows, shard_count);
+    CU(cudaGetLastError());
+    return NT_OK;
+}
+
+// ---------------- frame synchronisation flags (nt_sync.cuh) ----------------
+static int sync_only(const NtRenderArgs &a, cudaStream_t st) {
+    if (!a.sync_post_ptr && !a.sync_wait_ptr && !a.sync_done_ptr) return NT_OK;
+    nt::sync_kernel<<<1, 32, 0, st>>>(a.sync_post_ptr, a.sync_post_val, a.sync_wait_ptr, 1, a.sync_wait_val, a.sync_done_ptr, a.sync_done_val,
+                                      a.counters + NT_COUNTER_SLOTS * NT_NCOUNTERS + 2);
+    CU(cudaGetLastError());
+    return NT_OK;
+}
+
+extern "C" int nt_flags_wait_device(nt_scene *sc, const uint32_t *flags, uint32_t n, uint32_t value, void *cuda_stream) {
+    if (!sc || !flags || n == 0 || n > 1024 || ((uintptr_t)flags) % 4) return fail(NT_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lock(sc->mu);
+    CU(cudaSetDevice(sc->device));
+    // a wait that gives up is recorded with the scene's last frame (reported by nt_render_device_stats)
+    unsigned long long *timeouts = sc->ring_last >= 0 ? sc->ring[sc->ring_last].d + NT_COUNTER_SLOTS * NT_NCOUNTERS + 2 : nullptr;
+    nt::sync_kernel<<<1, 32, 0, (cudaStream_t)cuda_stream>>>(nullptr, 0, flags, n, value, nullptr, 0, timeouts);
     CU(cudaGetLastError());
     return NT_OK;
 }

@@ -10,6 +10,7 @@
 #define NT_MAT_STRIDE 12   // r g b ka kd ks shininess kr kt ior inv_ior pad
 #define NT_COUNTER_SLOTS 32
 #define NT_NCOUNTERS 8     // primary secondary shadow sphere plane triangle box light
+#define NT_COUNTER_EXTRA 3 // + next work item, blocks done, sync time-outs
 #define NT_BLOCK_THREADS 256
 #ifndef NT_MIN_BLOCKS_F64
 #define NT_MIN_BLOCKS_F64 4 // resident blocks/SM the flat render kernel is compiled for (64 registers); measured
@@ -113,11 +114,18 @@ struct NtRenderArgs {
     float inv_tiles_x;
     uint8_t *out;
     size_t stride;
-    unsigned long long *counters; // [NT_COUNTER_SLOTS][NT_NCOUNTERS] + 1 (next warp tile / next sample id)
+    unsigned long long *counters; // [NT_COUNTER_SLOTS][NT_NCOUNTERS] + NT_COUNTER_EXTRA: next warp tile / next sample id,
+                                  // blocks that finished (frame-done flag), sync time-outs
     void *samples;                // BVH scenes: per-sample radiance, R[3] each (see nt_bvh_trace.cuh)
     unsigned *n_launches;         // host counter: kernels launched for this frame (may be NULL)
     void *wf;                     // BVH scenes: wavefront workspace (nt_wavefront.cuh); NULL = per-lane state machine
     size_t wf_bytes;
+    // frame synchronisation of the multi-GPU exchange (include/nettracer_b200.h nt_frame_sync; nt_sync.cuh): all three are
+    // optional (NULL).  Flat scenes: done inside the render kernel; BVH scenes: by sync_kernel before / after the pipeline.
+    unsigned *sync_post_ptr;        // system-scope store of sync_post_val when the frame's first kernel starts
+    const unsigned *sync_wait_ptr;  // no pixel is stored before (int)(*sync_wait_ptr - sync_wait_val) >= 0
+    unsigned *sync_done_ptr;        // release-store of sync_done_val after the frame's last pixel store
+    unsigned sync_post_val, sync_wait_val, sync_done_val;
 };
 
 struct NtTraceArgs {

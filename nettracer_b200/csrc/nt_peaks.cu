@@ -30,10 +30,15 @@ template <> __device__ __forceinline__ float add_(float a, float b) { return __f
 // FMA = false: ILP independent mul-then-add chains, 2*ILP flops (2*ILP instructions) per step.
 template <typename T, bool FMA>
 __global__ void __launch_bounds__(256) peak_kernel(int iters, T seed, T *sink, long long *cycles) {
+    // cycles[2b] = SM clock ticks, cycles[2b + 1] = nanoseconds (%globaltimer) that block b spent in the loop: the clock
+    // estimate divides two intervals taken by the SAME block (round 1 divided one block's ticks by the whole launch's
+    // event time and was low by the number of waves)
     T v[ILP];
 #pragma unroll
     for (int i = 0; i < ILP; ++i) v[i] = seed + (T)(threadIdx.x + i);
     const T b = (T)0.9999, c = (T)0.0001;
+    unsigned long long g0, g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -42,11 +47,12 @@ __global__ void __launch_bounds__(256) peak_kernel(int iters, T seed, T *sink, l
             for (int i = 0; i < ILP; ++i) v[i] = FMA ? fma_<T>(v[i], b, c) : add_<T>(mul_<T>(v[i], b), c);
     }
     const long long t1 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
     T s = 0;
 #pragma unroll
     for (int i = 0; i < ILP; ++i) s += v[i];
     if (s == (T)123456.789) *sink = s; // never true; keeps the chains alive
-    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    if (threadIdx.x == 0) { cycles[2 * blockIdx.x] = t1 - t0; cycles[2 * blockIdx.x + 1] = (long long)(g1 - g0); }
 }
 
 template <typename T, bool FMA>
@@ -55,7 +61,7 @@ int run(int sm_count, double *gflops, double *mhz) {
     T *sink = nullptr;
     long long *cyc = nullptr;
     cudaEvent_t e0, e1;
-    if (cudaMalloc(&sink, sizeof(T)) || cudaMalloc(&cyc, sizeof(long long) * blocks)) return 1;
+    if (cudaMalloc(&sink, sizeof(T)) || cudaMalloc(&cyc, sizeof(long long) * 2 * blocks)) return 1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     int iters = 2000;
     float ms = 0;
@@ -74,11 +80,13 @@ int run(int sm_count, double *gflops, double *mhz) {
     const double flops = (double)blocks * threads * (double)iters * 4 * ILP * 2;
     *gflops = flops / (ms * 1e-3) / 1e9;
     if (mhz) {
-        long long h[8];
+        long long h[16];
         cudaMemcpy(h, cyc, sizeof h, cudaMemcpyDeviceToHost);
-        long long mx = 0;
-        for (long long c : h) mx = c > mx ? c : mx;
-        *mhz = (double)mx / (ms * 1e-3) / 1e6;
+        double best = 0; // the longest-running of the first 8 blocks gives the best-resolved ratio
+        long long ns = 0;
+        for (int b = 0; b < 8; ++b)
+            if (h[2 * b + 1] > ns) { ns = h[2 * b + 1]; best = (double)h[2 * b] / (double)h[2 * b + 1] * 1e3; }
+        *mhz = best;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(sink); cudaFree(cyc);

@@ -14,6 +14,7 @@
 #include <type_traits>
 
 #include "nt_device.h"
+#include "nt_sync.cuh"
 
 // what-if timing hooks (experiments only; the shipped build defines none of them)
 #ifdef NT_EXP_NOPLANES
@@ -867,6 +868,7 @@ render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRe
     const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
     Ctx<R, BVH> c;
     c.s = &s; c.v = &v; c.eps = (R)a.eps; c.eps_lo = (R)a.eps_lo; c.max_depth = a.max_depth;
+    frame_sync_begin(a); // multi-GPU exchange: acknowledge / wait before the first pixel store (the barrier in stage_scene orders it)
     stage_scene<R, BVH>(s, v, c);
 
     const unsigned tid = threadIdx.x, lane = tid & 31;
@@ -967,6 +969,7 @@ render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRe
         k.tri = queries * s.nt - k.tri;
     }
     flush_counters(k, a.counters, s_cnt);
+    frame_sync_end(a); // multi-GPU exchange: "this shard is written" once the last block is through
 }
 
 // Unit-level entry: nearest hit of arbitrary rays (nt_trace_rays).
@@ -1026,11 +1029,26 @@ inline int launch_render_t(const NtDevScene &s, const NtRenderArgs &a, cudaStrea
     unsigned grid = (unsigned)(sms[dev] * blocks_per_sm[dev]);
     if (grid > (n_tiles + wpb - 1) / wpb) grid = (n_tiles + wpb - 1) / wpb;
     if (BVH) {
-        if (a.wf) return launch_wavefront<R>(s, a, st, sms[dev], blocks_per_sm[dev]);
-        render_bvh_kernel<R><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
-        resolve_kernel<R><<<dim3((a.width + 255) / 256, a.vrows), 256, 0, st>>>(a);
-        if (a.n_launches) *a.n_launches += 2;
-        return (int)cudaGetLastError();
+        // many kernels per frame: the exchange flags (nt_sync.cuh) are handled before and after the pipeline
+        unsigned long long *timeouts = a.counters + NT_COUNTER_SLOTS * NT_NCOUNTERS + 2;
+        if (a.sync_post_ptr || a.sync_wait_ptr) {
+            sync_kernel<<<1, 32, 0, st>>>(a.sync_post_ptr, a.sync_post_val, a.sync_wait_ptr, 1, a.sync_wait_val, nullptr, 0, timeouts);
+            if (a.n_launches) *a.n_launches += 1;
+        }
+        int rc;
+        if (a.wf) rc = launch_wavefront<R>(s, a, st, sms[dev], blocks_per_sm[dev]);
+        else {
+            render_bvh_kernel<R><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
+            resolve_kernel<R><<<dim3((a.width + 255) / 256, a.vrows), 256, 0, st>>>(a);
+            if (a.n_launches) *a.n_launches += 2;
+            rc = (int)cudaGetLastError();
+        }
+        if (!rc && a.sync_done_ptr) {
+            sync_kernel<<<1, 32, 0, st>>>(nullptr, 0, nullptr, 0, 0, a.sync_done_ptr, a.sync_done_val, timeouts);
+            if (a.n_launches) *a.n_launches += 1;
+            rc = (int)cudaGetLastError();
+        }
+        return rc;
     } else if (a.spp == a.lanes) render_kernel<R, false, true><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
     else render_kernel<R, false, false><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
     if (a.n_launches) *a.n_launches += 1;

@@ -48,6 +48,19 @@ def load():
         "nt_cull_tables": (C.c_int, [C.POINTER(abi.nt_scene_desc), C.POINTER(u32), vp, C.c_size_t, vp, vp]),
         "nt_primary_rects": (C.c_int, [C.POINTER(abi.nt_scene_desc), C.POINTER(abi.nt_render_params), vp]),
         "nt_plane_free_lights": (C.c_int, [C.POINTER(abi.nt_scene_desc), C.POINTER(u32)]),
+        "nt_render_device_sync": (C.c_int, [vp, C.POINTER(abi.nt_render_params), vp, C.c_size_t, vp, C.POINTER(abi.nt_frame_sync)]),
+        "nt_flags_wait_device": (C.c_int, [vp, vp, u32, u32, vp]),
+        "nt_multi_create": (C.c_int, [C.POINTER(abi.nt_scene_desc), C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]),
+        "nt_multi_destroy": (None, [vp]),
+        "nt_multi_device_count": (C.c_int, [vp]),
+        "nt_multi_render": (C.c_int, [vp, C.POINTER(abi.nt_render_params), vp, C.c_size_t, C.POINTER(abi.nt_render_stats)]),
+        "nt_host_frame_open": (C.c_int, [C.c_char_p, C.c_size_t, u32, C.c_int, C.c_int, C.POINTER(vp)]),
+        "nt_host_frame_pixels": (vp, [vp]),
+        "nt_host_frame_post": (C.c_int, [vp, u32, u32]),
+        "nt_host_frame_wait_all": (C.c_int, [vp, u32, u32]),
+        "nt_host_frame_ack": (C.c_int, [vp, u32]),
+        "nt_host_frame_wait_ack": (C.c_int, [vp, u32, u32]),
+        "nt_host_frame_close": (None, [vp, C.c_int]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name, None)

@@ -65,9 +65,11 @@ class Renderer:
         return self.render_params(p, out)
 
     # -- device path --
-    def render_device(self, params: abi.nt_render_params, dev_ptr: int, row_stride_bytes: int, stream: int = 0):
-        check(self._lib.nt_render_device(self._h, C.byref(params), C.c_void_p(dev_ptr), row_stride_bytes,
-                                         C.c_void_p(stream)))
+    def render_device(self, params: abi.nt_render_params, dev_ptr: int, row_stride_bytes: int, stream: int = 0,
+                      sync: abi.nt_frame_sync | None = None):
+        """nt_render_device, or nt_render_device_sync when `sync` names frame-synchronisation flags."""
+        check(self._lib.nt_render_device_sync(self._h, C.byref(params), C.c_void_p(dev_ptr), row_stride_bytes,
+                                              C.c_void_p(stream), C.byref(sync) if sync is not None else None))
 
     def device_stats(self, stream: int = 0) -> dict:
         st = abi.nt_render_stats()

@@ -1,30 +1,44 @@
-"""Multi-GPU image sharding: one process per GPU, the scene replicated, image rows
-cut into bands of `band_rows` rows dealt round-robin to the ranks (band b -> rank b mod N), and ONE
-exchange per frame that lands the finished RGBA8 rows on rank 0 over NVLink.  This replaces the
-reference's thread/TCP tile distribution (hypothesised only — /root/reference/README:1-3 holds no
-code).  No exchange happens while rays are traced.
+"""Multi-GPU image sharding, one process per GPU: the scene replicated, image rows cut into bands
+of `band_rows` rows dealt round-robin to the ranks (band b -> rank b mod N), and ONE exchange per frame that lands
+the finished RGBA8 rows on rank 0.  This replaces the reference's thread/TCP tile distribution (hypothesised only —
+/root/reference/README:1-3 holds no code).  No exchange happens while rays are traced.  (One process driving several
+GPUs is nt_multi_render in the C ABI; `MultiRenderer` below wraps it.)
 
-Two exchange modes:
-  "gather"    every rank renders its bands into a compact device buffer; `torch.distributed.gather`
-              (NCCL send/recv over NVLink) brings them to rank 0, where nt_deinterleave_device
-              scatters them into the full frame.
-  "p2p_store" rank 0's frame buffer is opened on every rank through CUDA IPC and each rank's render
-              kernel stores its pixels straight into it (peer stores over NVLink overlap with the
-              tracing); one tiny all-reduce per frame orders "all shards written" before rank 0 reads.
+Exchange modes of `render()` (frame ends up in DEVICE memory of rank 0):
+  "p2p_store" (default) rank 0 owns two frame buffers (alternating per frame) plus a line of flags, all opened on every
+              rank through CUDA IPC.  Each rank's render kernel stores its pixels straight into rank 0's buffer over
+              NVLink while it traces, and its last block release-stores "frame f written" into the rank's flag; rank 0
+              then waits on its own stream for all flags (nt_flags_wait_device).  No collective, no host round trip:
+              round 1 ordered this with a 4-byte NCCL all-reduce that cost 49 us per frame.  Write-after-read safety:
+              rank 0's kernel for frame f acknowledges, when it starts, that everything enqueued before it on rank 0's
+              stream - the consumers of frames <= f-1 - has finished; a peer does not store frame f into the buffer
+              frame f-2 used before that acknowledgement has reached f-2 (nt_frame_sync in the C ABI).  The frame
+              returned by render() is therefore valid until rank 0's second next render() call.
+  "gather"    every rank renders into a compact device buffer; torch.distributed.gather (NCCL send/recv over
+              NVLink) brings them to rank 0, where nt_deinterleave_device scatters them into the full frame.
 
-The backend object does the device work, so the bookkeeping (band arithmetic, buffer strides,
-collective call order) can be exercised by world_size-2 gloo tests on CPU with a test-only backend;
-the product backend is `CudaBackend` and nothing else ships.
+`render_host()` (frame ends up in HOST memory of rank 0, the end-to-end path): one shared-memory host frame, mapped and
+page-locked by every rank (nt_host_frame_*), into which every rank's kernel stores its own bands over its own PCIe
+link - no gather and no device-to-host copy; completion and consumption are host flags in the same segment.
+
+The backend object does the device work, so the bookkeeping (band arithmetic, buffer strides, protocol order) can be
+exercised by world_size-2 gloo tests on CPU with a test-only backend; the product backend is `CudaBackend`.
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
 from . import abi
 from .scene import make_params, shard_rows
+
+SYNC_WORDS = 128          # rank 0's flag line: word r = frames rank r has completely stored, word ACK_WORD = frames consumed
+ACK_WORD = 64
+MAX_RANKS = 64
 
 
 class CudaBackend:
@@ -45,8 +59,17 @@ class CudaBackend:
     def stream_ptr(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def render_shard(self, params: abi.nt_render_params, out_ptr: int, row_stride: int):
-        self.renderer.render_device(params, out_ptr, row_stride, self.stream_ptr())
+    def render_shard(self, params: abi.nt_render_params, out_ptr: int, row_stride: int, sync=None):
+        self.renderer.render_device(params, out_ptr, row_stride, self.stream_ptr(), sync)
+
+    def wait_flags(self, flags_ptr: int, n: int, value: int):
+        self._check(self._lib.nt_flags_wait_device(self.renderer._h, C.c_void_p(flags_ptr), n, value & 0xffffffff,
+                                                   C.c_void_p(self.stream_ptr())))
+
+    def render_host(self, params: abi.nt_render_params, host_ptr: int, row_stride: int):
+        st = abi.nt_render_stats()
+        self._check(self._lib.nt_render(self.renderer._h, C.byref(params), C.c_void_p(host_ptr), row_stride, C.byref(st)))
+        return st.as_dict()
 
     def deinterleave(self, compact_all, shard_stride: int, full, width, height, band_rows, world):
         self._check(self._lib.nt_deinterleave_device(C.c_void_p(compact_all.data_ptr()), shard_stride,
@@ -54,10 +77,13 @@ class CudaBackend:
                                                      band_rows, world, self.device_index,
                                                      C.c_void_p(self.stream_ptr())))
 
-    # ---- peer frame buffer (p2p_store) ----
+    # ---- peer frame buffers (p2p_store) ----
     def peer_alloc(self, nbytes: int) -> int:
         p = C.c_void_p()
         self._check(self._lib.nt_device_malloc(self.device_index, nbytes, C.byref(p)))
+        t = self.wrap_bytes(p.value, nbytes)
+        t.zero_()
+        torch.cuda.synchronize(self.device)
         return p.value
 
     def peer_free(self, ptr: int):
@@ -77,28 +103,62 @@ class CudaBackend:
     def ipc_close(self, ptr: int):
         self._lib.nt_ipc_close(C.c_void_p(ptr), self.device_index)
 
-    def wrap(self, ptr: int, height: int, width: int):
+    def wrap_bytes(self, ptr: int, nbytes: int):
         class _Raw:
-            __cuda_array_interface__ = {"shape": (height, width, 4), "typestr": "|u1", "data": (ptr, False),
-                                        "version": 3, "strides": None}
+            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
         return torch.as_tensor(_Raw(), device=self.device)
+
+    def wrap(self, ptr: int, height: int, width: int):
+        return self.wrap_bytes(ptr, height * width * 4).view(height, width, 4)
+
+    # ---- shared host frame (render_host) ----
+    def host_frame_open(self, name: str, nbytes: int, world: int, create: bool):
+        h = C.c_void_p()
+        self._check(self._lib.nt_host_frame_open(name.encode(), nbytes, world, int(create), self.device_index, C.byref(h)))
+        return h, self._lib.nt_host_frame_pixels(h)
+
+    def host_frame_close(self, h, unlink: bool):
+        self._lib.nt_host_frame_close(h, int(unlink))
+
+    def host_post(self, h, rank, seq):
+        self._check(self._lib.nt_host_frame_post(h, rank, seq & 0xffffffff))
+
+    def host_wait_all(self, h, seq, timeout_ms=20000):
+        self._check(self._lib.nt_host_frame_wait_all(h, seq & 0xffffffff, timeout_ms))
+
+    def host_ack(self, h, seq):
+        self._check(self._lib.nt_host_frame_ack(h, seq & 0xffffffff))
+
+    def host_wait_ack(self, h, seq, timeout_ms=20000):
+        self._check(self._lib.nt_host_frame_wait_ack(h, seq & 0xffffffff, timeout_ms))
+
+    def host_view(self, pixels_ptr: int, height: int, width: int):
+        buf = (C.c_uint8 * (height * width * 4)).from_address(pixels_ptr)
+        return np.frombuffer(buf, dtype=np.uint8).reshape(height, width, 4)
 
     def stats(self) -> dict:
         return self.renderer.device_stats(self.stream_ptr())
+
+    def synchronize(self):
+        torch.cuda.synchronize(self.device)
 
     def close(self):
         self.renderer.close()
 
 
 class ShardedRenderer:
-    def __init__(self, backend, rank: int, world: int, band_rows: int = 16, mode: str = "gather", group=None):
+    def __init__(self, backend, rank: int, world: int, band_rows: int = 16, mode: str = "p2p_store", group=None):
         assert mode in ("gather", "p2p_store")
+        assert world <= MAX_RANKS
         self.b, self.rank, self.world, self.band_rows, self.group = backend, rank, world, band_rows, group
         self.mode = mode if world > 1 else "single"
         self._shape = None
-        self._peer_base = None   # rank 0: owned allocation; other ranks: opened IPC mapping
-        self._flag = None
+        self._peer = None        # p2p_store: [buffer 0, buffer 1, flag line] - rank 0 owns them, the others map them
+        self._seq = 0            # frames rendered through render() in p2p_store mode (flag values)
+        self._fulls = None       # rank 0: the two frame buffers as tensors
         self.full = self.shard = self.slots = None
+        self._hf = None          # shared host frame: (handle, pixels pointer, name, shape)
+        self._hseq = 0
 
     # -- buffers sized per (width, height) --
     def _prepare(self, width, height):
@@ -117,15 +177,16 @@ class ShardedRenderer:
                 self.slots = self.b.empty(self.world, self.max_rows, width, 4)
                 self.full = self.b.empty(height, width, 4)
         else:
-            handle = torch.zeros(64, dtype=torch.uint8)
+            sizes = [height * width * 4, height * width * 4, SYNC_WORDS * 4]
+            handles = torch.zeros(3, 64, dtype=torch.uint8)
             if self.rank == 0:
-                self._peer_base = self.b.peer_alloc(height * width * 4)
-                handle = torch.tensor(list(self.b.ipc_export(self._peer_base)), dtype=torch.uint8)
-                self.full = self.b.wrap(self._peer_base, height, width)
-            handle = self._bcast_bytes(handle)
+                self._peer = [self.b.peer_alloc(n) for n in sizes]   # zero-filled: flags and acknowledgement start at 0
+                handles = torch.tensor([list(self.b.ipc_export(p)) for p in self._peer], dtype=torch.uint8)
+                self._fulls = [self.b.wrap(self._peer[i], height, width) for i in range(2)]
+            handles = self._bcast_bytes(handles)
             if self.rank != 0:
-                self._peer_base = self.b.ipc_open(bytes(handle.tolist()))
-            self._flag = self.b.empty(4).zero_()
+                self._peer = [self.b.ipc_open(bytes(h.tolist())) for h in handles]
+            self._seq = 0
 
     def _bcast_bytes(self, t):
         if dist.get_backend(self.group) == "nccl":
@@ -136,18 +197,40 @@ class ShardedRenderer:
         return t
 
     def _release_peer(self):
-        if self._peer_base is not None:
+        if self._peer is not None:
+            # the peers close their mappings BEFORE rank 0 frees the allocations (freeing memory that is still mapped,
+            # or still being stored to, by another process is undefined)
+            if self.rank != 0:
+                self._sync_device()
+                for p in self._peer:
+                    self.b.ipc_close(p)
+            dist.barrier(group=self.group)
             if self.rank == 0:
-                self.full = None
-                self.b.peer_free(self._peer_base)
-            else:
-                self.b.ipc_close(self._peer_base)
-            self._peer_base = None
+                self._sync_device()
+                self._fulls = self.full = None
+                for p in self._peer:
+                    self.b.peer_free(p)
+            self._peer = None
+
+    def _sync_device(self):
+        self.b.synchronize()
 
     def shard_params(self, width, height, spp, max_depth, camera, precision=abi.NT_F64_STRICT, ray_epsilon=0.0):
         layout = abi.NT_LAYOUT_COMPACT if self.mode == "gather" else abi.NT_LAYOUT_FULL
         return make_params(width, height, spp, max_depth, camera, precision, ray_epsilon, self.rank, self.world,
                            self.band_rows, layout)
+
+    def frame_sync(self, seq: int) -> abi.nt_frame_sync:
+        """The flag operations of frame `seq` for this rank (p2p_store protocol, see the module docstring)."""
+        s = abi.nt_frame_sync()
+        s.struct_size = C.sizeof(abi.nt_frame_sync)
+        flags = self._peer[2]
+        if self.rank == 0:
+            s.post_at_start, s.post_at_start_value = flags + 4 * ACK_WORD, (seq - 1) & 0xffffffff
+        else:
+            s.wait_before_store, s.wait_value = flags + 4 * ACK_WORD, (seq - 2) & 0xffffffff
+        s.post_when_done, s.post_when_done_value = flags + 4 * self.rank, seq & 0xffffffff
+        return s
 
     def render(self, params: abi.nt_render_params, kernel_done=None):
         """Enqueue one frame on the current stream.  Returns the full device frame on rank 0, None
@@ -171,13 +254,113 @@ class ShardedRenderer:
                 return self.full
             dist.gather(self.shard, None, dst=0, group=self.group)
             return None
-        if self.my_rows:
-            self.b.render_shard(params, self._peer_base, w * 4)
+        # p2p_store: peer stores + flags, no collective.  A rank without rows still runs the flag protocol.
+        self._seq += 1
+        seq = self._seq
+        self.b.render_shard(params, self._peer[seq & 1], w * 4, self.frame_sync(seq))
         if kernel_done is not None:
             kernel_done.record()
-        dist.all_reduce(self._flag, group=self.group)  # "every shard is written", stream-ordered
-        return self.full if self.rank == 0 else None
+        if self.rank != 0:
+            return None
+        self.b.wait_flags(self._peer[2], self.world, seq)   # every shard of frame seq is in the buffer
+        self.full = self._fulls[seq & 1]
+        return self.full
+
+    # -- end to end: the frame in rank 0's HOST memory --
+    def _prepare_host(self, width, height):
+        if self._hf is not None and self._hf[3] == (width, height):
+            return
+        self._release_host()
+        name = torch.zeros(48, dtype=torch.uint8)
+        if self.rank == 0:
+            tag = f"/nt_frame_{os.getpid()}_{id(self) & 0xffffff:x}_{width}x{height}"
+            name[:len(tag)] = torch.tensor(list(tag.encode()), dtype=torch.uint8)
+        if self.world > 1:
+            name = self._bcast_bytes(name)
+        tag = bytes(name.tolist()).rstrip(b"\0").decode()
+        nbytes = width * height * 4
+        if self.rank == 0:
+            h, px = self.b.host_frame_open(tag, nbytes, self.world, True)
+        if self.world > 1:
+            dist.barrier(group=self.group)          # the segment exists before anyone attaches
+        if self.rank != 0:
+            h, px = self.b.host_frame_open(tag, nbytes, self.world, False)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        self._hf = (h, px, tag, (width, height))
+        self._hseq = 0
+
+    def _release_host(self):
+        if self._hf is not None:
+            self._sync_device()
+            if self.world > 1:
+                dist.barrier(group=self.group)
+            self.b.host_frame_close(self._hf[0], self.rank == 0)
+            self._hf = None
+
+    def render_host(self, params: abi.nt_render_params):
+        """One frame, end to end, into the host frame all ranks share (blocking).  `params` = shard_params(...) with
+        the FULL layout (p2p_store / single modes).  Returns (frame, stats): on rank 0 a numpy view [h, w, 4] of the
+        shared frame, valid until rank 0's next render_host call; None on the other ranks."""
+        w, h = params.width, params.height
+        assert params.layout == abi.NT_LAYOUT_FULL
+        self._prepare_host(w, h)
+        hf, px = self._hf[0], self._hf[1]
+        self._hseq += 1
+        seq = self._hseq
+        if self.rank == 0:
+            self.b.host_ack(hf, seq - 1)            # the caller is done with the previous frame
+        else:
+            self.b.host_wait_ack(hf, seq - 1)       # ... so it may be overwritten
+        st = self.b.render_host(params, px, w * 4)  # zero-copy stores into the shared frame; returns when they are done
+        self.b.host_post(hf, self.rank, seq)
+        if self.rank != 0:
+            return None, st
+        self.b.host_wait_all(hf, seq)
+        return self.b.host_view(px, h, w), st
 
     def close(self):
         self._release_peer()
+        self._release_host()
         self.b.close()
+
+
+class MultiRenderer:
+    """Several GPUs driven by ONE process through nt_multi_render (C ABI): the call a single-process host (the
+    reference's Java front end) would bind.  `render()` returns the whole frame in host memory."""
+
+    def __init__(self, scene, devices):
+        from .lib import check, load
+        self._check, self._lib = check, load()
+        desc, keep = scene.to_desc()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        self._h = C.c_void_p()
+        check(self._lib.nt_multi_create(C.byref(desc), devs, len(devices), C.byref(self._h)))
+        del keep
+        self.n = len(devices)
+
+    def render_params(self, params: abi.nt_render_params, out: np.ndarray | None = None, out_ptr: int | None = None):
+        """out: uint8 [height, width, 4] host array; or out_ptr: address of a (pinned) host buffer of that shape."""
+        if out is None and out_ptr is None:
+            out = np.zeros((params.height, params.width, 4), dtype=np.uint8)
+        ptr = out_ptr if out_ptr is not None else out.ctypes.data
+        st = abi.nt_render_stats()
+        self._check(self._lib.nt_multi_render(self._h, C.byref(params), C.c_void_p(ptr), params.width * 4, C.byref(st)))
+        return out, st.as_dict()
+
+    def render(self, camera, width, height, spp=1, max_depth=1, precision=abi.NT_F64_STRICT, band_rows=8, **kw):
+        p = make_params(width, height, spp, max_depth, camera.resolve(width, height), precision, band_rows=band_rows)
+        return self.render_params(p, **kw)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.nt_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

@@ -15,8 +15,11 @@ if len(sys.argv) > 5:
     spp = int(sys.argv[5])
 if len(sys.argv) > 6:
     depth = int(sys.argv[6])
+import os  # noqa: E402
+shards = int(os.environ.get("NT_ONE_SHARDS", "1"))  # render shard 0 of this many (band 8) instead of the whole frame
 scene, cam = factory()
 with Renderer(scene) as r:
     for _ in range(iters):
-        img, st = r.render(cam, w, h, spp, depth, abi.NT_F64_STRICT if prec == "f64" else abi.NT_F32_FAST)
+        img, st = r.render(cam, w, h, spp, depth, abi.NT_F64_STRICT if prec == "f64" else abi.NT_F32_FAST,
+                           shard_index=0, shard_count=shards, band_rows=8, layout=abi.NT_LAYOUT_COMPACT if shards > 1 else abi.NT_LAYOUT_FULL)
     print(name, prec, w, h, spp, depth, st)

@@ -34,15 +34,16 @@ def test_header_symbols_all_exported():
 
 def test_struct_layout_matches_header(tmp_path):
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "nettracer_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "nettracer_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    "sizeof(nt_scene_desc),sizeof(nt_render_params),sizeof(nt_render_stats),sizeof(nt_camera),sizeof(nt_peaks),"
-                   "offsetof(nt_render_params,camera),offsetof(nt_scene_desc,ambient));return 0;}\n")
+                   "offsetof(nt_render_params,camera),offsetof(nt_scene_desc,ambient),sizeof(nt_frame_sync),"
+                   "offsetof(nt_frame_sync,post_when_done));return 0;}\n")
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
     want = [C.sizeof(abi.nt_scene_desc), C.sizeof(abi.nt_render_params), C.sizeof(abi.nt_render_stats),
             C.sizeof(abi.nt_camera), C.sizeof(abi.nt_peaks), abi.nt_render_params.camera.offset,
-            abi.nt_scene_desc.ambient.offset]
+            abi.nt_scene_desc.ambient.offset, C.sizeof(abi.nt_frame_sync), abi.nt_frame_sync.post_when_done.offset]
     assert got == want
 
 
@@ -71,6 +72,29 @@ def test_no_device_means_error_not_fallback():
     assert e.value.code == abi.NT_ERR_NO_DEVICE
     with pytest.raises(lib.NetTracerError):
         measure_peaks(0)
+
+
+def test_multi_gpu_entry_points_refuse_without_gpu_and_validate():
+    """nt_multi_* / nt_host_frame_* (ABI v2): argument errors are reported before any device work, and without a GPU
+    they fail with NT_ERR_NO_DEVICE - no CPU rendering path hides behind them."""
+    L = lib.load()
+    s, cam = scenes.cornell_box()
+    d, keep = s.to_desc()
+    h = C.c_void_p()
+    assert L.nt_multi_create(C.byref(d), None, 1, C.byref(h)) == abi.NT_ERR_INVALID
+    devs = (C.c_int * 2)(0, 0)
+    assert L.nt_multi_create(C.byref(d), devs, 2, C.byref(h)) == abi.NT_ERR_INVALID and b"twice" in L.nt_last_error()
+    assert L.nt_multi_device_count(None) == 0
+    assert L.nt_host_frame_open(b"no-slash", 64, 1, 1, 0, C.byref(h)) == abi.NT_ERR_INVALID
+    assert L.nt_host_frame_open(b"/nt_test_x", 0, 1, 1, 0, C.byref(h)) == abi.NT_ERR_INVALID
+    assert L.nt_host_frame_wait_all(None, 1, 1) == abi.NT_ERR_INVALID
+    assert L.nt_flags_wait_device(None, None, 1, 1, None) == abi.NT_ERR_INVALID
+    if _has_gpu():
+        return
+    devs = (C.c_int * 1)(0)
+    assert L.nt_multi_create(C.byref(d), devs, 1, C.byref(h)) == abi.NT_ERR_NO_DEVICE and not h.value
+    assert L.nt_host_frame_open(b"/nt_test_x", 4096, 1, 1, 0, C.byref(h)) == abi.NT_ERR_NO_DEVICE
+    assert not os.path.exists("/dev/shm/nt_test_x")
 
 
 def test_invalid_scene_rejected_before_device_work():

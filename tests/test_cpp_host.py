@@ -67,3 +67,44 @@ def test_cpp_host_image_equals_oracle(tmp_path):
     ref, st = oracle.render(s, make_params(w, h, spp, depth, cam.resolve(w, h)))
     assert np.array_equal(img, ref[..., :3])
     assert f"{st['rays']} rays" in r.stdout
+
+
+def cornell_fixed():
+    """The scene render_demo builds for `cornell` (fixed sphere positions), through the Python host classes."""
+    s = Scene(ambient=(1, 1, 1), background=(0.02, 0.02, 0.03))
+    white = s.add_material(Material((0.75, 0.75, 0.75), ka=0.08, kd=0.85))
+    red = s.add_material(Material((0.75, 0.15, 0.15), ka=0.08, kd=0.85))
+    green = s.add_material(Material((0.15, 0.75, 0.15), ka=0.08, kd=0.85))
+    floor = s.add_material(Material((0.6, 0.6, 0.65), ka=0.08, kd=0.7, ks=0.2, shininess=40, kr=0.2))
+    mirror = s.add_material(Material((0.9, 0.9, 0.95), ka=0.02, kd=0.15, ks=0.6, shininess=120, kr=0.75))
+    glass = s.add_material(Material((0.95, 0.98, 1.0), ka=0.0, kd=0.05, ks=0.5, shininess=200, kr=0.1, kt=0.85, ior=1.5))
+    blue = s.add_material(Material((0.2, 0.35, 0.85), ka=0.1, kd=0.7, ks=0.4, shininess=30))
+    for n, d, m in [((0, 1, 0), 0.0, floor), ((0, -1, 0), -10.0, white), ((1, 0, 0), -6.0, red),
+                    ((-1, 0, 0), -6.0, green), ((0, 0, 1), -8.0, white), ((0, 0, -1), -16.0, white)]:
+        s.add_plane(n, d, m)
+    mats = [mirror, glass, blue, mirror, glass, blue, mirror, glass]
+    for k in range(8):
+        r = 0.95 + 0.05 * k
+        s.add_sphere((-4.2 + (k % 4) * 2.8, r + (0.5 * k if k % 3 == 1 else 0.0), -3.5 + (k // 4) * 4.5), r, mats[k])
+    s.add_light((-3.0, 9.2, 4.0), (0.65, 0.62, 0.6))
+    s.add_light((3.5, 8.8, -2.0), (0.45, 0.47, 0.5))
+    return s, Camera((0.0, 5.0, 15.0), (0.0, 3.2, 0.0), vfov_deg=42)
+
+
+@pytest.mark.gpu
+def test_cpp_host_multi_gpu_cornell_equals_oracle(tmp_path):
+    """No Python in the rendering process: render_demo drives every visible GPU through nt_multi_render (n_gpus = 0)
+    on the Cornell-style box at 960x540, 4 spp, depth 5; the PPM must equal the oracle's frame."""
+    from oracle import oracle
+    exe = build_demo()
+    out = tmp_path / "cornell.ppm"
+    w, h, spp, depth = 960, 540, 4, 5
+    r = subprocess.run([exe, str(out), str(w), str(h), str(spp), str(depth), "f64", "0", "cornell"], capture_output=True, text=True)
+    assert r.returncode == 0 and "multi-GPU:" in r.stdout, r.stdout + r.stderr
+    raw = out.read_bytes()
+    header = b"P6\n%d %d\n255\n" % (w, h)
+    img = np.frombuffer(raw[len(header):], dtype=np.uint8).reshape(h, w, 3)
+    s, cam = cornell_fixed()
+    ref, st = oracle.render(s, make_params(w, h, spp, depth, cam.resolve(w, h)))
+    assert np.array_equal(img, ref[..., :3])
+    assert f"{st['rays']} rays" in r.stdout
