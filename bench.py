@@ -2,29 +2,36 @@
 """bench.py — Mrays/s and ms/frame of the intersect-and-shade hot path (BASELINE.json `metric`).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--precision f64|f32] [--workload NAME]
-                  [--mode gather|p2p_store] [--impl reference]
+                  [--mode gather|p2p_store] [--impl reference] [--no-secondary]
 
 A step = one frame of the workload (default: BASELINE.json configs[2], the configuration the metric
 is quoted on: Cornell-style box, 1920x1080, 4 spp, depth 5).  N > 1 shards the SAME frame across the
 ranks in interleaved row bands (strong scaling) and lands it on rank 0 with one exchange per frame.
 
-value        whole-job Mrays/s, frame resident on the device: rays cast per frame (counted on the
-             device, deterministic) / mean device time per step (CUDA events, max over ranks).
-e2e          the same metric through the reference-facing call nt_render with a pinned HOST output
-             buffer (N = 1) or sharded render + exchange + device->host copy on rank 0 (N > 1), timed
-             by the host clock around blocking calls.
+value        whole-job Mrays/s, frame resident on the device of rank 0: rays cast per frame (counted on
+             the device, deterministic) / mean device time per step (CUDA events on the launching stream,
+             max over ranks; a step = render kernel + exchange: peer stores over NVLink + flag wait).
+e2e          the same metric through the reference-facing call with a HOST frame: nt_render into pinned
+             memory (N = 1); ShardedRenderer.render_host (N > 1) - every rank's kernel stores its bands
+             into one shared page-locked host frame, host flags order it - timed by rank 0's host clock.
+frame_check  after the timed regions rank 0 compares the device frame AND the host frame with the CPU
+             oracle's frame of the same parameters; a mismatch makes the run fail (exit code 1).
 roofline     the render kernel against the measured FP64 (strict) / FP32 (fast) issue-rate peak
-             (nt_measure_peaks, same process, same clocks): algorithmic flops by SURVEY.md §8(d)'s
-             convention / kernel time.  The path is FP-pipe bound; DRAM traffic is ~0.
+             (nt_measure_peaks, same process, same clocks): `frac` = algorithmic flops by SURVEY.md
+             §8(d)'s convention (every query credited with every primitive) / kernel time / peak;
+             `executed_frac` = the same weights on the tests the kernel really starts (instrumented twin
+             of the kernel, one extra launch); `frac_vs_fma_peak` = against the FMA rate the strict mode
+             may not use.  The path is FP-issue bound, not HBM or tensor bound.
+secondary    bounded runs of the other BASELINE.json configs (outside the headline's timed region).
 cpu_baseline the CPU oracle (a port of SPEC-PROVISIONAL.md — NOT NetTracer, whose sources do not exist
              here) on all host threads over a bounded sample of the same frame.
 --impl reference  times that same oracle alone (there is no reference implementation to run:
              /root/reference holds one README and the image has no JVM).
 """
 import argparse
+import hashlib
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -34,6 +41,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "Mrays/s"
 DEFAULT_WORKLOAD = "cfg3_cornell_1080p_4spp_d5"
+L2_NOTE = "GPU arm: 256 MiB memset between timed steps, outside each step's event pair; CPU arm: not applicable"
 
 
 def parse():
@@ -48,31 +56,44 @@ def parse():
     ap.add_argument("--band-rows", type=int, default=8)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the bounded runs of the other configs")
+    ap.add_argument("--no-frame-check", action="store_true")
     ap.add_argument("--bvh-build", default="host", choices=["host", "gpu"],
                     help="BVH scenes: binned-SAH build on the host (default) or LBVH build on the GPU")
     return ap.parse_args()
 
 
+def config_of(name, w, h, spp, depth):
+    """The SAME dictionary in both arms, so that the driver's config comparison sees one configuration."""
+    return {"workload": name, "width": w, "height": h, "spp": spp, "max_depth": depth, "l2": L2_NOTE}
+
+
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons of one GPU; only samples taken between
-    begin() and end() (the timed regions) are summarised."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons of one GPU through NVML, in this process, every ~2 ms; only samples
+    taken between begin() and end() (the timed regions) are summarised.  (Round 1 polled nvidia-smi every 50 ms and
+    never landed a sample inside a 15 ms timed region.)"""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.windows = index, [], []
-        self.proc = None
+        self._stop_flag = False
+        self.error = None
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.samples.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
-        except Exception:
-            pass
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._stop_flag:
+                t = time.perf_counter()
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                if any(a <= t and b is None for a, b in self.windows):  # the costlier queries only inside a window
+                    self.samples.append((t, sm, reasons_fn(h), nv.nvmlDeviceGetPowerUsage(h) / 1000.0))
+                time.sleep(0.002)
+        except Exception as e:  # no NVML: the line says so instead of inventing clocks
+            self.error = repr(e)
 
     def begin(self):
         self.windows.append([time.perf_counter(), None])
@@ -81,23 +102,25 @@ class ClockSampler(threading.Thread):
         self.windows[-1][1] = time.perf_counter()
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sel = [s for t, s in self.samples if any(a <= t <= (b or t) for a, b in self.windows)]
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(sel),
-               "window": "device-resident and e2e timed regions"}
-        try:
-            sm = sorted(float(s[0]) for s in sel)
-            if sm:
-                out["sm_mhz"] = sm[len(sm) // 2]
-                out["sm_max_mhz"] = float(sel[0][1])
-                out["power_w_max"] = max(float(s[2]) for s in sel)
-            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            for i, n in enumerate(names):
-                if any(s[3 + i].lower().startswith("active") for s in sel):
-                    out["reasons"].append(n)
-        except Exception:
-            pass
+        self._stop_flag = True
+        self.join(timeout=1.0)
+        out = {"sm_mhz": None, "sm_max_mhz": getattr(self, "max_sm", None), "reasons": [], "samples": len(self.samples),
+               "source": "NVML in-process, 2 ms period", "window": "device-resident and e2e timed regions"}
+        if self.error:
+            out["error"] = self.error
+        if self.samples:
+            sm = sorted(s[1] for s in self.samples)
+            out["sm_mhz"] = sm[len(sm) // 2]
+            out["sm_mhz_min"] = sm[0]
+            out["power_w_max"] = max(s[3] for s in self.samples)
+            bits = 0
+            for s in self.samples:
+                bits |= int(s[2])
+            # NVML reason bits: 0x4 sw_power_cap, 0x8 hw_slowdown, 0x20 sw_thermal, 0x40 hw_thermal, 0x80 hw_power_brake
+            for bit, name in ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"),
+                              (0x4, "sw_power_cap"), (0x80, "hw_power_brake_slowdown")):
+                if bits & bit:
+                    out["reasons"].append(name)
         return out
 
 
@@ -127,12 +150,16 @@ def workload(name):
     return scene, cam, w, h, spp, depth
 
 
+def uses_accel(scene):
+    return 1 if len(scene.spheres) + len(scene.triangles) > 64 else 0
+
+
 def cpu_oracle_sample(scene, cam, w, h, spp, depth, target_s):
     """All host threads over every k-th image row of the frame (k = 1 when a whole frame is cheap),
     repeated until ~target_s of CPU time has been spent."""
     from nettracer_b200.scene import make_params
     from oracle import oracle
-    accel = 1 if len(scene.spheres) + len(scene.triangles) > 64 else 0
+    accel = uses_accel(scene)
     p = make_params(w, h, spp, depth, cam.resolve(w, h))
     k = 64
     t0 = time.perf_counter()
@@ -162,7 +189,7 @@ def run_reference(a):
     scene, cam, w, h, spp, depth = workload(a.workload)
     from nettracer_b200.scene import make_params
     from oracle import oracle
-    accel = 1 if len(scene.spheres) + len(scene.triangles) > 64 else 0
+    accel = uses_accel(scene)
     p = make_params(w, h, spp, depth, cam.resolve(w, h))
     # size the per-step sample so that warmup+steps stay within ~2 minutes
     k = 64
@@ -183,13 +210,12 @@ def run_reference(a):
     val = rays / (ms * 1e-3) / 1e6
     rows = len(range(0, h, k))
     frame_ms = ms * h / rows
+    sample = f"every {k}th row ({rows} of {h} rows) per step" if k > 1 else "the whole frame per step"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": METRIC, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms, "ms_per_frame_extrapolated": frame_ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": a.workload, "width": w, "height": h, "spp": spp, "max_depth": depth,
-                       "sample": f"every {k}th row ({rows} of {h})"},
-            "cpu_baseline": {"value": val, "unit": METRIC, "cores": oracle.max_threads(), "kind": "port",
-                             "sample": f"every {k}th row ({rows} of {h} rows) per step",
+            "config": config_of(a.workload, w, h, spp, depth),
+            "cpu_baseline": {"value": val, "unit": METRIC, "cores": oracle.max_threads(), "kind": "port", "sample": sample,
                              "note": "no NetTracer source or JVM exists here; this is the SPEC-PROVISIONAL oracle"},
             "e2e": {"value": val, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -204,6 +230,7 @@ def main():
         return
     import ctypes as C
 
+    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -229,144 +256,228 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
+    def reduce_ranks(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
+    def max_over_ranks(x):
+        return reduce_ranks(x, dist.ReduceOp.MAX) if world > 1 else x
+
     def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return reduce_ranks(x, dist.ReduceOp.SUM) if world > 1 else x
 
     if a.bvh_build == "gpu":
         os.environ["NT_BVH_BUILD"] = "gpu"
-    scene, cam, w, h, spp, depth = workload(a.workload)
     prec = abi.NT_F64_STRICT if a.precision == "f64" else abi.NT_F32_FAST
-    t0 = time.perf_counter()
-    backend = CudaBackend(scene, local)
-    scene_create_s = time.perf_counter() - t0
-    sr = ShardedRenderer(backend, rank, world, band_rows=a.band_rows, mode=a.mode)
-    camera = cam.resolve(w, h)
-    sp = sr.shard_params(w, h, spp, depth, camera, prec)
-    info = backend.renderer.info()
-
+    strict = a.precision == "f64"
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     peaks = measure_peaks(local) if rank == 0 else None
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    peak_gf = (peaks["f64_nofma_gflops"] if strict else peaks["f32_fma_gflops"]) if peaks else None
 
-    # ---------- device-resident timing ----------
-    def step():
-        return sr.render(sp)
-
-    for _ in range(a.warmup):
-        step()
-        flush.zero_()
-    barrier()
-    # per-frame work of this rank (deterministic): rays and algorithmic flops
-    st = backend.stats()
-    rays_total = sum_over_ranks(float(st["rays"]))
-    flops_local = float(abi.algorithmic_flops(st))
-    flops_total = sum_over_ranks(flops_local)
-
-    if sampler:
-        sampler.begin()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(a.steps)]
-    barrier()
-    wall0 = time.perf_counter()
-    for e0, ek, e1 in ev:
-        flush.zero_()  # L2 flush between timed steps, outside the step's event pair
-        e0.record()
-        sr.render(sp, kernel_done=ek)  # render kernel | ek | exchange (+ deinterleave)
-        e1.record()
-    barrier()
-    wall = time.perf_counter() - wall0
-    if sampler:
-        sampler.end()
-    step_ms = [e0.elapsed_time(e1) for e0, ek, e1 in ev]
-    kern_ms = [e0.elapsed_time(ek) for e0, ek, e1 in ev]
-    ms_per_step = max_over_ranks(sum(step_ms) / len(step_ms))
-    kernel_ms_local = sum(kern_ms) / len(kern_ms)
-    kernel_ms = max_over_ranks(kernel_ms_local)
-    value = rays_total / (ms_per_step * 1e-3) / 1e6
-
-    # ---------- end-to-end through the host-buffer call ----------
-    host = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory()
-    e2e_times = []
-    for i in range(a.warmup + a.steps):
-        if i == a.warmup and sampler:
-            sampler.begin()
-        barrier()
+    def measure(name, steps, warmup, want_e2e, sample_clocks):
+        """One workload, sharded over the ranks: device-resident timing, optional end-to-end timing, frame check data.
+        Returns a dict on every rank (aggregates are identical on all ranks)."""
+        scene, cam, w, h, spp, depth = workload(name)
         t0 = time.perf_counter()
-        if world == 1:
-            full_p = make_params(w, h, spp, depth, camera, prec)
-            stats = abi.nt_render_stats()
-            from nettracer_b200.lib import check, load
-            check(load().nt_render(backend.renderer._h, C.byref(full_p), C.c_void_p(host.data_ptr()), w * 4, C.byref(stats)))
-        else:
-            full = sr.render(sp)
-            if rank == 0:
-                host.copy_(full, non_blocking=True)
-            torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if i >= a.warmup:
-            e2e_times.append(max_over_ranks(dt))
-    if sampler:
-        sampler.end()
-    clocks = sampler.stop() if sampler else None
-    e2e_ms = 1e3 * sum(e2e_times) / len(e2e_times)
-    e2e_val = rays_total / (e2e_ms * 1e-3) / 1e6
+        backend = CudaBackend(scene, local)
+        scene_create_s = time.perf_counter() - t0
+        sr = ShardedRenderer(backend, rank, world, band_rows=a.band_rows, mode=a.mode)
+        camera = cam.resolve(w, h)
+        sp = sr.shard_params(w, h, spp, depth, camera, prec)
+        info = backend.renderer.info()
+        for _ in range(warmup):
+            sr.render(sp)
+            flush.zero_()
+        barrier()
+        # per-frame work of this rank (deterministic): rays and algorithmic flops
+        st = backend.stats()
+        rays_total = sum_over_ranks(float(st["rays"]))
+        flops_local = float(abi.algorithmic_flops(st))
+        launches = backend.renderer.info()["last_launches"] + (1 if world > 1 and rank == 0 and sr.mode == "p2p_store" else 0)
+        # executed work: one launch of the instrumented twin (flat scenes; BVH counters are executed counts already)
+        xp = sr.shard_params(w, h, spp, depth, camera, prec)
+        xp.flags = abi.NT_RENDER_COUNT_EXECUTED
+        sr.render(xp)
+        barrier()
+        xst = backend.stats()
+        executed_local = float(abi.executed_flops(xst)) if not info["uses_bvh"] else flops_local
+        sr.render(sp)   # the frame the check below reads is a production frame again
+        barrier()
 
+        if sampler and sample_clocks:
+            sampler.begin()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+              for _ in range(steps)]
+        barrier()
+        wall0 = time.perf_counter()
+        full = None
+        for e0, ek, e1 in ev:
+            flush.zero_()  # L2 flush between timed steps, outside the step's event pair
+            e0.record()
+            full = sr.render(sp, kernel_done=ek)  # render kernel (+ flag posts) | ek | exchange: flag wait / gather
+            e1.record()
+        barrier()
+        wall = time.perf_counter() - wall0
+        if sampler and sample_clocks:
+            sampler.end()
+        ms_per_step = max_over_ranks(sum(e0.elapsed_time(e1) for e0, ek, e1 in ev) / steps)
+        kernel_ms_local = sum(e0.elapsed_time(ek) for e0, ek, e1 in ev) / steps
+        res = {"name": name, "w": w, "h": h, "spp": spp, "depth": depth, "info": info, "scene_create_s": scene_create_s,
+               "rays_total": rays_total, "flops_local": flops_local, "executed_local": executed_local,
+               "ms_per_step": ms_per_step, "kernel_ms_local": kernel_ms_local, "kernel_ms": max_over_ranks(kernel_ms_local),
+               "launches": launches, "wall": wall, "exchange": sr.mode if world > 1 else "none", "scene": scene, "cam": cam}
+        res["value"] = rays_total / (ms_per_step * 1e-3) / 1e6
+        dev_frame = full.cpu().numpy() if rank == 0 else None
+
+        # ---------- end to end: the frame in host memory ----------
+        host_frame = None
+        if want_e2e:
+            hp = make_params(w, h, spp, depth, camera, prec, shard_index=rank, shard_count=world, band_rows=a.band_rows)
+            host = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() if world == 1 else None
+            from nettracer_b200.lib import check, load
+
+            def e2e_frame():
+                if world == 1:
+                    stats = abi.nt_render_stats()
+                    check(load().nt_render(backend.renderer._h, C.byref(hp), C.c_void_p(host.data_ptr()), w * 4, C.byref(stats)))
+                    return host.numpy()
+                return sr.render_host(hp)[0]
+            for _ in range(warmup):
+                e2e_frame()
+            barrier()
+            if sampler and sample_clocks:
+                sampler.begin()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                host_frame = e2e_frame()   # rank 0 returns when every rank's bands are in the host frame
+            e2e_ms_local = 1e3 * (time.perf_counter() - t0) / steps
+            if sampler and sample_clocks:
+                sampler.end()
+            if rank == 0 and host_frame is not None:
+                host_frame = np.array(host_frame)
+            barrier()
+            res["e2e_ms"] = max_over_ranks(e2e_ms_local)
+        res["dev_frame"], res["host_frame"] = dev_frame, host_frame
+        sr.close()
+        return res
+
+    def frame_check(res):
+        """Rank 0: device frame and host frame against the oracle's frame (every k-th row when a whole frame would
+        take the host too long)."""
+        from oracle import oracle
+        scene, cam, w, h, spp, depth = res["scene"], res["cam"], res["w"], res["h"], res["spp"], res["depth"]
+        accel = uses_accel(scene)
+        p = make_params(w, h, spp, depth, cam.resolve(w, h))
+        k = 1 if not accel else max(1, -(-(w * h * spp) // 2_000_000))  # BVH scenes: ~2 M samples of oracle work
+        t0 = time.perf_counter()
+        ref, rst = oracle.render(scene, p, accel=accel, row_step=k)
+        rows = slice(0, h, k)
+        out = {"sha256_device_frame": hashlib.sha256(res["dev_frame"].tobytes()).hexdigest()[:16],
+               "rows_checked": len(range(0, h, k)), "oracle_s": time.perf_counter() - t0}
+        out["diff_pixels_vs_oracle"] = int((res["dev_frame"][rows] != ref[rows]).any(axis=-1).sum())
+        if k == 1:
+            out["rays_equal_oracle"] = bool(rst["rays"] == int(res["rays_total"]))
+        if res["host_frame"] is not None:
+            out["host_frame_equals_device_frame"] = bool(np.array_equal(res["host_frame"], res["dev_frame"]))
+        tol = 2 if strict else max(2, int(0.005 * out["rows_checked"] * w))  # strict: `pow` may move <= 2 pixels by 1 LSB
+        out["ok"] = bool(out["diff_pixels_vs_oracle"] <= tol and out.get("host_frame_equals_device_frame", True)
+                         and out.get("rays_equal_oracle", True))
+        return out
+
+    main_res = measure(a.workload, a.steps, a.warmup, True, True)
+    clocks = sampler.stop() if sampler else None
+
+    secondary = []
+    if not a.no_secondary:
+        # bounded runs of the other configs (BASELINE.json configs[1], [3], and [4] from 4 GPUs up), a few frames each
+        plan = [("cfg2_cornell_1080p_1spp_d1", 20, 3), ("cfg4_mesh1m_4k_4spp_d3", 3, 2)]
+        if world >= 4:
+            plan.append(("cfg5_mesh1m_8k_16spp_d5", 2, 1))
+        for name, steps, warmup in plan:
+            if name == a.workload:
+                continue
+            r = measure(name, steps, warmup, False, False)
+            entry = {"workload": name, "frames": steps, "ms_per_frame": r["ms_per_step"], "Mrays_per_s": r["value"],
+                     "rays_per_frame": r["rays_total"], "kernel_ms": r["kernel_ms"], "launches_per_frame": r["launches"],
+                     "uses_bvh": r["info"]["uses_bvh"], "scene_create_s": r["scene_create_s"], "dtype": a.precision}
+            if rank == 0:
+                entry["roofline_frac"] = r["flops_local"] / (r["kernel_ms_local"] * 1e-3) / 1e9 / peak_gf
+                if not a.no_frame_check:
+                    entry["frame_check"] = frame_check(r)
+            secondary.append(entry)
+
+    ok = True
     if rank == 0:
-        strict = a.precision == "f64"
-        per_frame_launches = backend.renderer.info()["last_launches"]
-        peak_gf = peaks["f64_nofma_gflops"] if strict else peaks["f32_fma_gflops"]
-        achieved_tf = flops_local / (kernel_ms_local * 1e-3) / 1e12
+        r = main_res
+        w, h, spp, depth, info = r["w"], r["h"], r["spp"], r["depth"], r["info"]
+        achieved_tf = r["flops_local"] / (r["kernel_ms_local"] * 1e-3) / 1e12
+        executed_tf = r["executed_local"] / (r["kernel_ms_local"] * 1e-3) / 1e12
+        fma_peak_tf = (peaks["f64_fma_gflops"] if strict else peaks["f32_fma_gflops"]) / 1e3
+        traffic = {"cfg3_cornell_1080p_4spp_d5": 7.423e7}.get(a.workload) if strict and world == 1 else None
         roof = {"bound": "fp64" if strict else "fp32", "achieved": achieved_tf, "peak": peak_gf / 1e3, "unit": "TFLOP/s",
                 "frac": achieved_tf / (peak_gf / 1e3),
-                "traffic": ({"cfg3_cornell_1080p_4spp_d5": 7.423e7}.get(a.workload) if strict else None),
-                "traffic_note": "dram read+write bytes of one render launch (ncu --set full, profiles/r01j_cfg3_f64_final.md): "
-                                "2.3 MB read + 71.9 MB written, of which 8.3 MB is the frame and the rest evicted local-memory "
-                                "(ray-tree stack and spill) lines; 1.5 % of HBM bandwidth - the kernel is FP-issue bound, not HBM bound",
-                "kernel": ("wf_trace_kernel + wf_shade_kernel (wavefront pipeline, all kernels of a frame)" if info["uses_bvh"] and per_frame_launches > 2
+                "executed": executed_tf, "executed_frac": executed_tf / (peak_gf / 1e3),
+                "frac_vs_fma_peak": achieved_tf / fma_peak_tf, "executed_frac_vs_fma_peak": executed_tf / fma_peak_tf,
+                "traffic": traffic,
+                "traffic_source": ("profile constant, not measured in this run: dram read + write bytes of one render launch from "
+                                   "ncu --set full (profiles/r01j_cfg3_f64_final.md): 2.3 MB read + 71.9 MB written, of which 8.3 MB "
+                                   "is the frame and the rest local-memory (ray-stack, spill) lines the L2 flush between steps "
+                                   "forces out; 1.5 % of HBM bandwidth") if traffic else None,
+                "kernel": ("wf_trace_kernel + wf_shade_kernel (wavefront pipeline, all kernels of a frame)" if info["uses_bvh"] and r["launches"] > 3
                            else "render_%skernel<%s>" % ("bvh_" if info["uses_bvh"] else "", "double" if strict else "float")),
-                "kernel_ms": kernel_ms_local, "algorithmic_flops_per_launch": flops_local,
+                "kernel_ms": r["kernel_ms_local"], "algorithmic_flops_per_launch": r["flops_local"],
+                "executed_flops_per_launch": r["executed_local"],
                 "peak_source": "nt_measure_peaks in this process: " + ("FP64 mul/add issue rate without FMA (strict mode may not fuse)"
                                                                         if strict else "FP32 FMA issue rate"),
                 "peaks_measured_gflops": peaks,
-                "note": "path is FP-pipe bound, not HBM/tensor (BASELINE.json north_star); flop convention SURVEY.md §8(d); "
-                        "traffic: see profiles/ (DRAM bytes per launch are ~0.3 MB)"}
-        line = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": ms_per_step, "ms_per_frame": ms_per_step, "higher_is_better": True,
+                "note": "path is FP-issue bound, not HBM/tensor (BASELINE.json north_star); flop convention SURVEY.md §8(d); `frac` "
+                        "credits every query with every primitive (algorithmic work), `executed_frac` counts the tests the kernel "
+                        "starts after culling; rank 0's shard when n_gpus > 1"}
+        e2e_val = r["rays_total"] / (r["e2e_ms"] * 1e-3) / 1e6
+        line = {"metric": METRIC, "value": r["value"], "unit": METRIC, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": r["ms_per_step"], "ms_per_frame": r["ms_per_step"], "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
-                "config": {"workload": a.workload, "width": w, "height": h, "spp": spp, "max_depth": depth,
-                           "rays_per_frame": rays_total, "sharding": f"{world} x interleaved {a.band_rows}-row bands" if world > 1 else "none",
-                           "exchange": (sr.mode if world > 1 else "none"), "uses_bvh": info["uses_bvh"],
-                           "l2": "256 MiB memset between timed steps (outside each step's event pair)",
-                           "scene_create_s": scene_create_s, "bvh_on_gpu": info.get("bvh_on_gpu", False),
-                           "bvh_build_ms": info.get("bvh_build_ms", 0.0), "bvh_nodes": info["bvh_nodes"]},
-                "e2e": {"value": e2e_val, "unit": METRIC, "ms_per_frame": e2e_ms, "h2d_bytes_per_step": C.sizeof(abi.nt_render_params),
-                        "d2h_bytes_per_step": h * w * 4 + 8 * 8 * 32,
-                        "api": "nt_render -> pinned host RGBA8" if world == 1 else "ShardedRenderer.render + D2H on rank 0"},
-                "gpu_launches": a.steps * (per_frame_launches + (1 if sr.mode == "gather" and world > 1 else 0)),
-                "gpu_launches_note": "per frame and rank, counted by the library (nt_scene_info): flat scenes 1 render kernel; BVH scenes "
-                                     "the wavefront pipeline's trace/shadow/shade kernels per level and chunk + sum + resolve "
-                                     "(or 2 with NT_WAVEFRONT=0); + deinterleave on rank 0 in gather mode",
-                "kernel_ms": kernel_ms, "wall_s_timed_region": wall, "clocks": clocks, "roofline": roof}
+                "config": config_of(a.workload, w, h, spp, depth),
+                "run": {"rays_per_frame": r["rays_total"],
+                        "sharding": f"{world} x interleaved {a.band_rows}-row bands" if world > 1 else "none",
+                        "exchange": ("peer stores over NVLink into rank 0's double-buffered frame + device flags (no collective)"
+                                     if r["exchange"] == "p2p_store" else r["exchange"]),
+                        "uses_bvh": info["uses_bvh"], "scene_create_s": r["scene_create_s"], "bvh_on_gpu": info.get("bvh_on_gpu", False),
+                        "bvh_build_ms": info.get("bvh_build_ms", 0.0), "bvh_nodes": info["bvh_nodes"]},
+                "e2e": {"value": e2e_val, "unit": METRIC, "ms_per_frame": r["e2e_ms"], "h2d_bytes_per_step": C.sizeof(abi.nt_render_params) * world,
+                        "d2h_bytes_per_step": h * w * 4 + 8 * abi_counter_bytes(abi) * world,
+                        "api": ("nt_render -> pinned host RGBA8 (zero-copy stores from the kernel)" if world == 1 else
+                                "ShardedRenderer.render_host: every rank's nt_render stores its bands into ONE shared page-locked host "
+                                "frame (nt_host_frame_*), host flags order it; rank 0's clock")},
+                "gpu_launches": a.steps * r["launches"],
+                "gpu_launches_note": "per frame on rank 0, counted by the library (nt_scene_info): flat scenes 1 render kernel (exchange flags "
+                                     "are posted inside it); BVH scenes the wavefront pipeline's kernels per level and chunk + sum + "
+                                     "resolve; + 1 flag-wait kernel on rank 0 when n_gpus > 1 (p2p_store) / + deinterleave (gather)",
+                "kernel_ms": r["kernel_ms"], "wall_s_timed_region": r["wall"], "clocks": clocks, "roofline": roof}
+        if not a.no_frame_check:
+            line["frame_check"] = frame_check(r)
+            ok = line["frame_check"]["ok"] and all(s.get("frame_check", {"ok": True})["ok"] for s in secondary)
+        if secondary:
+            line["secondary"] = secondary
         if world == 1 and not a.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_oracle_sample(scene, cam, w, h, spp, depth, a.cpu_seconds)
+            line["cpu_baseline"] = cpu_oracle_sample(r["scene"], r["cam"], w, h, spp, depth, a.cpu_seconds)
         emit(line)
     barrier()
-    sr.close()
     if world > 1:
         dist.destroy_process_group()
+    if not ok:
+        sys.stderr.write("bench.py: FRAME CHECK FAILED - the rendered frame differs from the oracle (see frame_check)\n")
+        sys.exit(1)
+
+
+def abi_counter_bytes(abi):
+    return 11 * 32  # NT_NCOUNTERS x NT_COUNTER_SLOTS 64-bit counters read back per call
 
 
 if __name__ == "__main__":

@@ -81,7 +81,12 @@ typedef struct nt_render_params {
      * owned by shard (b mod shard_count).  shard_count = 1 renders everything. */
     uint32_t shard_index, shard_count, band_rows;
     uint32_t layout;      /* enum nt_layout */
+    uint32_t flags;       /* NT_RENDER_* bits, 0 for production renders */
 } nt_render_params;
+
+/* Measurement aid: flat scenes are rendered by an instrumented twin of the kernel that also counts the primitive
+ * tests it really starts (nt_render_stats.*_tests_executed); same image, a little slower. */
+#define NT_RENDER_COUNT_EXECUTED 1u
 
 #define NT_MAX_DEPTH 16
 
@@ -95,6 +100,9 @@ typedef struct nt_render_stats {
     uint64_t triangle_tests;
     uint64_t box_tests;      /* BVH child boxes tested (0 for flat scenes) */
     uint64_t light_evals;    /* unoccluded light contributions shaded */
+    /* Tests the kernel really started (flat scenes, NT_RENDER_COUNT_EXECUTED only, else 0): what is left of the
+     * brute-force counts above after the conservative culling. */
+    uint64_t sphere_tests_executed, plane_tests_executed, triangle_tests_executed;
     double kernel_ms;        /* device time of the render kernel(s), CUDA events; nt_render only */
     double total_ms;         /* host wall time of the whole nt_render call */
 } nt_render_stats;

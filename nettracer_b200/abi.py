@@ -10,6 +10,7 @@ NT_OK, NT_ERR_INVALID, NT_ERR_NO_DEVICE, NT_ERR_CUDA, NT_ERR_NOMEM, NT_ERR_TIMEO
 NT_F64_STRICT, NT_F32_FAST = 0, 1
 NT_LAYOUT_FULL, NT_LAYOUT_COMPACT = 0, 1
 NT_MAX_DEPTH = 16
+NT_RENDER_COUNT_EXECUTED = 1
 
 _pd = C.POINTER(C.c_double)
 _pi = C.POINTER(C.c_int32)
@@ -38,7 +39,7 @@ class nt_render_params(C.Structure):
                 ("ray_epsilon", C.c_double),
                 ("camera", nt_camera),
                 ("shard_index", C.c_uint32), ("shard_count", C.c_uint32), ("band_rows", C.c_uint32),
-                ("layout", C.c_uint32)]
+                ("layout", C.c_uint32), ("flags", C.c_uint32)]
 
 
 class nt_render_stats(C.Structure):
@@ -47,6 +48,8 @@ class nt_render_stats(C.Structure):
                 ("sphere_tests", C.c_uint64), ("plane_tests", C.c_uint64),
                 ("triangle_tests", C.c_uint64), ("box_tests", C.c_uint64),
                 ("light_evals", C.c_uint64),
+                ("sphere_tests_executed", C.c_uint64), ("plane_tests_executed", C.c_uint64),
+                ("triangle_tests_executed", C.c_uint64),
                 ("kernel_ms", C.c_double), ("total_ms", C.c_double)]
 
     def as_dict(self):
@@ -91,3 +94,10 @@ FLOPS = {"sphere_tests": 17, "plane_tests": 11, "triangle_tests": 39, "box_tests
 
 def algorithmic_flops(stats: dict) -> int:
     return sum(stats[k] * v for k, v in FLOPS.items())
+
+
+def executed_flops(stats: dict) -> int:
+    """Same weights on the tests an instrumented flat-scene launch really started (NT_RENDER_COUNT_EXECUTED)."""
+    return (stats["sphere_tests_executed"] * FLOPS["sphere_tests"] + stats["plane_tests_executed"] * FLOPS["plane_tests"]
+            + stats["triangle_tests_executed"] * FLOPS["triangle_tests"] + stats["box_tests"] * FLOPS["box_tests"]
+            + stats["light_evals"] * FLOPS["light_evals"])

@@ -470,6 +470,7 @@ static int make_args(const nt_render_params *p, size_t stride, NtRenderArgs *a) 
         return fail(NT_ERR_INVALID, "%ux%u at %u spp has 2^31 samples or more: sample and tile indices are 32-bit; render it in shards", p->width, p->height, p->spp);
     if (p->precision != NT_F64_STRICT && p->precision != NT_F32_FAST) return fail(NT_ERR_INVALID, "unknown precision %u", p->precision);
     if (p->layout != NT_LAYOUT_FULL && p->layout != NT_LAYOUT_COMPACT) return fail(NT_ERR_INVALID, "unknown layout %u", p->layout);
+    if (p->flags & ~NT_RENDER_COUNT_EXECUTED) return fail(NT_ERR_INVALID, "unknown flags 0x%x", p->flags);
     const uint32_t scount = p->shard_count ? p->shard_count : 1;
     const uint32_t band = p->band_rows ? (p->band_rows > 65536 ? 65536 : p->band_rows) : 1; // height <= 65536: same partition
     if (p->shard_index >= scount) return fail(NT_ERR_INVALID, "shard_index %u >= shard_count %u", p->shard_index, scount);
@@ -501,6 +502,7 @@ static int make_args(const nt_render_params *p, size_t stride, NtRenderArgs *a) 
         a->cam[6 + k] = p->camera.dx[k]; a->cam[9 + k] = p->camera.dy[k];
     }
     a->stride = stride;
+    a->count_executed = p->flags & NT_RENDER_COUNT_EXECUTED;
     for (uint32_t i = 0; i < n; ++i) a->samp_off[i] = ((double)i + 0.5) / (double)n;
     a->inv_spp = 1.0 / (double)p->spp;
     return NT_OK;
@@ -597,6 +599,7 @@ static void sum_counters(const unsigned long long *h, nt_render_stats *s) {
         for (int i = 0; i < NT_NCOUNTERS; ++i) t[i] += h[slot * NT_NCOUNTERS + i];
     s->rays_primary = t[0]; s->rays_secondary = t[1]; s->rays_shadow = t[2];
     s->sphere_tests = t[3]; s->plane_tests = t[4]; s->triangle_tests = t[5]; s->box_tests = t[6]; s->light_evals = t[7];
+    s->sphere_tests_executed = t[8]; s->plane_tests_executed = t[9]; s->triangle_tests_executed = t[10];
 }
 
 extern "C" int nt_render(nt_scene *sc, const nt_render_params *p, uint8_t *rgba_out, size_t stride,

@@ -9,7 +9,7 @@
 #define NT_TRI_STRIDE 12   // v0[3] e1[3] e2[3] ng[3]  (R units; 16-byte aligned rows)
 #define NT_MAT_STRIDE 12   // r g b ka kd ks shininess kr kt ior inv_ior pad
 #define NT_COUNTER_SLOTS 32
-#define NT_NCOUNTERS 8     // primary secondary shadow sphere plane triangle box light
+#define NT_NCOUNTERS 11    // primary secondary shadow sphere plane triangle box light + sphere / plane / triangle tests started (instrumented kernel)
 #define NT_COUNTER_EXTRA 3 // + next work item, blocks done, sync time-outs
 #define NT_BLOCK_THREADS 256
 #ifndef NT_MIN_BLOCKS_F64
@@ -17,6 +17,12 @@
 #endif                      // on configs[2] strict: 2 -> 1.55 ms, 3 -> 1.35 ms, 4 -> 1.30 ms, 5 -> 1.40 ms
 #ifndef NT_MIN_BLOCKS_F32
 #define NT_MIN_BLOCKS_F32 4 // fast mode with culling: 3 -> 0.68 ms, 4 -> 0.61 ms (before culling: 3 -> 0.72, 4 -> 0.74)
+#endif
+#ifndef NT_MIN_BLOCKS_SMALL
+#define NT_MIN_BLOCKS_SMALL 3      // strict flat kernel, small launches (shards of a multi-GPU frame): 80 registers
+#endif
+#ifndef NT_SMALL_TILES_PER_WARP
+#define NT_SMALL_TILES_PER_WARP 8  // "small" = fewer warp tiles than this per resident warp (1/8 of configs[2]: 6.8; 1/4: 13.7)
 #endif
 #define NT_BVH_STACK 96     // entries; a 4-wide node pushes up to 3: scene creation checks 3*depth + 4 <= this
 #ifndef NT_MIN_BLOCKS_BVH
@@ -126,6 +132,7 @@ struct NtRenderArgs {
     const unsigned *sync_wait_ptr;  // no pixel is stored before (int)(*sync_wait_ptr - sync_wait_val) >= 0
     unsigned *sync_done_ptr;        // release-store of sync_done_val after the frame's last pixel store
     unsigned sync_post_val, sync_wait_val, sync_done_val;
+    uint32_t count_executed;        // flat scenes: launch the instrumented kernel (CountersX)
 };
 
 struct NtTraceArgs {

@@ -153,9 +153,18 @@ template <> struct Ld<float> {
     }
 };
 
-struct Counters { // per-thread work counters in registers (BVH and unit kernels)
+struct Counters { // per-thread work counters in registers
     unsigned prim, sec, shadow, sph, pln, tri, box, light;
 };
+// Instrumented flat kernel (NT_RENDER_COUNT_EXECUTED): additionally the primitive tests the kernel really STARTS - the
+// culling tables and the chord rule skip most of what the algorithmic counters above credit (those keep the brute-force
+// meaning).  A separate instantiation, so the product kernel carries no extra registers.
+struct CountersX : Counters {
+    unsigned xsph, xpln, xtri;
+};
+template <typename K> struct counts_executed { static constexpr bool value = false; };
+template <> struct counts_executed<CountersX> { static constexpr bool value = true; };
+#define NT_X(k, field, n) do { if constexpr (counts_executed<K>::value) (k).field += (n); } while (0)
 // ---- SPEC §3 intersections ----
 // Sphere, part 1 (branch-free, so two spheres can be interleaved): b and the discriminant.
 template <typename R>
@@ -428,9 +437,10 @@ __device__ __forceinline__ bool axis_candidate(R dk, R num, R bk) {
     if constexpr (sizeof(R) == 8) return (__double2hiint(num) ^ __double2hiint(dk)) >= 0 && fabs(num) < bk;
     else return true;
 }
-template <typename R>
-__device__ __forceinline__ void planes_nearest(const Ctx<R, false> &c, const V3<R> &o, const V3<R> &d, R &tb, Hit &best) {
+template <typename R, typename K>
+__device__ __forceinline__ void planes_nearest(const Ctx<R, false> &c, const V3<R> &o, const V3<R> &d, R &tb, Hit &best, K &k) {
     const NtDevScene &s = *c.s;
+    NT_X(k, xpln, s.nax[0] + s.nax[1] + s.nax[2] + s.ngen);
     R tm1 = plane_bound<R>(tb);
     unsigned addr = c.axl_addr;
     const R oo[3] = { o.x, o.y, o.z }, dd[3] = { d.x, d.y, d.z };
@@ -468,9 +478,10 @@ __device__ __forceinline__ void planes_nearest(const Ctx<R, false> &c, const V3<
     }
 }
 // Any plane with eps < t < dist?
-template <typename R>
-__device__ __forceinline__ bool planes_occluded(const Ctx<R, false> &c, const V3<R> &o, const V3<R> &d, R dist) {
+template <typename R, typename K>
+__device__ __forceinline__ bool planes_occluded(const Ctx<R, false> &c, const V3<R> &o, const V3<R> &d, R dist, K &k) {
     const NtDevScene &s = *c.s;
+    NT_X(k, xpln, s.nax[0] + s.nax[1] + s.nax[2] + s.ngen); // an upper bound when an occluder ends the loops early
     const R dm1 = plane_bound<R>(dist);
     unsigned addr = c.axl_addr;
     const R oo[3] = { o.x, o.y, o.z }, dd[3] = { d.x, d.y, d.z };
@@ -531,11 +542,13 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
     if constexpr (!BVH) {
         if (own >= 0) {
             R q[4];
+            NT_X(k, xsph, 1u);
             c.ld_sph((unsigned)own, q);
             if (hit_sphere<R>(q, o, d, c.eps, t)) { tb = t; best.kind = 0; best.idx = own; best.gid = own; mask = __ldg(s.nbr + own); }
             else mask &= ~(1ull << own);
         }
         unsigned long long m = mask & s.sph_bits;
+        NT_X(k, xsph, (unsigned)__popcll(m));
         while (m) {
             const unsigned i = (unsigned)__ffsll((long long)m) - 1u;
             m &= m - 1;
@@ -544,10 +557,11 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
             if (hit_sphere<R>(q, o, d, c.eps, t) && (t < tb || (t == tb && (int)i < best.gid))) { tb = t; best.kind = 0; best.idx = (int)i; best.gid = (int)i; }
         }
     }
-    if constexpr (!BVH && sizeof(R) == 8) planes_nearest<R>(c, o, d, tb, best);
+    if constexpr (!BVH && sizeof(R) == 8) planes_nearest<R, K>(c, o, d, tb, best, k);
     if constexpr (!BVH && sizeof(R) == 4) {
         // fast mode: the quotient is two instructions, so the plain SPEC §3 form in index order, two planes per
         // iteration and without branches around the division, beats the axis lists
+        NT_X(k, xpln, s.np);
         unsigned i = 0;
         for (; i + 2 <= s.np; i += 2) {
             R q0[4], q1[4], dn0, num0, dn1, num1;
@@ -569,6 +583,7 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
     if constexpr (!BVH) {
         if (s.nt) { // uniform
             unsigned long long m = s.ns >= 64 ? 0ull : mask >> s.ns;
+            NT_X(k, xtri, (unsigned)__popcll(m));
             while (m) {
                 const unsigned i = (unsigned)__ffsll((long long)m) - 1u;
                 m &= m - 1;
@@ -600,14 +615,16 @@ __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, c
             const unsigned i = (unsigned)__ffsll((long long)m) - 1u;
             m &= m - 1;
             R q[4];
+            NT_X(k, xsph, 1u);
             c.ld_sph(i, q);
             if (hit_sphere<R>(q, o, d, c.eps, t) && t < dist) { k.sph += s.ns - (i + 1); k.pln += s.np; k.tri += s.nt; return true; }
         }
     }
     if constexpr (!BVH && sizeof(R) == 8) {
-        if (planes && planes_occluded<R>(c, o, d, dist)) { k.pln += s.np - (first_occluding_plane<R>(c, o, d, dist) + 1); k.tri += s.nt; return true; }
+        if (planes && planes_occluded<R, K>(c, o, d, dist, k)) { k.pln += s.np - (first_occluding_plane<R>(c, o, d, dist) + 1); k.tri += s.nt; return true; }
     }
     if constexpr (!BVH && sizeof(R) == 4) {
+        NT_X(k, xpln, s.np); // an upper bound when an occluder ends the loop early
         unsigned i = 0;
         for (; i + 2 <= s.np; i += 2) {
             R q0[4], q1[4], dn0, num0, dn1, num1;
@@ -633,6 +650,7 @@ __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, c
                 const unsigned i = (unsigned)__ffsll((long long)m) - 1u;
                 m &= m - 1;
                 R q[9];
+                NT_X(k, xtri, 1u);
                 c.ld_tri(i, q);
                 if (hit_triangle<R>(q, o, d, c.eps, t) && t < dist) { k.tri += s.nt - (i + 1); return true; }
             }
@@ -842,7 +860,12 @@ __device__ __forceinline__ void flush_counter_values(const unsigned vals[NT_NCOU
 }
 __device__ __forceinline__ void flush_counters(const Counters &k, unsigned long long *counters,
                                                unsigned long long *s_cnt) {
-    const unsigned vals[NT_NCOUNTERS] = { k.prim, k.sec, k.shadow, k.sph, k.pln, k.tri, k.box, k.light };
+    const unsigned vals[NT_NCOUNTERS] = { k.prim, k.sec, k.shadow, k.sph, k.pln, k.tri, k.box, k.light, 0u, 0u, 0u };
+    flush_counter_values(vals, counters, s_cnt);
+}
+__device__ __forceinline__ void flush_counters(const CountersX &k, unsigned long long *counters,
+                                               unsigned long long *s_cnt) {
+    const unsigned vals[NT_NCOUNTERS] = { k.prim, k.sec, k.shadow, k.sph, k.pln, k.tri, k.box, k.light, k.xsph, k.xpln, k.xtri };
     flush_counter_values(vals, counters, s_cnt);
 }
 
@@ -859,8 +882,12 @@ __device__ __forceinline__ void flush_counters(const Counters &k, unsigned long 
 // registers with ~220 bytes of spills (configs[2] f64: 1.39 -> 1.30 ms; f32 prefers 3 blocks: 0.80 -> 0.72 ms).
 // (Work counters in shared memory as well removed the remaining spills but cost more instructions than it
 // saved: 1.34 ms against 1.30.)
-template <typename R, bool BVH, bool SINGLE>
-__global__ void __launch_bounds__(NT_BLOCK_THREADS, sizeof(R) == 8 ? NT_MIN_BLOCKS_F64 : NT_MIN_BLOCKS_F32)
+// MINB != 0: the same kernel compiled for another number of resident blocks per SM.  The strict kernel exists twice:
+// 4 blocks (64 registers) for whole frames, NT_MIN_BLOCKS_SMALL = 3 (80 registers, fewer spills, less contention per
+// scheduler) for small launches - a 1/8-frame shard of an 8-GPU render is bound by the latency of its deepest tiles, not
+// by throughput, and measured 0.153 ms against 0.166 (a whole frame: 0.831 against 0.810; profiles/r02a_ab_patches.txt).
+template <typename R, bool BVH, bool SINGLE, bool EXEC = false, int MINB = 0>
+__global__ void __launch_bounds__(NT_BLOCK_THREADS, MINB ? MINB : (sizeof(R) == 8 ? NT_MIN_BLOCKS_F64 : NT_MIN_BLOCKS_F32))
 render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRenderArgs a) {
     __shared__ unsigned long long s_cnt[NT_NCOUNTERS];
     __shared__ R s_state[4][NT_BLOCK_THREADS]; // acc r g b, W
@@ -872,8 +899,8 @@ render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRe
     stage_scene<R, BVH>(s, v, c);
 
     const unsigned tid = threadIdx.x, lane = tid & 31;
-    Counters k = { 0, 0, 0, 0, 0, 0, 0, 0 };
-    typedef Counters KT;
+    typedef typename std::conditional<EXEC, CountersX, Counters>::type KT; // EXEC: also the tests really started
+    KT k{};
     R *accp = &s_state[0][tid], *Wp = &s_state[3][tid];
     const unsigned warps_per_block = NT_BLOCK_THREADS / 32, total_warps = gridDim.x * warps_per_block;
     const unsigned n_tiles = a.tiles_x * a.tiles_y;
@@ -1014,7 +1041,8 @@ namespace nt {
 
 template <typename R, bool BVH>
 inline int launch_render_t(const NtDevScene &s, const NtRenderArgs &a, cudaStream_t st) {
-    static int blocks_per_sm[64] = { 0 }, sms[64] = { 0 }; // per device, resolved once
+    static int blocks_per_sm[64] = { 0 }, blocks_small[64] = { 0 }, sms[64] = { 0 }; // per device, resolved once
+    constexpr int MINB_SMALL = sizeof(R) == 8 && !BVH ? NT_MIN_BLOCKS_SMALL : 0; // strict flat kernel only
     int dev = 0;
     cudaGetDevice(&dev);
     const size_t smem = flat_smem_bytes<R>(s, BVH);
@@ -1022,7 +1050,12 @@ inline int launch_render_t(const NtDevScene &s, const NtRenderArgs &a, cudaStrea
     if (!sms[dev]) {
         cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
         if (BVH) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[dev], render_bvh_kernel<R>, NT_BLOCK_THREADS, 4096);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[dev], render_kernel<R, false, true>, NT_BLOCK_THREADS, 4096);
+        else {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[dev], render_kernel<R, false, true>, NT_BLOCK_THREADS, 4096);
+            if constexpr (MINB_SMALL != 0)
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_small[dev], render_kernel<R, false, true, false, MINB_SMALL>, NT_BLOCK_THREADS, 4096);
+            if (blocks_small[dev] < 1) blocks_small[dev] = 1;
+        }
         if (blocks_per_sm[dev] < 1) blocks_per_sm[dev] = 1;
     }
     const unsigned n_tiles = a.tiles_x * a.tiles_y, wpb = NT_BLOCK_THREADS / 32;
@@ -1049,9 +1082,29 @@ inline int launch_render_t(const NtDevScene &s, const NtRenderArgs &a, cudaStrea
             rc = (int)cudaGetLastError();
         }
         return rc;
-    } else if (a.spp == a.lanes) render_kernel<R, false, true><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
-    else render_kernel<R, false, false><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
-    if (a.n_launches) *a.n_launches += 1;
+    }
+    if constexpr (!BVH) {
+        // fewer than NT_SMALL_TILES_PER_WARP warp tiles per resident warp: the small-launch variant (NT_SMALL_LAUNCH=0 / 1
+        // forces the choice, A/B)
+        bool small = MINB_SMALL != 0 && !a.count_executed && n_tiles < (unsigned)NT_SMALL_TILES_PER_WARP * (unsigned)(sms[dev] * blocks_per_sm[dev]) * wpb;
+        if (const char *e = getenv("NT_SMALL_LAUNCH")) small = MINB_SMALL != 0 && !a.count_executed && e[0] == '1';
+        if constexpr (MINB_SMALL != 0) {
+            if (small) {
+                grid = (unsigned)(sms[dev] * blocks_small[dev]);
+                if (grid > (n_tiles + wpb - 1) / wpb) grid = (n_tiles + wpb - 1) / wpb;
+                if (a.spp == a.lanes) render_kernel<R, false, true, false, MINB_SMALL><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
+                else render_kernel<R, false, false, false, MINB_SMALL><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
+                if (a.n_launches) *a.n_launches += 1;
+                return (int)cudaGetLastError();
+            }
+        }
+        if (a.count_executed) { // instrumented twin (nt_render_params.flags & NT_RENDER_COUNT_EXECUTED): measurement only
+            if (a.spp == a.lanes) render_kernel<R, false, true, true><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
+            else render_kernel<R, false, false, true><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
+        } else if (a.spp == a.lanes) render_kernel<R, false, true><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
+        else render_kernel<R, false, false><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
+        if (a.n_launches) *a.n_launches += 1;
+    }
     return (int)cudaGetLastError();
 }
 

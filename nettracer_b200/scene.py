@@ -138,7 +138,7 @@ class Scene:
 
 def make_params(width, height, spp, max_depth, camera: abi.nt_camera, precision=abi.NT_F64_STRICT,
                 ray_epsilon=0.0, shard_index=0, shard_count=1, band_rows=16,
-                layout=abi.NT_LAYOUT_FULL) -> abi.nt_render_params:
+                layout=abi.NT_LAYOUT_FULL, flags=0) -> abi.nt_render_params:
     p = abi.nt_render_params()
     p.struct_size = C.sizeof(abi.nt_render_params)
     p.width, p.height, p.spp, p.max_depth = int(width), int(height), int(spp), int(max_depth)
@@ -147,6 +147,7 @@ def make_params(width, height, spp, max_depth, camera: abi.nt_camera, precision=
     p.camera = camera
     p.shard_index, p.shard_count, p.band_rows = int(shard_index), int(shard_count), int(band_rows)
     p.layout = int(layout)
+    p.flags = int(flags)
     return p
 
 

@@ -47,7 +47,7 @@ def test_scene_flattening_and_generators_are_deterministic():
 def test_params_and_shard_bookkeeping():
     cam = Camera((0, 1, 5), (0, 0, 0))
     p = make_params(64, 48, 4, 3, cam.resolve(64, 48), shard_index=1, shard_count=3, band_rows=5)
-    assert p.struct_size == 144 and p.width == 64 and p.shard_count == 3
+    assert p.struct_size == 152 and p.flags == 0 and p.width == 64 and p.shard_count == 3
     h, band, n = 48, 5, 3
     rows = [owned_rows(h, band, i, n) for i in range(n)]
     assert sorted(np.concatenate(rows).tolist()) == list(range(h))
