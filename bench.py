@@ -380,12 +380,17 @@ def main():
         rows = slice(0, h, k)
         out = {"sha256_device_frame": hashlib.sha256(res["dev_frame"].tobytes()).hexdigest()[:16],
                "rows_checked": len(range(0, h, k)), "oracle_s": time.perf_counter() - t0}
-        out["diff_pixels_vs_oracle"] = int((res["dev_frame"][rows] != ref[rows]).any(axis=-1).sum())
-        if k == 1:
+        diff = np.abs(res["dev_frame"][rows].astype(np.int16) - ref[rows].astype(np.int16)).max(axis=-1)
+        # strict mode: any difference counts; fast mode (no bit contract, SPEC section 7): pixels more than 1 LSB off
+        out["diff_pixels_vs_oracle"] = int((diff > (0 if strict else 1)).sum())
+        out["max_abs_diff"] = int(diff.max())
+        if k == 1 and strict:
             out["rays_equal_oracle"] = bool(rst["rays"] == int(res["rays_total"]))
         if res["host_frame"] is not None:
             out["host_frame_equals_device_frame"] = bool(np.array_equal(res["host_frame"], res["dev_frame"]))
-        tol = 2 if strict else max(2, int(0.005 * out["rows_checked"] * w))  # strict: `pow` may move <= 2 pixels by 1 LSB
+        # strict: `pow` may move <= 2 pixels by 1 LSB; fast: >= 99.5 % of the pixels within 1 LSB (tests/test_parity_gpu.py)
+        tol = 2 if strict else max(2, int(0.005 * out["rows_checked"] * w))
+        out["tolerance_pixels"] = tol
         out["ok"] = bool(out["diff_pixels_vs_oracle"] <= tol and out.get("host_frame_equals_device_frame", True)
                          and out.get("rays_equal_oracle", True))
         return out

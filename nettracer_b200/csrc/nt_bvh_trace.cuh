@@ -76,6 +76,19 @@ __device__ __forceinline__ void query_start(const Ctx<R, true> &c, BvhQuery<R> &
     // kilometres away) is first slid along the exact ray to where it enters the scene bounds: only the
     // box tests use the shifted copy, the primitive tests keep the original ray.
     float m = 4e-6f * (fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz)) + s.max_abs);
+    // SPEC §3's sphere test takes the direction as a unit vector, but §4 does not re-normalise reflected / refracted
+    // directions: |d|^2 = L2 drifts from 1 along a mirror chain (1 + 1e-4 at depth 5 is common, every bounce amplifies
+    // it), and the rule then accepts roots t whose point o + d t lies at distance sqrt(r^2 + (L2 - 1) t^2) <= r +
+    // sqrt(L2 - 1) t from the centre - OUTSIDE the sphere and possibly outside its box.  Boxes may only cull what the
+    // rule cannot hit, so they grow by that bound with t <= the largest distance from the origin to a scene point;
+    // ~1e-8 of the scene size for a unit direction.  (Found by bench.py's frame check against the brute-force oracle.)
+    const float grow = [&] {
+        const R l2 = dot(d, d);
+        if (!(l2 > R(1))) return l2 == l2 ? 0.0f : CUDART_INF_F;
+        const float far_ = 1.7320508f * (fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz)) + s.max_abs);
+        return __fsqrt_ru(Math<R>::up(l2 - R(1))) * far_ * 1.00001f;
+    }();
+    m += grow;
     float tn = 0.0f, tf = CUDART_INF_F;
     slab(s.blo[0], s.bhi[0], ox, ix, m, tn, tf);
     slab(s.blo[1], s.bhi[1], oy, iy, m, tn, tf);
@@ -86,7 +99,7 @@ __device__ __forceinline__ void query_start(const Ctx<R, true> &c, BvhQuery<R> &
         const R ts = (R)tn;
         const V3<R> os = { o.x + d.x * ts, o.y + d.y * ts, o.z + d.z * ts }; // a point of the exact ray
         ox = (float)os.x; oy = (float)os.y; oz = (float)os.z;
-        m = 4e-6f * (fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz)) + s.max_abs);
+        m = 4e-6f * (fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz)) + s.max_abs) + grow; // grow: from the ORIGINAL origin, where t is measured
         q.tshift = ts;
     }
     // near plane of an axis: lo when the ray runs in +axis, hi otherwise; each moved outward by m

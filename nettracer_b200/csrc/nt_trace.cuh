@@ -544,8 +544,13 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
             R q[4];
             NT_X(k, xsph, 1u);
             c.ld_sph((unsigned)own, q);
-            if (hit_sphere<R>(q, o, d, c.eps, t)) { tb = t; best.kind = 0; best.idx = own; best.gid = own; mask = __ldg(s.nbr + own); }
-            else mask &= ~(1ull << own);
+            if (hit_sphere<R>(q, o, d, c.eps, t)) {
+                tb = t; best.kind = 0; best.idx = own; best.gid = own;
+                // the chord argument needs a unit direction: SPEC §4 does not re-normalise, and with |d|^2 = 1 + e the
+                // sphere rule accepts points up to sqrt(e) t outside a ball (nt_bvh_trace.cuh query_start).  The
+                // neighbour table is dilated by 1e-3; beyond e = 1e-8 (a long mirror chain) every primitive is tested.
+                if (fabs(dot(d, d) - R(1)) <= R(sizeof(R) == 8 ? 1e-8 : 1e-4)) mask = __ldg(s.nbr + own);
+            } else mask &= ~(1ull << own);
         }
         unsigned long long m = mask & s.sph_bits;
         NT_X(k, xsph, (unsigned)__popcll(m));

@@ -153,6 +153,31 @@ def random_mixed(n_spheres, n_planes, n_triangles, n_lights=2, seed=1, glassy=Tr
     return s, cam
 
 
+def mirror_field(n_spheres=3000, seed=7):
+    """Parity-test scene: thousands of small mirror and glass spheres that see each other at distances of many radii,
+    so that ray trees run along mirror chains.  SPEC-PROVISIONAL section 4 does not re-normalise secondary directions;
+    along such chains |d| drifts from 1 (every bounce off a small, distant sphere amplifies the drift) and the sphere
+    rule of section 3 then accepts points off the sphere - any acceleration structure has to stay conservative for
+    that (nt_bvh_trace.cuh query_start, oracle ray_grow).  > 64 bounded primitives: the BVH path."""
+    rng = SplitMix64(seed)
+    s = Scene(ambient=(1.0, 1.0, 1.0), background=(0.3, 0.4, 0.6))
+    mirror = s.add_material(Material((0.9, 0.9, 0.95), ka=0.02, kd=0.1, ks=0.6, shininess=120.0, kr=0.9))
+    glass = s.add_material(Material((0.95, 0.98, 1.0), ka=0.0, kd=0.05, ks=0.5, shininess=200.0, kr=0.1, kt=0.85, ior=1.5))
+    matte = s.add_material(Material((0.7, 0.5, 0.3), ka=0.1, kd=0.8, ks=0.2, shininess=20.0, kr=0.3))
+    s.add_plane((0, 1, 0), -22.0, matte)
+    for i in range(n_spheres):
+        c = (rng.uniform(-20, 20), rng.uniform(-20, 20), rng.uniform(-45, -5))
+        s.add_sphere(c, rng.uniform(0.4, 0.9), [mirror, mirror, mirror, glass][i % 4])
+    for i in range(8):
+        c = np.array([rng.uniform(-20, 20), rng.uniform(-20, 20), rng.uniform(-45, -5)])
+        vs = [c + np.array([rng.uniform(-5, 5) for _ in range(3)]) for _ in range(3)]
+        s.add_triangle(*vs, mirror)
+    s.add_light((-20.0, 60.0, 30.0), (0.7, 0.7, 0.65))
+    s.add_light((40.0, 30.0, 20.0), (0.4, 0.42, 0.5))
+    cam = Camera(eye=(0.0, 2.0, 20.0), at=(0.0, 0.0, -25.0), up=(0, 1, 0), vfov_deg=50.0)
+    return s, cam
+
+
 CONFIGS = {
     # name: (scene factory, width, height, spp, max_depth) — BASELINE.json configs[1..4]
     "cfg2_cornell_1080p_1spp_d1": (cornell_box, 1920, 1080, 1, 1),

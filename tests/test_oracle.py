@@ -148,3 +148,20 @@ def test_sample_costs_add_up():
     assert int(cost[..., 0].sum()) == ref["rays"] == st["rays"]
     assert int(cost[..., 1].sum()) == ref["rays_primary"] + ref["rays_secondary"]
     assert cost[..., 1].min() == 1 and cost[..., 1].max() <= 2 ** 5 - 1
+
+
+def test_oracle_bvh_stays_conservative_along_mirror_chains():
+    """SPEC section 4 does not re-normalise secondary directions, so |d| drifts along mirror chains and section 3's sphere
+    rule accepts points OFF the sphere (at distance sqrt(r^2 + (|d|^2 - 1) t^2) from the centre).  The oracle's BVH
+    (accel=1: the checker of the million-triangle configs) must still return exactly the brute-force answer; round 1's
+    boxes did not (41 pixels of this frame differed at depth 6, 409 at depth 8), found by bench.py's frame check."""
+    from nettracer_b200 import scenes
+    s, cam = scenes.mirror_field()
+    w, h = 120, 90
+    for depth in (6, 8):
+        p = make_params(w, h, 4, depth, cam.resolve(w, h))
+        brute, st0 = oracle.render(s, p, accel=0)
+        bvh, st1 = oracle.render(s, p, accel=1)
+        assert np.array_equal(brute, bvh)
+        for k in ("rays_primary", "rays_secondary", "rays_shadow", "light_evals"):
+            assert st0[k] == st1[k], k

@@ -69,6 +69,19 @@ def test_bvh_equals_bruteforce_oracle(seed):
         assert st[k] == rst[k], k
 
 
+@pytest.mark.parametrize("depth", [6, 8])
+def test_bvh_conservative_along_mirror_chains(depth):
+    """Thousands of small mirror spheres, deep trees (6: wavefront pipeline, 8: per-lane state machine): SPEC §4 does not
+    re-normalise directions, |d| drifts along a chain and §3's sphere rule then accepts points off the sphere - the
+    boxes of the BVH have to grow with sqrt(|d|^2 - 1) (query_start) or hits are lost.  Against the BRUTE-FORCE oracle."""
+    s, cam = scenes.mirror_field()
+    img, st, ref, rst, info = render_both(s, cam, 160, 120, 4, depth)
+    assert info["uses_bvh"]
+    assert_images_match(img, ref, f"mirror field depth={depth}")
+    for k in COUNTER_KEYS:
+        assert st[k] == rst[k], k
+
+
 @pytest.mark.parametrize("mode", ["wavefront_chunked", "state_machine", "deep_trees"])
 def test_bvh_render_paths_agree(mode, monkeypatch):
     """BVH scenes have two schedules of the same arithmetic: the wavefront pipeline (nt_wavefront.cuh; default,
