@@ -13,7 +13,7 @@ value        whole-job Mrays/s, frame resident on the device of rank 0: rays cas
              max over ranks; a step = render kernel + exchange: peer stores over NVLink + flag wait).
 e2e          the same metric through the reference-facing call with a HOST frame: nt_render into pinned
              memory (N = 1); ShardedRenderer.render_host (N > 1) - every rank's kernel stores its bands
-             into one shared page-locked host frame, host flags order it - timed by rank 0's host clock.
+             into one shared page-locked host frame and posts its flag there - timed by rank 0's host clock.
 frame_check  after the timed regions rank 0 compares the device frame AND the host frame with the CPU
              oracle's frame of the same parameters; a mismatch makes the run fail (exit code 1).
 roofline     the render kernel against the measured FP64 (strict) / FP32 (fast) issue-rate peak
@@ -458,8 +458,9 @@ def main():
                 "e2e": {"value": e2e_val, "unit": METRIC, "ms_per_frame": r["e2e_ms"], "h2d_bytes_per_step": C.sizeof(abi.nt_render_params) * world,
                         "d2h_bytes_per_step": h * w * 4 + 8 * abi_counter_bytes(abi) * world,
                         "api": ("nt_render -> pinned host RGBA8 (zero-copy stores from the kernel)" if world == 1 else
-                                "ShardedRenderer.render_host: every rank's nt_render stores its bands into ONE shared page-locked host "
-                                "frame (nt_host_frame_*), host flags order it; rank 0's clock")},
+                                "ShardedRenderer.render_host: every rank's kernel stores its bands into ONE shared page-locked host "
+                                "frame (nt_host_frame_*) and posts its completion flag there; rank 0's host spins on the flags; "
+                                "rank 0's clock")},
                 "gpu_launches": a.steps * r["launches"],
                 "gpu_launches_note": "per frame on rank 0, counted by the library (nt_scene_info): flat scenes 1 render kernel (exchange flags "
                                      "are posted inside it); BVH scenes the wavefront pipeline's kernels per level and chunk + sum + "

@@ -235,7 +235,8 @@ int nt_ipc_close(void *dev_ptr, int device);
  * rank and page-locked for its GPU, so that nt_render (host pointer = nt_host_frame_pixels) stores
  * each rank's bands straight into the one frame that rank 0's host reads: the end-to-end path of a
  * sharded render without a gather and without a device-to-host copy.  Protocol per frame `seq`
- * (1, 2, ...): every rank: nt_host_frame_wait_ack(seq - 1); nt_render(...); nt_host_frame_post(rank, seq);
+ * (1, 2, ...): every rank: nt_host_frame_wait_ack(seq - 1); nt_render(...); nt_host_frame_post(rank, seq) - or the
+ * asynchronous form, nt_render_device_sync with the rank's flag as post_when_done (see nt_host_frame_flag);
  * rank 0: nt_host_frame_wait_all(seq), reads the pixels, nt_host_frame_ack(seq). */
 typedef struct nt_host_frame nt_host_frame;
 /* create != 0: make the segment (rank 0); 0: attach to an existing one.  device: the GPU of the calling
@@ -243,6 +244,11 @@ typedef struct nt_host_frame nt_host_frame;
 int nt_host_frame_open(const char *name, size_t frame_bytes, uint32_t n_ranks, int create, int device,
                        nt_host_frame **out);
 uint8_t *nt_host_frame_pixels(nt_host_frame *frame);
+/* The flag word of `rank` ("frames this rank has completely stored"), as a pointer both the host and - the segment being
+ * page-locked and mapped - this process's GPU can use: nt_render_device_sync(..., rgba_out_dev = nt_host_frame_pixels(),
+ * sync.post_when_done = nt_host_frame_flag(frame, rank)) makes the render kernel itself post the flag after its last
+ * pixel store, so that the rank's host never has to wait for its GPU (nt_host_frame_wait_all on rank 0 sees it). */
+uint32_t *nt_host_frame_flag(nt_host_frame *frame, uint32_t rank);
 int nt_host_frame_post(nt_host_frame *frame, uint32_t rank, uint32_t seq);
 int nt_host_frame_wait_all(nt_host_frame *frame, uint32_t seq, uint32_t timeout_ms);
 int nt_host_frame_ack(nt_host_frame *frame, uint32_t seq);

@@ -83,7 +83,7 @@ EXPORTS = [
     "nt_measure_peaks", "nt_cull_tables", "nt_primary_rects", "nt_plane_free_lights",
     "nt_render_device_sync", "nt_flags_wait_device",
     "nt_multi_create", "nt_multi_destroy", "nt_multi_device_count", "nt_multi_render",
-    "nt_host_frame_open", "nt_host_frame_pixels", "nt_host_frame_post", "nt_host_frame_wait_all",
+    "nt_host_frame_open", "nt_host_frame_pixels", "nt_host_frame_flag", "nt_host_frame_post", "nt_host_frame_wait_all",
     "nt_host_frame_ack", "nt_host_frame_wait_ack", "nt_host_frame_close",
 ]
 

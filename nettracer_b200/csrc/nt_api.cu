@@ -681,6 +681,13 @@ extern "C" int nt_render_device_sync(nt_scene *sc, const nt_render_params *p, vo
     if (((uintptr_t)rgba_out_dev) % 4) return fail(NT_ERR_INVALID, "output pointer must be 4-byte aligned");
     CU(cudaSetDevice(sc->device));
     a.out = (uint8_t *)rgba_out_dev;
+    {   // a page-locked HOST frame as the target (nt_host_frame_pixels, cudaHostAlloc): the stores cross PCIe, and one row of
+        // 32 / lanes pixels per warp tile makes the widest contiguous write (see nt_render)
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, rgba_out_dev) == cudaSuccess && at.type == cudaMemoryTypeHost && !getenv("NT_TILE_W"))
+            set_tile_shape(&a, 32u / a.lanes);
+        cudaGetLastError();
+    }
     return launch(sc, a, p->precision, (cudaStream_t)cuda_stream, sync);
 }
 

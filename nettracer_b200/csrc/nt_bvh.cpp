@@ -2,13 +2,18 @@
 // Two trees (spheres, triangles) hang off one root so every leaf holds a single primitive kind and
 // indexes a contiguous run of the BVH-ordered device array of that kind.
 // Boxes are float, rounded outward: they may only ever cull (SPEC-PROVISIONAL §3 "conservative
-// culling only").  On-GPU build is SURVEY.md §8 row (f3), not this round.
+// culling only").  The on-GPU builder is nt_bvh_gpu.cu.
 #include "nt_bvh.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <thread>
 
 namespace {
 
@@ -37,28 +42,64 @@ inline float f_up(double x) {
 
 struct Ref { Box box; int c; int n; };
 
+// Subtrees are built by separate host threads (round 1 built the million-triangle tree of configs[3] on one core in
+// 425 ms - most of nt_scene_create).  Nodes come from a preallocated array through an atomic counter, so their ids
+// depend on the timing, but the TREE does not (every split is a deterministic function of its primitive range), and the
+// 4-wide tree the device traverses is laid out afterwards by a sequential depth-first walk (collapse4): same
+// device tree, same traversal, whatever the thread count.
 struct Builder {
-    std::vector<NtBvhNode> &nodes;
+    std::vector<NtBvhNode> &nodes; // preallocated: one inner node per primitive is an upper bound
+    std::atomic<int> &next_node;
     const std::vector<Box> &boxes;
     std::vector<float> cen[3];
     std::vector<int> &order;
-    int type_flag, leaf_max;
+    int type_flag, leaf_max, grain, hw;
 
-    Builder(std::vector<NtBvhNode> &n, const std::vector<Box> &b, std::vector<int> &o, int tf, int lm)
-        : nodes(n), boxes(b), order(o), type_flag(tf), leaf_max(lm) {
+    Builder(std::vector<NtBvhNode> &n, std::atomic<int> &next, const std::vector<Box> &b, std::vector<int> &o, int tf, int lm)
+        : nodes(n), next_node(next), boxes(b), order(o), type_flag(tf), leaf_max(lm) {
+        hw = (int)std::max(1u, std::thread::hardware_concurrency());
+        grain = std::max<int>(4096, (int)(b.size() / (4 * (size_t)hw))); // ranges larger than this get their own thread
         for (int a = 0; a < 3; ++a) {
             cen[a].resize(b.size());
             for (size_t i = 0; i < b.size(); ++i) cen[a][i] = 0.5f * (b[i].lo[a] + b[i].hi[a]);
         }
     }
 
+    // The few nodes at the top of a large tree hold most primitives each: their passes over [b, e) are cut into chunks
+    // worked by separate threads (partial results merged in chunk order, min / max / counts only: same result).
+    bool big(int b, int e) const { return e - b > 8 * grain && hw > 1; }
+    template <typename F> void chunks(int b, int e, F fn) const {
+        const int n = e - b, nth = big(b, e) ? std::min(std::min(16, hw), n / (2 * grain)) : 1;
+        if (nth <= 1) { fn(0, b, e); return; }
+        std::vector<std::thread> th;
+        for (int t = 1; t < nth; ++t) th.emplace_back([=, &fn] { fn(t, b + (int)((long long)n * t / nth), b + (int)((long long)n * (t + 1) / nth)); });
+        fn(0, b, b + n / nth);
+        for (auto &t : th) t.join();
+    }
+
     Ref build(int b, int e, int depth) {
         Box bounds, cb;
         bounds.reset(); cb.reset();
-        for (int i = b; i < e; ++i) {
-            const int p = order[i];
-            bounds.grow(boxes[p]);
-            for (int a = 0; a < 3; ++a) { cb.lo[a] = std::min(cb.lo[a], cen[a][p]); cb.hi[a] = std::max(cb.hi[a], cen[a][p]); }
+        if (!big(b, e)) {
+            for (int i = b; i < e; ++i) {
+                const int p = order[i];
+                bounds.grow(boxes[p]);
+                for (int a = 0; a < 3; ++a) { cb.lo[a] = std::min(cb.lo[a], cen[a][p]); cb.hi[a] = std::max(cb.hi[a], cen[a][p]); }
+            }
+        } else {
+            Box pb[16], pc[16];
+            for (int t = 0; t < 16; ++t) { pb[t].reset(); pc[t].reset(); }
+            chunks(b, e, [&](int t, int cb_, int ce_) {
+                Box bb, cc;
+                bb.reset(); cc.reset();
+                for (int i = cb_; i < ce_; ++i) {
+                    const int p = order[i];
+                    bb.grow(boxes[p]);
+                    for (int a = 0; a < 3; ++a) { cc.lo[a] = std::min(cc.lo[a], cen[a][p]); cc.hi[a] = std::max(cc.hi[a], cen[a][p]); }
+                }
+                pb[t] = bb; pc[t] = cc;
+            });
+            for (int t = 0; t < 16; ++t) { bounds.grow(pb[t]); cb.grow(pc[t]); }
         }
         const int count = e - b;
         if (count <= leaf_max) return Ref{ bounds, b, count | type_flag };
@@ -74,11 +115,27 @@ struct Builder {
                 Box bb[NB]; int bc[NB];
                 for (int i = 0; i < NB; ++i) { bb[i].reset(); bc[i] = 0; }
                 const float sc = NB / ext;
-                for (int i = b; i < e; ++i) {
-                    const int p = order[i];
-                    int bi = (int)((cen[a][p] - cb.lo[a]) * sc);
-                    bi = bi < 0 ? 0 : bi >= NB ? NB - 1 : bi;
-                    bb[bi].grow(boxes[p]); bc[bi]++;
+                if (!big(b, e)) {
+                    for (int i = b; i < e; ++i) {
+                        const int p = order[i];
+                        int bi = (int)((cen[a][p] - cb.lo[a]) * sc);
+                        bi = bi < 0 ? 0 : bi >= NB ? NB - 1 : bi;
+                        bb[bi].grow(boxes[p]); bc[bi]++;
+                    }
+                } else {
+                    struct Part { Box bb[NB]; int bc[NB]; };
+                    std::vector<Part> parts(16);
+                    for (Part &pt : parts) for (int i = 0; i < NB; ++i) { pt.bb[i].reset(); pt.bc[i] = 0; }
+                    chunks(b, e, [&](int t, int cb_, int ce_) {
+                        Part &pt = parts[(size_t)t];
+                        for (int i = cb_; i < ce_; ++i) {
+                            const int p = order[i];
+                            int bi = (int)((cen[a][p] - cb.lo[a]) * sc);
+                            bi = bi < 0 ? 0 : bi >= NB ? NB - 1 : bi;
+                            pt.bb[bi].grow(boxes[p]); pt.bc[bi]++;
+                        }
+                    });
+                    for (const Part &pt : parts) for (int i = 0; i < NB; ++i) { bb[i].grow(pt.bb[i]); bc[i] += pt.bc[i]; }
                 }
                 float ra[NB]; int rc[NB];
                 Box acc; acc.reset(); int cnt = 0;
@@ -111,15 +168,22 @@ struct Builder {
             std::nth_element(order.begin() + b, order.begin() + mid, order.begin() + e,
                              [&](int x, int y) { return cen[a][x] < cen[a][y]; });
         }
-        const int id = (int)nodes.size();
-        nodes.emplace_back();
-        const Ref l = build(b, mid, depth + 1), r = build(mid, e, depth + 1);
+        const int id = next_node.fetch_add(1);
+        Ref l, r;
+        if (mid - b > grain && e - mid > grain) {
+            std::thread left([&] { l = build(b, mid, depth + 1); });
+            r = build(mid, e, depth + 1);
+            left.join();
+        } else {
+            l = build(b, mid, depth + 1);
+            r = build(mid, e, depth + 1);
+        }
         nt_bvh_set_children(nodes[id], l.box.lo, l.box.hi, l.c, l.n, r.box.lo, r.box.hi, r.c, r.n);
         return Ref{ bounds, id, 0 };
     }
 };
 
-Ref build_set(std::vector<NtBvhNode> &nodes, const std::vector<Box> &boxes, std::vector<int> &order,
+Ref build_set(std::vector<NtBvhNode> &nodes, std::atomic<int> &next_node, const std::vector<Box> &boxes, std::vector<int> &order,
               int type_flag, int leaf_max) {
     order.resize(boxes.size());
     for (size_t i = 0; i < boxes.size(); ++i) order[i] = (int)i;
@@ -127,7 +191,7 @@ Ref build_set(std::vector<NtBvhNode> &nodes, const std::vector<Box> &boxes, std:
         Ref r; r.box.reset(); r.c = 0; r.n = -1;
         return r;
     }
-    Builder bld(nodes, boxes, order, type_flag, leaf_max);
+    Builder bld(nodes, next_node, boxes, order, type_flag, leaf_max);
     return bld.build(0, (int)boxes.size(), 0);
 }
 
@@ -204,24 +268,40 @@ void nt_bvh_build(const double *spheres, uint32_t ns, const double *triangles, u
         const double *s = spheres + 4 * (size_t)i;
         for (int a = 0; a < 3; ++a) { sb[i].lo[a] = f_down(s[a] - s[3]); sb[i].hi[a] = f_up(s[a] + s[3]); }
     }
-    for (uint32_t i = 0; i < nt; ++i) {
-        const double *t = triangles + 9 * (size_t)i;
-        for (int a = 0; a < 3; ++a) {
-            tb[i].lo[a] = f_down(std::min(t[a], std::min(t[3 + a], t[6 + a])));
-            tb[i].hi[a] = f_up(std::max(t[a], std::max(t[3 + a], t[6 + a])));
-        }
+    {
+        const unsigned nth = nt > 65536 ? std::min(16u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+        auto work = [&](uint32_t i0, uint32_t i1) {
+            for (uint32_t i = i0; i < i1; ++i) {
+                const double *t = triangles + 9 * (size_t)i;
+                for (int a = 0; a < 3; ++a) {
+                    tb[i].lo[a] = f_down(std::min(t[a], std::min(t[3 + a], t[6 + a])));
+                    tb[i].hi[a] = f_up(std::max(t[a], std::max(t[3 + a], t[6 + a])));
+                }
+            }
+        };
+        std::vector<std::thread> th;
+        for (unsigned k = 1; k < nth; ++k) th.emplace_back(work, (uint32_t)((uint64_t)nt * k / nth), (uint32_t)((uint64_t)nt * (k + 1) / nth));
+        work(0, nt / nth);
+        for (auto &t : th) t.join();
     }
     for (const auto *v : { &sb, &tb })
         for (const Box &b : *v)
             for (int a = 0; a < 3; ++a) max_abs = std::max(max_abs, std::max(std::fabs(b.lo[a]), std::fabs(b.hi[a])));
-    out.nodes.clear();
-    out.nodes.reserve((size_t)(ns + nt) / 2 + 8);
-    out.nodes.emplace_back(); // root joins the two trees
-    const Ref rs = build_set(out.nodes, sb, out.sph_order, 0, leaf_max);
-    const Ref rt = build_set(out.nodes, tb, out.tri_order, 0x100, leaf_max);
+    const auto T0 = std::chrono::steady_clock::now();
+    out.nodes.assign((size_t)ns + nt + 2, NtBvhNode{}); // nodes[0]: the root that joins the two trees
+    std::atomic<int> next_node{ 1 };
+    Ref rs, rt;
+    {
+        std::thread spheres_thread([&] { rs = build_set(out.nodes, next_node, sb, out.sph_order, 0, leaf_max); });
+        rt = build_set(out.nodes, next_node, tb, out.tri_order, 0x100, leaf_max);
+        spheres_thread.join();
+    }
+    out.nodes.resize((size_t)next_node.load());
     nt_bvh_set_children(out.nodes[0], rs.box.lo, rs.box.hi, rs.c, rs.n, rt.box.lo, rt.box.hi, rt.c, rt.n);
     out.max_abs = max_abs;
+    const auto T1 = std::chrono::steady_clock::now();
     collapse4(out);
+    if (getenv("NT_BVH_TIMES")) fprintf(stderr, "bvh: build %.1f ms collapse %.1f ms\n", std::chrono::duration<double, std::milli>(T1 - T0).count(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T1).count());
     Box all = rs.box;
     all.grow(rt.box);
     for (int a = 0; a < 3; ++a) { out.blo[a] = all.lo[a]; out.bhi[a] = all.hi[a]; }

@@ -104,6 +104,9 @@ extern "C" int nt_host_frame_open(const char *name, size_t frame_bytes, uint32_t
 }
 
 extern "C" uint8_t *nt_host_frame_pixels(nt_host_frame *f) { return f ? f->base + kHeaderBytes : nullptr; }
+extern "C" uint32_t *nt_host_frame_flag(nt_host_frame *f, uint32_t rank) {
+    return f && rank < f->n_ranks ? (uint32_t *)&f->line(2 + rank)->v : nullptr;
+}
 
 static int wait_line(Line *l, uint32_t seq, uint32_t timeout_ms) {
     if ((int32_t)(l->v.load(std::memory_order_acquire) - seq) >= 0) return NT_OK;

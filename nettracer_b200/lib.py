@@ -56,6 +56,7 @@ def load():
         "nt_multi_render": (C.c_int, [vp, C.POINTER(abi.nt_render_params), vp, C.c_size_t, C.POINTER(abi.nt_render_stats)]),
         "nt_host_frame_open": (C.c_int, [C.c_char_p, C.c_size_t, u32, C.c_int, C.c_int, C.POINTER(vp)]),
         "nt_host_frame_pixels": (vp, [vp]),
+        "nt_host_frame_flag": (vp, [vp, u32]),
         "nt_host_frame_post": (C.c_int, [vp, u32, u32]),
         "nt_host_frame_wait_all": (C.c_int, [vp, u32, u32]),
         "nt_host_frame_ack": (C.c_int, [vp, u32]),

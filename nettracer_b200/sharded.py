@@ -19,7 +19,9 @@ Exchange modes of `render()` (frame ends up in DEVICE memory of rank 0):
 
 `render_host()` (frame ends up in HOST memory of rank 0, the end-to-end path): one shared-memory host frame, mapped and
 page-locked by every rank (nt_host_frame_*), into which every rank's kernel stores its own bands over its own PCIe
-link - no gather and no device-to-host copy; completion and consumption are host flags in the same segment.
+link - no gather and no device-to-host copy.  Completion flags live in the same segment and are posted BY THE KERNELS
+(the last block of a rank's launch, after its last pixel store), so no rank's host waits for its own GPU; rank 0's host
+spins on them, and acknowledges consumption with a host flag the other hosts check before their next launch.
 
 The backend object does the device work, so the bookkeeping (band arithmetic, buffer strides, protocol order) can be
 exercised by world_size-2 gloo tests on CPU with a test-only backend; the product backend is `CudaBackend`.
@@ -65,11 +67,6 @@ class CudaBackend:
     def wait_flags(self, flags_ptr: int, n: int, value: int):
         self._check(self._lib.nt_flags_wait_device(self.renderer._h, C.c_void_p(flags_ptr), n, value & 0xffffffff,
                                                    C.c_void_p(self.stream_ptr())))
-
-    def render_host(self, params: abi.nt_render_params, host_ptr: int, row_stride: int):
-        st = abi.nt_render_stats()
-        self._check(self._lib.nt_render(self.renderer._h, C.byref(params), C.c_void_p(host_ptr), row_stride, C.byref(st)))
-        return st.as_dict()
 
     def deinterleave(self, compact_all, shard_stride: int, full, width, height, band_rows, world):
         self._check(self._lib.nt_deinterleave_device(C.c_void_p(compact_all.data_ptr()), shard_stride,
@@ -119,6 +116,13 @@ class CudaBackend:
 
     def host_frame_close(self, h, unlink: bool):
         self._lib.nt_host_frame_close(h, int(unlink))
+
+    def render_to_host_frame(self, params, h, pixels_ptr: int, row_stride: int, rank: int, seq: int):
+        """Asynchronous: the kernel stores into the shared host frame and posts this rank's flag when it is done."""
+        s = abi.nt_frame_sync()
+        s.struct_size = C.sizeof(abi.nt_frame_sync)
+        s.post_when_done, s.post_when_done_value = self._lib.nt_host_frame_flag(h, rank), seq & 0xffffffff
+        self.renderer.render_device(params, pixels_ptr, row_stride, self.stream_ptr(), s)
 
     def host_post(self, h, rank, seq):
         self._check(self._lib.nt_host_frame_post(h, rank, seq & 0xffffffff))
@@ -298,10 +302,13 @@ class ShardedRenderer:
             self.b.host_frame_close(self._hf[0], self.rank == 0)
             self._hf = None
 
-    def render_host(self, params: abi.nt_render_params):
-        """One frame, end to end, into the host frame all ranks share (blocking).  `params` = shard_params(...) with
-        the FULL layout (p2p_store / single modes).  Returns (frame, stats): on rank 0 a numpy view [h, w, 4] of the
-        shared frame, valid until rank 0's next render_host call; None on the other ranks."""
+    def render_host(self, params: abi.nt_render_params, want_stats: bool = False):
+        """One frame, end to end, into the host frame all ranks share.  `params` = shard_params(...) with the FULL
+        layout (p2p_store / single modes).  Every rank's render kernel stores its bands into the shared page-locked
+        frame over its own PCIe link and - its last block - posts the rank's flag in the same segment; no rank's host
+        waits for its own GPU.  Rank 0 spins on the flags and returns (frame, stats): a numpy view [h, w, 4] of the
+        shared frame, valid until rank 0's next render_host call; the other ranks return (None, stats) as soon as
+        their kernel is enqueued.  stats: this rank's counters when want_stats (costs a stream synchronisation)."""
         w, h = params.width, params.height
         assert params.layout == abi.NT_LAYOUT_FULL
         self._prepare_host(w, h)
@@ -312,8 +319,8 @@ class ShardedRenderer:
             self.b.host_ack(hf, seq - 1)            # the caller is done with the previous frame
         else:
             self.b.host_wait_ack(hf, seq - 1)       # ... so it may be overwritten
-        st = self.b.render_host(params, px, w * 4)  # zero-copy stores into the shared frame; returns when they are done
-        self.b.host_post(hf, self.rank, seq)
+        self.b.render_to_host_frame(params, hf, px, w * 4, self.rank, seq)
+        st = self.b.stats() if want_stats else None
         if self.rank != 0:
             return None, st
         self.b.host_wait_all(hf, seq)

@@ -155,8 +155,11 @@ class OracleHostBackend:
     def host_wait_ack(self, h, seq, timeout_ms=0):
         self._spin(h + 64, seq & 0xffffffff)
 
-    def render_host(self, params, host_ptr, row_stride):
-        self.render_shard(params, host_ptr, row_stride)
+    def render_to_host_frame(self, params, h, pixels_ptr, row_stride, rank, seq):
+        self.render_shard(params, pixels_ptr, row_stride)
+        self.host_post(h, rank, seq)
+
+    def stats(self):
         return {}
 
     def host_view(self, px, h, w):
