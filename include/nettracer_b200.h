@@ -87,6 +87,13 @@ typedef struct nt_render_params {
 /* Measurement aid: flat scenes are rendered by an instrumented twin of the kernel that also counts the primitive
  * tests it really starts (nt_render_stats.*_tests_executed); same image, a little slower. */
 #define NT_RENDER_COUNT_EXECUTED 1u
+/* Rule switches (SPEC-PROVISIONAL.md section 8): rules the reference would dictate and that are [OPEN] while its sources
+ * are missing.  0 = the defaults of sections 2-5; every switch is implemented by the CUDA path AND the oracle. */
+#define NT_RULE_QUANTIZE_TRUNCATE 2u   /* section 5: q = (int)(c*255) instead of (int)(c*255 + 0.5) */
+#define NT_RULE_ATTENUATE_INV_SQUARE 4u /* section 4: a light's colour is scaled by 1/d2 (d2 = squared distance to the light) */
+#define NT_RULE_SAMPLE_CORNER 8u       /* section 2: sample offsets i/n, j/n (cell corner) instead of (i+0.5)/n, (j+0.5)/n */
+#define NT_RULE_RENORMALIZE 16u        /* section 4: reflected / refracted directions are re-normalised, d * (1/sqrt(dot(d,d))) */
+#define NT_RULE_MASK 30u
 
 #define NT_MAX_DEPTH 16
 

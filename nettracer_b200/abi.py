@@ -11,6 +11,8 @@ NT_F64_STRICT, NT_F32_FAST = 0, 1
 NT_LAYOUT_FULL, NT_LAYOUT_COMPACT = 0, 1
 NT_MAX_DEPTH = 16
 NT_RENDER_COUNT_EXECUTED = 1
+NT_RULE_QUANTIZE_TRUNCATE, NT_RULE_ATTENUATE_INV_SQUARE, NT_RULE_SAMPLE_CORNER, NT_RULE_RENORMALIZE = 2, 4, 8, 16
+NT_RULE_MASK = 30
 
 _pd = C.POINTER(C.c_double)
 _pi = C.POINTER(C.c_int32)

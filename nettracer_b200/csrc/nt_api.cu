@@ -20,6 +20,8 @@
 #include "nt_sync.cuh"
 
 static_assert(NT_MAX_DEPTH == NT_MAX_DEPTH_DEV, "depth limits must agree");
+static_assert(NT_RULE_QUANTIZE_TRUNCATE == NT_DEV_RULE_TRUNCATE && NT_RULE_ATTENUATE_INV_SQUARE == NT_DEV_RULE_ATTENUATE &&
+              NT_RULE_RENORMALIZE == NT_DEV_RULE_RENORMALIZE, "rule bits must agree");
 
 // ---------------- errors ----------------
 static thread_local char g_err[512] = "";
@@ -470,7 +472,7 @@ static int make_args(const nt_render_params *p, size_t stride, NtRenderArgs *a) 
         return fail(NT_ERR_INVALID, "%ux%u at %u spp has 2^31 samples or more: sample and tile indices are 32-bit; render it in shards", p->width, p->height, p->spp);
     if (p->precision != NT_F64_STRICT && p->precision != NT_F32_FAST) return fail(NT_ERR_INVALID, "unknown precision %u", p->precision);
     if (p->layout != NT_LAYOUT_FULL && p->layout != NT_LAYOUT_COMPACT) return fail(NT_ERR_INVALID, "unknown layout %u", p->layout);
-    if (p->flags & ~NT_RENDER_COUNT_EXECUTED) return fail(NT_ERR_INVALID, "unknown flags 0x%x", p->flags);
+    if (p->flags & ~(NT_RENDER_COUNT_EXECUTED | NT_RULE_MASK)) return fail(NT_ERR_INVALID, "unknown flags 0x%x", p->flags);
     const uint32_t scount = p->shard_count ? p->shard_count : 1;
     const uint32_t band = p->band_rows ? (p->band_rows > 65536 ? 65536 : p->band_rows) : 1; // height <= 65536: same partition
     if (p->shard_index >= scount) return fail(NT_ERR_INVALID, "shard_index %u >= shard_count %u", p->shard_index, scount);
@@ -503,7 +505,9 @@ static int make_args(const nt_render_params *p, size_t stride, NtRenderArgs *a) 
     }
     a->stride = stride;
     a->count_executed = p->flags & NT_RENDER_COUNT_EXECUTED;
-    for (uint32_t i = 0; i < n; ++i) a->samp_off[i] = ((double)i + 0.5) / (double)n;
+    a->rules = p->flags & NT_RULE_MASK;
+    const double half = (p->flags & NT_RULE_SAMPLE_CORNER) ? 0.0 : 0.5; // SPEC-PROVISIONAL section 8
+    for (uint32_t i = 0; i < n; ++i) a->samp_off[i] = ((double)i + half) / (double)n;
     a->inv_spp = 1.0 / (double)p->spp;
     return NT_OK;
 }

@@ -269,6 +269,7 @@ __device__ __forceinline__ void lane_lights_from(const Ctx<R, true> &c, Lane<R> 
                 wt = kt;
                 const R sterm = eta * cosi - Math<R>::sqrt_(kk);
                 T = { d.x * eta + N.x * sterm, d.y * eta + N.y * sterm, d.z * eta + N.z * sterm };
+                if (c.rules & NT_DEV_RULE_RENORMALIZE) T = scale(T, Math<R>::rcp(Math<R>::sqrt_(dot(T, T)))); // SPEC §8
             }
         }
         if (wt > R(0)) {
@@ -285,6 +286,7 @@ __device__ __forceinline__ void lane_lights_from(const Ctx<R, true> &c, Lane<R> 
             k.sec++;
             const R two = R(2) * cosi;
             ln.d = { d.x + N.x * two, d.y + N.y * two, d.z + N.z * two };
+            if (c.rules & NT_DEV_RULE_RENORMALIZE) ln.d = scale(ln.d, Math<R>::rcp(Math<R>::sqrt_(dot(ln.d, ln.d))));
             ln.W = ln.W * wr; ln.depth = ln.depth + 1;
             descend = true;
         } else if (wt > R(0)) {
@@ -352,7 +354,13 @@ __device__ __forceinline__ void lane_advance(const Ctx<R, true> &c, Lane<R> &ln,
         Ld<R>::g4(mp, m0);     // r g b ka
         Ld<R>::g4(mp + 4, m1); // kd ks shininess kr
         const R *lp = v.lights + 6 * l;
-        const R lc[3] = { __ldg(lp + 3), __ldg(lp + 4), __ldg(lp + 5) };
+        R lc[3] = { __ldg(lp + 3), __ldg(lp + 4), __ldg(lp + 5) };
+        if (c.rules & NT_DEV_RULE_ATTENUATE) { // SPEC §8: light colour scaled by 1 / d2 (d2 exactly as the light loop computed it)
+            const V3<R> Lv = { __ldg(lp) - P.x, __ldg(lp + 1) - P.y, __ldg(lp + 2) - P.z };
+            const R att = Math<R>::rcp(dot(Lv, Lv));
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) lc[ch] = lc[ch] * att;
+        }
         const R kdn = m1[0] * ln.ndl;
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) ln.local[ch] = ln.local[ch] + lc[ch] * (m0[ch] * kdn);
@@ -394,14 +402,13 @@ render_bvh_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ 
     __shared__ unsigned long long s_cnt[NT_NCOUNTERS];
     const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
     Ctx<R, true> c;
-    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.eps_lo = (R)a.eps_lo; c.max_depth = a.max_depth;
+    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.eps_lo = (R)a.eps_lo; c.max_depth = a.max_depth; c.rules = a.rules;
     stage_scene<R, true>(s, v, c);
 
     const unsigned lane = threadIdx.x & 31;
     const unsigned n_sids = a.tiles_x * a.tiles_y * (a.spp / a.lanes) * 32;
     unsigned long long *next_sid = a.counters + NT_COUNTER_SLOTS * NT_NCOUNTERS;
     R *samples = (R *)a.samples;
-    const R rn = (R)a.n;
     Counters k = { 0, 0, 0, 0, 0, 0, 0, 0 };
 
     Lane<R> ln;
@@ -427,7 +434,7 @@ render_bvh_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ 
                     if (m.live) {
                         // SPEC §2: regular n x n grid
                         const unsigned si = m.sidx % a.n, sj = m.sidx / a.n;
-                        const R ox = Math<R>::div((R)si + R(0.5), rn), oy = Math<R>::div((R)sj + R(0.5), rn);
+                        const R ox = (R)a.samp_off[si], oy = (R)a.samp_off[sj]; // (i + 0.5) / n (or i / n, SPEC §8), divided on the host
                         const R fx = (R)m.px + ox, fy = (R)m.y + oy;
                         const V3<R> D = { ((R)a.cam[3] + (R)a.cam[6] * fx) + (R)a.cam[9] * fy,
                                           ((R)a.cam[4] + (R)a.cam[7] * fx) + (R)a.cam[10] * fy,
@@ -491,7 +498,8 @@ resolve_kernel(const __grid_constant__ NtRenderArgs a) {
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         const R cv = sum[ch] * inv_spp;
-        const unsigned qv = cv <= R(0) ? 0u : cv >= R(1) ? 255u : (unsigned)(int)(cv * R(255) + R(0.5));
+        unsigned qv = cv <= R(0) ? 0u : cv >= R(1) ? 255u : (unsigned)(int)(cv * R(255) + R(0.5));
+        if ((a.rules & NT_DEV_RULE_TRUNCATE) && cv > R(0) && cv < R(1)) qv = (unsigned)(int)(cv * R(255)); // SPEC §8
         rgba |= qv << (8 * ch);
     }
     const unsigned y = ((vr / a.band_rows) * a.shard_count + a.shard_index) * a.band_rows + vr % a.band_rows;
@@ -505,7 +513,7 @@ __global__ void __launch_bounds__(NT_BLOCK_THREADS)
 trace_bvh_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtTraceArgs a) {
     const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
     Ctx<R, true> c;
-    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.eps_lo = (R)a.eps_lo; c.max_depth = 1;
+    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.eps_lo = (R)a.eps_lo; c.max_depth = 1; c.rules = 0;
     stage_scene<R, true>(s, v, c);
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;

@@ -39,6 +39,10 @@
 #endif
 #define NT_LEAF_MAX 4       // (count-1) is stored in 2 bits of a leaf ref
 #define NT_MAX_DEPTH_DEV 16 // == NT_MAX_DEPTH of the public header
+// Rule switches, == NT_RULE_* of the public header (nt_api.cu checks): SPEC-PROVISIONAL section 8
+#define NT_DEV_RULE_TRUNCATE 2u
+#define NT_DEV_RULE_ATTENUATE 4u
+#define NT_DEV_RULE_RENORMALIZE 16u
 
 // 64-byte BVH2 node: both child boxes (float, rounded outward) + child refs.
 //   q0 = lo0.x lo0.y lo0.z hi0.x | q1 = hi0.y hi0.z lo1.x lo1.y | q2 = lo1.z hi1.x hi1.y hi1.z
@@ -133,6 +137,7 @@ struct NtRenderArgs {
     unsigned *sync_done_ptr;        // release-store of sync_done_val after the frame's last pixel store
     unsigned sync_post_val, sync_wait_val, sync_done_val;
     uint32_t count_executed;        // flat scenes: launch the instrumented kernel (CountersX)
+    uint32_t rules;                 // NT_DEV_RULE_* bits (SPEC-PROVISIONAL section 8); 0 = the default rules
 };
 
 struct NtTraceArgs {

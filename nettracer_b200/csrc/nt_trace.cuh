@@ -392,6 +392,7 @@ template <typename R, bool BVH> struct Ctx {
     unsigned axl_addr, gen_addr;                      // flat scenes: axis-aligned plane lists, general-plane index list
     R eps, eps_lo; // eps_lo: see plane_below_eps
     unsigned max_depth;
+    unsigned rules; // NT_DEV_RULE_* bits (SPEC §8); the flat kernel reads them only in its RULES instantiation
     __device__ __forceinline__ void ld_sph(unsigned i, R *q) const {
         if constexpr (BVH) Ld<R>::g4(v->sph + 4 * (size_t)i, q); else Ld<R>::s4(sph_addr + i * (4 * (unsigned)sizeof(R)), q);
     }
@@ -671,7 +672,8 @@ __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, c
 // `pmask`: address of the warp's primary-ray mask (tile_mask) in shared memory.  `own` of the current ray:
 // -2 primary ray (mask = *pmask), -1 no culling information (all bounded primitives), >= 0 the ray starts on
 // that sphere (see nearest_hit).  Kept as ONE register instead of a live 64-bit mask: the kernel is register-bound.
-template <typename R, bool BVH, typename K>
+// RULES: the instantiation that honours the rule switches of SPEC §8 (c.rules); the default kernel compiles them out.
+template <typename R, bool BVH, typename K, bool RULES = false>
 __device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R> d, R *accp, R *Wp, const unsigned long long *pmask,
                                              K &k) {
     const NtDevScene &s = *c.s;
@@ -742,7 +744,14 @@ __device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R
                 Ld<R>::g4(mp, m0);     // r g b ka
                 Ld<R>::g4(mp + 4, m1); // kd ks shininess kr
                 const R kdn = m1[0] * ndl;
-                const R lc[3] = { __ldg(lp + 3), __ldg(lp + 4), __ldg(lp + 5) };
+                R lc[3] = { __ldg(lp + 3), __ldg(lp + 4), __ldg(lp + 5) };
+                if constexpr (RULES) {
+                    if (c.rules & NT_DEV_RULE_ATTENUATE) { // SPEC §8: light colour scaled by 1 / d2
+                        const R att = Math<R>::rcp(d2);
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) lc[ch] = lc[ch] * att;
+                    }
+                }
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) local[ch] = local[ch] + lc[ch] * (m0[ch] * kdn);
                 const R two = R(2) * ndl;
@@ -772,6 +781,8 @@ __device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R
                         wt = kt;
                         const R sterm = eta * cosi - Math<R>::sqrt_(kk);
                         T = { d.x * eta + N.x * sterm, d.y * eta + N.y * sterm, d.z * eta + N.z * sterm };
+                        if constexpr (RULES) // SPEC §8: re-normalised secondary directions
+                            if (c.rules & NT_DEV_RULE_RENORMALIZE) T = scale(T, Math<R>::rcp(Math<R>::sqrt_(dot(T, T))));
                     }
                 }
                 if (wt > R(0)) {
@@ -786,7 +797,9 @@ __device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R
                 if (wr > R(0)) {
                     k.sec++;
                     const R two = R(2) * cosi;
-                    const V3<R> Rd = { d.x + N.x * two, d.y + N.y * two, d.z + N.z * two };
+                    V3<R> Rd = { d.x + N.x * two, d.y + N.y * two, d.z + N.z * two };
+                    if constexpr (RULES)
+                        if (c.rules & NT_DEV_RULE_RENORMALIZE) Rd = scale(Rd, Math<R>::rcp(Math<R>::sqrt_(dot(Rd, Rd))));
                     o = P; d = Rd; *Wp = *Wp * wr; depth = depth + 1;
                     descend = true;
                 } else if (wt > R(0)) {
@@ -891,7 +904,7 @@ __device__ __forceinline__ void flush_counters(const CountersX &k, unsigned long
 // 4 blocks (64 registers) for whole frames, NT_MIN_BLOCKS_SMALL = 3 (80 registers, fewer spills, less contention per
 // scheduler) for small launches - a 1/8-frame shard of an 8-GPU render is bound by the latency of its deepest tiles, not
 // by throughput, and measured 0.153 ms against 0.166 (a whole frame: 0.831 against 0.810; profiles/r02a_ab_patches.txt).
-template <typename R, bool BVH, bool SINGLE, bool EXEC = false, int MINB = 0>
+template <typename R, bool BVH, bool SINGLE, bool EXEC = false, int MINB = 0, bool RULES = false>
 __global__ void __launch_bounds__(NT_BLOCK_THREADS, MINB ? MINB : (sizeof(R) == 8 ? NT_MIN_BLOCKS_F64 : NT_MIN_BLOCKS_F32))
 render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRenderArgs a) {
     __shared__ unsigned long long s_cnt[NT_NCOUNTERS];
@@ -899,7 +912,7 @@ render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRe
     __shared__ unsigned long long s_pmask[NT_BLOCK_THREADS / 32]; // per warp: primary-ray candidates of its tile
     const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
     Ctx<R, BVH> c;
-    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.eps_lo = (R)a.eps_lo; c.max_depth = a.max_depth;
+    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.eps_lo = (R)a.eps_lo; c.max_depth = a.max_depth; c.rules = a.rules;
     frame_sync_begin(a); // multi-GPU exchange: acknowledge / wait before the first pixel store (the barrier in stage_scene orders it)
     stage_scene<R, BVH>(s, v, c);
 
@@ -948,7 +961,7 @@ render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRe
                     const V3<R> dir = scale(D, Math<R>::rcp(Math<R>::sqrt_(dot(D, D))));
                     const V3<R> eye = { (R)a.cam[0], (R)a.cam[1], (R)a.cam[2] };
                     k.prim++;
-                    trace_sample<R, BVH, KT>(c, eye, dir, accp, Wp, &s_pmask[tid >> 5], k);
+                    trace_sample<R, BVH, KT, RULES>(c, eye, dir, accp, Wp, &s_pmask[tid >> 5], k);
                 }
             }
             asm volatile("" : "+r"(tile)); // pixel coordinates are recomputed below, not carried across the trace
@@ -983,7 +996,9 @@ render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRe
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
                     const R cv = sum[ch] * inv_spp;
-                    const unsigned q = cv <= R(0) ? 0u : cv >= R(1) ? 255u : (unsigned)(int)(cv * R(255) + R(0.5));
+                    unsigned q = cv <= R(0) ? 0u : cv >= R(1) ? 255u : (unsigned)(int)(cv * R(255) + R(0.5));
+                    if constexpr (RULES) // SPEC §8: truncation instead of rounding
+                        if ((a.rules & NT_DEV_RULE_TRUNCATE) && cv > R(0) && cv < R(1)) q = (unsigned)(int)(cv * R(255));
                     rgba |= q << (8 * ch);
                 }
                 const size_t row = a.layout == 1 ? vr : y;
@@ -1010,7 +1025,7 @@ __global__ void __launch_bounds__(NT_BLOCK_THREADS)
 trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtTraceArgs a) {
     const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
     Ctx<R, BVH> c;
-    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.eps_lo = (R)a.eps_lo; c.max_depth = 1;
+    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.eps_lo = (R)a.eps_lo; c.max_depth = 1; c.rules = 0;
     stage_scene<R, BVH>(s, v, c);
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
@@ -1091,8 +1106,8 @@ inline int launch_render_t(const NtDevScene &s, const NtRenderArgs &a, cudaStrea
     if constexpr (!BVH) {
         // fewer than NT_SMALL_TILES_PER_WARP warp tiles per resident warp: the small-launch variant (NT_SMALL_LAUNCH=0 / 1
         // forces the choice, A/B)
-        bool small = MINB_SMALL != 0 && !a.count_executed && n_tiles < (unsigned)NT_SMALL_TILES_PER_WARP * (unsigned)(sms[dev] * blocks_per_sm[dev]) * wpb;
-        if (const char *e = getenv("NT_SMALL_LAUNCH")) small = MINB_SMALL != 0 && !a.count_executed && e[0] == '1';
+        bool small = MINB_SMALL != 0 && !a.count_executed && !a.rules && n_tiles < (unsigned)NT_SMALL_TILES_PER_WARP * (unsigned)(sms[dev] * blocks_per_sm[dev]) * wpb;
+        if (const char *e = getenv("NT_SMALL_LAUNCH")) small = MINB_SMALL != 0 && !a.count_executed && !a.rules && e[0] == '1';
         if constexpr (MINB_SMALL != 0) {
             if (small) {
                 grid = (unsigned)(sms[dev] * blocks_small[dev]);
@@ -1103,7 +1118,10 @@ inline int launch_render_t(const NtDevScene &s, const NtRenderArgs &a, cudaStrea
                 return (int)cudaGetLastError();
             }
         }
-        if (a.count_executed) { // instrumented twin (nt_render_params.flags & NT_RENDER_COUNT_EXECUTED): measurement only
+        if (a.rules) { // SPEC §8 rule switches: the instantiation that reads them (a little slower than the default kernel)
+            if (a.spp == a.lanes) render_kernel<R, false, true, false, 0, true><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
+            else render_kernel<R, false, false, false, 0, true><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
+        } else if (a.count_executed) { // instrumented twin (nt_render_params.flags & NT_RENDER_COUNT_EXECUTED): measurement only
             if (a.spp == a.lanes) render_kernel<R, false, true, true><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
             else render_kernel<R, false, false, true><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
         } else if (a.spp == a.lanes) render_kernel<R, false, true><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);

@@ -88,9 +88,8 @@ __device__ __forceinline__ bool wf_ray(const NtRenderArgs &a, const NtWfArgs &w,
     if (w.level == 1) {
         const SampleMap m = map_sample(a, w.sid0 + rec);
         if (!m.live) return false;
-        const R rn = (R)a.n;
         const unsigned si = m.sidx % a.n, sj = m.sidx / a.n;
-        const R ox = Math<R>::div((R)si + R(0.5), rn), oy = Math<R>::div((R)sj + R(0.5), rn);
+        const R ox = (R)a.samp_off[si], oy = (R)a.samp_off[sj]; // (i + 0.5) / n (or i / n, SPEC §8), divided on the host
         const R fx = (R)m.px + ox, fy = (R)m.y + oy;
         const V3<R> D = { ((R)a.cam[3] + (R)a.cam[6] * fx) + (R)a.cam[9] * fy,
                           ((R)a.cam[4] + (R)a.cam[7] * fx) + (R)a.cam[10] * fy,
@@ -116,7 +115,7 @@ wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
     __shared__ unsigned long long s_cnt[NT_NCOUNTERS];
     const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
     Ctx<R, true> c;
-    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.eps_lo = (R)a.eps_lo; c.max_depth = a.max_depth;
+    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.eps_lo = (R)a.eps_lo; c.max_depth = a.max_depth; c.rules = a.rules;
     stage_scene<R, true>(s, v, c);
     const unsigned lane = threadIdx.x & 31;
     const NtWfLevel &L = w.lv[w.level - 1];
@@ -229,7 +228,7 @@ wf_shade_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
     __shared__ unsigned long long s_cnt[NT_NCOUNTERS];
     const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
     Ctx<R, true> c;
-    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.eps_lo = (R)a.eps_lo; c.max_depth = a.max_depth;
+    c.s = &s; c.v = &v; c.eps = (R)a.eps; c.eps_lo = (R)a.eps_lo; c.max_depth = a.max_depth; c.rules = a.rules;
     stage_scene<R, true>(s, v, c);
     const NtWfLevel &L = w.lv[w.level - 1];
     const unsigned n_rec = w.level == 1 ? w.n_samples : w.counts[w.level];
@@ -278,7 +277,12 @@ wf_shade_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
                         const R dist = Math<R>::sqrt_(d2);
                         const V3<R> Ld_ = scale(Lv, Math<R>::rcp(dist));
                         const R ndl = dot(N, Ld_);
-                        const R lc[3] = { __ldg(lp + 3), __ldg(lp + 4), __ldg(lp + 5) };
+                        R lc[3] = { __ldg(lp + 3), __ldg(lp + 4), __ldg(lp + 5) };
+                        if (a.rules & NT_DEV_RULE_ATTENUATE) { // SPEC §8
+                            const R att = Math<R>::rcp(d2);
+#pragma unroll
+                            for (int ch = 0; ch < 3; ++ch) lc[ch] = lc[ch] * att;
+                        }
                         const R kdn = m1[0] * ndl;
 #pragma unroll
                         for (int ch = 0; ch < 3; ++ch) local[ch] = local[ch] + lc[ch] * (m0[ch] * kdn);
@@ -307,6 +311,7 @@ wf_shade_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
                                 wt = kt;
                                 const R sterm = eta * cosi - Math<R>::sqrt_(kk);
                                 T = { d.x * eta + N.x * sterm, d.y * eta + N.y * sterm, d.z * eta + N.z * sterm };
+                                if (a.rules & NT_DEV_RULE_RENORMALIZE) T = scale(T, Math<R>::rcp(Math<R>::sqrt_(dot(T, T)))); // SPEC §8
                             }
                         }
                         if (wt > R(0)) { k.sec++; trans = true; Wt = W * wt; }
@@ -315,6 +320,7 @@ wf_shade_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
                             refl = true; Wr = W * wr;
                             const R two = R(2) * cosi;
                             Rd = { d.x + N.x * two, d.y + N.y * two, d.z + N.z * two };
+                            if (a.rules & NT_DEV_RULE_RENORMALIZE) Rd = scale(Rd, Math<R>::rcp(Math<R>::sqrt_(dot(Rd, Rd))));
                         }
                         kids = (unsigned char)((refl ? 1 : 0) | (trans ? 2 : 0));
                     }

@@ -44,6 +44,7 @@ typedef struct {
     onode *nodes;
     int n_nodes;
     double bvh_ext; /* largest |coordinate| of a bounded primitive */
+    uint32_t rules; /* NT_RULE_* bits of the render call (SPEC section 8) */
     int *bvh_prims; /* global primitive ids */
 } octx;
 
@@ -259,13 +260,18 @@ static void trace(const octx *c, v3 o, v3 dir, double W, uint32_t depth, double 
         if (occluded(c, P, L, dist, k)) continue;
         k->light++;
         double kdn = kd * ndl;
-        for (int ch = 0; ch < 3; ++ch) local[ch] = local[ch] + lp[3 + ch] * (col[ch] * kdn);
+        double lc[3] = { lp[3], lp[4], lp[5] };
+        if (c->rules & NT_RULE_ATTENUATE_INV_SQUARE) { /* SPEC section 8 */
+            double att = 1 / d2;
+            for (int ch = 0; ch < 3; ++ch) lc[ch] = lc[ch] * att;
+        }
+        for (int ch = 0; ch < 3; ++ch) local[ch] = local[ch] + lc[ch] * (col[ch] * kdn);
         double two = 2 * ndl;
         v3 R = { N.x * two - L.x, N.y * two - L.y, N.z * two - L.z };
         double rv = -dot3(R, dir);
         if (ks > 0 && rv > 0) {
             double s = ks * pow(rv, shin);
-            for (int ch = 0; ch < 3; ++ch) local[ch] = local[ch] + lp[3 + ch] * s;
+            for (int ch = 0; ch < 3; ++ch) local[ch] = local[ch] + lc[ch] * s;
         }
     }
     for (int ch = 0; ch < 3; ++ch) acc[ch] = acc[ch] + W * local[ch];
@@ -287,10 +293,12 @@ static void trace(const octx *c, v3 o, v3 dir, double W, uint32_t depth, double 
     if (wr > 0) {
         double two = 2 * cosi;
         v3 Rd = { dir.x + N.x * two, dir.y + N.y * two, dir.z + N.z * two };
+        if (c->rules & NT_RULE_RENORMALIZE) Rd = scale3(Rd, 1 / sqrt(dot3(Rd, Rd))); /* SPEC section 8 */
         k->sec++;
         trace(c, P, Rd, W * wr, depth + 1, acc, k);
     }
     if (wt > 0) {
+        if (c->rules & NT_RULE_RENORMALIZE) T = scale3(T, 1 / sqrt(dot3(T, T)));
         k->sec++;
         trace(c, P, T, W * wt, depth + 1, acc, k);
     }
@@ -470,7 +478,8 @@ static void render_row(const ojob *jb, uint32_t vr, ocount *k) {
         double sum[3] = { 0, 0, 0 };
         for (uint32_t s = 0; s < p->spp; ++s) {
             uint32_t i = s % (uint32_t)n, j = s / (uint32_t)n;
-            double ox = ((double)i + 0.5) / (double)n, oy = ((double)j + 0.5) / (double)n;
+            const double half = (p->flags & NT_RULE_SAMPLE_CORNER) ? 0.0 : 0.5; /* SPEC section 8 */
+            double ox = ((double)i + half) / (double)n, oy = ((double)j + half) / (double)n;
             double fx = (double)x + ox, fy = (double)y + oy;
             v3 D = { (cam->p00[0] + cam->dx[0] * fx) + cam->dy[0] * fy,
                      (cam->p00[1] + cam->dx[1] * fx) + cam->dy[1] * fy,
@@ -493,7 +502,8 @@ static void render_row(const ojob *jb, uint32_t vr, ocount *k) {
         for (int ch = 0; ch < 3; ++ch) {
             double cv = sum[ch] * inv_spp;
             if (jb->radiance_out) jb->radiance_out[((size_t)y * p->width + x) * 3 + ch] = cv;
-            if (px) px[ch] = cv <= 0 ? 0 : cv >= 1 ? 255 : (uint8_t)(int)(cv * 255 + 0.5);
+            if (px) px[ch] = cv <= 0 ? 0 : cv >= 1 ? 255
+                              : (p->flags & NT_RULE_QUANTIZE_TRUNCATE) ? (uint8_t)(int)(cv * 255) : (uint8_t)(int)(cv * 255 + 0.5);
         }
         if (px) px[3] = 255;
     }
@@ -527,6 +537,7 @@ static int render_impl(const nt_scene_desc *desc, const nt_render_params *p, uin
     octx c;
     int rc = ctx_init(&c, desc, p->ray_epsilon, p->max_depth, accel);
     if (rc) return rc;
+    c.rules = p->flags & NT_RULE_MASK;
     ojob jb;
     memset(&jb, 0, sizeof jb);
     jb.c = &c; jb.p = p; jb.rgba_out = rgba_out; jb.stride = stride; jb.radiance_out = radiance_out;

@@ -21,7 +21,8 @@ def scale(a, s):
 
 
 class PyTracer:
-    def __init__(self, arrays, ambient, background, eps=1e-6, max_depth=1):
+    def __init__(self, arrays, ambient, background, eps=1e-6, max_depth=1, rules=0):
+        self.rules = rules  # NT_RULE_* bits (SPEC section 8): 2 truncate, 4 inverse-square lights, 8 corner samples, 16 re-normalise
         self.a = {k: v.tolist() for k, v in arrays.items()}
         self.ambient, self.background, self.eps, self.max_depth = list(ambient), list(background), eps, max_depth
         self.ns, self.np_, self.nt = len(self.a["spheres"]), len(self.a["planes"]), len(self.a["triangles"])
@@ -123,15 +124,19 @@ class PyTracer:
             if self.occluded(P, L, dist):
                 continue
             kdn = kd * ndl
+            lc = list(lp[3:6])
+            if self.rules & 4:
+                att = 1 / dot(Lv, Lv)
+                lc = [v * att for v in lc]
             for c in range(3):
-                local[c] = local[c] + lp[3 + c] * (col[c] * kdn)
+                local[c] = local[c] + lc[c] * (col[c] * kdn)
             two = 2 * ndl
             R = (N[0] * two - L[0], N[1] * two - L[1], N[2] * two - L[2])
             rv = -dot(R, d)
             if ks > 0 and rv > 0:
                 s = ks * math.pow(rv, shin)
                 for c in range(3):
-                    local[c] = local[c] + lp[3 + c] * s
+                    local[c] = local[c] + lc[c] * s
         for c in range(3):
             acc[c] = acc[c] + W * local[c]
         if not depth < self.max_depth:
@@ -149,8 +154,13 @@ class PyTracer:
                 T = (d[0] * eta + N[0] * s, d[1] * eta + N[1] * s, d[2] * eta + N[2] * s)
         if wr > 0:
             two = 2 * cosi
-            self.trace(P, (d[0] + N[0] * two, d[1] + N[1] * two, d[2] + N[2] * two), W * wr, depth + 1, acc)
+            Rd = (d[0] + N[0] * two, d[1] + N[1] * two, d[2] + N[2] * two)
+            if self.rules & 16:
+                Rd = scale(Rd, 1 / math.sqrt(dot(Rd, Rd)))
+            self.trace(P, Rd, W * wr, depth + 1, acc)
         if wt > 0:
+            if self.rules & 16:
+                T = scale(T, 1 / math.sqrt(dot(T, T)))
             self.trace(P, T, W * wt, depth + 1, acc)
 
     def render(self, cam, width, height, spp):
@@ -162,7 +172,8 @@ class PyTracer:
                 tot = [0.0, 0.0, 0.0]
                 for s in range(spp):
                     i, j = s % n, s // n
-                    fx, fy = x + (i + 0.5) / n, y + (j + 0.5) / n
+                    half = 0.0 if self.rules & 8 else 0.5
+                    fx, fy = x + (i + half) / n, y + (j + half) / n
                     D = tuple((p00[c] + dx[c] * fx) + dy[c] * fy for c in range(3))
                     d = scale(D, 1 / math.sqrt(dot(D, D)))
                     acc = [0.0, 0.0, 0.0]
@@ -172,6 +183,6 @@ class PyTracer:
                 px = []
                 for c in range(3):
                     cv = tot[c] * (1.0 / spp)
-                    px.append(0 if cv <= 0 else 255 if cv >= 1 else int(cv * 255 + 0.5))
+                    px.append(0 if cv <= 0 else 255 if cv >= 1 else int(cv * 255) if self.rules & 2 else int(cv * 255 + 0.5))
                 img[y][x] = px + [255]
         return img

@@ -69,6 +69,36 @@ def test_bvh_equals_bruteforce_oracle(seed):
         assert st[k] == rst[k], k
 
 
+@pytest.mark.parametrize("rules", [abi.NT_RULE_QUANTIZE_TRUNCATE, abi.NT_RULE_ATTENUATE_INV_SQUARE, abi.NT_RULE_SAMPLE_CORNER,
+                                   abi.NT_RULE_RENORMALIZE, abi.NT_RULE_MASK])
+def test_rule_switches_every_path(rules, monkeypatch):
+    """SPEC §8: the rule switches (rules the missing reference would dictate) through every CUDA path - flat kernel,
+    wavefront pipeline, per-lane state machine - against the oracle with the same switches; bit-exact like the defaults."""
+    s, cam = scenes.cornell_box()
+    img, st, ref, rst, info = render_both(s, cam, 240, 135, 4, 5, flags=rules)
+    assert_images_match(img, ref, f"flat rules={rules}")
+    for k in COUNTER_KEYS + FLAT_TEST_KEYS:
+        assert st[k] == rst[k], k
+    base, _ = oracle.render(s, make_params(240, 135, 4, 5, cam.resolve(240, 135)))
+    if rules != abi.NT_RULE_RENORMALIZE:   # (re-normalising moves no 8-bit value of this frame)
+        assert not np.array_equal(ref, base)
+    s, cam = scenes.random_mixed(150, 2, 300, seed=4)
+    for wavefront in ("1", "0"):
+        monkeypatch.setenv("NT_WAVEFRONT", wavefront)
+        img, st, ref, rst, info = render_both(s, cam, 192, 128, 4, 4, flags=rules)
+        assert info["uses_bvh"]
+        assert_images_match(img, ref, f"bvh wavefront={wavefront} rules={rules}")
+        for k in COUNTER_KEYS:
+            assert st[k] == rst[k], k
+
+
+def test_renormalize_rule_on_mirror_field():
+    s, cam = scenes.mirror_field()
+    img, st, ref, rst, info = render_both(s, cam, 160, 120, 4, 8, flags=abi.NT_RULE_RENORMALIZE)
+    assert_images_match(img, ref, "mirror field, re-normalised")
+    assert st["rays"] == rst["rays"]
+
+
 @pytest.mark.parametrize("depth", [6, 8])
 def test_bvh_conservative_along_mirror_chains(depth):
     """Thousands of small mirror spheres, deep trees (6: wavefront pipeline, 8: per-lane state machine): SPEC §4 does not
