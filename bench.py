@@ -364,6 +364,41 @@ def main():
             barrier()
             res["e2e_ms"] = max_over_ranks(e2e_ms_local)
         res["dev_frame"], res["host_frame"] = dev_frame, host_frame
+
+        # ---------- two frames in flight (extra; NOT the headline): consecutive frames on two streams ----------
+        # A shard's launch ends on the latency of its deepest tile; an animation does not have to
+        # wait for it - frame f + 1 can fill the SMs frame f's tail leaves idle.  Two independent ShardedRenderers (own
+        # scene copy, own frame buffers and flags), even frames on one stream, odd frames on the other; the time is the
+        # bracket over all frames / their number, no L2 flush inside the bracket (it would serialise the two streams).
+        if want_e2e and not info["uses_bvh"]:
+            backend_b = CudaBackend(scene, local)
+            sr_b = ShardedRenderer(backend_b, rank, world, band_rows=a.band_rows, mode=a.mode)
+            streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+            pair = [(sr, streams[0]), (sr_b, streams[1])]
+            for i in range(4):
+                with torch.cuda.stream(pair[i & 1][1]):
+                    pair[i & 1][0].render(sp)
+            barrier()
+            n_pipe = max(steps, 20)
+            t0 = time.perf_counter()
+            e_beg = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            e_end = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            for i in range(2):
+                e_beg[i].record(streams[i])
+            for i in range(n_pipe):
+                with torch.cuda.stream(pair[i & 1][1]):
+                    pair[i & 1][0].render(sp)
+            for i in range(2):
+                e_end[i].record(streams[i])
+            barrier()
+            span = max(e_beg[0].elapsed_time(e_end[0]), e_beg[0].elapsed_time(e_end[1]), e_beg[1].elapsed_time(e_end[0]),
+                       e_beg[1].elapsed_time(e_end[1]))
+            ms_pipe = max_over_ranks(span / n_pipe)
+            res["pipelined"] = {"frames_in_flight": 2, "frames": n_pipe, "ms_per_frame": ms_pipe,
+                                "Mrays_per_s": rays_total / (ms_pipe * 1e-3) / 1e6,
+                                "note": "throughput of consecutive frames on two streams (device-resident, no L2 flush inside "
+                                        "the bracket); the headline `value` is one frame at a time"}
+            sr_b.close()
         sr.close()
         return res
 
@@ -381,15 +416,17 @@ def main():
         out = {"sha256_device_frame": hashlib.sha256(res["dev_frame"].tobytes()).hexdigest()[:16],
                "rows_checked": len(range(0, h, k)), "oracle_s": time.perf_counter() - t0}
         diff = np.abs(res["dev_frame"][rows].astype(np.int16) - ref[rows].astype(np.int16)).max(axis=-1)
-        # strict mode: any difference counts; fast mode (no bit contract, SPEC section 7): pixels more than 1 LSB off
-        out["diff_pixels_vs_oracle"] = int((diff > (0 if strict else 1)).sum())
+        # strict mode: any difference counts; fast mode (no bit contract, SPEC section 7): pixels more than 1 LSB off (flat
+        # scenes) / 2 LSB off (BVH scenes), the tolerances of tests/test_parity_gpu.py::test_fast_mode_tolerance*
+        lsb = 0 if strict else (2 if accel else 1)
+        out["diff_pixels_vs_oracle"] = int((diff > lsb).sum())
         out["max_abs_diff"] = int(diff.max())
         if k == 1 and strict:
             out["rays_equal_oracle"] = bool(rst["rays"] == int(res["rays_total"]))
         if res["host_frame"] is not None:
             out["host_frame_equals_device_frame"] = bool(np.array_equal(res["host_frame"], res["dev_frame"]))
         # strict: `pow` may move <= 2 pixels by 1 LSB; fast: >= 99.5 % of the pixels within 1 LSB (tests/test_parity_gpu.py)
-        tol = 2 if strict else max(2, int(0.005 * out["rows_checked"] * w))
+        tol = 2 if strict else max(2, int((0.01 if accel else 0.005) * out["rows_checked"] * w))
         out["tolerance_pixels"] = tol
         out["ok"] = bool(out["diff_pixels_vs_oracle"] <= tol and out.get("host_frame_equals_device_frame", True)
                          and out.get("rays_equal_oracle", True))
@@ -469,6 +506,8 @@ def main():
         if not a.no_frame_check:
             line["frame_check"] = frame_check(r)
             ok = line["frame_check"]["ok"] and all(s.get("frame_check", {"ok": True})["ok"] for s in secondary)
+        if "pipelined" in r:
+            line["pipelined"] = r["pipelined"]
         if secondary:
             line["secondary"] = secondary
         if world == 1 and not a.no_cpu_baseline:

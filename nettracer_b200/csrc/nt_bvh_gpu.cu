@@ -145,6 +145,102 @@ __global__ void karras_kernel(const uint64_t *keys, int m, int2 *children, int *
     if (i == 0) parent_inner[0] = -1;
 }
 
+// ---- 4a'. PLOC (parallel locally-ordered clustering, Meister & Bittner 2018) instead of the radix tree ----
+// The clusters start as the primitives in Morton order.  Every round each cluster looks at its NT_PLOC_RADIUS neighbours
+// on either side and picks the one whose union with it has the smallest surface area; mutually-nearest pairs merge into
+// a new inner node (which takes the place of the left partner), the array is compacted, and the next round starts - about
+// log_1.6(n) rounds.  An agglomerative build guided by surface area: close to the binned-SAH tree in traversal cost
+// (DESIGN.md section 4.4), at a few milliseconds for a million triangles.  Inner node ids are handed out in DEscending order by
+// prefix sums, so that the last merge - the root - is node 0 (what emit4_kernel expects) and the tree is deterministic.
+#ifndef NT_PLOC_RADIUS
+#define NT_PLOC_RADIUS 8 // configs[3]: 8 / 16 / 32 / 64 trace alike (73.2 / 73.2 / 73.4 / 74.7 ms with the old collapse); the search costs r
+#endif
+__device__ __forceinline__ float union_area(const FBox &a, const FBox &b) {
+    const float dx = fmaxf(a.hi[0], b.hi[0]) - fminf(a.lo[0], b.lo[0]), dy = fmaxf(a.hi[1], b.hi[1]) - fminf(a.lo[1], b.lo[1]),
+                dz = fmaxf(a.hi[2], b.hi[2]) - fminf(a.lo[2], b.lo[2]);
+    return dx * dy + dy * dz + dz * dx;
+}
+__global__ void ploc_nearest_kernel(const FBox *cbox, int c, int *nn) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    const FBox me = cbox[i];
+    float best = CUDART_INF_F;
+    int bj = i == 0 ? 1 : i - 1;
+    const int j0 = max(0, i - NT_PLOC_RADIUS), j1 = min(c - 1, i + NT_PLOC_RADIUS);
+    for (int j = j0; j <= j1; ++j) {
+        if (j == i) continue;
+        const float a = union_area(me, cbox[j]);
+        // Ties (a regular mesh is full of them) are broken by a total order on PAIRS, so that the globally best pair is nearest
+        // for both of its members and every round merges at least one pair: first the aligned pairs {2k, 2k+1} - a run of
+        // equal areas then merges completely in one round, as a balanced tree, instead of one pair per round from its left
+        // end -, then the smaller (min index, max index).
+        if (a < best) { best = a; bj = j; }
+        else if (a == best) {
+            const bool al = (i ^ j) == 1, bal = (i ^ bj) == 1;
+            if ((al && !bal) || (al == bal && (min(i, j) < min(i, bj) || (min(i, j) == min(i, bj) && max(i, j) < max(i, bj))))) bj = j;
+        }
+    }
+    nn[i] = bj;
+}
+// flags: low 32 bits = the cluster survives the round (alone or as the merged pair), high 32 bits = it merges (left partner)
+__global__ void ploc_flags_kernel(const int *nn, int c, unsigned long long *flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    const int j = nn[i];
+    const bool mutual = nn[j] == i;
+    flags[i] = (mutual && i > j ? 0ull : 1ull) | (mutual && i < j ? 1ull << 32 : 0ull);
+}
+__global__ void ploc_apply_kernel(const int *nn, int c, const unsigned long long *flags, const unsigned long long *scan, int next_id,
+                                  const FBox *cbox_in, const int *cnode_in, const int *ccount_in, FBox *cbox_out, int *cnode_out,
+                                  int *ccount_out, int2 *children, int *parent_inner, int *parent_leaf, FBox *nbox, int *count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    const unsigned long long f = flags[i];
+    if (!(f & 1ull)) return; // the right partner of a merging pair: absorbed
+    const int pos = (int)(scan[i] & 0xffffffffull);
+    if (f >> 32) {
+        const int j = nn[i], id = next_id - (int)(scan[i] >> 32);
+        const int a = cnode_in[i], b = cnode_in[j];
+        FBox u;
+        for (int k = 0; k < 3; ++k) { u.lo[k] = fminf(cbox_in[i].lo[k], cbox_in[j].lo[k]); u.hi[k] = fmaxf(cbox_in[i].hi[k], cbox_in[j].hi[k]); }
+        const int cnt = ccount_in[i] + ccount_in[j];
+        children[id] = make_int2(a, b);
+        nbox[id] = u;
+        count[id] = cnt;
+        if (a < 0) parent_leaf[~a] = id; else parent_inner[a] = id;
+        if (b < 0) parent_leaf[~b] = id; else parent_inner[b] = id;
+        cbox_out[pos] = u; cnode_out[pos] = id; ccount_out[pos] = cnt;
+    } else {
+        cbox_out[pos] = cbox_in[i]; cnode_out[pos] = cnode_in[i]; ccount_out[pos] = ccount_in[i];
+    }
+}
+__global__ void ploc_init_kernel(int m, int *cnode, int *ccount) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) { cnode[i] = ~i; ccount[i] = 1; }
+}
+// Position of every tree leaf (= primitive) in the depth-first order of the tree, and of every inner node's first leaf:
+// the sum, over the ancestors below which the walk comes up from the RIGHT child, of the left sibling's leaf count.
+__device__ __forceinline__ int dfs_start(int child, int node, const int2 *children, const int *count, const int *parent_inner) {
+    int pos = 0;
+    while (node >= 0) {
+        const int2 ch = children[node];
+        if (ch.y == child) pos += ch.x < 0 ? 1 : count[ch.x];
+        child = node;
+        node = parent_inner[node];
+    }
+    return pos;
+}
+__global__ void ploc_order_kernel(int m, const int2 *children, const int *count, const int *parent_inner, const int *parent_leaf,
+                                  const uint32_t *vals_sorted, int *leaf_pos, int *range_lo, uint32_t *order_out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < m) {
+        const int pos = dfs_start(~t, parent_leaf[t], children, count, parent_inner);
+        leaf_pos[t] = pos;
+        order_out[pos] = vals_sorted[t];
+    }
+    if (t < m - 1) range_lo[t] = dfs_start(t, parent_inner[t], children, count, parent_inner);
+}
+
 // 4b. boxes bottom-up: the second thread to arrive at a node fits it and climbs on
 __global__ void fit_kernel(int m, const int2 *children, const int *parent_inner, const int *parent_leaf, const FBox *cbox,
                            FBox *nbox, int *visits, int *count) {
@@ -183,8 +279,8 @@ __device__ __forceinline__ int leaf_ref(uint32_t first, uint32_t count, int kind
 // 5b. emit the 4-wide nodes of one set at nodes[offset + index4[i]].  A child is a leaf when it is a single
 // primitive or an inner node holding <= leaf_max primitives (its range in Morton order is contiguous).
 __global__ void emit4_kernel(int m, int leaf_max, int kind, const int2 *children, const FBox *cbox, const FBox *nbox,
-                             const int *count, const int *range_lo, const uint32_t *flag, const uint32_t *index4, int offset,
-                             NtBvhNode4 *nodes) {
+                             const int *count, const int *range_lo, const int *leaf_pos, const uint32_t *flag, const uint32_t *index4,
+                             int offset, NtBvhNode4 *nodes) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m - 1 || !flag[i]) return;
     NtBvhNode4 node;
@@ -198,7 +294,7 @@ __global__ void emit4_kernel(int m, int leaf_max, int kind, const int2 *children
     auto put = [&](int c) {
         const FBox b = c < 0 ? cbox[~c] : nbox[c];
         for (int a = 0; a < 3; ++a) { node.lo[a][ns] = b.lo[a]; node.hi[a][ns] = b.hi[a]; }
-        node.ref[ns] = c < 0 ? leaf_ref((uint32_t)~c, 1u, kind)
+        node.ref[ns] = c < 0 ? leaf_ref((uint32_t)(leaf_pos ? leaf_pos[~c] : ~c), 1u, kind) // PLOC: depth-first position; radix tree: Morton order
                      : count[c] <= leaf_max ? leaf_ref((uint32_t)range_lo[c], (uint32_t)count[c], kind)
                                             : offset + (int)index4[c];
         ++ns;
@@ -210,6 +306,60 @@ __global__ void emit4_kernel(int m, int leaf_max, int kind, const int2 *children
         else { const int2 g = children[cs[q]]; put(g.x); put(g.y); }
     }
     nodes[offset + (int)index4[i]] = node;
+}
+
+// 5'. Collapse of a PLOC tree, as the host builder does it (nt_bvh.cpp emit4): a 4-wide node starts with the two children
+// of its binary node and keeps opening the inner child with the LARGEST box until it has four slots.  (The radix-tree
+// path's fixed "grandchildren" rule ignores the boxes; on configs[3] the greedy rule is what makes a PLOC tree trace like the SAH
+// tree.)  Level-synchronous: queue entry q of a level is the binary node that becomes 4-wide node `base + q`; its inner
+// kids are appended to the next level's queue, whose positions are their node ids.  Refs are local to the set.
+__global__ void collapse_level_kernel(const int *queue, int n_queue, int base, int next_base, int *next_queue, int *next_count,
+                                      int leaf_max, int kind, const int2 *children, const FBox *cbox, const FBox *nbox, const int *count,
+                                      const int *range_lo, const int *leaf_pos, NtBvhNode4 *out) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_queue) return;
+    int kids[4];
+    int nk = 2;
+    { const int2 ch = children[queue[q]]; kids[0] = ch.x; kids[1] = ch.y; }
+    auto inner = [&](int c) { return c >= 0 && count[c] > leaf_max; };
+    auto area = [&](int c) { const FBox &b = nbox[c]; const float dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2]; return dx * dy + dy * dz + dz * dx; };
+    while (nk < 4) {
+        int best = -1;
+        float ba = -1.0f;
+        for (int k = 0; k < nk; ++k)
+            if (inner(kids[k]) && area(kids[k]) > ba) { ba = area(kids[k]); best = k; }
+        if (best < 0) break;
+        const int2 ch = children[kids[best]];
+        for (int k = best; k + 1 < nk; ++k) kids[k] = kids[k + 1]; // erase, then append both (the host's order)
+        kids[nk - 1] = ch.x; kids[nk] = ch.y;
+        ++nk;
+    }
+    NtBvhNode4 node;
+    for (int k = 0; k < 4; ++k) {
+        for (int a = 0; a < 3; ++a) { node.lo[a][k] = CUDART_INF_F; node.hi[a][k] = -CUDART_INF_F; }
+        node.ref[k] = -1;
+        node.pad[k] = 0;
+    }
+    for (int k = 0; k < nk; ++k) {
+        const int c = kids[k];
+        const FBox b = c < 0 ? cbox[~c] : nbox[c];
+        for (int a = 0; a < 3; ++a) { node.lo[a][k] = b.lo[a]; node.hi[a][k] = b.hi[a]; }
+        if (c < 0) node.ref[k] = leaf_ref((uint32_t)leaf_pos[~c], 1u, kind);
+        else if (count[c] <= leaf_max) node.ref[k] = leaf_ref((uint32_t)range_lo[c], (uint32_t)count[c], kind);
+        else {
+            const int slot = atomicAdd(next_count, 1);
+            next_queue[slot] = c;
+            node.ref[k] = next_base + slot;
+        }
+    }
+    out[base + q] = node;
+}
+__global__ void offset_refs_kernel(const NtBvhNode4 *in, int n, int offset, NtBvhNode4 *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    NtBvhNode4 node = in[i];
+    for (int k = 0; k < 4; ++k) if (node.ref[k] >= 0) node.ref[k] += offset;
+    out[offset + i] = node;
 }
 
 struct SetResult { int ref; FBox box; int nodes4; int max_depth; };
@@ -233,11 +383,64 @@ struct SetBuild {
     DevBuf<uint32_t> vals, vals_sorted, flag, index4;
     DevBuf<int2> children;
     DevBuf<unsigned char> temp;
+    DevBuf<int> leaf_pos;
+    DevBuf<NtBvhNode4> tmp4; // PLOC: the set's 4-wide nodes with set-local refs (emit() shifts them)
+    DevBuf<uint32_t> order; // PLOC: primitive ids in the depth-first order of the tree (the BVH order)
+    bool ploc = true;
+    int ploc_rounds = 0;
     int h_bounds[6];
     int nodes4 = 0, depth = 0;
+    const uint32_t *order_ptr() const { return ploc && m >= 2 ? order.p : vals_sorted.p; }
+
+    // PLOC rounds (see ploc_nearest_kernel); fills children / parents / nbox / count, root = inner node 0
+    int run_ploc(cudaStream_t st) {
+        const int T = 256;
+        DevBuf<FBox> cb[2];
+        DevBuf<int> cn[2], cc[2], nn;
+        DevBuf<unsigned long long> flags, scan;
+        DevBuf<unsigned char> stemp;
+        for (int k = 0; k < 2; ++k) { CUCHK(cb[k].alloc(m)); CUCHK(cn[k].alloc(m)); CUCHK(cc[k].alloc(m)); }
+        CUCHK(nn.alloc(m)); CUCHK(flags.alloc(m + 1)); CUCHK(scan.alloc(m + 1));
+        size_t sbytes = 0;
+        CUCHK(cub::DeviceScan::ExclusiveSum(nullptr, sbytes, flags.p, scan.p, (int)m + 1, st));
+        CUCHK(stemp.alloc(sbytes));
+        CUCHK(cudaMemcpyAsync(cb[0].p, cbox.p, sizeof(FBox) * m, cudaMemcpyDeviceToDevice, st));
+        ploc_init_kernel<<<(m + T - 1) / T, T, 0, st>>>((int)m, cn[0].p, cc[0].p);
+        int c = (int)m, next_id = (int)m - 2, cur = 0;
+        unsigned long long *h_tot = nullptr;
+        CUCHK(cudaMallocHost((void **)&h_tot, 8));
+        int rc = 0;
+        while (c > 1 && rc == 0) {
+            ploc_nearest_kernel<<<(c + T - 1) / T, T, 0, st>>>(cb[cur].p, c, nn.p);
+            ploc_flags_kernel<<<(c + T - 1) / T, T, 0, st>>>(nn.p, c, flags.p);
+            rc = (int)cudaMemsetAsync(flags.p + c, 0, 8, st); // the scan's last element = the totals
+            if (!rc) rc = (int)cub::DeviceScan::ExclusiveSum(stemp.p, sbytes, flags.p, scan.p, c + 1, st);
+            if (rc) break;
+            ploc_apply_kernel<<<(c + T - 1) / T, T, 0, st>>>(nn.p, c, flags.p, scan.p, next_id, cb[cur].p, cn[cur].p, cc[cur].p, cb[cur ^ 1].p,
+                                                            cn[cur ^ 1].p, cc[cur ^ 1].p, children.p, parent_inner.p, parent_leaf.p, nbox.p, count.p);
+            rc = (int)cudaMemcpyAsync(h_tot, scan.p + c, 8, cudaMemcpyDeviceToHost, st);
+            if (!rc) rc = (int)cudaStreamSynchronize(st);
+            if (rc) break;
+            const int kept = (int)(*h_tot & 0xffffffffull), merged = (int)(*h_tot >> 32);
+            if (merged == 0 || kept != c - merged) { rc = (int)cudaErrorUnknown; break; } // cannot happen: the closest pair is always mutual
+            next_id -= merged;
+            c = kept;
+            cur ^= 1;
+            ++ploc_rounds;
+        }
+        cudaFreeHost(h_tot);
+        if (rc) return rc;
+        const int root_parent = -1;
+        CUCHK(cudaMemcpyAsync(parent_inner.p, &root_parent, 4, cudaMemcpyHostToDevice, st));
+        CUCHK(leaf_pos.alloc(m)); CUCHK(order.alloc(m));
+        ploc_order_kernel<<<(m + T - 1) / T, T, 0, st>>>((int)m, children.p, count.p, parent_inner.p, parent_leaf.p, vals_sorted.p, leaf_pos.p,
+                                                        range_lo.p, order.p);
+        return (int)cudaGetLastError();
+    }
 
     int run(const double *d_prims, uint32_t n_, int kind_, int leaf_max_, cudaStream_t st) {
         n = n_; kind = kind_; leaf_max = leaf_max_;
+        if (const char *e = getenv("NT_BVH_GPU_ALGO")) ploc = strcmp(e, "lbvh") != 0; // "lbvh": the Morton radix tree of round 1
         if (n == 0) return 0;
         m = n; // one radix-tree leaf per primitive; subtrees of <= leaf_max primitives become the BVH leaves
         const int T = 256;
@@ -260,8 +463,35 @@ struct SetBuild {
             CUCHK(count.alloc(ni)); CUCHK(range_lo.alloc(ni));
             CUCHK(cudaMemsetAsync(visits.p, 0, sizeof(int) * ni, st));
             CUCHK(cudaMemsetAsync(max_depth.p, 0, sizeof(int), st));
-            karras_kernel<<<(ni + T - 1) / T, T, 0, st>>>(ckey.p, (int)m, children.p, parent_inner.p, parent_leaf.p, range_lo.p);
-            fit_kernel<<<(m + T - 1) / T, T, 0, st>>>((int)m, children.p, parent_inner.p, parent_leaf.p, cbox.p, nbox.p, visits.p, count.p);
+            if (ploc) {
+                const int prc = run_ploc(st);
+                if (prc == (int)cudaErrorUnknown) ploc = false; // a round without a mutual pair (NaN boxes?): the radix tree always works
+                else if (prc) return prc;
+            }
+            if (!ploc) {
+                karras_kernel<<<(ni + T - 1) / T, T, 0, st>>>(ckey.p, (int)m, children.p, parent_inner.p, parent_leaf.p, range_lo.p);
+                fit_kernel<<<(m + T - 1) / T, T, 0, st>>>((int)m, children.p, parent_inner.p, parent_leaf.p, cbox.p, nbox.p, visits.p, count.p);
+            }
+            if (ploc) { // greedy collapse, level by level (collapse_level_kernel)
+                DevBuf<int> queue[2], qcount;
+                CUCHK(queue[0].alloc(ni)); CUCHK(queue[1].alloc(ni)); CUCHK(qcount.alloc(1)); CUCHK(tmp4.alloc(ni));
+                const int root = 0;
+                CUCHK(cudaMemcpyAsync(queue[0].p, &root, 4, cudaMemcpyHostToDevice, st));
+                int nq = 1, base = 0, cur = 0, levels = 0;
+                while (nq > 0) {
+                    CUCHK(cudaMemsetAsync(qcount.p, 0, 4, st));
+                    collapse_level_kernel<<<(nq + T - 1) / T, T, 0, st>>>(queue[cur].p, nq, base, base + nq, queue[cur ^ 1].p, qcount.p, leaf_max, kind,
+                                                                         children.p, cbox.p, nbox.p, count.p, range_lo.p, leaf_pos.p, tmp4.p);
+                    int next = 0;
+                    CUCHK(cudaMemcpyAsync(&next, qcount.p, 4, cudaMemcpyDeviceToHost, st));
+                    CUCHK(cudaStreamSynchronize(st));
+                    base += nq; nq = next; cur ^= 1; ++levels;
+                }
+                nodes4 = base;
+                depth = 2 * levels; // the caller turns binary depth into 4-wide depth by halving
+                CUCHK(cudaGetLastError());
+                return 0;
+            }
             depth_kernel<<<(ni + T - 1) / T, T, 0, st>>>((int)m, parent_inner.p, count.p, leaf_max, flag.p, max_depth.p);
             size_t sb = 0;
             DevBuf<unsigned char> stemp;
@@ -292,7 +522,13 @@ struct SetBuild {
             return 0;
         }
         const int T = 256;
-        emit4_kernel<<<(m - 1 + T - 1) / T, T, 0, st>>>((int)m, leaf_max, kind, children.p, cbox.p, nbox.p, count.p, range_lo.p, flag.p, index4.p, offset, nodes);
+        if (ploc) {
+            offset_refs_kernel<<<(nodes4 + T - 1) / T, T, 0, st>>>(tmp4.p, nodes4, offset, nodes);
+            *set_ref = offset;
+            CUCHK(cudaGetLastError());
+            return 0;
+        }
+        emit4_kernel<<<(m - 1 + T - 1) / T, T, 0, st>>>((int)m, leaf_max, kind, children.p, cbox.p, nbox.p, count.p, range_lo.p, ploc ? leaf_pos.p : nullptr, flag.p, index4.p, offset, nodes);
         *set_ref = offset; // inner node 0 is the root: depth 0, index 0 of the set
         CUCHK(cudaGetLastError());
         return 0;
@@ -332,8 +568,8 @@ int nt_bvh_build_gpu(const double *d_spheres, uint32_t ns, const double *d_trian
     }
     cudaError_t e = cudaMemcpyAsync(nodes, &root, sizeof root, cudaMemcpyHostToDevice, st);
     sph_order.resize(ns); tri_order.resize(nt);
-    if (e == cudaSuccess && ns) e = cudaMemcpyAsync(sph_order.data(), sb.vals_sorted.p, sizeof(int) * ns, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && nt) e = cudaMemcpyAsync(tri_order.data(), tb.vals_sorted.p, sizeof(int) * nt, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && ns) e = cudaMemcpyAsync(sph_order.data(), sb.order_ptr(), sizeof(int) * ns, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && nt) e = cudaMemcpyAsync(tri_order.data(), tb.order_ptr(), sizeof(int) * nt, cudaMemcpyDeviceToHost, st);
     if (timing) cudaEventRecord(e1, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { cudaFree(nodes); return (int)e; }
@@ -341,7 +577,8 @@ int nt_bvh_build_gpu(const double *d_spheres, uint32_t ns, const double *d_trian
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
         fprintf(stderr, "[nt_bvh_build_gpu] %u spheres + %u triangles -> %u 4-wide nodes: %.3f ms on the stream (boxes, Morton, sort, "
-                        "radix tree, fit, collapse, order download; includes the temporary cudaMallocs)\n", ns, nt, total, ms);
+                        "%s, collapse, order download; includes the temporary cudaMallocs; PLOC rounds %d + %d)\n", ns, nt, total, ms,
+                tb.ploc ? "PLOC" : "radix tree + fit", sb.ploc_rounds, tb.ploc_rounds);
         cudaEventDestroy(e0); cudaEventDestroy(e1);
     }
     float mx = 0;

@@ -82,7 +82,10 @@ __device__ __forceinline__ void query_start(const Ctx<R, true> &c, BvhQuery<R> &
     // sqrt(L2 - 1) t from the centre - OUTSIDE the sphere and possibly outside its box.  Boxes may only cull what the
     // rule cannot hit, so they grow by that bound with t <= the largest distance from the origin to a scene point;
     // ~1e-8 of the scene size for a unit direction.  (Found by bench.py's frame check against the brute-force oracle.)
+    // (Strict mode only.  The fast mode has no bit contract, its sphere test is a different formula (SPEC §7), and binary32
+    // normals of small distant spheres are unit vectors to 1e-4 at best: growing boxes for that would swallow the tree.)
     const float grow = [&] {
+        if constexpr (sizeof(R) == 4) return 0.0f;
         const R l2 = dot(d, d);
         if (!(l2 > R(1))) return l2 == l2 ? 0.0f : CUDART_INF_F;
         const float far_ = 1.7320508f * (fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz)) + s.max_abs);
