@@ -159,7 +159,7 @@ static uint32_t plane_free_lights(const nt_scene_desc *d) {
     return nt_cull_plane_free_lights(d->spheres, d->n_spheres, d->triangles, d->n_triangles, d->planes, d->n_planes, d->lights, d->n_lights, kPlaneFreeEps);
 }
 
-static const size_t kSmemBudget = 39 * 1024; // + 8.3 KB of static shared memory + list padding stays under the 48 KB default limit
+static const size_t kSmemBudget = 38 * 1024; // + 8.3 KB of static shared memory + list padding + light rooms (<= 1.1 KB) stays under the 48 KB default limit
 static const size_t kCounterBytes = sizeof(unsigned long long) * (NT_COUNTER_SLOTS * NT_NCOUNTERS + NT_COUNTER_EXTRA);
 static const uint32_t kFlatMaxBounded = 64;
 
@@ -288,6 +288,27 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
     }
     for (uint32_t i = 0; i < np; ++i)
         if (((pln_code[i / 16] >> (2 * (i % 16))) & 3u) == 3u) pgen.push_back((int)i);
+    // at most two axis-aligned planes per axis (a room): the same entries as [3][2] slots padded with (NaN, -1), for the
+    // straight-line nearest-plane routine; NT_SLAB=0 keeps the list loops (A/B, tests)
+    std::vector<double> axs64(12, std::nan(""));
+    std::vector<float> axs32(12, std::nanf(""));
+    bool slab = !use_bvh && nax[0] + nax[1] + nax[2] > 0 && nax[0] <= 2 && nax[1] <= 2 && nax[2] <= 2;
+    if (const char *e = getenv("NT_SLAB")) if (e[0] == '0') slab = false;
+    {
+        const long long m64 = -1;
+        const int m32 = -1;
+        for (int j = 0; j < 6; ++j) { memcpy(&axs64[2 * j + 1], &m64, 8); memcpy(&axs32[4 * (j / 2) + 2 + (j % 2)], &m32, 4); } // binary32: p0 p1 i0 i1 per axis
+        size_t src = 0;
+        for (int k = 0; k < 3 && slab; ++k)
+            for (uint32_t j = 0; j < nax[k]; ++j, ++src)
+                for (int e = 0; e < 2; ++e) { axs64[4 * k + 2 * j + e] = axl64[2 * src + e]; axs32[4 * k + 2 * e + j] = axl32[2 * src + e]; }
+    }
+    // light rooms (nt_cull.h): shadow queries from inside skip the axis-aligned planes; NT_LIGHT_ROOMS=0 disables (A/B, tests)
+    std::vector<double> room64(8 * (size_t)nl + 8, 0.0);
+    std::vector<float> room32(8 * (size_t)nl + 8, 0.0f);
+    bool rooms = !use_bvh && nl > 0 && nl <= 16 && nax[0] + nax[1] + nax[2] > 0;
+    if (const char *e = getenv("NT_LIGHT_ROOMS")) if (e[0] == '0') rooms = false;
+    if (rooms) nt_cull_light_rooms(d->planes, np, d->lights, nl, room64.data(), room32.data());
     for (uint32_t k = 0; k < nt; ++k) {
         const int i = tri_order[k];
         const double *t = d->triangles + 9 * (size_t)i;
@@ -337,6 +358,14 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
     for (int k = 0; k < 3; ++k) ds.nax[k] = nax[k];
     ds.ngen = (uint32_t)pgen.size();
     UP(axl64, ds.axl64); UP(axl32, ds.axl32); UP(pgen, ds.pgen);
+    ds.slab = slab ? 1 : 0; ds.rooms = rooms ? 1 : 0;
+    for (int w = 0; w < 2; ++w) { // the layout of nt_trace.cuh stage_scene, R = float / double
+        const size_t rs = w ? 8 : 4;
+        const size_t r_units = (size_t)ns * 4 + (size_t)np * 4 + (size_t)nt * NT_TRI_STRIDE + 2 * ((size_t)nax[0] + nax[1] + nax[2]);
+        ds.room_off[w] = (uint32_t)(r_units * rs + ((pgen.size() + 3) & ~(size_t)3) * 4);
+        ds.axs_off[w] = ds.room_off[w] + (uint32_t)((rooms ? 8 * (size_t)nl : 0) * rs);
+    }
+    UP(axs64, ds.axs64); UP(axs32, ds.axs32); UP(room64, ds.room64); UP(room32, ds.room32);
     // flat scenes: conservative culling tables (nt_cull.h); NT_CULL=0 renders by brute force (A/B, tests)
     ds.cull = 0; ds.lbuf_k = NT_LBUF_K;
     ds.sph_bits = ns >= 64 ? ~0ull : (1ull << ns) - 1ull;

@@ -228,3 +228,42 @@ uint32_t nt_cull_plane_free_lights(const double *spheres, uint32_t ns, const dou
     }
     return out;
 }
+
+void nt_cull_light_rooms(const double *planes, uint32_t np, const double *lights, uint32_t nl, double *rooms, float *rooms32) {
+    const double inf = HUGE_VAL;
+    for (uint32_t l = 0; l < nl; ++l) {
+        const double *L = lights + 6 * (size_t)l;
+        double lo[3] = { -inf, -inf, -inf }, hi[3] = { inf, inf, inf }, scale = 0, smin = inf;
+        bool ok = true;
+        for (int a = 0; a < 3; ++a) scale = std::max(scale, std::fabs(L[a]));
+        for (uint32_t i = 0; i < np; ++i) {
+            const double *p = planes + 4 * (size_t)i;
+            for (int k = 0; k < 3; ++k) {
+                if (!(std::fabs(p[k]) == 1.0 && p[(k + 1) % 3] == 0.0 && p[(k + 2) % 3] == 0.0)) continue;
+                const double pk = p[k] * p[3]; // exact: the plane is x_k = pk
+                scale = std::max(scale, std::fabs(pk));
+                if (!std::isfinite(pk) || pk == L[k]) { ok = false; continue; }
+                smin = std::min(smin, std::fabs(L[k] - pk));
+                if (pk < L[k]) lo[k] = std::max(lo[k], pk); else hi[k] = std::min(hi[k], pk);
+            }
+        }
+        double *r = rooms + 8 * (size_t)l;
+        float *rf = rooms32 + 8 * (size_t)l;
+        if (!(scale > 0) || !std::isfinite(scale)) scale = 1.0;
+        const double delta = std::ldexp(scale, -33), delta32 = std::ldexp(scale, -16);
+        ok = ok && std::isfinite(L[0]) && std::isfinite(L[1]) && std::isfinite(L[2]);
+        if (ok && smin < 1e3 * delta) ok = false; // light (nearly) on a plane: no room
+        for (int k = 0; k < 3; ++k) {
+            r[2 * k] = ok ? lo[k] - delta : inf;
+            r[2 * k + 1] = ok ? hi[k] + delta : -inf;
+            // float box: rounded INWARD from the dilated double box (the dilation stays >= delta32 / 2)
+            rf[2 * k] = ok ? std::nextafterf((float)(lo[k] - delta32), HUGE_VALF) : HUGE_VALF;
+            rf[2 * k + 1] = ok ? std::nextafterf((float)(hi[k] + delta32), -HUGE_VALF) : -HUGE_VALF;
+        }
+        const bool any = ok && std::isfinite(smin); // no axis-aligned plane at all: nothing to prove, no cap
+        r[6] = !ok ? 0.0 : any ? 0.5 * smin / delta : inf;
+        r[7] = !ok ? 0.0 : any ? smin * 1e12 : inf;
+        rf[6] = ok ? HUGE_VALF : 0.0f;
+        rf[7] = ok ? HUGE_VALF : 0.0f;
+    }
+}

@@ -48,3 +48,21 @@ void nt_cull_primary_rects(const double *bsph, uint32_t nb, const double cam[12]
 // n.x = d on the plane (SPEC-PROVISIONAL §1).  At most 32 lights.
 uint32_t nt_cull_plane_free_lights(const double *spheres, uint32_t ns, const double *triangles, uint32_t nt, const double *planes,
                                    uint32_t np, const double *lights, uint32_t nl, double eps_min);
+
+// "Light rooms" (flat scenes, strict and fast mode): per point light the axis-aligned box between the nearest
+// axis-aligned planes (normal exactly +-e_k) on either side of the light.  rooms[l] = { lo_x, hi_x, lo_y, hi_y, lo_z,
+// hi_z, cap_per_eps, cap_max }.  A shadow query whose origin P satisfies lo_k <= P_k <= hi_k on all three axes and
+// whose light distance satisfies dist <= min(eps * cap_per_eps, cap_max) cannot be stopped by ANY axis-aligned plane,
+// so the kernel skips the axis lists (general planes are still tested).  Proof, on the doubles the exact rule itself
+// works with (SPEC-PROVISIONAL section 3 in its axis form t = fl(fl(p - P_k) / L_k), L_k = fl(fl(l_k - P_k) * fl(1 / dist))),
+// for a plane below the light (p < l_k, s = l_k - p; mirrored above), u = 2^-53:
+//   P_k > p:  num < 0, so t > 0 needs L_k < 0, i.e. P_k > l_k; then num / L_k = dist (P_k - p) / (P_k - l_k) (1 + 5u') >=
+//             dist (1 + s / dist)(1 - 6u) and s / dist >= s / cap_max = 1e-12: t >= dist, not an occluder;
+//   P_k == p: num = 0, t = 0: a miss;
+//   p - delta <= P_k < p (lo_k = p - delta): 0 < num <= delta, t > 0 needs L_k > 0, L_k >= (s / dist)(1 - 3u), hence
+//             t <= delta dist / s (1 + 6u) <= delta eps cap_per_eps / s_min (1 + 6u) = eps / 2 (1 + 6u) < eps: a miss.
+// delta = 2^-33 x (largest |plane position| or |light coordinate|): five orders above the rounding of a hit point
+// that lies on a wall, so the test passes for (nearly) every query inside the room; s_min = the light's smallest
+// distance to an axis-aligned plane; a light ON such a plane gets an empty room (lo = +inf).  The fast mode uses the
+// float-rounded box with delta32 = 2^-16 x scale and no distance cap (it has no bit-level contract, SPEC section 7).
+void nt_cull_light_rooms(const double *planes, uint32_t np, const double *lights, uint32_t nl, double *rooms, float *rooms32);

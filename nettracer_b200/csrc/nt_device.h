@@ -93,6 +93,14 @@ struct NtDevScene {
     const double *axl64;
     const float *axl32;
     const int *pgen;
+    // flat scenes, slab == 1: no axis has more than two axis-aligned planes; axs64 / axs32 = [3][2] (position, index bits)
+    // pairs, missing entries padded with (NaN, -1): the straight-line nearest-plane routine (nt_trace.cuh planes_nearest_slab)
+    uint32_t slab;
+    // flat scenes, rooms == 1: room64 / room32 = [nl][8] light rooms (nt_cull.h nt_cull_light_rooms)
+    uint32_t rooms;
+    uint32_t room_off[2], axs_off[2]; // byte offsets of the staged rooms / slab entries in dynamic shared memory, [0] binary32, [1] binary64
+    const double *axs64, *room64;
+    const float *axs32, *room32;
     const NtBvhNode4 *nodes;
     // flat scenes: conservative culling tables (nt_cull.h); cull == 0 -> every query tests every primitive
     uint32_t cull, lbuf_k;

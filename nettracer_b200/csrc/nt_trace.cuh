@@ -77,6 +77,8 @@ template <> struct Math<double> {
 #endif
     static __device__ __forceinline__ float up(double x) { return __double2float_ru(x); }
     static __device__ __forceinline__ double inf() { return CUDART_INF; }
+    // SPEC §2 / §4: len = sqrt(x), inv = 1 / len - two correctly rounded operations, in this order
+    static __device__ __forceinline__ void len_inv(double x, double &len, double &inv) { len = sqrt(x); inv = 1.0 / len; }
 };
 template <> struct Math<float> {
     static __device__ __forceinline__ float rcp(float x) { return 1.0f / x; }
@@ -85,6 +87,8 @@ template <> struct Math<float> {
     static __device__ __forceinline__ float pow_(float a, float b) { return __powf(a, b); }
     static __device__ __forceinline__ float up(float x) { return x; }
     static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
+    // fast mode: one MUFU.RSQ instead of MUFU.SQRT + MUFU.RCP
+    static __device__ __forceinline__ void len_inv(float x, float &len, float &inv) { inv = rsqrtf(x); len = x * inv; }
 };
 
 // ---- loads: 128-bit; read-only path for global data, ld.shared by 32-bit shared address for the
@@ -385,7 +389,11 @@ static __device__ __forceinline__ unsigned long long tile_mask(const NtDevScene 
 // base; pointers kept in a struct made the compiler rebuild the shared window address per iteration.
 extern __shared__ __align__(16) unsigned char nt_smem[];
 
-template <typename R, bool BVH> struct Ctx {
+// LEAN: the launch has neither triangles nor general (non-axis-aligned) planes - their loops are compiled out.  The flat
+// kernels' hot code must stay inside the instruction cache (no_instruction stalls), and loops that
+// never run still sit between the hot blocks.
+template <typename R, bool BVH, bool LEAN = false> struct Ctx {
+    static constexpr bool lean = LEAN;
     const NtDevScene *s;
     const NtSceneView<R> *v;
     unsigned sph_addr, pln_addr, tri_addr, code_addr; // 32-bit shared-memory byte addresses of the staged arrays
@@ -438,8 +446,123 @@ __device__ __forceinline__ bool axis_candidate(R dk, R num, R bk) {
     if constexpr (sizeof(R) == 8) return (__double2hiint(num) ^ __double2hiint(dk)) >= 0 && fabs(num) < bk;
     else return true;
 }
-template <typename R, typename K>
-__device__ __forceinline__ void planes_nearest(const Ctx<R, false> &c, const V3<R> &o, const V3<R> &d, R &tb, Hit &best, K &k) {
+#ifdef NT_EXP_SLAB
+// The axis lists of the routine below as a shared subroutine: the straight-line slab routine (planes_nearest_slab)
+// falls back to it in the rare cases it cannot decide, and scenes with more than two planes on an axis use it always.
+template <typename R> struct PlaneHit { R t; int idx; }; // idx < 0: no axis-aligned plane beats the bound
+template <typename R, bool LEAN>
+__device__ __noinline__ PlaneHit<R> planes_nearest_lists(const Ctx<R, false, LEAN> &c, const V3<R> &o, const V3<R> &d, R tb, int best_gid) {
+    const NtDevScene &s = *c.s;
+    struct { int idx, gid; } best = { -1, best_gid };
+    R tm1 = plane_bound<R>(tb);
+    unsigned addr = c.axl_addr;
+    const R oo[3] = { o.x, o.y, o.z }, dd[3] = { d.x, d.y, d.z };
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { // unrolled over the axes (no selects, list lengths straight from the constant bank)
+        const unsigned n = s.nax[k];
+        const R ok = oo[k], dk = dd[k];
+        R bk = fabs(dk) * tm1;
+#pragma unroll 1
+        for (unsigned j = 0; j < n; ++j, addr += 2u * (unsigned)sizeof(R)) {
+            R p, t;
+            int idx;
+            Ld<R>::s2(addr, p, idx);
+            const R num = p - ok;
+            if (!axis_candidate<R>(dk, num, bk)) continue;
+            if (!plane_finish<R>(dk, num, c.eps, c.eps_lo, t)) continue;
+            const int gid = (int)s.ns + idx;
+            if (t < tb || (t == tb && gid < best.gid)) {
+                tb = t; best.idx = idx; best.gid = gid;
+                tm1 = plane_bound<R>(tb); bk = fabs(dk) * tm1;
+            }
+        }
+    }
+    return { tb, best.idx };
+}
+// Strict mode, scenes with at most two axis-aligned planes per axis (NtDevScene::slab - a room): the nearest of them in
+// straight-line code.  The list loops above are a chain of dependent steps (load, subtract, compare, branch; a division
+// as soon as a candidate turns up, whose result bounds the next plane): ~500 cycles of latency per query for a warp that
+// issues one binary64 instruction every 8 cycles.  Here the six entries are loaded and tested independently, the
+// candidates of the three axes are ordered by cross-multiplication, and ONE quotient is divided:
+//   * per axis both planes share the divisor d_k, so the candidate with the smaller |num| has the smaller (or equal)
+//     quotient; candidates = same sign as d_k, |num| < |d_k| bound (plane_bound: can be nearer than tb), not provably
+//     <= eps (plane_below_eps);
+//   * candidates a, b of two axes: |num_a| |d_b| < |num_b| |d_a| (1 - 1e-15) implies q_a < q_b (1 - 6e-16), i.e. the
+//     correctly rounded quotients differ and a is strictly nearer; products below 1e-290 (lost relative precision) and
+//     anything inside the margins - which includes every tie the smallest-global-id rule would have to break - are
+//     left to the list routine.  So is a winner whose quotient turns out <= eps (its axis may hold a second candidate).
+// Returns false when the list routine has to decide (nothing is modified then).  Bit-identical results; the GPU tests
+// run every flat scene with NT_SLAB=0 / 1 against the oracle.
+template <bool LEAN>
+__device__ __forceinline__ bool planes_nearest_slab(const Ctx<double, false, LEAN> &c, const V3<double> &o, const V3<double> &d, double &tb, Hit &best) {
+    const double tm1 = plane_bound<double>(tb);
+    const double oo[3] = { o.x, o.y, o.z }, dd[3] = { d.x, d.y, d.z };
+    bool slow = false;
+    int wi = -1;                       // running winner: plane index, |num|, |d_k|, num, d_k
+    double wa = 0, wd = 0, wn = 0, wk = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double p0, p1;
+        int i0, i1;
+        Ld<double>::s2(c.sph_addr + c.s->axs_off[1] + 32u * k, p0, i0);
+        Ld<double>::s2(c.sph_addr + c.s->axs_off[1] + 32u * k + 16u, p1, i1);
+        const double ok = oo[k], dk = dd[k], adk = fabs(dk), bk = adk * tm1, lo = adk * c.eps_lo;
+        double n0 = p0 - ok, n1 = p1 - ok, a0 = fabs(n0), a1 = fabs(n1);
+        const bool lo_ok = lo >= 2.2250738585072014e-308;
+        const int hk = __double2hiint(dk);
+        const bool c0 = (__double2hiint(n0) ^ hk) >= 0 && a0 < bk && !(a0 <= lo && lo_ok); // padding: p = NaN, never a candidate
+        const bool c1 = (__double2hiint(n1) ^ hk) >= 0 && a1 < bk && !(a1 <= lo && lo_ok);
+        if (c0 && c1 && a0 <= a1 * (1.0 + 1e-15) && a1 <= a0 * (1.0 + 1e-15)) slow = true; // two planes ahead, (nearly) coincident
+        if (c1 && (!c0 || a1 < a0)) { n0 = n1; a0 = a1; i0 = i1; }
+        if (c0 || c1) {
+            if (wi < 0) { wi = i0; wa = a0; wd = adk; wn = n0; wk = dk; }
+            else {
+                const double pa = wa * adk, pb = a0 * wd; // q_w < q_k  <=>  pa < pb
+                if (!(fmin(pa, pb) >= 1e-290)) slow = true;
+                else if (pb < pa * (1.0 - 1e-15)) { wi = i0; wa = a0; wd = adk; wn = n0; wk = dk; }
+                else if (!(pa < pb * (1.0 - 1e-15))) slow = true;
+            }
+        }
+    }
+    if (slow) return false;
+    if (wi < 0) return true; // no axis-aligned plane can be nearer than tb
+    const double t = plane_quotient<double>(wn, wk);
+    if (!(t > c.eps)) return false;
+    const int gid = (int)c.s->ns + wi;
+    if (t < tb || (t == tb && gid < best.gid)) { tb = t; best.kind = 1; best.idx = wi; best.gid = gid; }
+    return true;
+}
+template <typename R, typename K, bool LEAN>
+__device__ __forceinline__ void planes_nearest(const Ctx<R, false, LEAN> &c, const V3<R> &o, const V3<R> &d, R &tb, Hit &best, K &k) {
+    const NtDevScene &s = *c.s;
+    NT_X(k, xpln, s.nax[0] + s.nax[1] + s.nax[2] + s.ngen);
+    bool lists = true;
+    if constexpr (sizeof(R) == 8) {
+        if (s.slab) lists = !planes_nearest_slab(c, o, d, tb, best);
+    }
+    if (lists) {
+        const PlaneHit<R> ph = planes_nearest_lists<R>(c, o, d, tb, best.gid);
+        if (ph.idx >= 0) { tb = ph.t; best.kind = 1; best.idx = ph.idx; best.gid = (int)s.ns + ph.idx; }
+    }
+    R tm1 = plane_bound<R>(tb);
+    if constexpr (!LEAN) {
+#pragma unroll 1
+        for (unsigned j = 0; j < s.ngen; ++j) {
+            int idx;
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(idx) : "r"(c.gen_addr + 4u * j));
+            R q[4], dn, num, t;
+            c.ld_pln((unsigned)idx, q);
+            plane_eval<R>(q, 3, o, d, dn, num);
+            if (plane_reject<R>(dn, num, tm1)) continue;
+            if (!plane_finish<R>(dn, num, c.eps, c.eps_lo, t)) continue;
+            const int gid = (int)s.ns + idx;
+            if (t < tb || (t == tb && gid < best.gid)) { tb = t; best.kind = 1; best.idx = idx; best.gid = gid; tm1 = plane_bound<R>(tb); }
+        }
+    }
+}
+#else
+template <typename R, typename K, bool LEAN>
+__device__ __forceinline__ void planes_nearest(const Ctx<R, false, LEAN> &c, const V3<R> &o, const V3<R> &d, R &tb, Hit &best, K &k) {
     const NtDevScene &s = *c.s;
     NT_X(k, xpln, s.nax[0] + s.nax[1] + s.nax[2] + s.ngen);
     R tm1 = plane_bound<R>(tb);
@@ -465,30 +588,34 @@ __device__ __forceinline__ void planes_nearest(const Ctx<R, false> &c, const V3<
             }
         }
     }
+    if constexpr (!LEAN) {
 #pragma unroll 1
-    for (unsigned j = 0; j < s.ngen; ++j) {
-        int idx;
-        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(idx) : "r"(c.gen_addr + 4u * j));
-        R q[4], dn, num, t;
-        c.ld_pln((unsigned)idx, q);
-        plane_eval<R>(q, 3, o, d, dn, num);
-        if (plane_reject<R>(dn, num, tm1)) continue;
-        if (!plane_finish<R>(dn, num, c.eps, c.eps_lo, t)) continue;
-        const int gid = (int)s.ns + idx;
-        if (t < tb || (t == tb && gid < best.gid)) { tb = t; best.kind = 1; best.idx = idx; best.gid = gid; tm1 = plane_bound<R>(tb); }
+        for (unsigned j = 0; j < s.ngen; ++j) {
+            int idx;
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(idx) : "r"(c.gen_addr + 4u * j));
+            R q[4], dn, num, t;
+            c.ld_pln((unsigned)idx, q);
+            plane_eval<R>(q, 3, o, d, dn, num);
+            if (plane_reject<R>(dn, num, tm1)) continue;
+            if (!plane_finish<R>(dn, num, c.eps, c.eps_lo, t)) continue;
+            const int gid = (int)s.ns + idx;
+            if (t < tb || (t == tb && gid < best.gid)) { tb = t; best.kind = 1; best.idx = idx; best.gid = gid; tm1 = plane_bound<R>(tb); }
+        }
     }
 }
+#endif
 // Any plane with eps < t < dist?
-template <typename R, typename K>
-__device__ __forceinline__ bool planes_occluded(const Ctx<R, false> &c, const V3<R> &o, const V3<R> &d, R dist, K &k) {
+// `axis` false: the query's origin lies in its light's room (in_light_room), no axis-aligned plane can stop it.
+template <typename R, typename K, bool LEAN>
+__device__ __forceinline__ bool planes_occluded(const Ctx<R, false, LEAN> &c, const V3<R> &o, const V3<R> &d, R dist, bool axis, K &k) {
     const NtDevScene &s = *c.s;
-    NT_X(k, xpln, s.nax[0] + s.nax[1] + s.nax[2] + s.ngen); // an upper bound when an occluder ends the loops early
+    NT_X(k, xpln, (axis ? s.nax[0] + s.nax[1] + s.nax[2] : 0u) + s.ngen); // an upper bound when an occluder ends the loops early
     const R dm1 = plane_bound<R>(dist);
     unsigned addr = c.axl_addr;
     const R oo[3] = { o.x, o.y, o.z }, dd[3] = { d.x, d.y, d.z };
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const unsigned n = s.nax[k];
+        const unsigned n = axis ? s.nax[k] : 0u;
         const R ok = oo[k], dk = dd[k], bk = fabs(dk) * dm1;
 #pragma unroll 1
         for (unsigned j = 0; j < n; ++j, addr += 2u * (unsigned)sizeof(R)) {
@@ -500,22 +627,24 @@ __device__ __forceinline__ bool planes_occluded(const Ctx<R, false> &c, const V3
             if (plane_finish<R>(dk, num, c.eps, c.eps_lo, t) && t < dist) return true;
         }
     }
+    if constexpr (!LEAN) {
 #pragma unroll 1
-    for (unsigned j = 0; j < s.ngen; ++j) {
-        int idx;
-        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(idx) : "r"(c.gen_addr + 4u * j));
-        R q[4], dn, num, t;
-        c.ld_pln((unsigned)idx, q);
-        plane_eval<R>(q, 3, o, d, dn, num);
-        if (plane_reject<R>(dn, num, dm1)) continue;
-        if (plane_finish<R>(dn, num, c.eps, c.eps_lo, t) && t < dist) return true;
+        for (unsigned j = 0; j < s.ngen; ++j) {
+            int idx;
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(idx) : "r"(c.gen_addr + 4u * j));
+            R q[4], dn, num, t;
+            c.ld_pln((unsigned)idx, q);
+            plane_eval<R>(q, 3, o, d, dn, num);
+            if (plane_reject<R>(dn, num, dm1)) continue;
+            if (plane_finish<R>(dn, num, c.eps, c.eps_lo, t) && t < dist) return true;
+        }
     }
     return false;
 }
 // Rare path (a plane occludes the light): index of the FIRST occluding plane in index order, for the work
 // counters' sequential rule.  Plain SPEC §3 formula; gives the same t as the list forms above, bit for bit.
-template <typename R>
-__device__ __noinline__ unsigned first_occluding_plane(const Ctx<R, false> &c, const V3<R> &o, const V3<R> &d, R dist) {
+template <typename R, bool LEAN>
+__device__ __noinline__ unsigned first_occluding_plane(const Ctx<R, false, LEAN> &c, const V3<R> &o, const V3<R> &d, R dist) {
     const NtDevScene &s = *c.s;
 #pragma unroll 1
     for (unsigned i = 0; i < s.np; ++i) {
@@ -527,14 +656,35 @@ __device__ __noinline__ unsigned first_occluding_plane(const Ctx<R, false> &c, c
     return s.np - 1;
 }
 
+// Fast mode, scenes with at most two axis-aligned planes per axis (NtDevScene::slab): t = (p - o_k) / d_k for both planes
+// of an axis with ONE packed subtract and ONE packed multiply (sm_100 add.f32x2 / mul.f32x2), the reciprocal of d_k
+// shared; staged per axis as p0 p1 i0 i1 so that a 128-bit shared load delivers the position pair in an aligned
+// register pair.  Padding entries hold p = NaN (never > eps); d_k = 0 gives +-inf or NaN, never a hit.
+template <bool LEAN>
+__device__ __forceinline__ void planes_nearest_slab32(const Ctx<float, false, LEAN> &c, const V3<float> &o, const V3<float> &d, float &tb, Hit &best) {
+    const float oo[3] = { o.x, o.y, o.z }, dd[3] = { d.x, d.y, d.z };
+    int wi = -1;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float q[4];
+        Ld<float>::s4(c.sph_addr + c.s->axs_off[0] + 16u * k, q); // p0 p1 i0 i1
+        const float inv = __frcp_rn(dd[k]), nok = -oo[k];
+        const float2 t = __fmul2_rn(__fadd2_rn(make_float2(q[0], q[1]), make_float2(nok, nok)), make_float2(inv, inv));
+        const float t0 = t.x > c.eps ? t.x : CUDART_INF_F, t1 = t.y > c.eps ? t.y : CUDART_INF_F;
+        if (t0 < tb) { tb = t0; wi = __float_as_int(q[2]); }
+        if (t1 < tb) { tb = t1; wi = __float_as_int(q[3]); }
+    }
+    if (wi >= 0) { best.kind = 1; best.idx = wi; best.gid = (int)c.s->ns + wi; }
+}
+
 // SPEC §3 nearest hit: smallest t; equal t -> smallest global primitive id.
 // Flat scenes: `mask` = the bounded primitives this ray can possibly hit (per lane).  `own` >= 0: the ray
 // starts on sphere `own` (a reflection / refraction child): that sphere is tested first, and when it is hit
 // the segment up to that hit is a chord of its ball, so only the balls touching it (nbr[own]) can stop the
 // ray earlier.  Bounded primitives come in index order; the only out-of-order test is `own`, hence the
 // explicit tie rule in the sphere loop.
-template <typename R, bool BVH, typename K>
-__device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o, const V3<R> &d, unsigned long long mask,
+template <typename R, bool BVH, typename K, bool LEAN>
+__device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH, LEAN> &c, const V3<R> &o, const V3<R> &d, unsigned long long mask,
                                             int own, R &tb, Hit &best, K &k) {
     const NtDevScene &s = *c.s;
     tb = Math<R>::inf();
@@ -569,6 +719,19 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
         // iteration and without branches around the division, beats the axis lists
         NT_X(k, xpln, s.np);
         unsigned i = 0;
+        if (s.slab) { // a room: the slab form below covers every axis-aligned plane, the loop the general ones
+            planes_nearest_slab32(c, o, d, tb, best);
+#pragma unroll 1
+            for (unsigned j = 0; !LEAN && j < s.ngen; ++j) {
+                int idx;
+                asm volatile("ld.shared.s32 %0, [%1];" : "=r"(idx) : "r"(c.gen_addr + 4u * j));
+                R q[4], dn, num;
+                c.ld_pln((unsigned)idx, q);
+                plane_eval<R>(q, 3, o, d, dn, num);
+                if (plane_finish<R>(dn, num, c.eps, c.eps_lo, t) && t < tb) { tb = t; best.kind = 1; best.idx = idx; best.gid = (int)s.ns + idx; }
+            }
+            i = s.np;
+        }
         for (; i + 2 <= s.np; i += 2) {
             R q0[4], q1[4], dn0, num0, dn1, num1;
             c.ld_pln(i, q0);
@@ -586,7 +749,7 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
         }
     }
     if constexpr (BVH) k.pln += s.np;
-    if constexpr (!BVH) {
+    if constexpr (!BVH && !LEAN) {
         if (s.nt) { // uniform
             unsigned long long m = s.ns >= 64 ? 0ull : mask >> s.ns;
             NT_X(k, xtri, (unsigned)__popcll(m));
@@ -602,17 +765,29 @@ __device__ __forceinline__ bool nearest_hit(const Ctx<R, BVH> &c, const V3<R> &o
     return best.kind >= 0;
 }
 
+// Is the origin P of a shadow query towards light l inside the light's room (nt_cull.h nt_cull_light_rooms: no axis-aligned
+// plane can stop the query then)?  Six comparisons against the staged box and one against the distance cap.
+template <typename R, bool LEAN>
+__device__ __forceinline__ bool in_light_room(const Ctx<R, false, LEAN> &c, unsigned l, const V3<R> &P, R dist) {
+    R a[4], b[4];
+    const unsigned addr = c.sph_addr + c.s->room_off[sizeof(R) == 8] + l * (8u * (unsigned)sizeof(R));
+    Ld<R>::s4(addr, a);
+    Ld<R>::s4(addr + 4u * (unsigned)sizeof(R), b);
+    return (P.x >= a[0]) & (P.x <= a[1]) & (P.y >= a[2]) & (P.y <= a[3]) & (P.z >= b[0]) & (P.z <= b[1]) & (dist <= b[2]);
+}
+
 // SPEC §3 occlusion: any primitive hit (t > eps) with t < dist; first found ends the query.
 // Counters follow the sequential rule (tests up to and including the first occluder); a culled primitive is
 // a certain miss, so the first occluder found in mask order is the first one in index order.
 // Flat scenes count the tests NOT made: k.sph / k.pln / k.tri are deficits against "every query tests every
 // primitive" and are touched only when a query ends early (the kernel's flush turns them into test counts:
 // queries * n - deficit); an update per query was a spilled load-add-store on the common path.
-// `planes`: false when the host proved that no plane can lie between this query's origin and its light (the
-// origin is on a bounded primitive and the light's bit of NtDevScene::lfree is set, nt_cull.h).
-template <typename R, bool BVH, typename K>
-__device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, const V3<R> &d, R dist, unsigned long long mask,
-                                         bool planes, K &k) {
+// `planes`: 0 when the host proved that no plane can lie between this query's origin and its light (the
+// origin is on a bounded primitive and the light's bit of NtDevScene::lfree is set, nt_cull.h); 2 when the origin
+// lies in the light's room (only general planes are tested); 1 = every plane.
+template <typename R, bool BVH, typename K, bool LEAN>
+__device__ __forceinline__ bool occluded(const Ctx<R, BVH, LEAN> &c, const V3<R> &o, const V3<R> &d, R dist, unsigned long long mask,
+                                         int planes, K &k) {
     const NtDevScene &s = *c.s;
     R t;
     if constexpr (!BVH) {
@@ -627,29 +802,42 @@ __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, c
         }
     }
     if constexpr (!BVH && sizeof(R) == 8) {
-        if (planes && planes_occluded<R, K>(c, o, d, dist, k)) { k.pln += s.np - (first_occluding_plane<R>(c, o, d, dist) + 1); k.tri += s.nt; return true; }
+        if (planes && planes_occluded<R, K>(c, o, d, dist, planes == 1, k)) { k.pln += s.np - (first_occluding_plane<R>(c, o, d, dist) + 1); k.tri += s.nt; return true; }
     }
     if constexpr (!BVH && sizeof(R) == 4) {
-        NT_X(k, xpln, s.np); // an upper bound when an occluder ends the loop early
-        unsigned i = 0;
-        for (; i + 2 <= s.np; i += 2) {
-            R q0[4], q1[4], dn0, num0, dn1, num1;
-            c.ld_pln(i, q0);
-            c.ld_pln(i + 1, q1);
-            plane_eval<R>(q0, 3, o, d, dn0, num0);
-            plane_eval<R>(q1, 3, o, d, dn1, num1);
-            if (plane_finish<R>(dn0, num0, c.eps, c.eps_lo, t) && t < dist) { k.pln += s.np - (i + 1); k.tri += s.nt; return true; }
-            if (plane_finish<R>(dn1, num1, c.eps, c.eps_lo, t) && t < dist) { k.pln += s.np - (i + 2); k.tri += s.nt; return true; }
-        }
-        if (i < s.np) {
-            R q[4], dn, num;
-            c.ld_pln(i, q);
-            plane_eval<R>(q, 3, o, d, dn, num);
-            if (plane_finish<R>(dn, num, c.eps, c.eps_lo, t) && t < dist) { k.pln += s.np - (i + 1); k.tri += s.nt; return true; }
+        if (planes == 2) { // origin in the light's room: general planes only
+            NT_X(k, xpln, s.ngen);
+#pragma unroll 1
+            for (unsigned j = 0; !LEAN && j < s.ngen; ++j) {
+                int idx;
+                asm volatile("ld.shared.s32 %0, [%1];" : "=r"(idx) : "r"(c.gen_addr + 4u * j));
+                R q[4], dn, num;
+                c.ld_pln((unsigned)idx, q);
+                plane_eval<R>(q, 3, o, d, dn, num);
+                if (plane_finish<R>(dn, num, c.eps, c.eps_lo, t) && t < dist) { k.pln += s.np - ((unsigned)idx + 1); k.tri += s.nt; return true; }
+            }
+        } else {
+            NT_X(k, xpln, s.np); // an upper bound when an occluder ends the loop early
+            unsigned i = 0;
+            for (; i + 2 <= s.np; i += 2) {
+                R q0[4], q1[4], dn0, num0, dn1, num1;
+                c.ld_pln(i, q0);
+                c.ld_pln(i + 1, q1);
+                plane_eval<R>(q0, 3, o, d, dn0, num0);
+                plane_eval<R>(q1, 3, o, d, dn1, num1);
+                if (plane_finish<R>(dn0, num0, c.eps, c.eps_lo, t) && t < dist) { k.pln += s.np - (i + 1); k.tri += s.nt; return true; }
+                if (plane_finish<R>(dn1, num1, c.eps, c.eps_lo, t) && t < dist) { k.pln += s.np - (i + 2); k.tri += s.nt; return true; }
+            }
+            if (i < s.np) {
+                R q[4], dn, num;
+                c.ld_pln(i, q);
+                plane_eval<R>(q, 3, o, d, dn, num);
+                if (plane_finish<R>(dn, num, c.eps, c.eps_lo, t) && t < dist) { k.pln += s.np - (i + 1); k.tri += s.nt; return true; }
+            }
         }
     }
     if constexpr (BVH) k.pln += s.np;
-    if constexpr (!BVH) {
+    if constexpr (!BVH && !LEAN) {
         if (s.nt) { // uniform
             unsigned long long m = s.ns >= 64 ? 0ull : mask >> s.ns;
             while (m) {
@@ -673,8 +861,8 @@ __device__ __forceinline__ bool occluded(const Ctx<R, BVH> &c, const V3<R> &o, c
 // -2 primary ray (mask = *pmask), -1 no culling information (all bounded primitives), >= 0 the ray starts on
 // that sphere (see nearest_hit).  Kept as ONE register instead of a live 64-bit mask: the kernel is register-bound.
 // RULES: the instantiation that honours the rule switches of SPEC §8 (c.rules); the default kernel compiles them out.
-template <typename R, bool BVH, typename K, bool RULES = false>
-__device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R> d, R *accp, R *Wp, const unsigned long long *pmask,
+template <typename R, bool BVH, typename K, bool RULES = false, bool LEAN = false>
+__device__ __forceinline__ void trace_sample(const Ctx<R, BVH, LEAN> &c, V3<R> o, V3<R> d, R *accp, R *Wp, const unsigned long long *pmask,
                                              K &k) {
     const NtDevScene &s = *c.s;
     const NtSceneView<R> &v = *c.v;
@@ -708,10 +896,12 @@ __device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R
                 c.ld_pln(h.idx, q);
                 Ng = { q[0], q[1], q[2] };
                 mat = __ldg(s.pln_mat + h.idx);
-            } else {
+            } else if constexpr (!LEAN) {
                 const R *tp = v.tri + (size_t)h.idx * NT_TRI_STRIDE + 9;
                 Ng = { __ldg(tp), __ldg(tp + 1), __ldg(tp + 2) };
                 mat = __ldg(s.tri_mat + h.idx);
+            } else {
+                Ng = { R(0), R(0), R(0) }; mat = 0; // not reachable: a LEAN launch has no triangles
             }
             // material rows are re-read where they are used (128-bit __ldg, L1 hits) instead of being kept
             // live across the occlusion queries: the kernel is register-bound
@@ -731,13 +921,18 @@ __device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R
                 const R *lp = v.lights + 6 * l;
                 const V3<R> Lv = { __ldg(lp) - P.x, __ldg(lp + 1) - P.y, __ldg(lp + 2) - P.z };
                 const R d2 = dot(Lv, Lv);
-                const R dist = Math<R>::sqrt_(d2);
-                const V3<R> L = scale(Lv, Math<R>::rcp(dist));
+                R dist, inv_dist;
+                Math<R>::len_inv(d2, dist, inv_dist);
+                const V3<R> L = scale(Lv, inv_dist);
                 const R ndl = dot(N, L);
                 if (!(ndl > R(0))) continue;
                 k.shadow++;
                 const unsigned long long lmask = s.cull ? lbuf_mask<R>(s, l, Lv) : s.all_bits;
-                const bool planes = sizeof(R) == 4 || h.kind == 1 || !((s.lfree >> l) & 1u); // strict mode only: see nt_cull.h
+                int planes = 1; // strict mode only: 0 = plane-free light (nt_cull.h); both modes: 2 = origin in the light's room
+                if constexpr (sizeof(R) == 8) planes = h.kind == 1 || !((s.lfree >> l) & 1u);
+                if constexpr (!BVH) {
+                    if (planes && s.rooms && in_light_room<R>(c, l, P, dist)) planes = 2;
+                }
                 if (occluded<R, BVH, K>(c, P, L, dist, lmask, planes, k)) continue;
                 k.light++;
                 R m0[4], m1[4];
@@ -823,8 +1018,8 @@ __device__ __forceinline__ void trace_sample(const Ctx<R, BVH> &c, V3<R> o, V3<R
 // ---- block-level plumbing ----
 
 // Stage the flat intersection data in shared memory with 128-bit loads.
-template <typename R, bool BVH>
-__device__ __forceinline__ void stage_scene(const NtDevScene &s, const NtSceneView<R> &v, Ctx<R, BVH> &c) {
+template <typename R, bool BVH, bool LEAN>
+__device__ __forceinline__ void stage_scene(const NtDevScene &s, const NtSceneView<R> &v, Ctx<R, BVH, LEAN> &c) {
     const unsigned n_sph = BVH ? 0u : s.ns * 4, n_pln = s.np * 4, n_tri = BVH ? 0u : s.nt * NT_TRI_STRIDE;
     R *smem = (R *)nt_smem;
     constexpr int VEC = 16 / sizeof(R);
@@ -848,6 +1043,17 @@ __device__ __forceinline__ void stage_scene(const NtDevScene &s, const NtSceneVi
         for (unsigned i = threadIdx.x; i < n_ax; i += blockDim.x) smem[n_sph + n_pln + n_tri + i] = __ldg(axl + i);
         int *gen = (int *)(smem + n_sph + n_pln + n_tri + n_ax);
         for (unsigned i = threadIdx.x; i < s.ngen; i += blockDim.x) gen[i] = __ldg(s.pgen + i);
+        // light rooms [nl][8] (slot 6 becomes this launch's distance cap min(eps * cap_per_eps, cap_max)), slab entries [3][2][2]
+        R *room = (R *)(gen + ((s.ngen + 3u) & ~3u));
+        const R *rsrc = (const R *)(sizeof(R) == 8 ? (const void *)s.room64 : (const void *)s.room32);
+        const R *asrc = (const R *)(sizeof(R) == 8 ? (const void *)s.axs64 : (const void *)s.axs32);
+        const unsigned n_room = s.rooms ? 8u * s.nl : 0u;
+        for (unsigned i = threadIdx.x; i < n_room; i += blockDim.x) {
+            R v = __ldg(rsrc + i);
+            if ((i & 7u) == 6u) { const R cap = c.eps * v, cmax = __ldg(rsrc + i + 1); v = cap < cmax ? cap : cmax; }
+            room[i] = v;
+        }
+        for (unsigned i = threadIdx.x; i < 12u; i += blockDim.x) room[n_room + i] = __ldg(asrc + i);
     }
     __syncthreads();
     unsigned base = (unsigned)__cvta_generic_to_shared(nt_smem);
@@ -904,14 +1110,14 @@ __device__ __forceinline__ void flush_counters(const CountersX &k, unsigned long
 // 4 blocks (64 registers) for whole frames, NT_MIN_BLOCKS_SMALL = 3 (80 registers, fewer spills, less contention per
 // scheduler) for small launches - a 1/8-frame shard of an 8-GPU render is bound by the latency of its deepest tiles, not
 // by throughput, and measured 0.153 ms against 0.166 (a whole frame: 0.831 against 0.810; profiles/r02a_ab_patches.txt).
-template <typename R, bool BVH, bool SINGLE, bool EXEC = false, int MINB = 0, bool RULES = false>
+template <typename R, bool BVH, bool SINGLE, bool EXEC = false, int MINB = 0, bool RULES = false, bool LEAN = false>
 __global__ void __launch_bounds__(NT_BLOCK_THREADS, MINB ? MINB : (sizeof(R) == 8 ? NT_MIN_BLOCKS_F64 : NT_MIN_BLOCKS_F32))
 render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRenderArgs a) {
     __shared__ unsigned long long s_cnt[NT_NCOUNTERS];
     __shared__ R s_state[4][NT_BLOCK_THREADS]; // acc r g b, W
     __shared__ unsigned long long s_pmask[NT_BLOCK_THREADS / 32]; // per warp: primary-ray candidates of its tile
     const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
-    Ctx<R, BVH> c;
+    Ctx<R, BVH, LEAN> c;
     c.s = &s; c.v = &v; c.eps = (R)a.eps; c.eps_lo = (R)a.eps_lo; c.max_depth = a.max_depth; c.rules = a.rules;
     frame_sync_begin(a); // multi-GPU exchange: acknowledge / wait before the first pixel store (the barrier in stage_scene orders it)
     stage_scene<R, BVH>(s, v, c);
@@ -958,10 +1164,12 @@ render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRe
                     const V3<R> D = { ((R)a.cam[3] + (R)a.cam[6] * fx) + (R)a.cam[9] * fy,
                                       ((R)a.cam[4] + (R)a.cam[7] * fx) + (R)a.cam[10] * fy,
                                       ((R)a.cam[5] + (R)a.cam[8] * fx) + (R)a.cam[11] * fy };
-                    const V3<R> dir = scale(D, Math<R>::rcp(Math<R>::sqrt_(dot(D, D))));
+                    R dlen, dinv;
+                    Math<R>::len_inv(dot(D, D), dlen, dinv);
+                    const V3<R> dir = scale(D, dinv);
                     const V3<R> eye = { (R)a.cam[0], (R)a.cam[1], (R)a.cam[2] };
                     k.prim++;
-                    trace_sample<R, BVH, KT, RULES>(c, eye, dir, accp, Wp, &s_pmask[tid >> 5], k);
+                    trace_sample<R, BVH, KT, RULES, LEAN>(c, eye, dir, accp, Wp, &s_pmask[tid >> 5], k);
                 }
             }
             asm volatile("" : "+r"(tile)); // pixel coordinates are recomputed below, not carried across the trace
@@ -1049,6 +1257,7 @@ inline size_t flat_smem_bytes(const NtDevScene &s, bool bvh) {
     if (bvh) return n * sizeof(R) + (size_t)((((s.np + 15) / 16) + 3) & ~3u) * sizeof(unsigned);
     n += (size_t)s.ns * 4 + (size_t)s.nt * NT_TRI_STRIDE;
     n += 2 * ((size_t)s.nax[0] + s.nax[1] + s.nax[2]);          // axis-aligned plane lists
+    n += (s.rooms ? 8 * (size_t)s.nl : 0) + 12;                  // light rooms, slab entries
     return n * sizeof(R) + (((size_t)s.ngen + 3) & ~(size_t)3) * sizeof(int);
 }
 
@@ -1106,13 +1315,18 @@ inline int launch_render_t(const NtDevScene &s, const NtRenderArgs &a, cudaStrea
     if constexpr (!BVH) {
         // fewer than NT_SMALL_TILES_PER_WARP warp tiles per resident warp: the small-launch variant (NT_SMALL_LAUNCH=0 / 1
         // forces the choice, A/B)
+        bool lean = s.nt == 0 && s.ngen == 0;
+        if (const char *e = getenv("NT_LEAN")) if (e[0] == '0') lean = false; // A/B, tests
         bool small = MINB_SMALL != 0 && !a.count_executed && !a.rules && n_tiles < (unsigned)NT_SMALL_TILES_PER_WARP * (unsigned)(sms[dev] * blocks_per_sm[dev]) * wpb;
         if (const char *e = getenv("NT_SMALL_LAUNCH")) small = MINB_SMALL != 0 && !a.count_executed && !a.rules && e[0] == '1';
         if constexpr (MINB_SMALL != 0) {
             if (small) {
                 grid = (unsigned)(sms[dev] * blocks_small[dev]);
                 if (grid > (n_tiles + wpb - 1) / wpb) grid = (n_tiles + wpb - 1) / wpb;
-                if (a.spp == a.lanes) render_kernel<R, false, true, false, MINB_SMALL><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
+                if (lean) {
+                    if (a.spp == a.lanes) render_kernel<R, false, true, false, MINB_SMALL, false, true><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
+                    else render_kernel<R, false, false, false, MINB_SMALL, false, true><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
+                } else if (a.spp == a.lanes) render_kernel<R, false, true, false, MINB_SMALL><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
                 else render_kernel<R, false, false, false, MINB_SMALL><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
                 if (a.n_launches) *a.n_launches += 1;
                 return (int)cudaGetLastError();
@@ -1124,6 +1338,9 @@ inline int launch_render_t(const NtDevScene &s, const NtRenderArgs &a, cudaStrea
         } else if (a.count_executed) { // instrumented twin (nt_render_params.flags & NT_RENDER_COUNT_EXECUTED): measurement only
             if (a.spp == a.lanes) render_kernel<R, false, true, true><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
             else render_kernel<R, false, false, true><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
+        } else if (lean) { // neither triangles nor general planes: the specialisation without their loops
+            if (a.spp == a.lanes) render_kernel<R, false, true, false, 0, false, true><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
+            else render_kernel<R, false, false, false, 0, false, true><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
         } else if (a.spp == a.lanes) render_kernel<R, false, true><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
         else render_kernel<R, false, false><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);
         if (a.n_launches) *a.n_launches += 1;

@@ -1,5 +1,6 @@
 """A/B timing of library variants (development aid): python scripts/gpu_ab.py [name ...]
-Each name is nettracer_b200/variants/libnt_<name>.so ("main" = the shipped library).  Prints, per variant and
+Each name is nettracer_b200/variants/libnt_<name>.so ("main" = the shipped library), optionally followed by
+":ENV=VALUE,ENV=VALUE" (environment switches read at scene creation / launch, e.g. main:NT_SLAB=0).  Prints, per variant and
 precision, the median / min kernel time of configs[2] over 40 frames, the 1/8-frame time, an image hash and the ray
 count (variants must agree bit for bit)."""
 import hashlib
@@ -30,9 +31,13 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
                   f"sha {hashlib.sha1(np.ascontiguousarray(img).tobytes()).hexdigest()[:12]}", flush=True)
     sys.exit(0)
 
-for name in sys.argv[1:] or ["main"]:
+for spec in sys.argv[1:] or ["main"]:
+    name, _, envs = spec.partition(":")
     env = dict(os.environ)
+    for kv in filter(None, envs.split(",")):
+        key, _, val = kv.partition("=")
+        env[key] = val
     if name != "main":
         env["NT_LIB_PATH"] = os.path.abspath(f"nettracer_b200/variants/libnt_{name}.so")
-    print(name, flush=True)
+    print(spec, flush=True)
     subprocess.run([sys.executable, __file__, "--child"], env=env, check=False)
