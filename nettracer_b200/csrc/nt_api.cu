@@ -538,6 +538,9 @@ static int make_args(const nt_render_params *p, size_t stride, NtRenderArgs *a) 
     const double half = (p->flags & NT_RULE_SAMPLE_CORNER) ? 0.0 : 0.5; // SPEC-PROVISIONAL section 8
     for (uint32_t i = 0; i < n; ++i) a->samp_off[i] = ((double)i + half) / (double)n;
     a->inv_spp = 1.0 / (double)p->spp;
+    for (int k = 0; k < 12; ++k) a->camf[k] = (float)a->cam[k];
+    for (int k = 0; k < 8; ++k) a->samp_off_f[k] = (float)a->samp_off[k];
+    a->inv_spp_f = (float)a->inv_spp;
     return NT_OK;
 }
 

@@ -437,12 +437,12 @@ render_bvh_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ 
                     if (m.live) {
                         // SPEC §2: regular n x n grid
                         const unsigned si = m.sidx % a.n, sj = m.sidx / a.n;
-                        const R ox = (R)a.samp_off[si], oy = (R)a.samp_off[sj]; // (i + 0.5) / n (or i / n, SPEC §8), divided on the host
+                        const R ox = ArgsView<R>::samp_off(a, si), oy = ArgsView<R>::samp_off(a, sj); // (i + 0.5) / n (or i / n, SPEC §8), divided on the host
                         const R fx = (R)m.px + ox, fy = (R)m.y + oy;
-                        const V3<R> D = { ((R)a.cam[3] + (R)a.cam[6] * fx) + (R)a.cam[9] * fy,
-                                          ((R)a.cam[4] + (R)a.cam[7] * fx) + (R)a.cam[10] * fy,
-                                          ((R)a.cam[5] + (R)a.cam[8] * fx) + (R)a.cam[11] * fy };
-                        const V3<R> eye = { (R)a.cam[0], (R)a.cam[1], (R)a.cam[2] };
+                        const V3<R> D = { (ArgsView<R>::cam(a, 3) + ArgsView<R>::cam(a, 6) * fx) + ArgsView<R>::cam(a, 9) * fy,
+                                          (ArgsView<R>::cam(a, 4) + ArgsView<R>::cam(a, 7) * fx) + ArgsView<R>::cam(a, 10) * fy,
+                                          (ArgsView<R>::cam(a, 5) + ArgsView<R>::cam(a, 8) * fx) + ArgsView<R>::cam(a, 11) * fy };
+                        const V3<R> eye = { ArgsView<R>::cam(a, 0), ArgsView<R>::cam(a, 1), ArgsView<R>::cam(a, 2) };
                         ln.d = scale(D, Math<R>::rcp(Math<R>::sqrt_(dot(D, D))));
                         ln.sid = (unsigned)sid; ln.W = R(1); ln.depth = 1; ln.sp = 0; ln.phase = 0; ln.active = true;
                         ln.acc[0] = ln.acc[1] = ln.acc[2] = R(0);

@@ -124,6 +124,8 @@ struct NtRenderArgs {
     double cam[12];    // eye p00 dx dy
     double samp_off[8]; // SPEC §2 sample offsets (i + 0.5) / n, i < n
     double inv_spp;     // 1 / spp
+    float camf[12], samp_off_f[8], inv_spp_f; // the same values rounded to binary32 on the host: the fast kernels paid a
+                                              // conversion (F2F + flush test, 3 instructions on the XU / FP64 pipes) per use
     alignas(8) uint16_t prect[64][4]; // flat scenes with culling: pixel rectangle x0 x1 y0 y1 of every bounded primitive (nt_cull.h)
     // division-free tile arithmetic (nt_trace.cuh tile_origin / row_to_y): twx, twy, lanes are powers of two
     uint32_t log2_twx, log2_twy, log2_lanes;
@@ -146,6 +148,24 @@ struct NtRenderArgs {
     unsigned sync_post_val, sync_wait_val, sync_done_val;
     uint32_t count_executed;        // flat scenes: launch the instrumented kernel (CountersX)
     uint32_t rules;                 // NT_DEV_RULE_* bits (SPEC-PROVISIONAL section 8); 0 = the default rules
+};
+
+// per-precision view of the camera / sample arguments (constant bank)
+#ifdef __CUDACC__
+#define NT_HD __host__ __device__
+#else
+#define NT_HD
+#endif
+template <typename R> struct ArgsView;
+template <> struct ArgsView<double> {
+    static NT_HD inline double cam(const NtRenderArgs &a, int i) { return a.cam[i]; }
+    static NT_HD inline double samp_off(const NtRenderArgs &a, unsigned i) { return a.samp_off[i]; }
+    static NT_HD inline double inv_spp(const NtRenderArgs &a) { return a.inv_spp; }
+};
+template <> struct ArgsView<float> {
+    static NT_HD inline float cam(const NtRenderArgs &a, int i) { return a.camf[i]; }
+    static NT_HD inline float samp_off(const NtRenderArgs &a, unsigned i) { return a.samp_off_f[i]; }
+    static NT_HD inline float inv_spp(const NtRenderArgs &a) { return a.inv_spp_f; }
 };
 
 struct NtTraceArgs {

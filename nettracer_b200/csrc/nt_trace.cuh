@@ -668,7 +668,7 @@ __device__ __forceinline__ void planes_nearest_slab32(const Ctx<float, false, LE
     for (int k = 0; k < 3; ++k) {
         float q[4];
         Ld<float>::s4(c.sph_addr + c.s->axs_off[0] + 16u * k, q); // p0 p1 i0 i1
-        const float inv = __frcp_rn(dd[k]), nok = -oo[k];
+        const float inv = __fdividef(1.0f, dd[k]), nok = -oo[k];
         const float2 t = __fmul2_rn(__fadd2_rn(make_float2(q[0], q[1]), make_float2(nok, nok)), make_float2(inv, inv));
         const float t0 = t.x > c.eps ? t.x : CUDART_INF_F, t1 = t.y > c.eps ? t.y : CUDART_INF_F;
         if (t0 < tb) { tb = t0; wi = __float_as_int(q[2]); }
@@ -1159,15 +1159,15 @@ render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRe
                     // SPEC §2: regular n x n grid, sample s = r*L + j
                     const unsigned sidx = r * L + j;
                     const unsigned sj = (sidx * a.n_mul) >> 16, si = sidx - sj * a.n; // sidx / n, sidx % n (sidx < 64, n <= 8)
-                    const R ox = (R)a.samp_off[si], oy = (R)a.samp_off[sj]; // (i + 0.5) / n, divided on the host (IEEE, same value)
+                    const R ox = ArgsView<R>::samp_off(a, si), oy = ArgsView<R>::samp_off(a, sj); // (i + 0.5) / n, divided on the host (IEEE, same value)
                     const R fx = (R)px + ox, fy = (R)y + oy;
-                    const V3<R> D = { ((R)a.cam[3] + (R)a.cam[6] * fx) + (R)a.cam[9] * fy,
-                                      ((R)a.cam[4] + (R)a.cam[7] * fx) + (R)a.cam[10] * fy,
-                                      ((R)a.cam[5] + (R)a.cam[8] * fx) + (R)a.cam[11] * fy };
+                    const V3<R> D = { (ArgsView<R>::cam(a, 3) + ArgsView<R>::cam(a, 6) * fx) + ArgsView<R>::cam(a, 9) * fy,
+                                      (ArgsView<R>::cam(a, 4) + ArgsView<R>::cam(a, 7) * fx) + ArgsView<R>::cam(a, 10) * fy,
+                                      (ArgsView<R>::cam(a, 5) + ArgsView<R>::cam(a, 8) * fx) + ArgsView<R>::cam(a, 11) * fy };
                     R dlen, dinv;
                     Math<R>::len_inv(dot(D, D), dlen, dinv);
                     const V3<R> dir = scale(D, dinv);
-                    const V3<R> eye = { (R)a.cam[0], (R)a.cam[1], (R)a.cam[2] };
+                    const V3<R> eye = { ArgsView<R>::cam(a, 0), ArgsView<R>::cam(a, 1), ArgsView<R>::cam(a, 2) };
                     k.prim++;
                     trace_sample<R, BVH, KT, RULES, LEAN>(c, eye, dir, accp, Wp, &s_pmask[tid >> 5], k);
                 }
@@ -1199,7 +1199,7 @@ render_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRe
             vr += pw >> a.log2_twx;
             if (px < a.width && vr < a.vrows && j == 0) {
                 const unsigned y = row_to_y(a, vr);
-                const R inv_spp = (R)a.inv_spp; // 1 / spp, divided on the host
+                const R inv_spp = ArgsView<R>::inv_spp(a); // 1 / spp, divided on the host
                 unsigned rgba = 0xff000000u;
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {

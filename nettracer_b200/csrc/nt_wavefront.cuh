@@ -89,12 +89,12 @@ __device__ __forceinline__ bool wf_ray(const NtRenderArgs &a, const NtWfArgs &w,
         const SampleMap m = map_sample(a, w.sid0 + rec);
         if (!m.live) return false;
         const unsigned si = m.sidx % a.n, sj = m.sidx / a.n;
-        const R ox = (R)a.samp_off[si], oy = (R)a.samp_off[sj]; // (i + 0.5) / n (or i / n, SPEC §8), divided on the host
+        const R ox = ArgsView<R>::samp_off(a, si), oy = ArgsView<R>::samp_off(a, sj); // (i + 0.5) / n (or i / n, SPEC §8), divided on the host
         const R fx = (R)m.px + ox, fy = (R)m.y + oy;
-        const V3<R> D = { ((R)a.cam[3] + (R)a.cam[6] * fx) + (R)a.cam[9] * fy,
-                          ((R)a.cam[4] + (R)a.cam[7] * fx) + (R)a.cam[10] * fy,
-                          ((R)a.cam[5] + (R)a.cam[8] * fx) + (R)a.cam[11] * fy };
-        o = { (R)a.cam[0], (R)a.cam[1], (R)a.cam[2] };
+        const V3<R> D = { (ArgsView<R>::cam(a, 3) + ArgsView<R>::cam(a, 6) * fx) + ArgsView<R>::cam(a, 9) * fy,
+                          (ArgsView<R>::cam(a, 4) + ArgsView<R>::cam(a, 7) * fx) + ArgsView<R>::cam(a, 10) * fy,
+                          (ArgsView<R>::cam(a, 5) + ArgsView<R>::cam(a, 8) * fx) + ArgsView<R>::cam(a, 11) * fy };
+        o = { ArgsView<R>::cam(a, 0), ArgsView<R>::cam(a, 1), ArgsView<R>::cam(a, 2) };
         d = scale(D, Math<R>::rcp(Math<R>::sqrt_(dot(D, D))));
         W = R(1);
         return true;
