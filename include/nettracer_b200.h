@@ -149,6 +149,13 @@ int nt_primary_rects(const nt_scene_desc *desc, const nt_render_params *params, 
  * then skip the planes).  Same eligibility as nt_cull_tables. */
 int nt_plane_free_lights(const nt_scene_desc *desc, uint32_t *mask_out);
 
+/* Diagnostic, host only: the "light rooms" nt_scene_create derives for a flat scene (nettracer_b200/csrc/nt_cull.h
+ * nt_cull_light_rooms).  rooms_out[n_lights][8] = { lo_x, hi_x, lo_y, hi_y, lo_z, hi_z, cap_per_eps, cap_max }: a shadow
+ * query towards light l whose origin P has lo_k <= P_k <= hi_k on every axis and whose light distance is <= min(ray_epsilon
+ * * cap_per_eps, cap_max) cannot be stopped by a plane with a normal of exactly +-e_k, and skips those planes.  Works for
+ * any scene (a light without a room gets an empty box); NT_ERR_INVALID for NULL arguments. */
+int nt_light_rooms(const nt_scene_desc *desc, double *rooms_out);
+
 /* ---- render ---- */
 /* Host buffer (pageable or pinned), blocking.  Renders the shard named in params, copies the
  * result to rgba_out.  stats may be NULL. */

@@ -444,6 +444,15 @@ extern "C" int nt_primary_rects(const nt_scene_desc *desc, const nt_render_param
     return NT_OK;
 }
 
+extern "C" int nt_light_rooms(const nt_scene_desc *desc, double *rooms_out) {
+    int rc = validate_desc(desc);
+    if (rc) return rc;
+    if (!rooms_out) return fail(NT_ERR_INVALID, "rooms_out is NULL");
+    std::vector<float> f32(8 * (size_t)desc->n_lights + 8);
+    nt_cull_light_rooms(desc->planes, desc->n_planes, desc->lights, desc->n_lights, rooms_out, f32.data());
+    return NT_OK;
+}
+
 extern "C" int nt_plane_free_lights(const nt_scene_desc *desc, uint32_t *mask_out) {
     int rc = validate_desc(desc);
     if (rc) return rc;

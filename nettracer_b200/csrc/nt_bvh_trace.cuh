@@ -134,18 +134,28 @@ __device__ __forceinline__ void query_inner_step(const Ctx<R, true> &c, BvhQuery
     const float4 fx = __ldg(n + (3 - q.nearx)), fy = __ldg(n + (5 - q.neary)), fz = __ldg(n + (7 - q.nearz));
     const int4 rf = __ldg((const int4 *)(n + 6));
     k.box += 4;
-    const float nxa[4] = { nx.x, nx.y, nx.z, nx.w }, nya[4] = { ny.x, ny.y, ny.z, ny.w }, nza[4] = { nz.x, nz.y, nz.z, nz.w };
-    const float fxa[4] = { fx.x, fx.y, fx.z, fx.w }, fya[4] = { fy.x, fy.y, fy.z, fy.w }, fza[4] = { fz.x, fz.y, fz.z, fz.w };
+    // The 24 slab products as 12 packed binary32 FMAs (sm_100 fma.rn.f32x2): children (0, 1) and (2, 3) of one plane
+    // sit in an aligned register pair of its 128-bit load, the ray's reciprocal direction and plane offset are scalar
+    // operands broadcast to both halves (SASS: FFMA2 R, R.F32x2.HI_LO, R.F32, -R.F32).  Entry = max3 + max, exit =
+    // min3 + min with the query's bound folded in, so that one comparison decides; an empty slot holds an inverted
+    // infinite box (both builders) and fails it without looking at its ref.
+    const float2 ix = make_float2(q.ix, q.ix), iy = make_float2(q.iy, q.iy), iz = make_float2(q.iz, q.iz);
+    const float2 cnx = make_float2(-q.cnx, -q.cnx), cny = make_float2(-q.cny, -q.cny), cnz = make_float2(-q.cnz, -q.cnz);
+    const float2 cfx = make_float2(-q.cfx, -q.cfx), cfy = make_float2(-q.cfy, -q.cfy), cfz = make_float2(-q.cfz, -q.cfz);
+    const float2 ax[2] = { __ffma2_rn(make_float2(nx.x, nx.y), ix, cnx), __ffma2_rn(make_float2(nx.z, nx.w), ix, cnx) };
+    const float2 ay[2] = { __ffma2_rn(make_float2(ny.x, ny.y), iy, cny), __ffma2_rn(make_float2(ny.z, ny.w), iy, cny) };
+    const float2 az[2] = { __ffma2_rn(make_float2(nz.x, nz.y), iz, cnz), __ffma2_rn(make_float2(nz.z, nz.w), iz, cnz) };
+    const float2 bx[2] = { __ffma2_rn(make_float2(fx.x, fx.y), ix, cfx), __ffma2_rn(make_float2(fx.z, fx.w), ix, cfx) };
+    const float2 by[2] = { __ffma2_rn(make_float2(fy.x, fy.y), iy, cfy), __ffma2_rn(make_float2(fy.z, fy.w), iy, cfy) };
+    const float2 bz[2] = { __ffma2_rn(make_float2(fz.x, fz.y), iz, cfz), __ffma2_rn(make_float2(fz.z, fz.w), iz, cfz) };
     const int ra[4] = { rf.x, rf.y, rf.z, rf.w };
     int key[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float tn = fmaxf(fmaxf(__fmaf_rn(nxa[j], q.ix, -q.cnx), __fmaf_rn(nya[j], q.iy, -q.cny)),
-                               fmaxf(__fmaf_rn(nza[j], q.iz, -q.cnz), 0.0f));
-        const float tf = fminf(fminf(__fmaf_rn(fxa[j], q.ix, -q.cfx), __fmaf_rn(fya[j], q.iy, -q.cfy)),
-                               __fmaf_rn(fza[j], q.iz, -q.cfz));
-        const bool hit = ra[j] != NT_REF_EMPTY && tn <= tf && tn <= q.tmaxf;
-        key[j] = hit ? ((__float_as_int(tn) & ~3) | j) : 0x7fffffff; // tn >= 0: integer order == float order
+        const int h = j >> 1;
+        const float tn = fmaxf(fmaxf(j & 1 ? ax[h].y : ax[h].x, j & 1 ? ay[h].y : ay[h].x), fmaxf(j & 1 ? az[h].y : az[h].x, 0.0f));
+        const float tf = fminf(fminf(j & 1 ? bx[h].y : bx[h].x, j & 1 ? by[h].y : by[h].x), fminf(j & 1 ? bz[h].y : bz[h].x, q.tmaxf));
+        key[j] = tn <= tf ? ((__float_as_int(tn) & ~3) | j) : 0x7fffffff; // tn >= 0: integer order == float order
     }
     // Next = the nearest hit child; the other hit children are pushed in slot order with their entry distance
     // (a pop discards entries that start beyond the current bound).  A full sort of the four keys (the first

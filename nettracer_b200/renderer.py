@@ -123,6 +123,16 @@ def plane_free_lights(scene: Scene) -> int:
     return int(m.value)
 
 
+def light_rooms(scene: Scene) -> np.ndarray:
+    """Per light the axis-aligned room [lo_x, hi_x, lo_y, hi_y, lo_z, hi_z, cap_per_eps, cap_max] inside which a shadow
+    query skips the axis-aligned planes (nt_light_rooms: host only).  float64 [n_lights, 8]."""
+    desc, keep = scene.to_desc()
+    out = np.zeros((max(desc.n_lights, 1), 8), dtype=np.float64)
+    check(load().nt_light_rooms(C.byref(desc), out.ctypes.data))
+    del keep
+    return out[:desc.n_lights]
+
+
 def measure_peaks(device=0) -> dict:
     p = abi.nt_peaks()
     check(load().nt_measure_peaks(int(device), C.byref(p)))

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from nettracer_b200 import scenes
-from nettracer_b200.renderer import cull_tables, plane_free_lights, primary_rects
+from nettracer_b200.renderer import cull_tables, light_rooms, plane_free_lights, primary_rects
 from nettracer_b200.scene import Camera, Material, Scene, make_params
 
 EPS = 1e-6
@@ -400,3 +400,102 @@ def test_diagnostic_entry_points_refuse_ineligible_scenes_and_bad_arguments():
             primary_rects(sc, p)
         with pytest.raises(NetTracerError):
             plane_free_lights(sc)
+
+
+def _axis_plane_occludes_exact(P, light, planes, eps):
+    """SPEC §3 / §4 in their exact operation order (binary64, no FMA): shadow ray from P towards the light; does any plane
+    with a normal of exactly +-e_k give eps < t < dist?"""
+    Lv = light[:3] - P
+    d2 = (Lv[:, 0] * Lv[:, 0] + Lv[:, 1] * Lv[:, 1]) + Lv[:, 2] * Lv[:, 2]
+    dist = np.sqrt(d2)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv = 1.0 / dist
+        L = Lv * inv[:, None]
+        occ = np.zeros(len(P), dtype=bool)
+        for pl in planes:
+            n = pl[:3]
+            if not (np.abs(n).max() == 1.0 and np.count_nonzero(n) == 1):
+                continue
+            dn = (n[0] * L[:, 0] + n[1] * L[:, 1]) + n[2] * L[:, 2]
+            num = pl[3] - ((n[0] * P[:, 0] + n[1] * P[:, 1]) + n[2] * P[:, 2])
+            t = num / dn
+            occ |= (dn != 0) & (t > eps) & (t < dist)
+    return occ, dist
+
+
+def _room_samples(room, light, rng, n):
+    """Points that stress the room test: uniform inside, exactly on every face, within a few ulps and within the dilation
+    of every face (both sides), far away along the faces, next to the light."""
+    lo, hi = room[0:6:2].copy(), room[1:6:2].copy()
+    span = np.where(np.isfinite(hi - lo), hi - lo, 50.0)
+    lo_f = np.where(np.isfinite(lo), lo, light[:3] - 25.0)
+    hi_f = np.where(np.isfinite(hi), hi, light[:3] + 25.0)
+    P = lo_f + (hi_f - lo_f) * rng.random((n, 3))
+    out = [P, light[:3] + rng.normal(size=(n // 4, 3)) * 1e-3]
+    for k in range(3):
+        for face in (lo[k], hi[k]):
+            if not np.isfinite(face):
+                continue
+            for off in (0.0, 1e-16, -1e-16, 3e-15, -3e-15, 1e-12, -1e-12, 1e-10 * span[k], -1e-10 * span[k], 1e-9, -1e-9, 1e-7, -1e-7):
+                Q = lo_f + (hi_f - lo_f) * rng.random((n // 8, 3))
+                Q[:, k] = face + off
+                out.append(Q)
+                R_ = Q.copy()  # grazing: far along the face, so that the direction component towards the plane is tiny
+                R_[:, (k + 1) % 3] = light[(k + 1) % 3] + rng.choice([-1, 1], n // 8) * 10.0 ** rng.uniform(0, 4, n // 8)
+                out.append(R_)
+    return np.concatenate(out)
+
+
+@pytest.mark.parametrize("eps", [1e-6, 1e-7, 1e-3, 1e-9])
+def test_light_rooms_are_conservative(eps):
+    """nt_light_rooms: whenever the kernel's test passes (P inside the box, dist <= min(eps * cap_per_eps, cap_max)) the
+    exact rule must not find an axis-aligned plane between P and the light - the Cornell box, rooms with lights near a
+    wall, open rooms (missing walls), several planes per axis, lights outside the box and lights ON a plane."""
+    rng = np.random.default_rng(5)
+    cases = [scenes.cornell_box()[0]]
+    for _ in range(40):
+        s = Scene()
+        m = s.add_material(Material())
+        for k in range(3):
+            for _j in range(int(rng.integers(0, 4))):
+                n = [0.0, 0.0, 0.0]
+                n[k] = float(rng.choice([-1.0, 1.0]))
+                s.add_plane(tuple(n), float(np.round(rng.uniform(-20, 20), int(rng.integers(0, 4)))), m)
+        if rng.random() < 0.3:
+            v = rng.normal(size=3)
+            s.add_plane(tuple(v / np.linalg.norm(v)), 30.0, m)  # a general plane: never part of a room
+        s.add_sphere((0, 0, 0), 1.0, m)
+        for _l in range(3):
+            lp = rng.uniform(-25, 25, size=3)
+            if rng.random() < 0.3 and len(s.planes):
+                pl = s.planes[int(rng.integers(len(s.planes)))]
+                k = int(np.argmax(np.abs(pl[:3])))
+                if abs(pl[k]) == 1.0:
+                    lp[k] = pl[k] * pl[3] + float(rng.choice([0.0, 1e-12, 1e-9, 1e-6, 1e-3, 0.5]))
+            s.add_light(tuple(lp))
+        cases.append(s)
+    passed = 0
+    for scene in cases:
+        a = scene.arrays()
+        rooms = light_rooms(scene)
+        assert rooms.shape == (len(a["lights"]), 8)
+        for l, light in enumerate(a["lights"]):
+            room = rooms[l]
+            P = _room_samples(room, light, rng, 4000)
+            occ, dist = _axis_plane_occludes_exact(P, light, a["planes"], eps)
+            cap = min(eps * room[6], room[7])
+            inside = ((P[:, 0] >= room[0]) & (P[:, 0] <= room[1]) & (P[:, 1] >= room[2]) & (P[:, 1] <= room[3]) &
+                      (P[:, 2] >= room[4]) & (P[:, 2] <= room[5]) & (dist <= cap))
+            assert not (inside & occ).any(), (l, light, room, P[inside & occ][:3])
+            passed += int(inside.sum())
+    assert passed > 100000, "the rooms must accept the bulk of the inside points, or the test proves nothing"
+
+
+def test_light_rooms_cornell_values():
+    scene = scenes.cornell_box()[0]
+    rooms = light_rooms(scene)
+    d = 16.0 * 2.0 ** -33
+    np.testing.assert_allclose(rooms[0, :6], [-6 - d, 6 + d, 0 - d, 10 + d, -8 - d, 16 + d], rtol=0, atol=1e-15)
+    assert rooms[0, 6] == pytest.approx(0.5 * 0.8 / d, rel=1e-12) and rooms[0, 7] == pytest.approx(0.8e12, rel=1e-12)
+    # hit points of a 1080p frame lie well inside the caps: the longest shadow ray of the box is ~18 units
+    assert 1e-6 * rooms[:, 6].min() > 30.0

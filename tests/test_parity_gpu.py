@@ -170,6 +170,75 @@ def test_plane_free_lights_off_equals_on(monkeypatch):
     assert_images_match(outs[0][1][0], ref, "eps 1e-9")
 
 
+def _room_scene(open_room):
+    """Axis-aligned room (closed, or with the ceiling and one wall missing and a tilted mirror wall instead), glass and
+    mirror spheres, one light near a wall and one OUTSIDE the room: shadow queries inside and outside the light rooms."""
+    from nettracer_b200.scene import Camera, Material, Scene
+    s = Scene(ambient=(1.0, 1.0, 1.0), background=(0.1, 0.1, 0.2))
+    wall = s.add_material(Material((0.7, 0.7, 0.6), ka=0.1, kd=0.8, ks=0.2, shininess=20.0, kr=0.15))
+    glass = s.add_material(Material((0.9, 0.95, 1.0), ka=0.0, kd=0.1, ks=0.4, shininess=90.0, kr=0.1, kt=0.8, ior=1.4))
+    mirror = s.add_material(Material((0.9, 0.9, 0.9), ka=0.05, kd=0.2, ks=0.5, shininess=60.0, kr=0.7))
+    s.add_plane((0, 1, 0), 0.0, wall)
+    s.add_plane((1, 0, 0), -5.0, wall)
+    s.add_plane((0, 0, 1), -7.0, wall)
+    s.add_plane((0, 0, -1), -9.0, wall)
+    if open_room:
+        n = np.array([-1.0, 0.2, 0.1])
+        n /= np.linalg.norm(n)
+        s.add_plane(tuple(n), -6.0, mirror)   # a general plane instead of the right wall; no ceiling
+    else:
+        s.add_plane((-1, 0, 0), -5.0, wall)
+        s.add_plane((0, -1, 0), -8.0, wall)
+    s.add_sphere((-1.5, 1.2, -1.0), 1.2, glass)
+    s.add_sphere((1.8, 1.0, 0.5), 1.0, mirror)
+    s.add_sphere((0.2, 0.6, 2.5), 0.6, glass)
+    s.add_light((-4.9, 7.5, 3.0), (0.6, 0.6, 0.55))      # 0.1 from the left wall
+    s.add_light((2.0, 12.0, -3.0), (0.4, 0.4, 0.45))     # above the ceiling of the closed room
+    return s, Camera(eye=(0.5, 3.5, 8.5), at=(0.0, 1.5, 0.0), up=(0, 1, 0), vfov_deg=55.0)
+
+
+@pytest.mark.parametrize("open_room", [False, True])
+def test_light_rooms_and_lean_kernel_equal_oracle(open_room, monkeypatch):
+    """Shadow queries from inside a light's room skip the axis-aligned planes (NT_LIGHT_ROOMS), and launches without
+    triangles / general planes use the kernel specialisation without their loops (NT_LEAN): every combination of the
+    two switches gives the oracle's image and counters, strict mode; the fast mode stays within its tolerance of the
+    strict image.  The closed room has a light outside it (its room test never passes), the open one a general plane."""
+    s, cam = _room_scene(open_room)
+    w, h = 256, 160
+    p = make_params(w, h, 4, 5, cam.resolve(w, h), abi.NT_F64_STRICT)
+    ref, rst = oracle.render(s, p)
+    imgs = []
+    for rooms in ("1", "0"):
+        for lean in ("1", "0"):
+            monkeypatch.setenv("NT_LIGHT_ROOMS", rooms)
+            monkeypatch.setenv("NT_LEAN", lean)
+            with Renderer(s) as r:
+                assert not r.info()["uses_bvh"]
+                img, st = r.render_params(p)
+                fast, _ = r.render_params(make_params(w, h, 4, 5, cam.resolve(w, h), abi.NT_F32_FAST))
+            assert_images_match(img, ref, f"rooms={rooms} lean={lean}")
+            for k in COUNTER_KEYS + FLAT_TEST_KEYS:
+                assert st[k] == rst[k], (k, rooms, lean)
+            d = np.abs(fast.astype(int) - ref.astype(int))[..., :3].max(axis=-1)
+            assert (d <= 2).mean() > 0.97, (rooms, lean, float((d <= 2).mean()))
+            imgs.append(fast)
+    assert np.array_equal(imgs[0], imgs[1]) and np.array_equal(imgs[2], imgs[3]), "NT_LEAN must not change the fast image"
+
+
+def test_fast_slab_planes_off_equals_on(monkeypatch):
+    """Fast mode: the packed slab form of the axis-aligned planes (NT_SLAB, rooms with at most two planes per axis)
+    against the plain plane loop: the same image up to the odd 1-LSB pixel (different rounding of t)."""
+    s, cam = scenes.cornell_box()
+    p = make_params(320, 180, 4, 5, cam.resolve(320, 180), abi.NT_F32_FAST)
+    with Renderer(s) as r:
+        a, _ = r.render_params(p)
+    monkeypatch.setenv("NT_SLAB", "0")
+    with Renderer(s) as r:
+        b, _ = r.render_params(p)
+    d = np.abs(a.astype(int) - b.astype(int))[..., :3].max(axis=-1)
+    assert (d <= 1).mean() > 0.999 and d.max() <= 8, (float((d <= 1).mean()), int(d.max()))
+
+
 @pytest.mark.parametrize("w,h,spp", [(33, 17, 1), (200, 75, 1), (37, 19, 4), (320, 180, 4), (50, 30, 16), (21, 13, 64)])
 def test_pinned_host_buffer_equals_pageable(w, h, spp):
     """nt_render stores straight into a PINNED caller buffer (zero copy over PCIe) with one-row warp tiles (32 / lanes
