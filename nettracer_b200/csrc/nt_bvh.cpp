@@ -292,7 +292,11 @@ void nt_bvh_build(const double *spheres, uint32_t ns, const double *triangles, u
     std::atomic<int> next_node{ 1 };
     Ref rs, rt;
     {
-        std::thread spheres_thread([&] { rs = build_set(out.nodes, next_node, sb, out.sph_order, 0, leaf_max); });
+        // spheres: their own leaf size (NT_BVH_LEAF_SPH; see nt_api.cu) - a leaf of several small scattered spheres is a box
+        // that is mostly empty, and every ray through it pays the exact sphere tests
+        int leaf_sph = 1;
+        if (const char *e = getenv("NT_BVH_LEAF_SPH")) leaf_sph = std::min(std::max(atoi(e), 1), NT_LEAF_MAX);
+        std::thread spheres_thread([&] { rs = build_set(out.nodes, next_node, sb, out.sph_order, 0, leaf_sph); });
         rt = build_set(out.nodes, next_node, tb, out.tri_order, 0x100, leaf_max);
         spheres_thread.join();
     }

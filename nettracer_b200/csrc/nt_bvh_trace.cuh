@@ -32,8 +32,8 @@ template <typename R> struct BvhQuery { // scalars only: lives in registers (the
     V3<R> o, d;
     R tb;          // nearest: best t so far; any: the distance bound
     Hit best;
-    // binary32 copy of the ray for the box tests (origin shifted by tshift): t = plane*i - c, with the
-    // margin folded into c (cn*: near planes moved outward, cf*: far planes moved outward)
+    // binary32 copy of the ray for the box tests (origin shifted by tshift): t = plane*i + c, with the
+    // margin folded into c (cn*: near planes moved outward, cf*: far planes moved outward; both stored negated)
     float ix, iy, iz, cnx, cny, cnz, cfx, cfy, cfz, tmaxf;
     int nearx, neary, nearz; // float4 index of the near plane of each axis inside a node (lo: a, hi: 3 + a)
     R tshift;      // box-test frame: t' = t - tshift (0 unless the origin lies outside the scene bounds)
@@ -43,9 +43,9 @@ template <typename R> struct BvhQuery { // scalars only: lives in registers (the
 };
 
 // Start a query: planes (unbounded, staged in shared memory) are tested here, then the tree is armed.
-template <typename R>
+template <typename R, typename K>
 __device__ __forceinline__ void query_start(const Ctx<R, true> &c, BvhQuery<R> &q, const V3<R> &o, const V3<R> &d,
-                                            R tmax, bool any, Counters &k) {
+                                            R tmax, bool any, K &k) {
     const NtDevScene &s = *c.s;
     q.o = o; q.d = d; q.tb = tmax; q.any = any; q.done = false; q.found = false;
     q.best.kind = -1; q.best.idx = -1; q.best.gid = 0x7fffffff;
@@ -108,9 +108,10 @@ __device__ __forceinline__ void query_start(const Ctx<R, true> &c, BvhQuery<R> &
     // near plane of an axis: lo when the ray runs in +axis, hi otherwise; each moved outward by m
     const bool px = !(dx < 0.0f), py = !(dy < 0.0f), pz = !(dz < 0.0f);
     q.nearx = px ? 0 : 3; q.neary = py ? 1 : 4; q.nearz = pz ? 2 : 5;
-    q.cnx = (px ? ox + m : ox - m) * ix; q.cfx = (px ? ox - m : ox + m) * ix;
-    q.cny = (py ? oy + m : oy - m) * iy; q.cfy = (py ? oy - m : oy + m) * iy;
-    q.cnz = (pz ? oz + m : oz - m) * iz; q.cfz = (pz ? oz - m : oz + m) * iz;
+    // stored negated: they are the addends of the slab FMAs
+    q.cnx = -((px ? ox + m : ox - m) * ix); q.cfx = -((px ? ox - m : ox + m) * ix);
+    q.cny = -((py ? oy + m : oy - m) * iy); q.cfy = -((py ? oy - m : oy + m) * iy);
+    q.cnz = -((pz ? oz + m : oz - m) * iz); q.cfz = -((pz ? oz - m : oz + m) * iz);
     q.tmaxf = Math<R>::up(q.tb - q.tshift);
     q.cur = 0;
 }
@@ -127,8 +128,8 @@ template <typename R> __device__ __forceinline__ void query_pop(BvhQuery<R> &q, 
 // One inner node of the 4-wide tree: 7 x 128-bit loads (near planes, far planes, refs), 4 slab tests as
 // 6 FMAs + max3/min3 each, then the nearest hit child (min over four (t_near bits | slot) keys) is visited next
 // and the other hit children are pushed with their entry distance.
-template <typename R>
-__device__ __forceinline__ void query_inner_step(const Ctx<R, true> &c, BvhQuery<R> &q, int2 *stack, Counters &k) {
+template <typename R, typename K>
+__device__ __forceinline__ void query_inner_step(const Ctx<R, true> &c, BvhQuery<R> &q, int2 *stack, K &k) {
     const float4 *n = (const float4 *)(c.s->nodes + q.cur);
     const float4 nx = __ldg(n + q.nearx), ny = __ldg(n + q.neary), nz = __ldg(n + q.nearz);
     const float4 fx = __ldg(n + (3 - q.nearx)), fy = __ldg(n + (5 - q.neary)), fz = __ldg(n + (7 - q.nearz));
@@ -140,8 +141,8 @@ __device__ __forceinline__ void query_inner_step(const Ctx<R, true> &c, BvhQuery
     // min3 + min with the query's bound folded in, so that one comparison decides; an empty slot holds an inverted
     // infinite box (both builders) and fails it without looking at its ref.
     const float2 ix = make_float2(q.ix, q.ix), iy = make_float2(q.iy, q.iy), iz = make_float2(q.iz, q.iz);
-    const float2 cnx = make_float2(-q.cnx, -q.cnx), cny = make_float2(-q.cny, -q.cny), cnz = make_float2(-q.cnz, -q.cnz);
-    const float2 cfx = make_float2(-q.cfx, -q.cfx), cfy = make_float2(-q.cfy, -q.cfy), cfz = make_float2(-q.cfz, -q.cfz);
+    const float2 cnx = make_float2(q.cnx, q.cnx), cny = make_float2(q.cny, q.cny), cnz = make_float2(q.cnz, q.cnz);
+    const float2 cfx = make_float2(q.cfx, q.cfx), cfy = make_float2(q.cfy, q.cfy), cfz = make_float2(q.cfz, q.cfz);
     const float2 ax[2] = { __ffma2_rn(make_float2(nx.x, nx.y), ix, cnx), __ffma2_rn(make_float2(nx.z, nx.w), ix, cnx) };
     const float2 ay[2] = { __ffma2_rn(make_float2(ny.x, ny.y), iy, cny), __ffma2_rn(make_float2(ny.z, ny.w), iy, cny) };
     const float2 az[2] = { __ffma2_rn(make_float2(nz.x, nz.y), iz, cnz), __ffma2_rn(make_float2(nz.z, nz.w), iz, cnz) };
@@ -171,8 +172,11 @@ __device__ __forceinline__ void query_inner_step(const Ctx<R, true> &c, BvhQuery
 }
 
 // One leaf: up to 4 primitives of one kind, exact tests in R.
-template <typename R>
-__device__ __forceinline__ void query_leaf_step(const Ctx<R, true> &c, BvhQuery<R> &q, const int2 *stack, Counters &k) {
+// `o`, `d`: the query's exact ray.  The per-lane state machine passes q.o / q.d; the wavefront kernels keep the strict
+// mode's ray in shared memory while the lane walks inner nodes (nt_wavefront.cuh) and hand it in from there.
+template <typename R, typename K>
+__device__ __forceinline__ void query_leaf_step(const Ctx<R, true> &c, BvhQuery<R> &q, const V3<R> &o, const V3<R> &d, const int2 *stack,
+                                                K &k) {
     const int code = -2 - q.cur;
     const int first = code & 0x3ffffff, count = ((code >> 26) & 3) + 1;
     const bool is_tri = (code >> 28) & 1;
@@ -180,8 +184,8 @@ __device__ __forceinline__ void query_leaf_step(const Ctx<R, true> &c, BvhQuery<
         const int idx = first + j;
         R t;
         bool hit;
-        if (is_tri) { R p[9]; c.ld_tri(idx, p); k.tri++; hit = hit_triangle<R>(p, q.o, q.d, c.eps, t); }
-        else { R p[4]; c.ld_sph(idx, p); k.sph++; hit = hit_sphere<R>(p, q.o, q.d, c.eps, t); }
+        if (is_tri) { R p[9]; c.ld_tri(idx, p); k.tri++; hit = hit_triangle<R>(p, o, d, c.eps, t); }
+        else { R p[4]; c.ld_sph(idx, p); k.sph++; hit = hit_sphere<R>(p, o, d, c.eps, t); }
         if (!hit) continue;
         if (q.any) {
             if (t < q.tb) { q.found = true; q.done = true; q.cur = NT_REF_EMPTY; return; }
@@ -479,7 +483,7 @@ render_bvh_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ 
                     __ballot_sync(0xffffffffu, ln.active && !q.done && ref_is_leaf(q.cur)) != 0) break;
             }
             const bool leaf = ln.active && !q.done && ref_is_leaf(q.cur);
-            if (leaf) query_leaf_step<R>(c, q, bstack, k);
+            if (leaf) query_leaf_step<R>(c, q, q.o, q.d, bstack, k);
             const unsigned parked = __ballot_sync(0xffffffffu, !ln.active || q.done);
             if (parked == 0xffffffffu || __popc(parked) >= NT_ADVANCE_THRESHOLD) break;
         }
@@ -538,7 +542,7 @@ trace_bvh_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ N
     query_start<R>(c, q, o, d, Math<R>::inf(), false, k);
     while (!q.done) {
         if (q.cur >= 0) query_inner_step<R>(c, q, bstack, k);
-        else query_leaf_step<R>(c, q, bstack, k);
+        else query_leaf_step<R>(c, q, q.o, q.d, bstack, k);
     }
     a.t_out[i] = q.best.kind >= 0 ? (double)q.tb : -1.0;
     a.prim_out[i] = q.best.kind >= 0 ? q.best.gid : -1;

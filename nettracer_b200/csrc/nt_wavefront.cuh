@@ -50,6 +50,30 @@ struct NtWfArgs {
 
 namespace nt {
 
+// Work counters of the traversal kernels in per-thread shared-memory slots: eight live registers less in a loop that
+// spilled its binary32 box parameters (64 registers, 4 blocks per SM).  Only the box-test count, bumped at every node,
+// stays in a register; the others change once per ray or per leaf.
+__shared__ unsigned nt_wf_cnt[7][NT_BLOCK_THREADS];
+template <int I> struct SmCounter {
+    __device__ __forceinline__ void operator++(int) { nt_wf_cnt[I][threadIdx.x] += 1u; }
+    __device__ __forceinline__ void operator+=(unsigned v) { nt_wf_cnt[I][threadIdx.x] += v; }
+    __device__ __forceinline__ unsigned get() const { return nt_wf_cnt[I][threadIdx.x]; }
+};
+struct CountersSm {
+    SmCounter<0> prim; SmCounter<1> sec; SmCounter<2> shadow; SmCounter<3> sph; SmCounter<4> pln; SmCounter<5> tri;
+    unsigned box;
+    SmCounter<6> light;
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) nt_wf_cnt[i][threadIdx.x] = 0u;
+        box = 0u;
+    }
+};
+__device__ __forceinline__ void flush_counters(const CountersSm &k, unsigned long long *counters, unsigned long long *s_cnt) {
+    const unsigned vals[NT_NCOUNTERS] = { k.prim.get(), k.sec.get(), k.shadow.get(), k.sph.get(), k.pln.get(), k.tri.get(), k.box, k.light.get(), 0u, 0u, 0u };
+    flush_counter_values(vals, counters, s_cnt);
+}
+
 template <typename R> struct WfHit {
     V3<R> P, Ng;
     int mat;
@@ -122,10 +146,15 @@ wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
     const unsigned n_rec = w.level == 1 ? w.n_samples : w.counts[w.level];
     const unsigned long long n_tasks = SHADOW ? (((unsigned long long)n_rec + 31) / 32) * 32 * s.nl : n_rec;
     unsigned long long *cursor = w.fetch + 2 * (w.level - 1) + (SHADOW ? 1 : 0);
-    Counters k = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    CountersSm k;
+    k.clear();
 
     BvhQuery<R> q;
     int2 bstack[NT_BVH_STACK];
+    // Strict mode: the exact ray (12 registers) is needed at the leaves only, and with it live the inner step spilled
+    // the binary32 box parameters and reloaded them for every node (12 local loads per visit): it waits in shared memory.
+    constexpr bool RAY_IN_SMEM = sizeof(R) == 8;
+    __shared__ R s_ray[RAY_IN_SMEM ? 6 : 1][RAY_IN_SMEM ? NT_BLOCK_THREADS : 1];
     q.done = true; q.cur = NT_REF_EMPTY; q.sp = 0; q.found = false; q.any = SHADOW;
     bool active = false, exhausted = false;
     unsigned rec = 0, light = 0;
@@ -148,6 +177,10 @@ wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
                         if (wf_ray<R>(a, w, rec, o, d, W)) {
                             if (w.level == 1) k.prim++;
                             query_start<R>(c, q, o, d, Math<R>::inf(), false, k);
+                            if constexpr (RAY_IN_SMEM) {
+                                s_ray[0][threadIdx.x] = o.x; s_ray[1][threadIdx.x] = o.y; s_ray[2][threadIdx.x] = o.z;
+                                s_ray[3][threadIdx.x] = d.x; s_ray[4][threadIdx.x] = d.y; s_ray[5][threadIdx.x] = d.z;
+                            }
                             active = true;
                         } else {
                             L.prim[rec] = -2;
@@ -180,6 +213,10 @@ wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
                             if (ndl > R(0)) {
                                 k.shadow++;
                                 query_start<R>(c, q, h.P, Ld, dist, true, k);
+                                if constexpr (RAY_IN_SMEM) {
+                                    s_ray[0][threadIdx.x] = h.P.x; s_ray[1][threadIdx.x] = h.P.y; s_ray[2][threadIdx.x] = h.P.z;
+                                    s_ray[3][threadIdx.x] = Ld.x; s_ray[4][threadIdx.x] = Ld.y; s_ray[5][threadIdx.x] = Ld.z;
+                                }
                                 active = true;
                             }
                         }
@@ -202,7 +239,15 @@ wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
                     __ballot_sync(0xffffffffu, active && !q.done && ref_is_leaf(q.cur)) != 0) break;
             }
             const bool leaf = active && !q.done && ref_is_leaf(q.cur);
-            if (leaf) query_leaf_step<R>(c, q, bstack, k);
+            if (leaf) {
+                if constexpr (RAY_IN_SMEM) {
+                    const V3<R> o = { s_ray[0][threadIdx.x], s_ray[1][threadIdx.x], s_ray[2][threadIdx.x] };
+                    const V3<R> d = { s_ray[3][threadIdx.x], s_ray[4][threadIdx.x], s_ray[5][threadIdx.x] };
+                    query_leaf_step<R>(c, q, o, d, bstack, k);
+                } else {
+                    query_leaf_step<R>(c, q, q.o, q.d, bstack, k);
+                }
+            }
             const unsigned parked = __ballot_sync(0xffffffffu, !active || q.done);
             if (parked == 0xffffffffu || (!exhausted && __popc(parked) >= NT_WF_REFILL)) break;
         }
