@@ -446,121 +446,6 @@ __device__ __forceinline__ bool axis_candidate(R dk, R num, R bk) {
     if constexpr (sizeof(R) == 8) return (__double2hiint(num) ^ __double2hiint(dk)) >= 0 && fabs(num) < bk;
     else return true;
 }
-#ifdef NT_EXP_SLAB
-// The axis lists of the routine below as a shared subroutine: the straight-line slab routine (planes_nearest_slab)
-// falls back to it in the rare cases it cannot decide, and scenes with more than two planes on an axis use it always.
-template <typename R> struct PlaneHit { R t; int idx; }; // idx < 0: no axis-aligned plane beats the bound
-template <typename R, bool LEAN>
-__device__ __noinline__ PlaneHit<R> planes_nearest_lists(const Ctx<R, false, LEAN> &c, const V3<R> &o, const V3<R> &d, R tb, int best_gid) {
-    const NtDevScene &s = *c.s;
-    struct { int idx, gid; } best = { -1, best_gid };
-    R tm1 = plane_bound<R>(tb);
-    unsigned addr = c.axl_addr;
-    const R oo[3] = { o.x, o.y, o.z }, dd[3] = { d.x, d.y, d.z };
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { // unrolled over the axes (no selects, list lengths straight from the constant bank)
-        const unsigned n = s.nax[k];
-        const R ok = oo[k], dk = dd[k];
-        R bk = fabs(dk) * tm1;
-#pragma unroll 1
-        for (unsigned j = 0; j < n; ++j, addr += 2u * (unsigned)sizeof(R)) {
-            R p, t;
-            int idx;
-            Ld<R>::s2(addr, p, idx);
-            const R num = p - ok;
-            if (!axis_candidate<R>(dk, num, bk)) continue;
-            if (!plane_finish<R>(dk, num, c.eps, c.eps_lo, t)) continue;
-            const int gid = (int)s.ns + idx;
-            if (t < tb || (t == tb && gid < best.gid)) {
-                tb = t; best.idx = idx; best.gid = gid;
-                tm1 = plane_bound<R>(tb); bk = fabs(dk) * tm1;
-            }
-        }
-    }
-    return { tb, best.idx };
-}
-// Strict mode, scenes with at most two axis-aligned planes per axis (NtDevScene::slab - a room): the nearest of them in
-// straight-line code.  The list loops above are a chain of dependent steps (load, subtract, compare, branch; a division
-// as soon as a candidate turns up, whose result bounds the next plane): ~500 cycles of latency per query for a warp that
-// issues one binary64 instruction every 8 cycles.  Here the six entries are loaded and tested independently, the
-// candidates of the three axes are ordered by cross-multiplication, and ONE quotient is divided:
-//   * per axis both planes share the divisor d_k, so the candidate with the smaller |num| has the smaller (or equal)
-//     quotient; candidates = same sign as d_k, |num| < |d_k| bound (plane_bound: can be nearer than tb), not provably
-//     <= eps (plane_below_eps);
-//   * candidates a, b of two axes: |num_a| |d_b| < |num_b| |d_a| (1 - 1e-15) implies q_a < q_b (1 - 6e-16), i.e. the
-//     correctly rounded quotients differ and a is strictly nearer; products below 1e-290 (lost relative precision) and
-//     anything inside the margins - which includes every tie the smallest-global-id rule would have to break - are
-//     left to the list routine.  So is a winner whose quotient turns out <= eps (its axis may hold a second candidate).
-// Returns false when the list routine has to decide (nothing is modified then).  Bit-identical results; the GPU tests
-// run every flat scene with NT_SLAB=0 / 1 against the oracle.
-template <bool LEAN>
-__device__ __forceinline__ bool planes_nearest_slab(const Ctx<double, false, LEAN> &c, const V3<double> &o, const V3<double> &d, double &tb, Hit &best) {
-    const double tm1 = plane_bound<double>(tb);
-    const double oo[3] = { o.x, o.y, o.z }, dd[3] = { d.x, d.y, d.z };
-    bool slow = false;
-    int wi = -1;                       // running winner: plane index, |num|, |d_k|, num, d_k
-    double wa = 0, wd = 0, wn = 0, wk = 0;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        double p0, p1;
-        int i0, i1;
-        Ld<double>::s2(c.sph_addr + c.s->axs_off[1] + 32u * k, p0, i0);
-        Ld<double>::s2(c.sph_addr + c.s->axs_off[1] + 32u * k + 16u, p1, i1);
-        const double ok = oo[k], dk = dd[k], adk = fabs(dk), bk = adk * tm1, lo = adk * c.eps_lo;
-        double n0 = p0 - ok, n1 = p1 - ok, a0 = fabs(n0), a1 = fabs(n1);
-        const bool lo_ok = lo >= 2.2250738585072014e-308;
-        const int hk = __double2hiint(dk);
-        const bool c0 = (__double2hiint(n0) ^ hk) >= 0 && a0 < bk && !(a0 <= lo && lo_ok); // padding: p = NaN, never a candidate
-        const bool c1 = (__double2hiint(n1) ^ hk) >= 0 && a1 < bk && !(a1 <= lo && lo_ok);
-        if (c0 && c1 && a0 <= a1 * (1.0 + 1e-15) && a1 <= a0 * (1.0 + 1e-15)) slow = true; // two planes ahead, (nearly) coincident
-        if (c1 && (!c0 || a1 < a0)) { n0 = n1; a0 = a1; i0 = i1; }
-        if (c0 || c1) {
-            if (wi < 0) { wi = i0; wa = a0; wd = adk; wn = n0; wk = dk; }
-            else {
-                const double pa = wa * adk, pb = a0 * wd; // q_w < q_k  <=>  pa < pb
-                if (!(fmin(pa, pb) >= 1e-290)) slow = true;
-                else if (pb < pa * (1.0 - 1e-15)) { wi = i0; wa = a0; wd = adk; wn = n0; wk = dk; }
-                else if (!(pa < pb * (1.0 - 1e-15))) slow = true;
-            }
-        }
-    }
-    if (slow) return false;
-    if (wi < 0) return true; // no axis-aligned plane can be nearer than tb
-    const double t = plane_quotient<double>(wn, wk);
-    if (!(t > c.eps)) return false;
-    const int gid = (int)c.s->ns + wi;
-    if (t < tb || (t == tb && gid < best.gid)) { tb = t; best.kind = 1; best.idx = wi; best.gid = gid; }
-    return true;
-}
-template <typename R, typename K, bool LEAN>
-__device__ __forceinline__ void planes_nearest(const Ctx<R, false, LEAN> &c, const V3<R> &o, const V3<R> &d, R &tb, Hit &best, K &k) {
-    const NtDevScene &s = *c.s;
-    NT_X(k, xpln, s.nax[0] + s.nax[1] + s.nax[2] + s.ngen);
-    bool lists = true;
-    if constexpr (sizeof(R) == 8) {
-        if (s.slab) lists = !planes_nearest_slab(c, o, d, tb, best);
-    }
-    if (lists) {
-        const PlaneHit<R> ph = planes_nearest_lists<R>(c, o, d, tb, best.gid);
-        if (ph.idx >= 0) { tb = ph.t; best.kind = 1; best.idx = ph.idx; best.gid = (int)s.ns + ph.idx; }
-    }
-    R tm1 = plane_bound<R>(tb);
-    if constexpr (!LEAN) {
-#pragma unroll 1
-        for (unsigned j = 0; j < s.ngen; ++j) {
-            int idx;
-            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(idx) : "r"(c.gen_addr + 4u * j));
-            R q[4], dn, num, t;
-            c.ld_pln((unsigned)idx, q);
-            plane_eval<R>(q, 3, o, d, dn, num);
-            if (plane_reject<R>(dn, num, tm1)) continue;
-            if (!plane_finish<R>(dn, num, c.eps, c.eps_lo, t)) continue;
-            const int gid = (int)s.ns + idx;
-            if (t < tb || (t == tb && gid < best.gid)) { tb = t; best.kind = 1; best.idx = idx; best.gid = gid; tm1 = plane_bound<R>(tb); }
-        }
-    }
-}
-#else
 template <typename R, typename K, bool LEAN>
 __device__ __forceinline__ void planes_nearest(const Ctx<R, false, LEAN> &c, const V3<R> &o, const V3<R> &d, R &tb, Hit &best, K &k) {
     const NtDevScene &s = *c.s;
@@ -603,7 +488,6 @@ __device__ __forceinline__ void planes_nearest(const Ctx<R, false, LEAN> &c, con
         }
     }
 }
-#endif
 // Any plane with eps < t < dist?
 // `axis` false: the query's origin lies in its light's room (in_light_room), no axis-aligned plane can stop it.
 template <typename R, typename K, bool LEAN>
