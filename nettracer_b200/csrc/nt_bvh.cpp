@@ -209,11 +209,28 @@ void nt_bvh_set_children(NtBvhNode &n, const float *lo0, const float *hi0, int c
     n.c0 = make_ref(c0, n0); n.c1 = make_ref(c1, n1); n.n0 = n0; n.n1 = n1;
 }
 
+// Two more roots behind the tree: copies of node 0 that keep only the slots of one set (the others become empty slots) -
+// [n - 2] triangles only, [n - 1] spheres only.  A query whose direction has drifted from unit length (SPEC section 4 does
+// not re-normalise) must grow the SPHERE boxes by sqrt(|d|^2 - 1) x reach (nt_bvh_trace.cuh query_arm); triangle tests do
+// not depend on |d|, so such a query walks the triangle set with plain boxes and only the sphere set with grown ones.
+void nt_bvh_append_set_roots(std::vector<NtBvhNode4> &n4, const int root_kinds[4]) {
+    const NtBvhNode4 root = n4[0];
+    for (int set = 1; set >= 0; --set) { // triangles first
+        NtBvhNode4 r = root;
+        for (int k = 0; k < 4; ++k)
+            if (root_kinds[k] != set) {
+                for (int a = 0; a < 3; ++a) { r.lo[a][k] = std::numeric_limits<float>::infinity(); r.hi[a][k] = -std::numeric_limits<float>::infinity(); }
+                r.ref[k] = -1;
+            }
+        n4.push_back(r);
+    }
+}
+
 // ---- BVH2 -> BVH4 collapse ----
 namespace {
-struct Cand { Box box; int ref; };
+struct Cand { Box box; int ref; int kind = -1; }; // kind: 0 sphere set, 1 triangle set (tracked for the root's slots only)
 
-int emit4(const std::vector<NtBvhNode> &n2, std::vector<NtBvhNode4> &n4, int node2, int depth, int &max_depth) {
+int emit4(const std::vector<NtBvhNode> &n2, std::vector<NtBvhNode4> &n4, int node2, int depth, int &max_depth, int *root_kinds = nullptr) {
     max_depth = std::max(max_depth, depth);
     std::vector<Cand> kids;
     auto children = [&](int id, Cand out[2]) {
@@ -223,6 +240,7 @@ int emit4(const std::vector<NtBvhNode> &n2, std::vector<NtBvhNode4> &n4, int nod
     };
     Cand two[2];
     children(node2, two);
+    if (root_kinds) { two[0].kind = 0; two[1].kind = 1; } // binary node 0 joins the sphere tree (c0) and the triangle tree (c1)
     for (const Cand &c : two) if (c.ref != -1) kids.push_back(c);
     while (kids.size() < 4) { // open the inner child with the largest box
         int best = -1;
@@ -230,7 +248,9 @@ int emit4(const std::vector<NtBvhNode> &n2, std::vector<NtBvhNode4> &n4, int nod
         for (size_t i = 0; i < kids.size(); ++i)
             if (kids[i].ref >= 0 && kids[i].box.half_area() > area) { area = kids[i].box.half_area(); best = (int)i; }
         if (best < 0) break;
+        const int kind = kids[best].kind;
         children(kids[best].ref, two);
+        two[0].kind = two[1].kind = kind;
         kids.erase(kids.begin() + best);
         for (const Cand &c : two) if (c.ref != -1) kids.push_back(c);
     }
@@ -246,6 +266,7 @@ int emit4(const std::vector<NtBvhNode> &n2, std::vector<NtBvhNode4> &n4, int nod
         node.pad[k] = 0;
     }
     for (size_t k = 0; k < kids.size(); ++k) node.ref[k] = kids[k].ref >= 0 ? emit4(n2, n4, kids[k].ref, depth + 1, max_depth) : kids[k].ref;
+    if (root_kinds) for (int k = 0; k < 4; ++k) root_kinds[k] = k < (int)kids.size() ? kids[k].kind : -1;
     n4[id] = node;
     return id;
 }
@@ -254,7 +275,9 @@ void collapse4(NtBvhBuild &out) {
     out.nodes4.clear();
     out.nodes4.reserve(out.nodes.size() / 2 + 4);
     out.depth4 = 0;
-    emit4(out.nodes, out.nodes4, 0, 1, out.depth4);
+    int root_kinds[4];
+    emit4(out.nodes, out.nodes4, 0, 1, out.depth4, root_kinds);
+    nt_bvh_append_set_roots(out.nodes4, root_kinds);
 }
 } // namespace
 

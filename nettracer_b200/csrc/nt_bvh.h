@@ -7,7 +7,8 @@
 
 struct NtBvhBuild {
     std::vector<NtBvhNode> nodes;  // binary tree (intermediate), nodes[0] is the root
-    std::vector<NtBvhNode4> nodes4; // collapsed 4-wide tree the device traverses, nodes4[0] is the root
+    std::vector<NtBvhNode4> nodes4; // collapsed 4-wide tree the device traverses, nodes4[0] is the root; the last two entries are
+                                    // the per-set roots (triangles only, spheres only: nt_bvh_append_set_roots)
     std::vector<int> sph_order;    // BVH-ordered position -> original sphere index
     std::vector<int> tri_order;    // BVH-ordered position -> original triangle index
     int depth4 = 0;                 // depth of the 4-wide tree (bounds the traversal stack)
@@ -17,6 +18,7 @@ struct NtBvhBuild {
 
 void nt_bvh_set_children(NtBvhNode &n, const float *lo0, const float *hi0, int c0, int n0,
                          const float *lo1, const float *hi1, int c1, int n1);
+void nt_bvh_append_set_roots(std::vector<NtBvhNode4> &n4, const int root_kinds[4]);
 void nt_bvh_build(const double *spheres, uint32_t ns, const double *triangles, uint32_t nt,
                   int leaf_max, NtBvhBuild &out);
 

@@ -552,7 +552,7 @@ int nt_bvh_build_gpu(const double *d_spheres, uint32_t ns, const double *d_trian
     if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
     if ((rc = sb.run(d_spheres, ns, 0, leaf_max, st)) != 0) return rc;
     if ((rc = tb.run(d_triangles, nt, 1, leaf_max, st)) != 0) return rc;
-    const uint32_t total = 1 + (uint32_t)sb.nodes4 + (uint32_t)tb.nodes4;
+    const uint32_t total = 1 + (uint32_t)sb.nodes4 + (uint32_t)tb.nodes4 + 2; // + the two per-set roots (nt_bvh.h)
     NtBvhNode4 *nodes = nullptr;
     CUCHK(cudaMalloc((void **)&nodes, sizeof(NtBvhNode4) * total));
     int sref, tref;
@@ -567,6 +567,13 @@ int nt_bvh_build_gpu(const double *d_spheres, uint32_t ns, const double *d_trian
         root.pad[k] = 0;
     }
     cudaError_t e = cudaMemcpyAsync(nodes, &root, sizeof root, cudaMemcpyHostToDevice, st);
+    NtBvhNode4 set_roots[2] = { root, root }; // [total - 2] triangles only (slot 1), [total - 1] spheres only (slot 0)
+    for (int set = 0; set < 2; ++set) {
+        const int drop = set == 0 ? 0 : 1;
+        for (int a = 0; a < 3; ++a) { set_roots[set].lo[a][drop] = INFINITY; set_roots[set].hi[a][drop] = -INFINITY; }
+        set_roots[set].ref[drop] = -1;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(nodes + total - 2, set_roots, sizeof set_roots, cudaMemcpyHostToDevice, st);
     sph_order.resize(ns); tri_order.resize(nt);
     if (e == cudaSuccess && ns) e = cudaMemcpyAsync(sph_order.data(), sb.order_ptr(), sizeof(int) * ns, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && nt) e = cudaMemcpyAsync(tri_order.data(), tb.order_ptr(), sizeof(int) * nt, cudaMemcpyDeviceToHost, st);

@@ -39,15 +39,161 @@ template <typename R> struct BvhQuery { // scalars only: lives in registers (the
     R tshift;      // box-test frame: t' = t - tshift (0 unless the origin lies outside the scene bounds)
     int cur;       // ref being visited, NT_REF_EMPTY when the query needs a pop
     int sp;
+    int pass;      // 0: one walk of the whole tree; 1: triangle set, the sphere set follows; 2: sphere set (query_arm)
+    float fix, fiy, fiz; // pass 2 only: reciprocals for the FAR planes (the margin is a cone there, see query_arm)
     bool any, done, found;
 };
+
+// Arm the tree walk of a query: the binary32 copy of the ray, the box margin, the entry slab against the scene bounds.
+//   pass 0  decide: one walk of the whole tree (from node 0) - or, when the direction has drifted from unit length so far
+//           that the sphere boxes must grow by more than the rounding margin, pass 1;
+//   pass 1  the triangle set only (root n_nodes - 2), plain margin; query_second_pass then arms
+//   pass 2  the sphere set only (root n_nodes - 1), grown margin: a cone (below), walked by query_inner_step_t<true>;
+//   pass 3  the same with the constant bound, for a caller whose loop has only the plain inner step.
+// Why two passes: SPEC §3's sphere test takes the direction as a unit vector, but §4 does not re-normalise reflected /
+// refracted directions: |d|^2 = L2 drifts from 1 along a mirror chain (every bounce off a small distant sphere amplifies
+// the drift by ~ 4 (t / r)^2), and the rule then accepts roots t whose point o + d t lies at distance sqrt(r^2 + (L2 - 1)
+// t^2) <= r + sqrt(L2 - 1) t from the centre - OUTSIDE the sphere and possibly outside its box.  Boxes may only cull what
+// the rule cannot hit, so sphere boxes grow by that bound with t <= the largest distance from the origin to a scene point
+// (found by bench.py's frame check against the brute-force oracle).  The triangle test does not depend on |d| (Moeller -
+// Trumbore is exact for any scaling of the direction), so triangle boxes never grow: after three sphere bounces the growth
+// is the whole scene, and a handful of such rays that walked the grown TRIANGLE tree tested every one of a million
+// triangles each (configs[4], depth 5: 15 s per frame instead of 0.19 - measured in round 2, the reason for the passes).
+// (Strict mode only.  The fast mode has no bit contract, its sphere test is a different formula (SPEC §7), and binary32
+// normals of small distant spheres are unit vectors to 1e-4 at best: growing boxes for that would swallow the tree.)
+template <typename R>
+__device__ __forceinline__ void query_arm(const Ctx<R, true> &c, BvhQuery<R> &q, const V3<R> &o, const V3<R> &d, int pass) {
+    const NtDevScene &s = *c.s;
+    float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
+    const float dx = (float)d.x, dy = (float)d.y, dz = (float)d.z;
+    // reciprocal direction, magnitude clamped so that plane*i - c never evaluates inf - inf
+    // ... and never 0 (an infinite direction component): an empty slot's far plane is -inf * i, which must stay -inf - the
+    // inner step tells empty slots by their inverted boxes alone
+    const float ix = copysignf(fmaxf(fminf(1.0f / fabsf(dx), 1e18f), 1e-30f), dx), iy = copysignf(fmaxf(fminf(1.0f / fabsf(dy), 1e18f), 1e-30f), dy),
+                iz = copysignf(fmaxf(fminf(1.0f / fabsf(dz), 1e18f), 1e-30f), dz);
+    q.ix = ix; q.iy = iy; q.iz = iz;
+    // Box margin: covers rounding the ray to binary32 (origin, direction, reciprocal, slab products).
+    // It grows with |origin|, so a far origin (a camera outside the scene, a hit on an unbounded plane
+    // kilometres away) is first slid along the exact ray to where it enters the scene bounds: only the
+    // box tests use the shifted copy, the primitive tests keep the original ray.
+    float m = 4e-6f * (fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz)) + s.max_abs);
+    float grow = [&] {
+        if constexpr (sizeof(R) == 4) return 0.0f;
+        const R l2 = dot(d, d);
+        if (!(l2 > R(1))) return l2 == l2 ? 0.0f : CUDART_INF_F;
+        const float far_ = 1.7320508f * (fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz)) + s.max_abs);
+        return __fsqrt_ru(Math<R>::up(l2 - R(1))) * far_ * 1.00001f;
+    }();
+    if (pass == 0 && !(grow <= 4.0f * m)) pass = 1; // also when grow is NaN
+    if (pass == 1) grow = 0.0f;
+    q.pass = pass;
+    const float grow_all = grow; // pass 2: the entry slab below keeps the constant bound, the node tests use the cone
+    m += grow;
+    float tn = 0.0f, tf = CUDART_INF_F;
+    slab(s.blo[0], s.bhi[0], ox, ix, m, tn, tf);
+    slab(s.blo[1], s.bhi[1], oy, iy, m, tn, tf);
+    slab(s.blo[2], s.bhi[2], oz, iz, m, tn, tf);
+    q.sp = 0;
+    if (!(tn <= tf) || tn > Math<R>::up(q.tb)) { q.done = true; q.cur = NT_REF_EMPTY; return; } // misses every bounded primitive (of this pass)
+    q.tshift = R(0);
+    if (tn > 0.0f) {
+        const R ts = (R)tn;
+        const V3<R> os = { o.x + d.x * ts, o.y + d.y * ts, o.z + d.z * ts }; // a point of the exact ray
+        ox = (float)os.x; oy = (float)os.y; oz = (float)os.z;
+        m = 4e-6f * (fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz)) + s.max_abs) + grow; // grow: from the ORIGINAL origin, where t is measured
+        q.tshift = ts;
+    }
+    // near plane of an axis: lo when the ray runs in +axis, hi otherwise; each moved outward by m
+    const bool px = !(dx < 0.0f), py = !(dy < 0.0f), pz = !(dz < 0.0f);
+    q.nearx = px ? 0 : 3; q.neary = py ? 1 : 4; q.nearz = pz ? 2 : 5;
+    if (pass == 3) pass = 2; // (q.pass already says 3: the caller walks with the plain inner step, see below)
+    else if (pass == 2 && grow_all < CUDART_INF_F) {
+        // Pass 2, the margin as a CONE: a root t of the sphere rule lies within alpha t of its sphere, alpha = sqrt(L2 - 1),
+        // so a box can hold a hit only if lo - alpha t <= o + d t <= hi + alpha t on every axis for some t: per axis
+        // t (|d| + alpha) >= (near plane - o) and t (|d| - alpha) <= (far plane - o) - the slab test with one reciprocal
+        // for the near planes and another for the far planes; an axis with |d| <= alpha (or nearly) bounds nothing above.
+        // t is measured from the ORIGINAL origin: the slid origin adds the constant alpha * tshift.  alpha is taken 0.1 %
+        // too large, which also covers the rounding of the two reciprocals.  (With the constant bound alpha * reach a ray
+        // after two sphere bounces walked the whole sphere tree: a few thousand such rays of configs[4] held every
+        // traversal kernel's tail for milliseconds - 394 ms per 1/8 frame against 176 ms with re-normalised directions.)
+        const float alpha = __fsqrt_ru(Math<R>::up(dot(d, d) - R(1))) * 1.001f;
+        const float mc = 4e-6f * (fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz)) + s.max_abs) + alpha * Math<R>::up(q.tshift) * 1.0001f;
+        const float adx = fabsf(dx), ady = fabsf(dy), adz = fabsf(dz);
+        const float inx = copysignf(1.0f / (adx + alpha), dx), iny = copysignf(1.0f / (ady + alpha), dy), inz = copysignf(1.0f / (adz + alpha), dz);
+        const bool bx = adx - alpha > 1e-3f * adx, by = ady - alpha > 1e-3f * ady, bz = adz - alpha > 1e-3f * adz;
+        q.ix = inx; q.iy = iny; q.iz = inz;
+        q.fix = bx ? copysignf(1.0f / (adx - alpha), dx) : 0.0f;
+        q.fiy = by ? copysignf(1.0f / (ady - alpha), dy) : 0.0f;
+        q.fiz = bz ? copysignf(1.0f / (adz - alpha), dz) : 0.0f;
+        q.cnx = -((px ? ox + mc : ox - mc) * inx); q.cfx = bx ? -((px ? ox - mc : ox + mc) * q.fix) : CUDART_INF_F;
+        q.cny = -((py ? oy + mc : oy - mc) * iny); q.cfy = by ? -((py ? oy - mc : oy + mc) * q.fiy) : CUDART_INF_F;
+        q.cnz = -((pz ? oz + mc : oz - mc) * inz); q.cfz = bz ? -((pz ? oz - mc : oz + mc) * q.fiz) : CUDART_INF_F;
+        q.tmaxf = Math<R>::up(q.tb - q.tshift);
+        q.done = false;
+        q.cur = (int)s.n_nodes - 1;
+        return;
+    }
+    q.fix = ix; q.fiy = iy; q.fiz = iz;
+    // stored negated: they are the addends of the slab FMAs
+    q.cnx = -((px ? ox + m : ox - m) * ix); q.cfx = -((px ? ox - m : ox + m) * ix);
+    q.cny = -((py ? oy + m : oy - m) * iy); q.cfy = -((py ? oy - m : oy + m) * iy);
+    q.cnz = -((pz ? oz + m : oz - m) * iz); q.cfz = -((pz ? oz - m : oz + m) * iz);
+    q.tmaxf = Math<R>::up(q.tb - q.tshift);
+    q.done = false;
+    q.cur = pass == 0 ? 0 : (int)s.n_nodes - 3 + pass; // pass 1: root n - 2 (triangles), pass 2 / 3: root n - 1 (spheres)
+}
+// A query that walked the triangle set alone (pass 1) goes on with the sphere set unless an occlusion query has already
+// found its occluder.  Called by the traversal loops for lanes whose walk has just ended:
+//   * moderate drift: pass 2 of query_arm, the sphere tree under the cone margin;
+//   * alpha = sqrt(|d|^2 - 1) >= NT_SWEEP_ALPHA (a third sphere bounce and beyond): the cone holds most of the scene and
+//     the rule itself accepts roots far off the spheres, so the walk degenerates into testing every sphere - one lane, ten
+//     thousand exact tests, milliseconds during which its traversal kernel cannot end.  The wavefront pipeline DEFERS such
+//     a ray to a list (query_wants_sweep) and a small kernel takes each listed ray with a whole warp: every lane tests the
+//     spheres i = lane (mod 32) with the exact rule, a butterfly picks the nearest.  The same answer as the walk, 1/32 of
+//     its latency, and none of its code in the traversal loop (inlined there, or called, it cost the common path 25 %).
+//     Only nearest-hit queries can drift: a shadow ray's direction is normalised (SPEC section 4).
+#ifndef NT_SWEEP_ALPHA
+#define NT_SWEEP_ALPHA 0.05f
+#endif
+template <typename R>
+__device__ __forceinline__ bool query_wants_sweep(const V3<R> &d) {
+    const R e = dot(d, d) - R(1);
+    return !(e < R(NT_SWEEP_ALPHA) * R(NT_SWEEP_ALPHA)); // also NaN
+}
+template <typename R>
+__device__ __forceinline__ void query_second_pass(const Ctx<R, true> &c, BvhQuery<R> &q, const V3<R> &o, const V3<R> &d) {
+    if (q.done && q.pass == 1 && !(q.any && q.found)) query_arm<R>(c, q, o, d, 2);
+}
+template <typename R> struct SweepHit { R t; int idx, gid; }; // idx < 0: nothing
+// The sweep (nt_wavefront.cuh wf_sweep_kernel): called by a whole warp with the same ray; returns the warp's nearest sphere
+// hit by the exact rule, ties to the smallest global id (SPEC section 3).
+template <typename R>
+__device__ __forceinline__ SweepHit<R> sweep_spheres(const R *sph, const int *sph_gid, unsigned ns, R eps, const V3<R> &so, const V3<R> &sd) {
+    const unsigned lane = threadIdx.x & 31;
+    R bt = Math<R>::inf();
+    int bidx = -1, bgid = 0x7fffffff;
+    for (unsigned i = lane; i < ns; i += 32) {
+        R p[4], t;
+        Ld<R>::g4(sph + 4 * (size_t)i, p);
+        if (!hit_sphere<R>(p, so, sd, eps, t)) continue;
+        const int gid = __ldg(sph_gid + i);
+        if (t < bt || (t == bt && gid < bgid)) { bt = t; bidx = (int)i; bgid = gid; }
+    }
+#pragma unroll 1
+    for (int off = 16; off; off >>= 1) {
+        const R t2 = __shfl_xor_sync(0xffffffffu, bt, off);
+        const int g2 = __shfl_xor_sync(0xffffffffu, bgid, off), i2 = __shfl_xor_sync(0xffffffffu, bidx, off);
+        if (t2 < bt || (t2 == bt && g2 < bgid)) { bt = t2; bgid = g2; bidx = i2; }
+    }
+    return { bt, bidx, bgid };
+}
 
 // Start a query: planes (unbounded, staged in shared memory) are tested here, then the tree is armed.
 template <typename R, typename K>
 __device__ __forceinline__ void query_start(const Ctx<R, true> &c, BvhQuery<R> &q, const V3<R> &o, const V3<R> &d,
                                             R tmax, bool any, K &k) {
     const NtDevScene &s = *c.s;
-    q.o = o; q.d = d; q.tb = tmax; q.any = any; q.done = false; q.found = false;
+    q.o = o; q.d = d; q.tb = tmax; q.any = any; q.done = false; q.found = false; q.pass = 0;
     q.best.kind = -1; q.best.idx = -1; q.best.gid = 0x7fffffff;
     q.cur = NT_REF_EMPTY; q.sp = 0;
     R t;
@@ -65,55 +211,7 @@ __device__ __forceinline__ void query_start(const Ctx<R, true> &c, BvhQuery<R> &
         }
     }
     if (s.n_nodes == 0) { q.done = true; return; }
-    float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
-    const float dx = (float)d.x, dy = (float)d.y, dz = (float)d.z;
-    // reciprocal direction, magnitude clamped so that plane*i - c never evaluates inf - inf
-    const float ix = copysignf(fminf(1.0f / fabsf(dx), 1e18f), dx), iy = copysignf(fminf(1.0f / fabsf(dy), 1e18f), dy),
-                iz = copysignf(fminf(1.0f / fabsf(dz), 1e18f), dz);
-    q.ix = ix; q.iy = iy; q.iz = iz;
-    // Box margin: covers rounding the ray to binary32 (origin, direction, reciprocal, slab products).
-    // It grows with |origin|, so a far origin (a camera outside the scene, a hit on an unbounded plane
-    // kilometres away) is first slid along the exact ray to where it enters the scene bounds: only the
-    // box tests use the shifted copy, the primitive tests keep the original ray.
-    float m = 4e-6f * (fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz)) + s.max_abs);
-    // SPEC §3's sphere test takes the direction as a unit vector, but §4 does not re-normalise reflected / refracted
-    // directions: |d|^2 = L2 drifts from 1 along a mirror chain (1 + 1e-4 at depth 5 is common, every bounce amplifies
-    // it), and the rule then accepts roots t whose point o + d t lies at distance sqrt(r^2 + (L2 - 1) t^2) <= r +
-    // sqrt(L2 - 1) t from the centre - OUTSIDE the sphere and possibly outside its box.  Boxes may only cull what the
-    // rule cannot hit, so they grow by that bound with t <= the largest distance from the origin to a scene point;
-    // ~1e-8 of the scene size for a unit direction.  (Found by bench.py's frame check against the brute-force oracle.)
-    // (Strict mode only.  The fast mode has no bit contract, its sphere test is a different formula (SPEC §7), and binary32
-    // normals of small distant spheres are unit vectors to 1e-4 at best: growing boxes for that would swallow the tree.)
-    const float grow = [&] {
-        if constexpr (sizeof(R) == 4) return 0.0f;
-        const R l2 = dot(d, d);
-        if (!(l2 > R(1))) return l2 == l2 ? 0.0f : CUDART_INF_F;
-        const float far_ = 1.7320508f * (fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz)) + s.max_abs);
-        return __fsqrt_ru(Math<R>::up(l2 - R(1))) * far_ * 1.00001f;
-    }();
-    m += grow;
-    float tn = 0.0f, tf = CUDART_INF_F;
-    slab(s.blo[0], s.bhi[0], ox, ix, m, tn, tf);
-    slab(s.blo[1], s.bhi[1], oy, iy, m, tn, tf);
-    slab(s.blo[2], s.bhi[2], oz, iz, m, tn, tf);
-    if (!(tn <= tf) || tn > Math<R>::up(q.tb)) { q.done = true; return; } // misses every bounded primitive
-    q.tshift = R(0);
-    if (tn > 0.0f) {
-        const R ts = (R)tn;
-        const V3<R> os = { o.x + d.x * ts, o.y + d.y * ts, o.z + d.z * ts }; // a point of the exact ray
-        ox = (float)os.x; oy = (float)os.y; oz = (float)os.z;
-        m = 4e-6f * (fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz)) + s.max_abs) + grow; // grow: from the ORIGINAL origin, where t is measured
-        q.tshift = ts;
-    }
-    // near plane of an axis: lo when the ray runs in +axis, hi otherwise; each moved outward by m
-    const bool px = !(dx < 0.0f), py = !(dy < 0.0f), pz = !(dz < 0.0f);
-    q.nearx = px ? 0 : 3; q.neary = py ? 1 : 4; q.nearz = pz ? 2 : 5;
-    // stored negated: they are the addends of the slab FMAs
-    q.cnx = -((px ? ox + m : ox - m) * ix); q.cfx = -((px ? ox - m : ox + m) * ix);
-    q.cny = -((py ? oy + m : oy - m) * iy); q.cfy = -((py ? oy - m : oy + m) * iy);
-    q.cnz = -((pz ? oz + m : oz - m) * iz); q.cfz = -((pz ? oz - m : oz + m) * iz);
-    q.tmaxf = Math<R>::up(q.tb - q.tshift);
-    q.cur = 0;
+    query_arm<R>(c, q, o, d, 0);
 }
 
 template <typename R> __device__ __forceinline__ void query_pop(BvhQuery<R> &q, const int2 *stack) {
@@ -128,8 +226,8 @@ template <typename R> __device__ __forceinline__ void query_pop(BvhQuery<R> &q, 
 // One inner node of the 4-wide tree: 7 x 128-bit loads (near planes, far planes, refs), 4 slab tests as
 // 6 FMAs + max3/min3 each, then the nearest hit child (min over four (t_near bits | slot) keys) is visited next
 // and the other hit children are pushed with their entry distance.
-template <typename R, typename K>
-__device__ __forceinline__ void query_inner_step(const Ctx<R, true> &c, BvhQuery<R> &q, int2 *stack, K &k) {
+template <bool CONE, typename R, typename K>
+__device__ __forceinline__ void query_inner_step_t(const Ctx<R, true> &c, BvhQuery<R> &q, int2 *stack, K &k) {
     const float4 *n = (const float4 *)(c.s->nodes + q.cur);
     const float4 nx = __ldg(n + q.nearx), ny = __ldg(n + q.neary), nz = __ldg(n + q.nearz);
     const float4 fx = __ldg(n + (3 - q.nearx)), fy = __ldg(n + (5 - q.neary)), fz = __ldg(n + (7 - q.nearz));
@@ -146,9 +244,11 @@ __device__ __forceinline__ void query_inner_step(const Ctx<R, true> &c, BvhQuery
     const float2 ax[2] = { __ffma2_rn(make_float2(nx.x, nx.y), ix, cnx), __ffma2_rn(make_float2(nx.z, nx.w), ix, cnx) };
     const float2 ay[2] = { __ffma2_rn(make_float2(ny.x, ny.y), iy, cny), __ffma2_rn(make_float2(ny.z, ny.w), iy, cny) };
     const float2 az[2] = { __ffma2_rn(make_float2(nz.x, nz.y), iz, cnz), __ffma2_rn(make_float2(nz.z, nz.w), iz, cnz) };
-    const float2 bx[2] = { __ffma2_rn(make_float2(fx.x, fx.y), ix, cfx), __ffma2_rn(make_float2(fx.z, fx.w), ix, cfx) };
-    const float2 by[2] = { __ffma2_rn(make_float2(fy.x, fy.y), iy, cfy), __ffma2_rn(make_float2(fy.z, fy.w), iy, cfy) };
-    const float2 bz[2] = { __ffma2_rn(make_float2(fz.x, fz.y), iz, cfz), __ffma2_rn(make_float2(fz.z, fz.w), iz, cfz) };
+    // far planes: the same reciprocals, except in the cone pass of a drifted direction (query_arm)
+    const float2 jx = CONE ? make_float2(q.fix, q.fix) : ix, jy = CONE ? make_float2(q.fiy, q.fiy) : iy, jz = CONE ? make_float2(q.fiz, q.fiz) : iz;
+    const float2 bx[2] = { __ffma2_rn(make_float2(fx.x, fx.y), jx, cfx), __ffma2_rn(make_float2(fx.z, fx.w), jx, cfx) };
+    const float2 by[2] = { __ffma2_rn(make_float2(fy.x, fy.y), jy, cfy), __ffma2_rn(make_float2(fy.z, fy.w), jy, cfy) };
+    const float2 bz[2] = { __ffma2_rn(make_float2(fz.x, fz.y), jz, cfz), __ffma2_rn(make_float2(fz.z, fz.w), jz, cfz) };
     const int ra[4] = { rf.x, rf.y, rf.z, rf.w };
     int key[4];
 #pragma unroll
@@ -156,7 +256,10 @@ __device__ __forceinline__ void query_inner_step(const Ctx<R, true> &c, BvhQuery
         const int h = j >> 1;
         const float tn = fmaxf(fmaxf(j & 1 ? ax[h].y : ax[h].x, j & 1 ? ay[h].y : ay[h].x), fmaxf(j & 1 ? az[h].y : az[h].x, 0.0f));
         const float tf = fminf(fminf(j & 1 ? bx[h].y : bx[h].x, j & 1 ? by[h].y : by[h].x), fminf(j & 1 ? bz[h].y : bz[h].x, q.tmaxf));
-        key[j] = tn <= tf ? ((__float_as_int(tn) & ~3) | j) : 0x7fffffff; // tn >= 0: integer order == float order
+        // (cone pass: an axis without a far bound multiplies the far plane by 0 - an empty slot's -inf becomes NaN, min
+        // ignores it and the inverted box could pass with an unbounded query: there the ref is looked at)
+        const bool hit = CONE ? (tn <= tf && ra[j] != NT_REF_EMPTY) : tn <= tf;
+        key[j] = hit ? ((__float_as_int(tn) & ~3) | j) : 0x7fffffff; // tn >= 0: integer order == float order
     }
     // Next = the nearest hit child; the other hit children are pushed in slot order with their entry distance
     // (a pop discards entries that start beyond the current bound).  A full sort of the four keys (the first
@@ -169,6 +272,11 @@ __device__ __forceinline__ void query_inner_step(const Ctx<R, true> &c, BvhQuery
     for (int j = 0; j < 4; ++j)
         if (key[j] != 0x7fffffff && j != slot) stack[q.sp++] = make_int2(ra[j], key[j] & ~3);
     q.cur = slot == 0 ? rf.x : slot == 1 ? rf.y : slot == 2 ? rf.z : rf.w;
+}
+template <typename R, typename K>
+__device__ __forceinline__ void query_inner_step(const Ctx<R, true> &c, BvhQuery<R> &q, int2 *stack, K &k) {
+    if (sizeof(R) == 8 && q.pass == 2) query_inner_step_t<true, R, K>(c, q, stack, k); // rare: cold copy of the step
+    else query_inner_step_t<false, R, K>(c, q, stack, k);
 }
 
 // One leaf: up to 4 primitives of one kind, exact tests in R.
@@ -484,6 +592,7 @@ render_bvh_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ 
             }
             const bool leaf = ln.active && !q.done && ref_is_leaf(q.cur);
             if (leaf) query_leaf_step<R>(c, q, q.o, q.d, bstack, k);
+            if (ln.active) query_second_pass<R>(c, q, q.o, q.d); // drifted directions: the sphere set after the triangle set
             const unsigned parked = __ballot_sync(0xffffffffu, !ln.active || q.done);
             if (parked == 0xffffffffu || __popc(parked) >= NT_ADVANCE_THRESHOLD) break;
         }
@@ -540,9 +649,13 @@ trace_bvh_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ N
     BvhQuery<R> q;
     int2 bstack[NT_BVH_STACK];
     query_start<R>(c, q, o, d, Math<R>::inf(), false, k);
-    while (!q.done) {
-        if (q.cur >= 0) query_inner_step<R>(c, q, bstack, k);
-        else query_leaf_step<R>(c, q, q.o, q.d, bstack, k);
+    for (;;) {
+        while (!q.done) {
+            if (q.cur >= 0) query_inner_step<R>(c, q, bstack, k);
+            else query_leaf_step<R>(c, q, q.o, q.d, bstack, k);
+        }
+        if (q.pass == 1 && !(q.any && q.found)) query_arm<R>(c, q, q.o, q.d, 2); // one ray per thread, no warp to share a sweep with
+        if (q.done) break;
     }
     a.t_out[i] = q.best.kind >= 0 ? (double)q.tb : -1.0;
     a.prim_out[i] = q.best.kind >= 0 ? q.best.gid : -1;

@@ -46,6 +46,13 @@ struct NtWfArgs {
     unsigned long long *fetch;    // [2 * NT_WF_MAX_DEPTH] task-fetch cursors (nearest, shadow) per level
     unsigned sid0, n_samples;     // this chunk: first sample id, sample count
     unsigned level;               // 1-based
+    // nearest-hit queries whose direction has drifted so far that their sphere pass would test every sphere
+    // (nt_bvh_trace.cuh query_second_pass): record indices, swept by wf_sweep_kernel after the level's nearest pass
+    unsigned *sweep_list, *sweep_count, sweep_cap;
+    // ... and those with a moderate drift, whose sphere pass walks the sphere tree under the cone margin: the same list
+    // mechanism, walked by the CONEPASS instantiation of wf_trace_kernel (the main kernel carries no cone code)
+    unsigned *cone_list, *cone_count;
+    unsigned long long *cone_fetch;
 };
 
 namespace nt {
@@ -133,7 +140,10 @@ __device__ __forceinline__ bool wf_ray(const NtRenderArgs &a, const NtWfArgs &w,
 
 // Persistent traversal kernel.  SHADOW == false: one task = one record, nearest hit.  SHADOW == true: one task =
 // (record, light), any hit between the hit point and the light.
-template <typename R, bool SHADOW>
+// CONEPASS: the second pass of the nearest-hit queries the main kernel deferred (NtWfArgs::cone_list): one task = one
+// listed record, whose nearest hit among planes and triangles is already in the record; the sphere set is walked under
+// the cone margin (query_arm pass 2) and the record keeps the nearer hit.
+template <typename R, bool SHADOW, bool CONEPASS = false>
 __global__ void __launch_bounds__(NT_BLOCK_THREADS, NT_MIN_BLOCKS_BVH)
 wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRenderArgs a, const __grid_constant__ NtWfArgs w) {
     __shared__ unsigned long long s_cnt[NT_NCOUNTERS];
@@ -143,9 +153,9 @@ wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
     stage_scene<R, true>(s, v, c);
     const unsigned lane = threadIdx.x & 31;
     const NtWfLevel &L = w.lv[w.level - 1];
-    const unsigned n_rec = w.level == 1 ? w.n_samples : w.counts[w.level];
+    const unsigned n_rec = CONEPASS ? min(*w.cone_count, w.sweep_cap) : w.level == 1 ? w.n_samples : w.counts[w.level];
     const unsigned long long n_tasks = SHADOW ? (((unsigned long long)n_rec + 31) / 32) * 32 * s.nl : n_rec;
-    unsigned long long *cursor = w.fetch + 2 * (w.level - 1) + (SHADOW ? 1 : 0);
+    unsigned long long *cursor = CONEPASS ? w.cone_fetch : w.fetch + 2 * (w.level - 1) + (SHADOW ? 1 : 0);
     CountersSm k;
     k.clear();
 
@@ -170,7 +180,23 @@ wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
             if (!active) {
                 const unsigned long long ti = base + __popc(idle & ((1u << lane) - 1));
                 if (ti < n_tasks) {
-                    if constexpr (!SHADOW) {
+                    if constexpr (CONEPASS) {
+                        rec = w.cone_list[ti];
+                        V3<R> o, d;
+                        R W;
+                        wf_ray<R>(a, w, rec, o, d, W);
+                        const int prim = L.prim[rec];
+                        q.o = o; q.d = d; q.tb = ((const R *)L.hit_t)[rec]; q.any = false; q.found = prim >= 0; q.sp = 0;
+                        q.best.kind = prim >= 0 ? prim >> 28 : -1; q.best.idx = prim >= 0 ? (prim & 0x0fffffff) : -1;
+                        q.best.gid = prim < 0 ? 0x7fffffff : (prim >> 28) == 1 ? (int)s.ns + (prim & 0x0fffffff)
+                                                           : __ldg(((prim >> 28) == 2 ? s.tri_gid : s.sph_gid) + (prim & 0x0fffffff));
+                        query_arm<R>(c, q, o, d, 2);
+                        if constexpr (RAY_IN_SMEM) {
+                            s_ray[0][threadIdx.x] = o.x; s_ray[1][threadIdx.x] = o.y; s_ray[2][threadIdx.x] = o.z;
+                            s_ray[3][threadIdx.x] = d.x; s_ray[4][threadIdx.x] = d.y; s_ray[5][threadIdx.x] = d.z;
+                        }
+                        active = true;
+                    } else if constexpr (!SHADOW) {
                         rec = w.level == 1 ? (unsigned)ti : L.tasks[ti];
                         V3<R> o, d;
                         R W;
@@ -234,7 +260,7 @@ wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
                 const bool inner = active && !q.done && q.cur >= 0;
                 const unsigned im = __ballot_sync(0xffffffffu, inner);
                 if (im == 0) break;
-                if (inner) query_inner_step<R>(c, q, bstack, k);
+                if (inner) query_inner_step_t<CONEPASS, R>(c, q, bstack, k);
                 if (__popc(im) < NT_DESCEND_MIN &&
                     __ballot_sync(0xffffffffu, active && !q.done && ref_is_leaf(q.cur)) != 0) break;
             }
@@ -248,6 +274,31 @@ wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
                     query_leaf_step<R>(c, q, q.o, q.d, bstack, k);
                 }
             }
+            // drifted directions (query_arm): the sphere set after the triangle set - a walk under the cone margin, or the
+            // whole warp sweeping every sphere for a ray whose cone holds the scene anyway
+            if constexpr (!CONEPASS) {
+                // a drifted direction (query_arm) has walked the triangle set only: its sphere pass is deferred - to the
+                // sweep list when the cone would hold the scene anyway, else to the cone list.  Shadow rays are normalised
+                // and never get here; a full list leaves the lane to walk the sphere set itself (constant margin).
+                if (active && q.done && q.pass == 1) {
+                    bool deferred = false;
+                    if constexpr (!SHADOW) {
+                        V3<R> d = q.d;
+                        if constexpr (RAY_IN_SMEM) d = { s_ray[3][threadIdx.x], s_ray[4][threadIdx.x], s_ray[5][threadIdx.x] };
+                        const bool wide = query_wants_sweep<R>(d);
+                        const unsigned slot = atomicAdd(wide ? w.sweep_count : w.cone_count, 1u);
+                        if (slot < w.sweep_cap) { (wide ? w.sweep_list : w.cone_list)[slot] = rec; q.pass = 2; deferred = true; }
+                    }
+                    if (!deferred && !(q.any && q.found)) {
+                        V3<R> o = q.o, d = q.d;
+                        if constexpr (RAY_IN_SMEM) {
+                            o = { s_ray[0][threadIdx.x], s_ray[1][threadIdx.x], s_ray[2][threadIdx.x] };
+                            d = { s_ray[3][threadIdx.x], s_ray[4][threadIdx.x], s_ray[5][threadIdx.x] };
+                        }
+                        query_arm<R>(c, q, o, d, 3);
+                    }
+                }
+            }
             const unsigned parked = __ballot_sync(0xffffffffu, !active || q.done);
             if (parked == 0xffffffffu || (!exhausted && __popc(parked) >= NT_WF_REFILL)) break;
         }
@@ -256,11 +307,45 @@ wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
             if constexpr (!SHADOW) {
                 ((R *)L.hit_t)[rec] = q.tb;
                 L.prim[rec] = q.best.kind >= 0 ? (q.best.kind << 28) | q.best.idx : -1;
-                L.vis[rec] = 0u;
+                if constexpr (!CONEPASS) L.vis[rec] = 0u;
             } else {
                 if (!q.found) atomicOr(L.vis + rec, 1u << light);
             }
             active = false;
+        }
+    }
+    flush_counters(k, a.counters, s_cnt);
+}
+
+// Deferred sphere sweeps of one level (see NtWfArgs::sweep_list): one warp per listed record.  The record holds the
+// nearest hit among planes and triangles (the query's pass 1); the warp tests EVERY sphere with the exact rule and the
+// record keeps the nearer of the two, ties to the smaller global id - what the walk of the grown sphere tree would have
+// returned.
+template <typename R>
+__global__ void __launch_bounds__(NT_BLOCK_THREADS)
+wf_sweep_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRenderArgs a, const __grid_constant__ NtWfArgs w) {
+    __shared__ unsigned long long s_cnt[NT_NCOUNTERS];
+    const NtSceneView<R> &v = *(const NtSceneView<R> *)(sizeof(R) == 8 ? (const void *)&s.v64 : (const void *)&s.v32);
+    const NtWfLevel &L = w.lv[w.level - 1];
+    const unsigned n = min(*w.sweep_count, w.sweep_cap), lane = threadIdx.x & 31;
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    Counters k = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    for (unsigned e = warp; e < n; e += n_warps) {
+        const unsigned rec = w.sweep_list[e];
+        V3<R> o, d;
+        R W;
+        wf_ray<R>(a, w, rec, o, d, W);
+        const SweepHit<R> h = sweep_spheres<R>(v.sph, s.sph_gid, s.ns, (R)a.eps, o, d);
+        k.sph += (s.ns + 31u - lane) / 32u;
+        if (lane == 0 && h.idx >= 0) {
+            const R tb = ((const R *)L.hit_t)[rec];
+            const int prim = L.prim[rec];
+            int gid = 0x7fffffff;
+            if (prim >= 0) gid = (prim >> 28) == 1 ? (int)s.ns + (prim & 0x0fffffff) : __ldg(((prim >> 28) == 2 ? s.tri_gid : s.sph_gid) + (prim & 0x0fffffff));
+            if (h.t < tb || (h.t == tb && h.gid < gid)) {
+                ((R *)L.hit_t)[rec] = h.t;
+                L.prim[rec] = h.idx; // kind 0
+            }
         }
     }
     flush_counters(k, a.counters, s_cnt);
@@ -448,13 +533,23 @@ inline size_t wf_bytes_per_sample(unsigned depth) {
     return b + 16; // slack for alignment
 }
 
+// Room for the deferred-sweep list of a chunk of n samples (strict mode only): one entry per 16 samples, 64 K to 4 M entries.
+template <typename R>
+inline size_t wf_sweep_bytes(size_t n_samples) {
+    if (sizeof(R) != 8) return 0;
+    size_t e = n_samples / 16;
+    e = e < (64u << 10) ? (64u << 10) : e > (4u << 20) ? (4u << 20) : e;
+    return 4 * e;
+}
+
 template <typename R>
 inline int launch_wavefront(const NtDevScene &s, const NtRenderArgs &a, cudaStream_t st, int sms, int blocks_per_sm) {
     const unsigned depth = a.max_depth;
     const unsigned n_sids = a.tiles_x * a.tiles_y * (a.spp / a.lanes) * 32;
-    const size_t header = 256;
+    const size_t header = 512;
     if (a.wf_bytes <= header + 4096) return (int)cudaErrorInvalidValue;
-    size_t S = (a.wf_bytes - header - 256 * 8 * depth) / wf_bytes_per_sample<R>(depth);
+    const size_t sweep_bytes = a.wf_bytes > 64 * wf_sweep_bytes<R>(n_sids) ? wf_sweep_bytes<R>(n_sids) : 0; // a tiny workspace keeps everything for records
+    size_t S = (a.wf_bytes - header - 256 * 8 * depth - sweep_bytes) / wf_bytes_per_sample<R>(depth);
     S &= ~(size_t)31;
     if (S > n_sids) S = n_sids;
     const size_t max_s = ((size_t)1 << 31) >> (depth - 1); // record indices must fit 32 bits
@@ -466,6 +561,9 @@ inline int launch_wavefront(const NtDevScene &s, const NtRenderArgs &a, cudaStre
     unsigned char *p = (unsigned char *)a.wf;
     w.counts = (unsigned *)p;                                  // [NT_WF_MAX_DEPTH + 2]
     w.fetch = (unsigned long long *)(p + 64);                  // [2 * NT_WF_MAX_DEPTH]
+    w.sweep_count = (unsigned *)(p + 192);                     // [NT_WF_MAX_DEPTH]: one counter per level (the header is zeroed per chunk)
+    w.cone_count = (unsigned *)(p + 224);                      // [NT_WF_MAX_DEPTH]
+    w.cone_fetch = (unsigned long long *)(p + 256);            // [NT_WF_MAX_DEPTH]
     p += header;
     auto take = [&](size_t bytes) { void *r = p; p += (bytes + 255) & ~(size_t)255; return r; };
     for (unsigned l = 1; l <= depth; ++l) {
@@ -480,7 +578,17 @@ inline int launch_wavefront(const NtDevScene &s, const NtRenderArgs &a, cudaStre
         L.tasks = l >= 2 ? (unsigned *)take(4 * cap) : nullptr;
         L.kids = (unsigned char *)take(cap);
     }
-    if ((size_t)(p - (unsigned char *)a.wf) > a.wf_bytes) return (int)cudaErrorInvalidValue;
+    // deferred sphere sweeps: whatever is left of the workspace, at most 4 M entries (a full list only means that the
+    // remaining rays walk the sphere tree themselves)
+    {
+        const size_t used = (size_t)(p - (unsigned char *)a.wf);
+        if (used > a.wf_bytes) return (int)cudaErrorInvalidValue;
+        size_t cap = (a.wf_bytes - used) / 8; // two lists
+        if (cap > sweep_bytes / 8) cap = sweep_bytes / 8;
+        w.sweep_list = (unsigned *)p;
+        w.cone_list = w.sweep_list + cap;
+        w.sweep_cap = (unsigned)cap;
+    }
 
     const size_t smem = flat_smem_bytes<R>(s, true);
     const unsigned grid_full = (unsigned)(sms * blocks_per_sm);
@@ -495,9 +603,21 @@ inline int launch_wavefront(const NtDevScene &s, const NtRenderArgs &a, cudaStre
             unsigned grid = grid_full;
             const size_t warps_needed = (bound + 31) / 32, wpb = NT_BLOCK_THREADS / 32;
             if (grid > (warps_needed + wpb - 1) / wpb) grid = (unsigned)((warps_needed + wpb - 1) / wpb);
+            unsigned *sweep_counts = w.sweep_count, *cone_counts = w.cone_count;
+            unsigned long long *cone_fetches = w.cone_fetch;
+            w.sweep_count = sweep_counts + (l - 1); w.cone_count = cone_counts + (l - 1); w.cone_fetch = cone_fetches + (l - 1);
             wf_trace_kernel<R, false><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a, w);
+            // second passes of drifted directions: a direction leaves unit length at a sphere bounce, so from level 2 on
+            const bool second = sizeof(R) == 8 && l >= 2 && s.ns > 0 && w.sweep_cap > 0;
+            if constexpr (sizeof(R) == 8) {
+                if (second) {
+                    wf_sweep_kernel<R><<<sms, NT_BLOCK_THREADS, 0, st>>>(s, a, w);
+                    wf_trace_kernel<R, false, true><<<sms, NT_BLOCK_THREADS, smem, st>>>(s, a, w);
+                }
+            }
             if (s.nl) wf_trace_kernel<R, true><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a, w);
-            if (a.n_launches) *a.n_launches += s.nl ? 3 : 2;
+            w.sweep_count = sweep_counts; w.cone_count = cone_counts; w.cone_fetch = cone_fetches;
+            if (a.n_launches) *a.n_launches += (s.nl ? 3 : 2) + (second ? 2 : 0);
             unsigned sgrid = (unsigned)(sms * 8);
             if (sgrid > (bound + NT_BLOCK_THREADS - 1) / NT_BLOCK_THREADS) sgrid = (unsigned)((bound + NT_BLOCK_THREADS - 1) / NT_BLOCK_THREADS);
             wf_shade_kernel<R><<<sgrid, NT_BLOCK_THREADS, smem, st>>>(s, a, w);
