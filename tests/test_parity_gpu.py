@@ -112,6 +112,26 @@ def test_bvh_conservative_along_mirror_chains(depth):
         assert st[k] == rst[k], k
 
 
+@pytest.mark.parametrize("variant", ["gpu_builder", "lists_full", "state_machine"])
+def test_drifted_directions_second_pass_variants(variant, monkeypatch):
+    """The sphere pass of a drifted direction (nt_bvh_trace.cuh query_arm) through its other routes: the per-set roots of the
+    GPU-built tree; a workspace so small that the deferral lists overflow or do not exist (the lane then walks the sphere
+    set itself under the constant margin); the per-lane state machine (cone walk inside the kernel).  Mirror field at
+    depth 5 against the brute-force oracle."""
+    if variant == "gpu_builder":
+        monkeypatch.setenv("NT_BVH_BUILD", "gpu")
+    elif variant == "lists_full":
+        monkeypatch.setenv("NT_WF_MB", "2")
+    else:
+        monkeypatch.setenv("NT_WAVEFRONT", "0")
+    s, cam = scenes.mirror_field()
+    img, st, ref, rst, info = render_both(s, cam, 128, 96, 4, 5)
+    assert info["uses_bvh"]
+    assert_images_match(img, ref, f"mirror field, {variant}")
+    for k in COUNTER_KEYS:
+        assert st[k] == rst[k], k
+
+
 @pytest.mark.parametrize("mode", ["wavefront_chunked", "state_machine", "deep_trees"])
 def test_bvh_render_paths_agree(mode, monkeypatch):
     """BVH scenes have two schedules of the same arithmetic: the wavefront pipeline (nt_wavefront.cuh; default,
