@@ -286,6 +286,27 @@ def test_pinned_host_buffer_equals_pageable(w, h, spp):
             assert stf[k] == rst[k], k
 
 
+def test_render_without_stats_into_pinned_frame():
+    """nt_render(stats = NULL) into a pinned frame of a flat scene: the kernel posts its completion flag into pinned host
+    memory and the call returns on it - no events, no counter copy.  Ten different frames in a row (a stale flag or a return
+    before the last pixel store would show as a frame of the previous camera), each equal to the call with stats."""
+    import ctypes as C
+    import torch
+    from nettracer_b200.lib import check, load
+    from nettracer_b200.scene import Camera
+    s, _ = scenes.cornell_box()
+    w, h = 240, 135
+    with Renderer(s) as r:
+        pinned = torch.zeros((h, w, 4), dtype=torch.uint8).pin_memory()
+        for i in range(10):
+            cam = Camera(eye=(0.3 * i - 1.5, 5.0, 15.0 - 0.4 * i), at=(0.0, 3.2, 0.0), up=(0, 1, 0), vfov_deg=42.0)
+            p = make_params(w, h, 4, 5, cam.resolve(w, h), abi.NT_F64_STRICT if i % 2 == 0 else abi.NT_F32_FAST)
+            ref, _ = r.render_params(p)
+            pinned.zero_()
+            check(load().nt_render(r._h, C.byref(p), C.c_void_p(pinned.data_ptr()), w * 4, None))
+            assert np.array_equal(pinned.numpy(), ref), f"frame {i}"
+
+
 def test_mesh_scene_reduced_bvh():
     s, cam = scenes.spheres_and_mesh(n_spheres=2000, mesh_n=96)
     img, st, ref, rst, info = render_both(s, cam, 256, 144, 4, 3, accel=1)
