@@ -84,7 +84,9 @@ __device__ __forceinline__ void query_arm(const Ctx<R, true> &c, BvhQuery<R> &q,
         const float far_ = 1.7320508f * (fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz)) + s.max_abs);
         return __fsqrt_ru(Math<R>::up(l2 - R(1))) * far_ * 1.00001f;
     }();
-    if (pass == 0 && !(grow <= 4.0f * m)) pass = 1; // also when grow is NaN
+    if constexpr (sizeof(R) == 8) { // the fast mode never grows boxes: it has one pass, and none of the code of the others
+        if (pass == 0 && !(grow <= 4.0f * m)) pass = 1; // also when grow is NaN
+    }
     if (pass == 1) grow = 0.0f;
     q.pass = pass;
     const float grow_all = grow; // pass 2: the entry slab below keeps the constant bound, the node tests use the cone
@@ -162,7 +164,9 @@ __device__ __forceinline__ bool query_wants_sweep(const V3<R> &d) {
 }
 template <typename R>
 __device__ __forceinline__ void query_second_pass(const Ctx<R, true> &c, BvhQuery<R> &q, const V3<R> &o, const V3<R> &d) {
-    if (q.done && q.pass == 1 && !(q.any && q.found)) query_arm<R>(c, q, o, d, 2);
+    if constexpr (sizeof(R) == 8) {
+        if (q.done && q.pass == 1 && !(q.any && q.found)) query_arm<R>(c, q, o, d, 2);
+    }
 }
 template <typename R> struct SweepHit { R t; int idx, gid; }; // idx < 0: nothing
 // The sweep (nt_wavefront.cuh wf_sweep_kernel): called by a whole warp with the same ray; returns the warp's nearest sphere

@@ -276,7 +276,7 @@ wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
             }
             // drifted directions (query_arm): the sphere set after the triangle set - a walk under the cone margin, or the
             // whole warp sweeping every sphere for a ray whose cone holds the scene anyway
-            if constexpr (!CONEPASS) {
+            if constexpr (!CONEPASS && sizeof(R) == 8) {
                 // a drifted direction (query_arm) has walked the triangle set only: its sphere pass is deferred - to the
                 // sweep list when the cone would hold the scene anyway, else to the cone list.  Shadow rays are normalised
                 // and never get here; a full list leaves the lane to walk the sphere set itself (constant margin).
