@@ -49,6 +49,9 @@ template <typename R> __device__ __forceinline__ V3<R> scale(const V3<R> &a, R s
     return { a.x * s, a.y * s, a.z * s };
 }
 
+// libdevice pow (non-integer shininess): ~2.4 KB of code that the benchmark scenes never run - out of line, so that it
+// does not sit between the hot blocks of the flat kernels (instruction cache)
+static __device__ __noinline__ double pow_slow(double a, double b) { return pow(a, b); }
 template <typename R> struct Math;
 template <> struct Math<double> {
     static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
@@ -72,7 +75,7 @@ template <> struct Math<double> {
             }
             return r;
         }
-        return pow(a, b);
+        return pow_slow(a, b);
     }
 #endif
     static __device__ __forceinline__ float up(double x) { return __double2float_ru(x); }
@@ -525,6 +528,18 @@ __device__ __forceinline__ bool planes_occluded(const Ctx<R, false, LEAN> &c, co
     }
     return false;
 }
+// The specialised kernels (LEAN) run for scenes whose shadow queries pass the room test nearly always: there the axis
+// lists above are cold code, and inlined they sat in the middle of the hot loop (2 KB).  Arguments by value, a context
+// rebuilt from them: nothing of the caller's state has to live in memory for the call.
+template <typename R>
+__device__ __noinline__ bool planes_occluded_cold(const NtDevScene *s, unsigned axl_addr, R eps, R eps_lo, R ox, R oy, R oz, R dx, R dy, R dz, R dist) {
+    Ctx<R, false, true> c;
+    c.s = s; c.v = nullptr; c.axl_addr = axl_addr; c.gen_addr = 0; c.sph_addr = c.pln_addr = c.tri_addr = c.code_addr = 0;
+    c.eps = eps; c.eps_lo = eps_lo; c.max_depth = 0; c.rules = 0;
+    Counters k{};
+    const V3<R> o = { ox, oy, oz }, d = { dx, dy, dz };
+    return planes_occluded<R, Counters, true>(c, o, d, dist, true, k);
+}
 // Rare path (a plane occludes the light): index of the FIRST occluding plane in index order, for the work
 // counters' sequential rule.  Plain SPEC §3 formula; gives the same t as the list forms above, bit for bit.
 template <typename R, bool LEAN>
@@ -686,7 +701,13 @@ __device__ __forceinline__ bool occluded(const Ctx<R, BVH, LEAN> &c, const V3<R>
         }
     }
     if constexpr (!BVH && sizeof(R) == 8) {
-        if (planes && planes_occluded<R, K>(c, o, d, dist, planes == 1, k)) { k.pln += s.np - (first_occluding_plane<R>(c, o, d, dist) + 1); k.tri += s.nt; return true; }
+        bool pocc = false;
+        if constexpr (LEAN && !counts_executed<K>::value) { // no general planes: planes == 2 has nothing to test
+            if (planes == 1) pocc = planes_occluded_cold<R>(c.s, c.axl_addr, c.eps, c.eps_lo, o.x, o.y, o.z, d.x, d.y, d.z, dist);
+        } else {
+            pocc = planes && planes_occluded<R, K>(c, o, d, dist, planes == 1, k);
+        }
+        if (pocc) { k.pln += s.np - (first_occluding_plane<R>(c, o, d, dist) + 1); k.tri += s.nt; return true; }
     }
     if constexpr (!BVH && sizeof(R) == 4) {
         if (planes == 2) { // origin in the light's room: general planes only
@@ -1199,7 +1220,8 @@ inline int launch_render_t(const NtDevScene &s, const NtRenderArgs &a, cudaStrea
     if constexpr (!BVH) {
         // fewer than NT_SMALL_TILES_PER_WARP warp tiles per resident warp: the small-launch variant (NT_SMALL_LAUNCH=0 / 1
         // forces the choice, A/B)
-        bool lean = s.nt == 0 && s.ngen == 0;
+        // ... and whose shadow queries skip the axis lists nearly always (light rooms) or have no plane at all
+        bool lean = s.nt == 0 && s.ngen == 0 && (s.rooms || s.np == 0);
         if (const char *e = getenv("NT_LEAN")) if (e[0] == '0') lean = false; // A/B, tests
         bool small = MINB_SMALL != 0 && !a.count_executed && !a.rules && n_tiles < (unsigned)NT_SMALL_TILES_PER_WARP * (unsigned)(sms[dev] * blocks_per_sm[dev]) * wpb;
         if (const char *e = getenv("NT_SMALL_LAUNCH")) small = MINB_SMALL != 0 && !a.count_executed && !a.rules && e[0] == '1';
