@@ -197,6 +197,37 @@ Ref build_set(std::vector<NtBvhNode> &nodes, std::atomic<int> &next_node, const 
 
 } // namespace
 
+// Binned-SAH binary tree over n boxes, one box per leaf: the top of the GPU builder's tree (nt_bvh_gpu.cu run_ploc), whose
+// clusters it joins.  children[2 t], children[2 t + 1] for inner node t of n - 1 (0 = the root, parents before children):
+// a child >= 0 is an inner node, a child < 0 is box ~child.  Deterministic; < 1 ms for a few thousand boxes.
+void nt_bvh_build_top(const float *boxes6, int n, std::vector<int> &children) {
+    children.clear();
+    if (n < 2) return;
+    std::vector<Box> bx((size_t)n);
+    for (int i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a) { bx[(size_t)i].lo[a] = boxes6[6 * (size_t)i + a]; bx[(size_t)i].hi[a] = boxes6[6 * (size_t)i + 3 + a]; }
+    std::vector<NtBvhNode> nodes((size_t)n + 2, NtBvhNode{});
+    std::atomic<int> next_node{ 0 };
+    std::vector<int> order;
+    const Ref root = build_set(nodes, next_node, bx, order, 0, 1);
+    // renumber breadth-first from the root (ids from the builder depend on its threads' timing; the tree does not)
+    std::vector<int> queue{ root.c }, new_id((size_t)next_node.load(), -1);
+    new_id[(size_t)root.c] = 0;
+    for (size_t h = 0; h < queue.size(); ++h) {
+        const NtBvhNode &nd = nodes[(size_t)queue[h]];
+        const int cs[2] = { nd.c0, nd.c1 }, ns[2] = { nd.n0, nd.n1 };
+        for (int k = 0; k < 2; ++k)
+            if (ns[k] == 0) { new_id[(size_t)cs[k]] = (int)queue.size(); queue.push_back(cs[k]); }
+    }
+    children.assign(2 * queue.size(), 0);
+    for (size_t h = 0; h < queue.size(); ++h) {
+        const NtBvhNode &nd = nodes[(size_t)queue[h]];
+        const int cs[2] = { nd.c0, nd.c1 }, ns[2] = { nd.n0, nd.n1 };
+        for (int k = 0; k < 2; ++k)
+            children[2 * h + k] = ns[k] == 0 ? new_id[(size_t)cs[k]] : ~order[(size_t)((-2 - cs[k]) & 0x3ffffff)]; // leaf ref: first | (count-1) << 26 | kind << 28
+    }
+}
+
 static int make_ref(int c, int n) {
     if (n == 0) return c;          // inner node
     if (n < 0) return -1;          // empty

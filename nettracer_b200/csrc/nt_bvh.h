@@ -18,6 +18,7 @@ struct NtBvhBuild {
 
 void nt_bvh_set_children(NtBvhNode &n, const float *lo0, const float *hi0, int c0, int n0,
                          const float *lo1, const float *hi1, int c1, int n1);
+void nt_bvh_build_top(const float *boxes6, int n, std::vector<int> &children);
 void nt_bvh_append_set_roots(std::vector<NtBvhNode4> &n4, const int root_kinds[4]);
 void nt_bvh_build(const double *spheres, uint32_t ns, const double *triangles, uint32_t nt,
                   int leaf_max, NtBvhBuild &out);

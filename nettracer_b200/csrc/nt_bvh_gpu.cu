@@ -214,6 +214,13 @@ __global__ void ploc_apply_kernel(const int *nn, int c, const unsigned long long
         cbox_out[pos] = cbox_in[i]; cnode_out[pos] = cnode_in[i]; ccount_out[pos] = ccount_in[i];
     }
 }
+// the clusters the host joined (run_ploc): cluster j's root learns its parent in the top tree
+__global__ void ploc_top_parents_kernel(const int *cnode, const int *cparent, int c, int *parent_inner, int *parent_leaf) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= c) return;
+    const int node = cnode[j];
+    if (node < 0) parent_leaf[~node] = cparent[j]; else parent_inner[node] = cparent[j];
+}
 __global__ void ploc_init_kernel(int m, int *cnode, int *ccount) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < m) { cnode[i] = ~i; ccount[i] = 1; }
@@ -410,7 +417,15 @@ struct SetBuild {
         unsigned long long *h_tot = nullptr;
         CUCHK(cudaMallocHost((void **)&h_tot, 8));
         int rc = 0;
-        while (c > 1 && rc == 0) {
+        // The agglomerative tree is good where clusters are small and poor at the top, where a few merges decide how the
+        // whole scene is cut (the 8 neighbours in Morton order are all a round ever sees): +25 % box tests per ray against the
+        // binned-SAH tree.  So the rounds stop at NT_PLOC_TOP clusters and the HOST joins those with its binned-SAH
+        // builder (nt_bvh_build_top: a few thousand boxes, < 1 ms) - the top twelve levels by the surface-area heuristic,
+        // everything below by PLOC.  NT_PLOC_TOP=1 builds the whole tree by PLOC (A/B).
+        int top = 1024; // configs[3]: 256 -> 68.5 ms, 1024 -> 66.1, 4096 -> 68.1, 16384 -> 70.7 (pure PLOC 73.3, host SAH 58.2)
+        if (const char *e = getenv("NT_PLOC_TOP")) top = atoi(e) > 0 ? atoi(e) : 1;
+        if ((int)m < 8 * top) top = 1;
+        while (c > top && rc == 0) {
             ploc_nearest_kernel<<<(c + T - 1) / T, T, 0, st>>>(cb[cur].p, c, nn.p);
             ploc_flags_kernel<<<(c + T - 1) / T, T, 0, st>>>(nn.p, c, flags.p);
             rc = (int)cudaMemsetAsync(flags.p + c, 0, 8, st); // the scan's last element = the totals
@@ -430,6 +445,43 @@ struct SetBuild {
         }
         cudaFreeHost(h_tot);
         if (rc) return rc;
+        if (c > 1) { // join the remaining clusters on the host: inner nodes 0 .. c - 2 (exactly the ids the rounds have left)
+            std::vector<FBox> hb((size_t)c);
+            std::vector<int> hn((size_t)c), hc((size_t)c), top_children;
+            CUCHK(cudaMemcpyAsync(hb.data(), cb[cur].p, sizeof(FBox) * (size_t)c, cudaMemcpyDeviceToHost, st));
+            CUCHK(cudaMemcpyAsync(hn.data(), cn[cur].p, sizeof(int) * (size_t)c, cudaMemcpyDeviceToHost, st));
+            CUCHK(cudaMemcpyAsync(hc.data(), cc[cur].p, sizeof(int) * (size_t)c, cudaMemcpyDeviceToHost, st));
+            CUCHK(cudaStreamSynchronize(st));
+            nt_bvh_build_top(&hb[0].lo[0], c, top_children);
+            const int nt_ = c - 1;
+            if ((int)top_children.size() != 2 * nt_) return (int)cudaErrorUnknown;
+            std::vector<int2> t_children((size_t)nt_);
+            std::vector<FBox> t_box((size_t)nt_);
+            std::vector<int> t_count((size_t)nt_), t_parent((size_t)nt_, -1), c_parent((size_t)c, -1);
+            for (int t = nt_ - 1; t >= 0; --t) { // parents come before children in nt_bvh_build_top's numbering
+                FBox u;
+                int cnt = 0, ref[2];
+                for (int k = 0; k < 2; ++k) {
+                    const int ch = top_children[2 * (size_t)t + k];
+                    const FBox &b = ch >= 0 ? t_box[(size_t)ch] : hb[(size_t)~ch];
+                    cnt += ch >= 0 ? t_count[(size_t)ch] : hc[(size_t)~ch];
+                    ref[k] = ch >= 0 ? ch : hn[(size_t)~ch];
+                    if (ch >= 0) t_parent[(size_t)ch] = t; else c_parent[(size_t)~ch] = t;
+                    if (k == 0) u = b;
+                    else for (int a = 0; a < 3; ++a) { u.lo[a] = fminf(u.lo[a], b.lo[a]); u.hi[a] = fmaxf(u.hi[a], b.hi[a]); }
+                }
+                t_children[(size_t)t] = make_int2(ref[0], ref[1]);
+                t_box[(size_t)t] = u;
+                t_count[(size_t)t] = cnt;
+            }
+            CUCHK(cudaMemcpyAsync(children.p, t_children.data(), sizeof(int2) * (size_t)nt_, cudaMemcpyHostToDevice, st));
+            CUCHK(cudaMemcpyAsync(nbox.p, t_box.data(), sizeof(FBox) * (size_t)nt_, cudaMemcpyHostToDevice, st));
+            CUCHK(cudaMemcpyAsync(count.p, t_count.data(), sizeof(int) * (size_t)nt_, cudaMemcpyHostToDevice, st));
+            CUCHK(cudaMemcpyAsync(parent_inner.p, t_parent.data(), sizeof(int) * (size_t)nt_, cudaMemcpyHostToDevice, st));
+            CUCHK(cudaMemcpyAsync(nn.p, c_parent.data(), sizeof(int) * (size_t)c, cudaMemcpyHostToDevice, st)); // nn: scratch
+            ploc_top_parents_kernel<<<(c + T - 1) / T, T, 0, st>>>(cn[cur].p, nn.p, c, parent_inner.p, parent_leaf.p);
+            CUCHK(cudaStreamSynchronize(st)); // the host vectors above are the copies' sources
+        }
         const int root_parent = -1;
         CUCHK(cudaMemcpyAsync(parent_inner.p, &root_parent, 4, cudaMemcpyHostToDevice, st));
         CUCHK(leaf_pos.alloc(m)); CUCHK(order.alloc(m));
@@ -550,7 +602,9 @@ int nt_bvh_build_gpu(const double *d_spheres, uint32_t ns, const double *d_trian
     const bool timing = getenv("NT_BVH_TIMING") != nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
-    if ((rc = sb.run(d_spheres, ns, 0, leaf_max, st)) != 0) return rc;
+    int leaf_sph = 1; // one sphere per leaf, as the host builder (nt_bvh.cpp): a leaf of scattered small spheres is mostly empty
+    if (const char *e = getenv("NT_BVH_LEAF_SPH")) leaf_sph = atoi(e) < 1 ? 1 : atoi(e) > NT_LEAF_MAX ? NT_LEAF_MAX : atoi(e);
+    if ((rc = sb.run(d_spheres, ns, 0, leaf_sph, st)) != 0) return rc;
     if ((rc = tb.run(d_triangles, nt, 1, leaf_max, st)) != 0) return rc;
     const uint32_t total = 1 + (uint32_t)sb.nodes4 + (uint32_t)tb.nodes4 + 2; // + the two per-set roots (nt_bvh.h)
     NtBvhNode4 *nodes = nullptr;

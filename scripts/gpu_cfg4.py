@@ -11,4 +11,4 @@ with Renderer(scene) as r:
     for _ in range(3):
         img, st = r.render(cam, w, h, spp, depth, abi.NT_F64_STRICT if prec == "f64" else abi.NT_F32_FAST)
         best = st if best is None or st["kernel_ms"] < best["kernel_ms"] else best
-print(f"{prec} kernel {best['kernel_ms']:.2f} ms rays {best['rays']} box {best['box_tests']} checksum {int(img.astype('uint64').sum())}")
+print(f"{prec} kernel {best['kernel_ms']:.2f} ms rays {best['rays']} box {best['box_tests']} tri {best['triangle_tests']} sph {best['sphere_tests']} checksum {int(img.astype('uint64').sum())}")
