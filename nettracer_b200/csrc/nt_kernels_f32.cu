@@ -18,7 +18,7 @@ size_t nt_sample_buffer_bytes(const NtDevScene &s, const NtRenderArgs &a, int pr
 }
 size_t nt_wavefront_min_bytes(const NtRenderArgs &a, int precision) {
     const size_t per = precision == 0 ? nt::wf_bytes_per_sample<double>(a.max_depth) : nt::wf_bytes_per_sample<float>(a.max_depth);
-    return 256 + 256 * 8 * (size_t)a.max_depth + 32 * per + 4096;
+    return 512 + 256 * 8 * (size_t)a.max_depth + 32 * per + 4096; // header (nt_wavefront.cuh launch_wavefront) + alignment + one warp of samples
 }
 size_t nt_wavefront_bytes(const NtDevScene &s, const NtRenderArgs &a, int precision) {
     return precision == 0 ? nt::wavefront_bytes<double>(s, a) : nt::wavefront_bytes<float>(s, a);
