@@ -364,7 +364,7 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
     ds.slab = slab ? 1 : 0; ds.rooms = rooms ? 1 : 0;
     for (int w = 0; w < 2; ++w) { // the layout of nt_trace.cuh stage_scene, R = float / double
         const size_t rs = w ? 8 : 4;
-        const size_t r_units = (size_t)ns * 4 + (size_t)np * 4 + (size_t)nt * NT_TRI_STRIDE + 2 * ((size_t)nax[0] + nax[1] + nax[2]);
+        const size_t r_units = (size_t)ns * 4 + (size_t)np * 4 + (size_t)nt * NT_TRI_STRIDE + ((2 * ((size_t)nax[0] + nax[1] + nax[2]) + 3) & ~(size_t)3);
         ds.room_off[w] = (uint32_t)(r_units * rs + ((pgen.size() + 3) & ~(size_t)3) * 4);
         ds.axs_off[w] = ds.room_off[w] + (uint32_t)((rooms ? 8 * (size_t)nl : 0) * rs);
     }

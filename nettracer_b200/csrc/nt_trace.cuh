@@ -940,13 +940,17 @@ __device__ __forceinline__ void stage_scene(const NtDevScene &s, const NtSceneVi
         for (unsigned i = threadIdx.x; i < n_tri / VEC; i += blockDim.x) { ((VT *)(smem + n_sph + n_pln))[i] = __ldg((const VT *)v.tri + i); }
     }
     const unsigned n_ax = BVH ? 0u : 2u * (s.nax[0] + s.nax[1] + s.nax[2]); // R units: (position, index bits) pairs
+    // what follows the lists is read with 128-bit shared loads (rooms, slab entries): the lists are padded to 16 bytes (an
+    // odd number of axis-aligned planes left the binary32 rooms 8-byte aligned - a misaligned-address fault, found by
+    // scripts/gpu_fuzz_flat.py)
+    const unsigned n_axp = (n_ax + 3u) & ~3u;
     if constexpr (BVH) {
         unsigned *codes = (unsigned *)(smem + n_sph + n_pln + n_tri);
         for (unsigned i = threadIdx.x; i < (s.np + 15) / 16; i += blockDim.x) codes[i] = __ldg(s.pln_code + i);
     } else {
         const R *axl = (const R *)(sizeof(R) == 8 ? (const void *)s.axl64 : (const void *)s.axl32);
         for (unsigned i = threadIdx.x; i < n_ax; i += blockDim.x) smem[n_sph + n_pln + n_tri + i] = __ldg(axl + i);
-        int *gen = (int *)(smem + n_sph + n_pln + n_tri + n_ax);
+        int *gen = (int *)(smem + n_sph + n_pln + n_tri + n_axp);
         for (unsigned i = threadIdx.x; i < s.ngen; i += blockDim.x) gen[i] = __ldg(s.pgen + i);
         // light rooms [nl][8] (slot 6 becomes this launch's distance cap min(eps * cap_per_eps, cap_max)), slab entries [3][2][2]
         R *room = (R *)(gen + ((s.ngen + 3u) & ~3u));
@@ -968,7 +972,7 @@ __device__ __forceinline__ void stage_scene(const NtDevScene &s, const NtSceneVi
     c.tri_addr = base + (n_sph + n_pln) * (unsigned)sizeof(R);
     c.code_addr = base + (n_sph + n_pln + n_tri) * (unsigned)sizeof(R);
     c.axl_addr = c.code_addr;
-    c.gen_addr = c.axl_addr + n_ax * (unsigned)sizeof(R);
+    c.gen_addr = c.axl_addr + n_axp * (unsigned)sizeof(R);
 }
 
 // Per-thread counters -> one atomic per counter per block, spread over NT_COUNTER_SLOTS slots.
@@ -1161,7 +1165,7 @@ inline size_t flat_smem_bytes(const NtDevScene &s, bool bvh) {
     size_t n = (size_t)s.np * 4;
     if (bvh) return n * sizeof(R) + (size_t)((((s.np + 15) / 16) + 3) & ~3u) * sizeof(unsigned);
     n += (size_t)s.ns * 4 + (size_t)s.nt * NT_TRI_STRIDE;
-    n += 2 * ((size_t)s.nax[0] + s.nax[1] + s.nax[2]);          // axis-aligned plane lists
+    n += (2 * ((size_t)s.nax[0] + s.nax[1] + s.nax[2]) + 3) & ~(size_t)3; // axis-aligned plane lists, padded to 16 bytes
     n += (s.rooms ? 8 * (size_t)s.nl : 0) + 12;                  // light rooms, slab entries
     return n * sizeof(R) + (((size_t)s.ngen + 3) & ~(size_t)3) * sizeof(int);
 }

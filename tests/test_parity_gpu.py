@@ -245,6 +245,35 @@ def test_light_rooms_and_lean_kernel_equal_oracle(open_room, monkeypatch):
     assert np.array_equal(imgs[0], imgs[1]) and np.array_equal(imgs[2], imgs[3]), "NT_LEAN must not change the fast image"
 
 
+@pytest.mark.parametrize("n_axis_planes", [1, 3, 5])
+def test_flat_odd_number_of_axis_planes(n_axis_planes):
+    """An odd number of axis-aligned planes: the staged plane lists are then an odd number of 8-byte entries in the fast
+    mode, and what follows them in shared memory (light rooms, slab entries) is read with 128-bit loads - the lists are
+    padded to 16 bytes (a misaligned-address fault found by scripts/gpu_fuzz_flat.py).  Both modes, against the oracle."""
+    from nettracer_b200.scene import Camera, Material, Scene
+    s = Scene(ambient=(1.0, 1.0, 1.0), background=(0.1, 0.1, 0.2))
+    m = s.add_material(Material((0.7, 0.7, 0.6), ka=0.1, kd=0.8, ks=0.2, shininess=20.0, kr=0.2))
+    g = s.add_material(Material((0.9, 0.95, 1.0), ka=0.0, kd=0.1, ks=0.4, shininess=90.0, kr=0.1, kt=0.8, ior=1.4))
+    walls = [((0, 1, 0), 0.0), ((1, 0, 0), -5.0), ((0, 0, 1), -7.0), ((-1, 0, 0), -5.0), ((0, -1, 0), -8.0)]
+    for n, d in walls[:n_axis_planes]:
+        s.add_plane(n, d, m)
+    s.add_sphere((-1.0, 1.2, -1.0), 1.2, g)
+    s.add_sphere((1.8, 1.0, 0.5), 1.0, m)
+    s.add_light((-3.0, 7.0, 3.0), (0.6, 0.6, 0.55))
+    cam = Camera(eye=(0.5, 3.5, 8.5), at=(0.0, 1.5, 0.0), up=(0, 1, 0), vfov_deg=55.0)
+    w, h = 160, 100
+    p = make_params(w, h, 4, 4, cam.resolve(w, h), abi.NT_F64_STRICT)
+    ref, rst = oracle.render(s, p)
+    with Renderer(s) as r:
+        img, st = r.render_params(p)
+        fast, _ = r.render_params(make_params(w, h, 4, 4, cam.resolve(w, h), abi.NT_F32_FAST))
+    assert_images_match(img, ref, f"{n_axis_planes} axis planes")
+    for k in COUNTER_KEYS + FLAT_TEST_KEYS:
+        assert st[k] == rst[k], k
+    d = np.abs(fast.astype(int) - ref.astype(int))[..., :3].max(axis=-1)
+    assert (d <= 2).mean() > 0.97
+
+
 def test_fast_slab_planes_off_equals_on(monkeypatch):
     """Fast mode: the packed slab form of the axis-aligned planes (NT_SLAB, rooms with at most two planes per axis)
     against the plain plane loop: the same image up to the odd 1-LSB pixel (different rounding of t)."""
