@@ -377,6 +377,17 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
     const char *ce = getenv("NT_CULL");
     if (!use_bvh && !(ce && ce[0] == '0') && nt_cull_build(d->spheres, ns, d->triangles, nt, d->lights, nl, ct)) {
         ds.cull = 1; ds.lbuf_k = ct.k;
+        {   // light buffers are trusted up to 1e5 x the smallest sphere radius from the light (nt_trace.cuh lbuf_mask); a scene
+            // whose own extent exceeds that gets no culling at all
+            double rmin = HUGE_VAL, ext = 0;
+            for (uint32_t j = 0; j < ns; ++j) {
+                rmin = std::min(rmin, d->spheres[4 * (size_t)j + 3]);
+                for (int a = 0; a < 3; ++a) ext = std::max(ext, std::fabs(d->spheres[4 * (size_t)j + a]) + d->spheres[4 * (size_t)j + 3]);
+            }
+            for (uint32_t l = 0; l < nl; ++l) for (int a = 0; a < 3; ++a) ext = std::max(ext, std::fabs(d->lights[6 * (size_t)l + a]));
+            ds.cull_far = ns ? (float)std::min(1e5 * rmin, 1e30) : 1e30f;
+            if (ns && !(2.0 * ext < 1e5 * rmin)) ds.cull = 0; // tiny spheres in a huge scene: brute force
+        }
         sc->h_bsph = ct.bsph;
         for (uint32_t j = 0; j < ns; ++j) { const double *m = d->materials + 10 * (size_t)d->sphere_mat[j]; if (m[7] > 0 && m[8] > 0) sc->heavy_bits |= 1ull << j; }
         for (uint32_t j = 0; j < nt; ++j) { const double *m = d->materials + 10 * (size_t)d->triangle_mat[j]; if (m[7] > 0 && m[8] > 0) sc->heavy_bits |= 1ull << (ns + j); }

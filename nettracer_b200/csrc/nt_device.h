@@ -104,6 +104,7 @@ struct NtDevScene {
     const NtBvhNode4 *nodes;
     // flat scenes: conservative culling tables (nt_cull.h); cull == 0 -> every query tests every primitive
     uint32_t cull, lbuf_k;
+    float cull_far; // shadow queries whose light is farther than this (max norm) look no light buffer up: see lbuf_mask
     uint32_t lfree; // bit l: no plane can lie between a point of a bounded primitive and light l (nt_cull_plane_free_lights)
     unsigned long long sph_bits, all_bits; // masks of the sphere bits / of all bounded primitives (flat scenes)
     const unsigned long long *lbuf; // [nl][6][lbuf_k][lbuf_k] light buffers

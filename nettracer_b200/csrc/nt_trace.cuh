@@ -335,7 +335,13 @@ __device__ __forceinline__ unsigned long long lbuf_mask(const NtDevScene &s, uns
     iu = min(max(iu, 0), K - 1);
     iv = min(max(iv, 0), K - 1);
     const unsigned cell = ((l * 6u + face) * (unsigned)K + (unsigned)iv) * (unsigned)K + (unsigned)iu; // < 2^32: <= 32 lights (nt_cull.h)
-    return __ldg(s.lbuf + cell);
+    // A query from very far away - a hit on an unbounded plane near the horizon, millions of units out - is beyond what the
+    // tables can promise: the sphere rule of SPEC section 3 cancels catastrophically there (its discriminant carries an
+    // error of ~1e-15 |o - c|^2, the size of r^2 from |o - c| ~ 1e6 r on), so it "hits" spheres the ray misses by a wide
+    // margin, and a culled GPU query would disagree with it.  Found by scripts/gpu_fuzz_flat.py (an exact image, one
+    // work counter off by two: a sphere the rule hit from 2.2e7 units away was not in its cell).  Beyond cull_far = 1e5 x the
+    // smallest radius every primitive is tested, as the rule does; m is the max norm of light - P.
+    return m > s.cull_far ? s.all_bits : __ldg(s.lbuf + cell);
 }
 
 // ---- warp-tile coordinates without integer division (they are recomputed around every trace instead of

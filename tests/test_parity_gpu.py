@@ -274,6 +274,29 @@ def test_flat_odd_number_of_axis_planes(n_axis_planes):
     assert (d <= 2).mean() > 0.97
 
 
+def test_flat_far_horizon_queries_fuzz_regression():
+    """Scene 141 of `scripts/gpu_fuzz_flat.py 142 31`: an open room whose floor is hit 2.2e7 units away near the horizon.
+    From there SPEC section 3's sphere rule cancels catastrophically and reports hits on spheres the ray misses by far;
+    the light buffers (which know geometry, not rounding) had culled such a sphere: image exact, two plane tests fewer
+    than the oracle.  Shadow queries farther than 1e5 x the smallest radius from their light now test every primitive
+    (`lbuf_mask`, `cull_far`).  The generator is the fuzzer's own, so the scene is the one that failed."""
+    import os
+    src = open(os.path.join(os.path.dirname(__file__), "..", "scripts", "gpu_fuzz_flat.py")).read()
+    gen = src[src.index("for it in range(n_scenes):"):src.index("    if only is not None and it not in only:")]
+    from nettracer_b200.scene import Camera, Material, Scene
+    env = dict(np=np, abi=abi, Camera=Camera, Material=Material, Scene=Scene, make_params=make_params,
+               rng=np.random.default_rng(31), n_scenes=142, keep=[])
+    exec(gen + "    keep.append((s, p))\n", env)
+    s, p = env["keep"][141]
+    ref, rst = oracle.render(s, p)
+    with Renderer(s) as r:
+        assert not r.info()["uses_bvh"]
+        img, st = r.render_params(p)
+    assert_images_match(img, ref, "fuzz seed 31 scene 141")
+    for k in COUNTER_KEYS + FLAT_TEST_KEYS:
+        assert st[k] == rst[k], k
+
+
 def test_fast_slab_planes_off_equals_on(monkeypatch):
     """Fast mode: the packed slab form of the axis-aligned planes (NT_SLAB, rooms with at most two planes per axis)
     against the plain plane loop: the same image up to the odd 1-LSB pixel (different rounding of t)."""
