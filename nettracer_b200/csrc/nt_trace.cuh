@@ -1269,7 +1269,8 @@ template <typename R>
 inline size_t wavefront_bytes(const NtDevScene &s, const NtRenderArgs &a) {
     if (!s.use_bvh || a.max_depth > NT_WF_MAX_DEPTH || s.nl > 32) return 0;
     const size_t n = (size_t)a.tiles_x * a.tiles_y * (a.spp / a.lanes) * 32;
-    return 512 + 256 * 8 * (size_t)a.max_depth + n * wf_bytes_per_sample<R>(a.max_depth) + wf_sweep_bytes<R>(n);
+    return 512 + 256 * 8 * (size_t)a.max_depth + n * wf_bytes_per_sample<R>(a.max_depth) + wf_sweep_bytes<R>(n) +
+           (wf_sort_mode() ? 4 * wf_sort_fixed_bytes() + n * wf_sort_bytes_per_sample(a.max_depth) + 1024 : 0);
 }
 
 template <typename R>

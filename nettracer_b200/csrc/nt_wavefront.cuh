@@ -30,6 +30,13 @@
 #define NT_WF_REFILL 16    // idle lanes before a warp pulls new tasks (configs[3] f64: 4 -> 70.0 ms, 8 -> 69.8, 16 -> 62.5, 24 -> 62.7)
 #endif
 
+#ifndef NT_WF_SORT_DEFAULT
+#define NT_WF_SORT_DEFAULT 2   // see wf_sort_mode: configs[3] f64 57.7 ms unsorted, 55.8 with 2, 56.0 with 6, 60.4 with 3 (profiles/r04_wf_sort.txt)
+#endif
+
+#ifndef NT_WF_REPULL
+#define NT_WF_REPULL 1
+#endif
 struct NtWfLevel {
     void *ray;            // R[7][cap]: ox oy oz dx dy dz W   (levels >= 2; level 1 rays come from the camera)
     void *hit_t;          // R[cap]
@@ -53,6 +60,10 @@ struct NtWfArgs {
     // mechanism, walked by the CONEPASS instantiation of wf_trace_kernel (the main kernel carries no cone code)
     unsigned *cone_list, *cone_count;
     unsigned long long *cone_fetch;
+    // the task list the level's kernels read: NULL = record i is task i (level 1), else lv[level - 1].tasks or a sorted
+    // copy of it (wf_sort_* below)
+    const unsigned *cur;
+    unsigned *sort_keys, *sort_out, *sort_hist; // scratch of the task sort: key per task, sorted list, bucket counters
 };
 
 namespace nt {
@@ -197,7 +208,7 @@ wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
                         }
                         active = true;
                     } else if constexpr (!SHADOW) {
-                        rec = w.level == 1 ? (unsigned)ti : L.tasks[ti];
+                        rec = w.cur ? w.cur[ti] : (unsigned)ti;
                         V3<R> o, d;
                         R W;
                         if (wf_ray<R>(a, w, rec, o, d, W)) {
@@ -221,7 +232,7 @@ wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
                         const unsigned long long ri64 = grp * 32ull + (within & 31u);
                         if (ri64 >= n_rec) continue_task = false;
                         const unsigned ri = (unsigned)(ri64 < n_rec ? ri64 : 0);
-                        rec = w.level == 1 ? ri : L.tasks[ri];
+                        rec = w.cur ? w.cur[ri] : ri;
                         const int prim = continue_task ? L.prim[rec] : -2;
                         if (prim >= 0) {
                             V3<R> o, d;
@@ -250,10 +261,14 @@ wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
                 }
             }
         }
-        if (__ballot_sync(0xffffffffu, active) == 0) {
+        const unsigned started = __ballot_sync(0xffffffffu, active);
+        if (started == 0) {
             if (exhausted) break;
             continue;
         }
+        // sparse tasks - records that hit nothing, lights behind the surface, samples of the last ragged tile start no query -:
+        // pull again before walking, or the warp walks with whatever share of its lanes the list happened to fill
+        if (NT_WF_REPULL && !exhausted && __popc(~started) >= NT_WF_REFILL) continue;
         // ---- traversal rounds (as in render_bvh_kernel) until enough lanes have finished ----
         for (;;) {
             for (;;) {
@@ -373,7 +388,7 @@ wf_shade_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
         R Wr = R(0), Wt = R(0);
         unsigned rec = 0;
         if (i < n_rec) {
-            rec = w.level == 1 ? i : L.tasks[i];
+            rec = w.cur ? w.cur[i] : i;
             const int prim = L.prim[rec];
             R *term = (R *)L.term;
             const size_t cap = L.cap;
@@ -522,6 +537,131 @@ wf_sum_kernel(const __grid_constant__ NtRenderArgs a, const __grid_constant__ Nt
     }
 }
 
+// ---- task sort (NT_WF_SORT) ---------------------------------------------------------------------------------------------
+// A level's task list is in creation order: the children of neighbouring samples, reflection and transmission rays
+// alternating.  Before a traversal pass the list can be bucket-sorted by where its rays start - a Morton code of the
+// origin's cell in the scene bounds, then the direction's octant (nearest-hit pass), or the cell of the hit point the
+// shadow rays leave from (shadow pass) - so that the lanes of a warp walk the same nodes.  Three small kernels: keys +
+// bucket histogram, exclusive scan, scatter; atomics are warp-aggregated with match.any, equal keys of one warp keep their
+// order.  The order of a task list never changes a result (every task writes its own record), only the schedule.
+#define NT_WF_SORT_BITS 18
+#define NT_WF_SORT_BUCKETS (1u << NT_WF_SORT_BITS)
+
+__device__ __forceinline__ unsigned wf_spread3(unsigned v) { // bits of v (<= 6 of them) to every third position
+    v &= 0x3fu;
+    v = (v | (v << 8)) & 0x0000300fu;
+    v = (v | (v << 4)) & 0x000030c3u;
+    v = (v | (v << 2)) & 0x00009249u;
+    return v;
+}
+template <int BITS>
+__device__ __forceinline__ unsigned wf_cell_code(const NtDevScene &s, float x, float y, float z) {
+    const float n = (float)(1 << BITS);
+    const float fx = (x - s.blo[0]) * (n / fmaxf(s.bhi[0] - s.blo[0], 1e-30f));
+    const float fy = (y - s.blo[1]) * (n / fmaxf(s.bhi[1] - s.blo[1], 1e-30f));
+    const float fz = (z - s.blo[2]) * (n / fmaxf(s.bhi[2] - s.blo[2], 1e-30f));
+    const unsigned ix = (unsigned)fminf(fmaxf(fx, 0.f), n - 1.f), iy = (unsigned)fminf(fmaxf(fy, 0.f), n - 1.f), iz = (unsigned)fminf(fmaxf(fz, 0.f), n - 1.f);
+    return wf_spread3(ix) | wf_spread3(iy) << 1 | wf_spread3(iz) << 2;
+}
+
+// HITPOINT == false: key of the record's ray (5 bits per axis + octant); true: key of what it hit (records without a hit go
+// to the last bucket: their shadow tasks end at once).
+template <typename R, bool HITPOINT>
+__global__ void __launch_bounds__(256)
+wf_sort_hist_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ NtRenderArgs a, const __grid_constant__ NtWfArgs w) {
+    const NtWfLevel &L = w.lv[w.level - 1];
+    const unsigned n = w.level == 1 ? w.n_samples : w.counts[w.level];
+    const unsigned stride = gridDim.x * blockDim.x, lane = threadIdx.x & 31;
+    for (unsigned base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+        const unsigned i = base + lane;
+        unsigned key = 0xffffffffu;
+        if (i < n) {
+            const unsigned rec = w.cur ? w.cur[i] : i;
+            V3<R> o, d;
+            R W;
+            key = NT_WF_SORT_BUCKETS - 1;
+            if constexpr (HITPOINT) {
+                // where the shadow rays start = what the record hit.  The primitive arrays of a BVH scene are in the
+                // depth-first order of the tree, so the index itself is a spatial code at every scale, and it costs one
+                // 4-byte gather (the hit point's cell needs the ray and t: 7 gathers of R, 2.2 ms per frame of configs[3]
+                // against 3.2 ms saved in the shadow passes).  Planes are unbounded: those few records use the cell.
+                const int prim = L.prim[rec];
+                if (prim >= 0) {
+                    const unsigned kind = (unsigned)prim >> 28, idx = (unsigned)prim & 0x0fffffffu;
+                    if (kind == 2) key = (unsigned)(((unsigned long long)idx << (NT_WF_SORT_BITS - 1)) / s.nt);
+                    else if (kind == 0) key = (1u << (NT_WF_SORT_BITS - 1)) + (unsigned)(((unsigned long long)idx << (NT_WF_SORT_BITS - 2)) / s.ns);
+                    else if (wf_ray<R>(a, w, rec, o, d, W)) {
+                        const R t = ((const R *)L.hit_t)[rec];
+                        key = (3u << (NT_WF_SORT_BITS - 2)) + wf_cell_code<5>(s, (float)(o.x + d.x * t), (float)(o.y + d.y * t), (float)(o.z + d.z * t));
+                    }
+                }
+            } else if (wf_ray<R>(a, w, rec, o, d, W)) {
+                key = wf_cell_code<5>(s, (float)o.x, (float)o.y, (float)o.z) << 3 | (d.x < R(0) ? 1u : 0u) | (d.y < R(0) ? 2u : 0u) | (d.z < R(0) ? 4u : 0u);
+            }
+            w.sort_keys[i] = key;
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (i < n && lane == (unsigned)__ffs(peers) - 1) atomicAdd(w.sort_hist + key, (unsigned)__popc(peers));
+    }
+}
+
+// Exclusive scan of the bucket counters in place, two launches: every block scans 1024 counters and posts its total, then
+// every block adds the totals of the blocks before it.  (One block walking all 2^18 counters took 0.45 ms.)
+static __device__ __forceinline__ unsigned wf_block_scan_1024(unsigned v, unsigned *s_warp, unsigned &total) { // inclusive
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, v, o); if ((int)lane >= o) v += u; }
+    if (lane == 31) s_warp[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned t = s_warp[lane];
+        for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, t, o); if ((int)lane >= o) t += u; }
+        s_warp[lane] = t;
+    }
+    __syncthreads();
+    total = s_warp[31];
+    return v + (wid ? s_warp[wid - 1] : 0u);
+}
+static __global__ void __launch_bounds__(1024) wf_sort_scan1_kernel(unsigned *hist, unsigned *sums) {
+    __shared__ unsigned s_warp[32];
+    const unsigned i = blockIdx.x * 1024 + threadIdx.x, c = hist[i];
+    unsigned total;
+    const unsigned inc = wf_block_scan_1024(c, s_warp, total);
+    hist[i] = inc - c;
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+static __global__ void __launch_bounds__(1024) wf_sort_scan2_kernel(unsigned *hist, const unsigned *sums) {
+    __shared__ unsigned s_warp[32];
+    static_assert(NT_WF_SORT_BUCKETS / 1024 <= 1024, "one block adds the block totals up");
+    unsigned total;
+    wf_block_scan_1024(threadIdx.x < blockIdx.x ? sums[threadIdx.x] : 0u, s_warp, total);
+    hist[blockIdx.x * 1024 + threadIdx.x] += total;
+}
+
+static __global__ void __launch_bounds__(256)
+wf_sort_scatter_kernel(const __grid_constant__ NtWfArgs w) {
+    const unsigned n = w.level == 1 ? w.n_samples : w.counts[w.level];
+    const unsigned stride = gridDim.x * blockDim.x, lane = threadIdx.x & 31;
+    for (unsigned base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+        const unsigned i = base + lane;
+        const unsigned key = i < n ? w.sort_keys[i] : 0xffffffffu;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const unsigned leader = (unsigned)__ffs(peers) - 1;
+        unsigned pos = 0;
+        if (i < n && lane == leader) pos = atomicAdd(w.sort_hist + key, (unsigned)__popc(peers));
+        pos = __shfl_sync(0xffffffffu, pos, leader);
+        if (i < n) w.sort_out[pos + __popc(peers & ((1u << lane) - 1))] = w.cur ? w.cur[i] : i;
+    }
+}
+
+// Scratch of the task sort for chunks of S samples: keys and the sorted list at the capacity of the deepest level, plus the
+// bucket counters.  Only workspaces that dwarf the counters sort at all (tests run the pipeline in 1 MB).
+inline size_t wf_sort_fixed_bytes() { return 4 * (size_t)NT_WF_SORT_BUCKETS + 4096 + 1024; } // + the alignment of three arrays
+inline size_t wf_sort_bytes_per_sample(unsigned depth) { return (size_t)8 << (depth - 1); }
+inline unsigned wf_sort_mode() { // bit 0: rays of levels >= 2 before the nearest-hit pass; bit 1: hit points of levels >= 2 before the shadow pass; bit 2: hit points of level 1
+    const char *e = getenv("NT_WF_SORT");
+    return e ? (unsigned)atoi(e) & 7u : NT_WF_SORT_DEFAULT;
+}
+
 // Bytes of workspace per sample for trees of depth D, and the layout of one chunk inside the workspace.
 template <typename R>
 inline size_t wf_bytes_per_sample(unsigned depth) {
@@ -549,7 +689,10 @@ inline int launch_wavefront(const NtDevScene &s, const NtRenderArgs &a, cudaStre
     const size_t header = 512;
     if (a.wf_bytes <= header + 4096) return (int)cudaErrorInvalidValue;
     const size_t sweep_bytes = a.wf_bytes > 64 * wf_sweep_bytes<R>(n_sids) ? wf_sweep_bytes<R>(n_sids) : 0; // a tiny workspace keeps everything for records
-    size_t S = (a.wf_bytes - header - 256 * 8 * depth - sweep_bytes) / wf_bytes_per_sample<R>(depth);
+    unsigned sort_mode = wf_sort_mode();
+    if (a.wf_bytes < 4 * wf_sort_fixed_bytes() || s.nl == 0) sort_mode = 0; // tiny workspaces keep everything for records
+    const size_t sort_fixed = sort_mode ? wf_sort_fixed_bytes() : 0;
+    size_t S = (a.wf_bytes - header - 256 * 8 * depth - sweep_bytes - sort_fixed) / (wf_bytes_per_sample<R>(depth) + (sort_mode ? wf_sort_bytes_per_sample(depth) : 0));
     S &= ~(size_t)31;
     if (S > n_sids) S = n_sids;
     const size_t max_s = ((size_t)1 << 31) >> (depth - 1); // record indices must fit 32 bits
@@ -578,6 +721,12 @@ inline int launch_wavefront(const NtDevScene &s, const NtRenderArgs &a, cudaStre
         L.tasks = l >= 2 ? (unsigned *)take(4 * cap) : nullptr;
         L.kids = (unsigned char *)take(cap);
     }
+    if (sort_mode) {
+        const size_t cap = S << (depth - 1);
+        w.sort_keys = (unsigned *)take(4 * cap);
+        w.sort_out = (unsigned *)take(4 * cap);
+        w.sort_hist = (unsigned *)take(4 * (size_t)NT_WF_SORT_BUCKETS + 4096); // + the scan's block totals
+    }
     // deferred sphere sweeps: whatever is left of the workspace, at most 4 M entries (a full list only means that the
     // remaining rays walk the sphere tree themselves)
     {
@@ -590,6 +739,7 @@ inline int launch_wavefront(const NtDevScene &s, const NtRenderArgs &a, cudaStre
         w.sweep_cap = (unsigned)cap;
     }
 
+    unsigned *const sort_scratch = w.sort_out;
     const size_t smem = flat_smem_bytes<R>(s, true);
     const unsigned grid_full = (unsigned)(sms * blocks_per_sm);
     for (unsigned sid0 = 0; sid0 < n_sids; sid0 += (unsigned)S) {
@@ -606,6 +756,25 @@ inline int launch_wavefront(const NtDevScene &s, const NtRenderArgs &a, cudaStre
             unsigned *sweep_counts = w.sweep_count, *cone_counts = w.cone_count;
             unsigned long long *cone_fetches = w.cone_fetch;
             w.sweep_count = sweep_counts + (l - 1); w.cone_count = cone_counts + (l - 1); w.cone_fetch = cone_fetches + (l - 1);
+            // the level's task list, and (NT_WF_SORT) its sorted copies: the level's own buffer and the scratch take turns
+            w.cur = l >= 2 ? w.lv[l - 1].tasks : nullptr;
+            unsigned *spare = sort_scratch;
+            unsigned sortgrid = (unsigned)(sms * 8);
+            if (sortgrid > (bound + 255) / 256) sortgrid = (unsigned)((bound + 255) / 256);
+            auto sort_tasks = [&](bool hitpoint) {
+                cudaMemsetAsync(w.sort_hist, 0, 4 * (size_t)NT_WF_SORT_BUCKETS, st);
+                if (hitpoint) wf_sort_hist_kernel<R, true><<<sortgrid, 256, 0, st>>>(s, a, w);
+                else wf_sort_hist_kernel<R, false><<<sortgrid, 256, 0, st>>>(s, a, w);
+                wf_sort_scan1_kernel<<<NT_WF_SORT_BUCKETS / 1024, 1024, 0, st>>>(w.sort_hist, w.sort_hist + NT_WF_SORT_BUCKETS);
+                wf_sort_scan2_kernel<<<NT_WF_SORT_BUCKETS / 1024, 1024, 0, st>>>(w.sort_hist, w.sort_hist + NT_WF_SORT_BUCKETS);
+                unsigned *dst = spare;
+                w.sort_out = dst;
+                wf_sort_scatter_kernel<<<sortgrid, 256, 0, st>>>(w);
+                spare = dst == sort_scratch ? w.lv[l - 1].tasks : sort_scratch; // a second sort of this level goes back into its own buffer (level 1 has none)
+                w.cur = dst;
+                if (a.n_launches) *a.n_launches += 4;
+            };
+            if (l >= 2 && (sort_mode & 1u)) sort_tasks(false);
             wf_trace_kernel<R, false><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a, w);
             // second passes of drifted directions: a direction leaves unit length at a sphere bounce, so from level 2 on
             const bool second = sizeof(R) == 8 && l >= 2 && s.ns > 0 && w.sweep_cap > 0;
@@ -615,11 +784,15 @@ inline int launch_wavefront(const NtDevScene &s, const NtRenderArgs &a, cudaStre
                     wf_trace_kernel<R, false, true><<<sms, NT_BLOCK_THREADS, smem, st>>>(s, a, w);
                 }
             }
+            if (s.nl && (sort_mode & (l >= 2 ? 2u : 4u)) && spare) sort_tasks(true);
             if (s.nl) wf_trace_kernel<R, true><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a, w);
             w.sweep_count = sweep_counts; w.cone_count = cone_counts; w.cone_fetch = cone_fetches;
             if (a.n_launches) *a.n_launches += (s.nl ? 3 : 2) + (second ? 2 : 0);
             unsigned sgrid = (unsigned)(sms * 8);
             if (sgrid > (bound + NT_BLOCK_THREADS - 1) / NT_BLOCK_THREADS) sgrid = (unsigned)((bound + NT_BLOCK_THREADS - 1) / NT_BLOCK_THREADS);
+            // shading reads and writes whole records: the creation-order list (coalesced) while it still exists
+            if (l == 1) w.cur = nullptr;
+            else if (w.cur == sort_scratch && !(sort_mode & 1u)) w.cur = w.lv[l - 1].tasks;
             wf_shade_kernel<R><<<sgrid, NT_BLOCK_THREADS, smem, st>>>(s, a, w);
         }
         unsigned ggrid = (unsigned)(sms * 8);
