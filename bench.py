@@ -460,16 +460,16 @@ def main():
         achieved_tf = r["flops_local"] / (r["kernel_ms_local"] * 1e-3) / 1e12
         executed_tf = r["executed_local"] / (r["kernel_ms_local"] * 1e-3) / 1e12
         fma_peak_tf = (peaks["f64_fma_gflops"] if strict else peaks["f32_fma_gflops"]) / 1e3
-        traffic = {"cfg3_cornell_1080p_4spp_d5": 7.423e7}.get(a.workload) if strict and world == 1 else None
+        traffic = {"cfg3_cornell_1080p_4spp_d5": 5.380e7}.get(a.workload) if strict and world == 1 else None
         roof = {"bound": "fp64" if strict else "fp32", "achieved": achieved_tf, "peak": peak_gf / 1e3, "unit": "TFLOP/s",
                 "frac": achieved_tf / (peak_gf / 1e3),
                 "executed": executed_tf, "executed_frac": executed_tf / (peak_gf / 1e3),
                 "frac_vs_fma_peak": achieved_tf / fma_peak_tf, "executed_frac_vs_fma_peak": executed_tf / fma_peak_tf,
                 "traffic": traffic,
                 "traffic_source": ("profile constant, not measured in this run: dram read + write bytes of one render launch from "
-                                   "ncu --set full (profiles/r01j_cfg3_f64_final.md): 2.3 MB read + 71.9 MB written, of which 8.3 MB "
-                                   "is the frame and the rest local-memory (ray-stack, spill) lines the L2 flush between steps "
-                                   "forces out; 1.5 % of HBM bandwidth") if traffic else None,
+                                   "ncu --set full (profiles/r02w_cfg3_f64_lean.md, the current kernel): 2.2 MB read + 51.6 MB written, of which "
+                                   "8.3 MB is the frame and the rest local-memory (ray-stack, spill) lines evicted from L2; "
+                                   "1.0 % of HBM bandwidth") if traffic else None,
                 "kernel": ("wf_trace_kernel + wf_shade_kernel (wavefront pipeline, all kernels of a frame)" if info["uses_bvh"] and r["launches"] > 3
                            else "render_%skernel<%s>" % ("bvh_" if info["uses_bvh"] else "", "double" if strict else "float")),
                 "kernel_ms": r["kernel_ms_local"], "algorithmic_flops_per_launch": r["flops_local"],

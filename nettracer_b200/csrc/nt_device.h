@@ -32,8 +32,9 @@
 #define NT_ADVANCE_THRESHOLD 32 // lanes parked with a finished query before the warp shades (8: 123 ms, 16: 106, 32: 94)
 #endif
 #ifndef NT_DESCEND_MIN
-#define NT_DESCEND_MIN 8      // fewer lanes than this still descending -> go test the waiting leaves (configs[3] f64,
-#endif                        // state machine: 2 -> 64.3 ms, 4 -> 63.1, 8 -> 62.9; wavefront: 4 -> 62.5, 8 -> 60.6)
+#define NT_DESCEND_MIN 12     // fewer lanes than this still descending -> go test the waiting leaves (configs[3] f64,
+#endif                        // state machine: 2 -> 64.3 ms, 4 -> 63.1, 8 -> 62.9; wavefront: 4 -> 62.5, 8 -> 60.6; last session,
+                              // wavefront with sorted shadow tasks: 8 -> 56.0, 12 -> 55.4, 16 -> 55.5, profiles/r04_wf_sort.txt)
 #ifndef NT_REFILL_THRESHOLD
 #define NT_REFILL_THRESHOLD 32 // idle lanes before the warp claims new samples (8: 105 ms, 24: 78.2, 32: 75.8)
 #endif

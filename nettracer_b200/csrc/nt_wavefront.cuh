@@ -27,7 +27,8 @@
 
 #define NT_WF_MAX_DEPTH 6  // deeper trees use the per-lane state machine (heap layout: 2^depth - 1 records per sample)
 #ifndef NT_WF_REFILL
-#define NT_WF_REFILL 16    // idle lanes before a warp pulls new tasks (configs[3] f64: 4 -> 70.0 ms, 8 -> 69.8, 16 -> 62.5, 24 -> 62.7)
+#define NT_WF_REFILL 20    // idle lanes before a warp pulls new tasks (configs[3] f64: 4 -> 70.0 ms, 8 -> 69.8, 16 -> 62.5, 24 -> 62.7;
+                           // with sparse pulls repeated and NT_DESCEND_MIN 12: 12 -> 57.0, 16 -> 55.4, 20 -> 54.8, 24 -> 54.9, 28 -> 56.1)
 #endif
 
 #ifndef NT_WF_SORT_DEFAULT
