@@ -69,6 +69,9 @@ __global__ void prim_boxes_kernel(const double *prims, uint32_t n, int kind, FBo
     }
 }
 
+#ifndef NT_MORTON_CUBE_DEFAULT
+#define NT_MORTON_CUBE_DEFAULT 1 // configs[3] strict: GPU-built tree 61.8 -> 58.0 ms (host SAH tree 54.9), profiles/r04_wf_sort.txt
+#endif
 __device__ __forceinline__ uint64_t spread21(uint64_t x) { // 21 bits -> every third bit
     x &= 0x1fffffull;
     x = (x | x << 32) & 0x1f00000000ffffull;
@@ -80,12 +83,17 @@ __device__ __forceinline__ uint64_t spread21(uint64_t x) { // 21 bits -> every t
 }
 
 // 2. Morton keys of the box centres inside the set's bounds
-__global__ void morton_kernel(const FBox *boxes, uint32_t n, const int *bounds, uint64_t *keys, uint32_t *vals) {
+// `cube`: one scale for the three axes (the largest extent).  A flat set - a terrain, a slab of spheres - then keeps the top
+// bits of its short axis constant and its coarse order is the 2D order of the surface, instead of being cut at every level
+// by an axis along which neighbours do not differ (per-axis scaling gave that axis a third of the key).
+__global__ void morton_kernel(const FBox *boxes, uint32_t n, const int *bounds, uint64_t *keys, uint32_t *vals, int cube) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t k = 0;
+    float ext = 0.0f;
+    for (int a = 0; a < 3; ++a) ext = fmaxf(ext, ord2f(bounds[3 + a]) - ord2f(bounds[a]));
     for (int a = 0; a < 3; ++a) {
-        const float lo = ord2f(bounds[a]), hi = ord2f(bounds[3 + a]);
+        const float lo = ord2f(bounds[a]), hi = cube ? lo + ext : ord2f(bounds[3 + a]);
         const float c = 0.5f * (boxes[i].lo[a] + boxes[i].hi[a]);
         float u = hi > lo ? (c - lo) / (hi - lo) : 0.0f;
         u = fminf(fmaxf(u, 0.0f), 1.0f);
@@ -493,6 +501,8 @@ struct SetBuild {
     int run(const double *d_prims, uint32_t n_, int kind_, int leaf_max_, cudaStream_t st) {
         n = n_; kind = kind_; leaf_max = leaf_max_;
         if (const char *e = getenv("NT_BVH_GPU_ALGO")) ploc = strcmp(e, "lbvh") != 0; // "lbvh": the Morton radix tree of round 1
+        int morton_cube = NT_MORTON_CUBE_DEFAULT;
+        if (const char *e = getenv("NT_MORTON_CUBE")) morton_cube = e[0] != '0';
         if (n == 0) return 0;
         m = n; // one radix-tree leaf per primitive; subtrees of <= leaf_max primitives become the BVH leaves
         const int T = 256;
@@ -501,7 +511,7 @@ struct SetBuild {
         const int init[6] = { INT32_MAX, INT32_MAX, INT32_MAX, INT32_MIN, INT32_MIN, INT32_MIN };
         CUCHK(cudaMemcpyAsync(bounds.p, init, sizeof init, cudaMemcpyHostToDevice, st));
         prim_boxes_kernel<<<(n + T - 1) / T, T, 0, st>>>(d_prims, n, kind, boxes.p, bounds.p);
-        morton_kernel<<<(n + T - 1) / T, T, 0, st>>>(boxes.p, n, bounds.p, keys.p, vals.p);
+        morton_kernel<<<(n + T - 1) / T, T, 0, st>>>(boxes.p, n, bounds.p, keys.p, vals.p, morton_cube);
         size_t tb = 0;
         CUCHK(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys.p, keys_sorted.p, vals.p, vals_sorted.p, (int)n, 0, 63, st));
         CUCHK(temp.alloc(tb));
