@@ -398,7 +398,7 @@ __device__ __forceinline__ void lane_lights_from(const Ctx<R, true> &c, Lane<R> 
                 wt = kt;
                 const R sterm = eta * cosi - Math<R>::sqrt_(kk);
                 T = { d.x * eta + N.x * sterm, d.y * eta + N.y * sterm, d.z * eta + N.z * sterm };
-                if (c.rules & NT_DEV_RULE_RENORMALIZE) T = scale(T, Math<R>::rcp(Math<R>::sqrt_(dot(T, T)))); // SPEC §8
+                if (fast_renormalises<R>::value || (c.rules & NT_DEV_RULE_RENORMALIZE)) T = scale(T, Math<R>::rcp(Math<R>::sqrt_(dot(T, T)))); // SPEC §8
             }
         }
         if (wt > R(0)) {
@@ -415,7 +415,7 @@ __device__ __forceinline__ void lane_lights_from(const Ctx<R, true> &c, Lane<R> 
             k.sec++;
             const R two = R(2) * cosi;
             ln.d = { d.x + N.x * two, d.y + N.y * two, d.z + N.z * two };
-            if (c.rules & NT_DEV_RULE_RENORMALIZE) ln.d = scale(ln.d, Math<R>::rcp(Math<R>::sqrt_(dot(ln.d, ln.d))));
+            if (fast_renormalises<R>::value || (c.rules & NT_DEV_RULE_RENORMALIZE)) ln.d = scale(ln.d, Math<R>::rcp(Math<R>::sqrt_(dot(ln.d, ln.d))));
             ln.W = ln.W * wr; ln.depth = ln.depth + 1;
             descend = true;
         } else if (wt > R(0)) {

@@ -172,6 +172,13 @@ struct CountersX : Counters {
 template <typename K> struct counts_executed { static constexpr bool value = false; };
 template <> struct counts_executed<CountersX> { static constexpr bool value = true; };
 #define NT_X(k, field, n) do { if constexpr (counts_executed<K>::value) (k).field += (n); } while (0)
+// The fast mode re-normalises reflected and refracted directions (what SPEC §8's NT_RULE_RENORMALIZE switches on in the
+// strict mode).  SPEC §4 does not, and a bounce off a sphere of radius r seen from distance t multiplies the error of
+// |d|^2 by ~4 (t / r)^2: harmless 1e-11 after one bounce in binary64, but 5e-4 in binary32 - and §3's sphere rule, written
+// for unit directions, then sees every sphere sqrt(5e-4) t ~ a unit larger at t = 50.  configs[3] (10 000 spheres of
+// radius 0.1 - 0.6 seen from 100 units): 4.7 % of the pixels - every mirror or glass sphere - more than 2 LSB from the
+// strict frame without it (found by `bench.py --precision f32`'s frame check, scripts/gpu_fastdiff_cfg4.py).
+template <typename R> struct fast_renormalises { static constexpr bool value = sizeof(R) == 4; };
 // ---- SPEC §3 intersections ----
 // Sphere, part 1 (branch-free, so two spheres can be interleaved): b and the discriminant.
 template <typename R>
@@ -887,8 +894,10 @@ __device__ __forceinline__ void trace_sample(const Ctx<R, BVH, LEAN> &c, V3<R> o
                         wt = kt;
                         const R sterm = eta * cosi - Math<R>::sqrt_(kk);
                         T = { d.x * eta + N.x * sterm, d.y * eta + N.y * sterm, d.z * eta + N.z * sterm };
-                        if constexpr (RULES) // SPEC §8: re-normalised secondary directions
-                            if (c.rules & NT_DEV_RULE_RENORMALIZE) T = scale(T, Math<R>::rcp(Math<R>::sqrt_(dot(T, T))));
+                        // SPEC §8: re-normalised secondary directions - a rule switch in the strict mode, always in the fast mode
+                        // (fast_renormalises below)
+                        if constexpr (RULES || fast_renormalises<R>::value)
+                            if (fast_renormalises<R>::value || (c.rules & NT_DEV_RULE_RENORMALIZE)) T = scale(T, Math<R>::rcp(Math<R>::sqrt_(dot(T, T))));
                     }
                 }
                 if (wt > R(0)) {
@@ -904,8 +913,8 @@ __device__ __forceinline__ void trace_sample(const Ctx<R, BVH, LEAN> &c, V3<R> o
                     k.sec++;
                     const R two = R(2) * cosi;
                     V3<R> Rd = { d.x + N.x * two, d.y + N.y * two, d.z + N.z * two };
-                    if constexpr (RULES)
-                        if (c.rules & NT_DEV_RULE_RENORMALIZE) Rd = scale(Rd, Math<R>::rcp(Math<R>::sqrt_(dot(Rd, Rd))));
+                    if constexpr (RULES || fast_renormalises<R>::value)
+                        if (fast_renormalises<R>::value || (c.rules & NT_DEV_RULE_RENORMALIZE)) Rd = scale(Rd, Math<R>::rcp(Math<R>::sqrt_(dot(Rd, Rd))));
                     o = P; d = Rd; *Wp = *Wp * wr; depth = depth + 1;
                     descend = true;
                 } else if (wt > R(0)) {

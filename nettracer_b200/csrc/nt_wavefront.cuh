@@ -457,7 +457,7 @@ wf_shade_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
                                 wt = kt;
                                 const R sterm = eta * cosi - Math<R>::sqrt_(kk);
                                 T = { d.x * eta + N.x * sterm, d.y * eta + N.y * sterm, d.z * eta + N.z * sterm };
-                                if (a.rules & NT_DEV_RULE_RENORMALIZE) T = scale(T, Math<R>::rcp(Math<R>::sqrt_(dot(T, T)))); // SPEC §8
+                                if (fast_renormalises<R>::value || (a.rules & NT_DEV_RULE_RENORMALIZE)) T = scale(T, Math<R>::rcp(Math<R>::sqrt_(dot(T, T)))); // SPEC §8
                             }
                         }
                         if (wt > R(0)) { k.sec++; trans = true; Wt = W * wt; }
@@ -466,7 +466,7 @@ wf_shade_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
                             refl = true; Wr = W * wr;
                             const R two = R(2) * cosi;
                             Rd = { d.x + N.x * two, d.y + N.y * two, d.z + N.z * two };
-                            if (a.rules & NT_DEV_RULE_RENORMALIZE) Rd = scale(Rd, Math<R>::rcp(Math<R>::sqrt_(dot(Rd, Rd))));
+                            if (fast_renormalises<R>::value || (a.rules & NT_DEV_RULE_RENORMALIZE)) Rd = scale(Rd, Math<R>::rcp(Math<R>::sqrt_(dot(Rd, Rd))));
                         }
                         kids = (unsigned char)((refl ? 1 : 0) | (trans ? 2 : 0));
                     }
