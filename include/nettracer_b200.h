@@ -156,6 +156,19 @@ int nt_plane_free_lights(const nt_scene_desc *desc, uint32_t *mask_out);
  * any scene (a light without a room gets an empty box); NT_ERR_INVALID for NULL arguments. */
 int nt_light_rooms(const nt_scene_desc *desc, double *rooms_out);
 
+/* Diagnostic, host only: the shadow grid nt_scene_create derives for light `light` of a BVH scene (nettracer_b200/csrc/
+ * nt_shadowgrid.h) - a K x K grid over the projection of the sphere set as seen from the light, each cell listing the
+ * spheres that can lie between the light and a point that projects into it; shadow queries test those with the exact rule
+ * and walk only the triangle set of the tree.  params_out[16] = light position, axis, U, V (3 each, binary32 as the device
+ * uses them), u0, v0, su, sv: a point X with w = (X - L).axis > 0 falls into cell (floor(((X - L).U / w - u0) su),
+ * floor(((X - L).V / w - v0) sv)); outside [0, K) or w <= 0 = no sphere in between.  *k_out = K, or 0 when the light has
+ * no grid (its queries walk the whole tree) - nothing else is written then.  off_out[K K + 1] / items_out[*n_items_out]:
+ * cell c lists items_out[off_out[c] - off_out[0] .. off_out[c + 1] - off_out[0]), sphere indices of the DESCRIPTION,
+ * ascending.  Buffers may be NULL / too small: the call then only reports K and *n_items_out.  Spheres only (no tree is
+ * built); NT_ERR_INVALID for a bad light index. */
+int nt_shadow_grid(const nt_scene_desc *desc, uint32_t light, float *params_out, uint32_t *k_out, uint32_t *off_out,
+                   size_t off_capacity, uint32_t *items_out, size_t items_capacity, size_t *n_items_out);
+
 /* ---- render ---- */
 /* Host buffer (pageable or pinned), blocking.  Renders the shard named in params, copies the
  * result to rgba_out.  A PINNED (page-locked) rgba_out receives the pixels straight from the kernel over PCIe (no device

@@ -82,7 +82,7 @@ EXPORTS = [
     "nt_render", "nt_render_device", "nt_render_device_stats", "nt_trace_rays",
     "nt_shard_rows", "nt_deinterleave_device",
     "nt_device_malloc", "nt_device_free", "nt_ipc_export", "nt_ipc_open", "nt_ipc_close",
-    "nt_measure_peaks", "nt_cull_tables", "nt_primary_rects", "nt_plane_free_lights", "nt_light_rooms",
+    "nt_measure_peaks", "nt_cull_tables", "nt_primary_rects", "nt_plane_free_lights", "nt_light_rooms", "nt_shadow_grid",
     "nt_render_device_sync", "nt_flags_wait_device",
     "nt_multi_create", "nt_multi_destroy", "nt_multi_device_count", "nt_multi_render",
     "nt_host_frame_open", "nt_host_frame_pixels", "nt_host_frame_flag", "nt_host_frame_post", "nt_host_frame_wait_all",

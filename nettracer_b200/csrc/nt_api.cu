@@ -16,6 +16,7 @@
 #include "../../include/nettracer_b200.h"
 #include "nt_bvh.h"
 #include "nt_cull.h"
+#include "nt_shadowgrid.h"
 #include "nt_device.h"
 #include "nt_sync.cuh"
 
@@ -395,6 +396,17 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
         if (!(pe && pe[0] == '0')) sc->lfree = plane_free_lights(d);
     }
     UP(ct.lbuf, ds.lbuf); UP(ct.nbr, ds.nbr); // 16-byte placeholders when culling is off
+    // BVH scenes: shadow grids (nt_shadowgrid.h); NT_SHADOW_GRID=0 keeps every occlusion query on the whole tree (A/B, tests)
+    {
+        std::vector<NtShadowGrid> grids(nl);
+        std::vector<uint32_t> sg_off, sg_items;
+        const char *ge = getenv("NT_SHADOW_GRID");
+        ds.sg_on = 0;
+        if (use_bvh && ns > 0 && nl > 0 && !(ge && ge[0] == '0'))
+            ds.sg_on = nt_shadow_grids_build(sph.data(), ns, lights.data(), nl, (double)ds.max_abs, grids, sg_off, sg_items) > 0 ? 1 : 0;
+        if (!ds.sg_on) { grids.assign(std::max<uint32_t>(nl, 1), NtShadowGrid{}); sg_off.clear(); sg_items.clear(); }
+        UP(grids, ds.sgrid); UP(sg_off, ds.sg_off); UP(sg_items, ds.sg_items);
+    }
 #undef UP
     CU(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&sc->ev0));
@@ -460,6 +472,37 @@ extern "C" int nt_primary_rects(const nt_scene_desc *desc, const nt_render_param
         for (int a = 0; a < 3; ++a) mx = std::max(mx, std::fabs(desc->spheres[4 * (size_t)i + a]) + desc->spheres[4 * (size_t)i + 3]);
     for (size_t i = 0; i < 9 * (size_t)desc->n_triangles; ++i) mx = std::max(mx, std::fabs(desc->triangles[i]));
     nt_cull_primary_rects(ct.bsph.data(), desc->n_spheres + desc->n_triangles, cam, p->width, p->height, 1e-5 * (eye_inf + mx), rects_out);
+    return NT_OK;
+}
+
+extern "C" int nt_shadow_grid(const nt_scene_desc *desc, uint32_t light, float *params_out, uint32_t *k_out, uint32_t *off_out,
+                              size_t off_capacity, uint32_t *items_out, size_t items_capacity, size_t *n_items_out) {
+    int rc = validate_desc(desc);
+    if (rc) return rc;
+    if (!k_out || !n_items_out) return fail(NT_ERR_INVALID, "NULL argument");
+    if (light >= desc->n_lights) return fail(NT_ERR_INVALID, "light %u >= n_lights %u", light, desc->n_lights);
+    const uint32_t ns = desc->n_spheres;
+    std::vector<double> sph(4 * (size_t)ns);
+    double mx = 0; // as nt_scene_create: the largest |coordinate| of a bounded primitive
+    for (uint32_t i = 0; i < ns; ++i) {
+        const double *s = desc->spheres + 4 * (size_t)i;
+        sph[4 * (size_t)i] = s[0]; sph[4 * (size_t)i + 1] = s[1]; sph[4 * (size_t)i + 2] = s[2]; sph[4 * (size_t)i + 3] = s[3] * s[3];
+        for (int a = 0; a < 3; ++a) mx = std::max(mx, std::fabs(s[a]) + s[3]);
+    }
+    for (size_t i = 0; i < 9 * (size_t)desc->n_triangles; ++i) mx = std::max(mx, std::fabs(desc->triangles[i]));
+    std::vector<NtShadowGrid> grids;
+    std::vector<uint32_t> off, items;
+    nt_shadow_grids_build(sph.data(), ns, desc->lights + 6 * (size_t)light, 1, mx, grids, off, items);
+    *k_out = 0; *n_items_out = 0;
+    if (grids.empty() || !grids[0].valid) return NT_OK;
+    const NtShadowGrid &g = grids[0];
+    *k_out = g.K; *n_items_out = items.size();
+    if (params_out) {
+        for (int k = 0; k < 3; ++k) { params_out[k] = g.L[k]; params_out[3 + k] = g.axis[k]; params_out[6 + k] = g.U[k]; params_out[9 + k] = g.V[k]; }
+        params_out[12] = g.u0; params_out[13] = g.v0; params_out[14] = g.su; params_out[15] = g.sv;
+    }
+    if (off_out && off_capacity >= off.size()) std::copy(off.begin(), off.end(), off_out);
+    if (items_out && items_capacity >= items.size()) std::copy(items.begin(), items.end(), items_out);
     return NT_OK;
 }
 

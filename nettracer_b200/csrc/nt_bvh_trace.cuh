@@ -50,6 +50,8 @@ template <typename R> struct BvhQuery { // scalars only: lives in registers (the
 //   pass 1  the triangle set only (root n_nodes - 2), plain margin; query_second_pass then arms
 //   pass 2  the sphere set only (root n_nodes - 1), grown margin: a cone (below), walked by query_inner_step_t<true>;
 //   pass 3  the same with the constant bound, for a caller whose loop has only the plain inner step.
+//   pass 4  the triangle set only and nothing after it: an occlusion query whose spheres came from the light's shadow grid
+//           (shadow_query_start).
 // Why two passes: SPEC §3's sphere test takes the direction as a unit vector, but §4 does not re-normalise reflected /
 // refracted directions: |d|^2 = L2 drifts from 1 along a mirror chain (every bounce off a small distant sphere amplifies
 // the drift by ~ 4 (t / r)^2), and the rule then accepts roots t whose point o + d t lies at distance sqrt(r^2 + (L2 - 1)
@@ -87,7 +89,7 @@ __device__ __forceinline__ void query_arm(const Ctx<R, true> &c, BvhQuery<R> &q,
     if constexpr (sizeof(R) == 8) { // the fast mode never grows boxes: it has one pass, and none of the code of the others
         if (pass == 0 && !(grow <= 4.0f * m)) pass = 1; // also when grow is NaN
     }
-    if (pass == 1) grow = 0.0f;
+    if (pass == 1 || pass == 4) grow = 0.0f;
     q.pass = pass;
     const float grow_all = grow; // pass 2: the entry slab below keeps the constant bound, the node tests use the cone
     m += grow;
@@ -142,7 +144,7 @@ __device__ __forceinline__ void query_arm(const Ctx<R, true> &c, BvhQuery<R> &q,
     q.cnz = -((pz ? oz + m : oz - m) * iz); q.cfz = -((pz ? oz - m : oz + m) * iz);
     q.tmaxf = Math<R>::up(q.tb - q.tshift);
     q.done = false;
-    q.cur = pass == 0 ? 0 : (int)s.n_nodes - 3 + pass; // pass 1: root n - 2 (triangles), pass 2 / 3: root n - 1 (spheres)
+    q.cur = pass == 0 ? 0 : pass == 4 ? (int)s.n_nodes - 2 : (int)s.n_nodes - 3 + pass; // pass 1 / 4: root n - 2 (triangles), pass 2 / 3: root n - 1 (spheres)
 }
 // A query that walked the triangle set alone (pass 1) goes on with the sphere set unless an occlusion query has already
 // found its occluder.  Called by the traversal loops for lanes whose walk has just ended:
@@ -195,7 +197,7 @@ __device__ __forceinline__ SweepHit<R> sweep_spheres(const R *sph, const int *sp
 // Start a query: planes (unbounded, staged in shared memory) are tested here, then the tree is armed.
 template <typename R, typename K>
 __device__ __forceinline__ void query_start(const Ctx<R, true> &c, BvhQuery<R> &q, const V3<R> &o, const V3<R> &d,
-                                            R tmax, bool any, K &k) {
+                                            R tmax, bool any, K &k, int pass0 = 0) {
     const NtDevScene &s = *c.s;
     q.o = o; q.d = d; q.tb = tmax; q.any = any; q.done = false; q.found = false; q.pass = 0;
     q.best.kind = -1; q.best.idx = -1; q.best.gid = 0x7fffffff;
@@ -215,7 +217,50 @@ __device__ __forceinline__ void query_start(const Ctx<R, true> &c, BvhQuery<R> &
         }
     }
     if (s.n_nodes == 0) { q.done = true; return; }
-    query_arm<R>(c, q, o, d, 0);
+    query_arm<R>(c, q, o, d, pass0);
+}
+
+// Occlusion query of light l from P (direction Ld, unit; the light at distance dist).  With a shadow grid for that light
+// (NtShadowGrid, nt_shadowgrid.h) the spheres that can lie between P and the light are the few listed in P's cell: they are
+// tested here with the exact rule, and the tree walk that follows covers the triangle set only (query_arm pass 4) - or is
+// not needed at all.  Same boolean as the walk of the whole tree: the lists are conservative, the test is the leaf's.
+template <typename R, typename K>
+__device__ __forceinline__ void shadow_query_start(const Ctx<R, true> &c, BvhQuery<R> &q, const V3<R> &P, const V3<R> &Ld, R dist,
+                                                   unsigned l, K &k) {
+    const NtDevScene &s = *c.s;
+    int pass0 = 0;
+    if (s.sg_on) {
+        const NtShadowGrid *g = s.sgrid + l;
+        const uint4 kb = __ldg((const uint4 *)&g->K); // K base valid pad
+        if (kb.z) {
+            const float4 g0 = __ldg((const float4 *)g), g1 = __ldg((const float4 *)g + 1), g2 = __ldg((const float4 *)g + 2), g3 = __ldg((const float4 *)g + 3);
+            // g0 = L.xyz axis.x | g1 = axis.yz U.xy | g2 = U.z V.xyz | g3 = u0 v0 su sv
+            const float dx = (float)P.x - g0.x, dy = (float)P.y - g0.y, dz = (float)P.z - g0.z;
+            const float w = dx * g0.w + dy * g1.x + dz * g1.y;
+            pass0 = 4;
+            if (w > 0.0f) {
+                const float iw = 1.0f / w;
+                const float fu = ((dx * g1.z + dy * g1.w + dz * g2.x) * iw - g3.x) * g3.z, fv = ((dx * g2.y + dy * g2.z + dz * g2.w) * iw - g3.y) * g3.w;
+                const float kf = (float)kb.x;
+                if (fu >= 0.0f && fv >= 0.0f && fu < kf && fv < kf) { // (NaN: outside)
+                    const unsigned cell = kb.y + (unsigned)fv * kb.x + (unsigned)fu;
+                    const uint32_t i0 = __ldg(s.sg_off + cell), i1 = __ldg(s.sg_off + cell + 1);
+                    for (uint32_t i = i0; i < i1; ++i) {
+                        const uint32_t idx = __ldg(s.sg_items + i);
+                        R p[4], t;
+                        c.ld_sph(idx, p);
+                        k.sph++;
+                        if (hit_sphere<R>(p, P, Ld, c.eps, t) && t < dist) {
+                            q.o = P; q.d = Ld; q.tb = dist; q.any = true; q.found = true; q.done = true; q.pass = 4;
+                            q.cur = NT_REF_EMPTY; q.sp = 0;
+                            return;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    query_start<R>(c, q, P, Ld, dist, true, k, pass0);
 }
 
 template <typename R> __device__ __forceinline__ void query_pop(BvhQuery<R> &q, const int2 *stack) {
@@ -375,7 +420,7 @@ __device__ __forceinline__ void lane_lights_from(const Ctx<R, true> &c, Lane<R> 
         if (!(ndl > R(0))) continue;
         k.shadow++;
         ln.ndl = ndl; ln.phase = 1 + (int)l;
-        query_start<R>(c, q, P, L, dist, true, k);
+        shadow_query_start<R>(c, q, P, L, dist, l, k);
         return;
     }
 #pragma unroll

@@ -81,6 +81,16 @@ struct NtSceneView {
     const R *globals;  // ambient[3] background[3] pad[2]
 };
 
+// BVH scenes: per point light a grid over the gnomonic projection of the sphere set as seen from the light (a shadow-map
+// frustum), each cell listing the spheres whose projection touches it (nt_shadowgrid.h).  A shadow query tests its cell's few
+// spheres with the exact rule and walks only the TRIANGLE set of the tree - the sphere set of configs[3] (10 000 small
+// spheres scattered in a slab: mostly empty boxes) was 35 % of all box tests.
+struct NtShadowGrid {
+    float L[3], axis[3], U[3], V[3]; // light position; the projection's axis and its two plane directions (orthonormal)
+    float u0, v0, su, sv;            // cell = floor((u - u0) * su), u = (P - L).U / (P - L).axis
+    uint32_t K, base, valid, pad;    // K x K cells; this light's K*K + 1 offsets start at sg_off[base]
+};
+
 struct NtDevScene {
     uint32_t ns, np, nt, nm, nl;
     uint32_t use_bvh, n_nodes;
@@ -103,6 +113,9 @@ struct NtDevScene {
     const double *axs64, *room64;
     const float *axs32, *room32;
     const NtBvhNode4 *nodes;
+    uint32_t sg_on;              // BVH scenes: shadow grids exist (nt_shadowgrid.h); a light's own `valid` says whether it has one
+    const NtShadowGrid *sgrid;   // [nl]
+    const uint32_t *sg_off, *sg_items; // per cell: first item; items = sphere indices (device order), ascending per cell
     // flat scenes: conservative culling tables (nt_cull.h); cull == 0 -> every query tests every primitive
     uint32_t cull, lbuf_k;
     float cull_far; // shadow queries whose light is farther than this (max norm) look no light buffer up: see lbuf_mask

@@ -250,7 +250,7 @@ wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
                             const R ndl = dot(N, Ld);
                             if (ndl > R(0)) {
                                 k.shadow++;
-                                query_start<R>(c, q, h.P, Ld, dist, true, k);
+                                shadow_query_start<R>(c, q, h.P, Ld, dist, light, k);
                                 if constexpr (RAY_IN_SMEM) {
                                     s_ray[0][threadIdx.x] = h.P.x; s_ray[1][threadIdx.x] = h.P.y; s_ray[2][threadIdx.x] = h.P.z;
                                     s_ray[3][threadIdx.x] = Ld.x; s_ray[4][threadIdx.x] = Ld.y; s_ray[5][threadIdx.x] = Ld.z;

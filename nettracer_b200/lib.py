@@ -49,6 +49,7 @@ def load():
         "nt_primary_rects": (C.c_int, [C.POINTER(abi.nt_scene_desc), C.POINTER(abi.nt_render_params), vp]),
         "nt_plane_free_lights": (C.c_int, [C.POINTER(abi.nt_scene_desc), C.POINTER(u32)]),
         "nt_light_rooms": (C.c_int, [C.POINTER(abi.nt_scene_desc), vp]),
+        "nt_shadow_grid": (C.c_int, [C.POINTER(abi.nt_scene_desc), u32, vp, C.POINTER(u32), vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
         "nt_render_device_sync": (C.c_int, [vp, C.POINTER(abi.nt_render_params), vp, C.c_size_t, vp, C.POINTER(abi.nt_frame_sync)]),
         "nt_flags_wait_device": (C.c_int, [vp, vp, u32, u32, vp]),
         "nt_multi_create": (C.c_int, [C.POINTER(abi.nt_scene_desc), C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]),

@@ -123,6 +123,24 @@ def plane_free_lights(scene: Scene) -> int:
     return int(m.value)
 
 
+def shadow_grid(scene: Scene, light: int):
+    """The shadow grid of one light of a BVH scene (nt_shadow_grid: host only): None when the light has none, else
+    (params float32[16], K, off uint32[K*K + 1] rebased to 0, items uint32[...]) - see include/nettracer_b200.h."""
+    desc, keep = scene.to_desc()
+    lib = load()
+    k, n = C.c_uint32(), C.c_size_t()
+    check(lib.nt_shadow_grid(C.byref(desc), light, None, C.byref(k), None, 0, None, 0, C.byref(n)))
+    if k.value == 0:
+        del keep
+        return None
+    params = np.zeros(16, dtype=np.float32)
+    off = np.zeros(k.value * k.value + 1, dtype=np.uint32)
+    items = np.zeros(max(n.value, 1), dtype=np.uint32)
+    check(lib.nt_shadow_grid(C.byref(desc), light, params.ctypes.data, C.byref(k), off.ctypes.data, off.size, items.ctypes.data, items.size, C.byref(n)))
+    del keep
+    return params, int(k.value), off - off[0], items[:n.value]
+
+
 def light_rooms(scene: Scene) -> np.ndarray:
     """Per light the axis-aligned room [lo_x, hi_x, lo_y, hi_y, lo_z, hi_z, cap_per_eps, cap_max] inside which a shadow
     query skips the axis-aligned planes (nt_light_rooms: host only).  float64 [n_lights, 8]."""

@@ -14,8 +14,9 @@ nvcc $COMMON -c nt_peaks.cu -o $OBJ/peaks.o &
 nvcc $COMMON -c nt_bvh.cpp -o $OBJ/bvh.o &
 nvcc $COMMON -c nt_bvh_gpu.cu -o $OBJ/bvhgpu.o &
 nvcc $COMMON -c nt_cull.cpp -o $OBJ/cull.o &
+nvcc $COMMON -c nt_shadowgrid.cpp -o $OBJ/shadowgrid.o &
 nvcc $COMMON -c nt_multi.cpp -o $OBJ/multi.o &
 nvcc $COMMON -c nt_hostframe.cpp -o $OBJ/hostframe.o &
 wait
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/libnt_$NAME.so $OBJ/f64.o $OBJ/f32.o $OBJ/api.o $OBJ/peaks.o $OBJ/bvh.o $OBJ/bvhgpu.o $OBJ/cull.o $OBJ/multi.o $OBJ/hostframe.o -lcudart -lpthread -lrt
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/libnt_$NAME.so $OBJ/f64.o $OBJ/f32.o $OBJ/api.o $OBJ/peaks.o $OBJ/bvh.o $OBJ/bvhgpu.o $OBJ/cull.o $OBJ/shadowgrid.o $OBJ/multi.o $OBJ/hostframe.o -lcudart -lpthread -lrt
 echo built $OUT/libnt_$NAME.so
