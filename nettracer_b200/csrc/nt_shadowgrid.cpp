@@ -69,12 +69,15 @@ int nt_shadow_grids_build(const double *sph, uint32_t ns, const double *lights, 
         g.su = (float)((double)K / du); g.sv = (float)((double)K / dv);
         g.K = K; g.base = (uint32_t)off.size();
         for (int k = 0; k < 3; ++k) { g.L[k] = fL[k]; g.axis[k] = fa[k]; g.U[k] = fU[k]; g.V[k] = fV[k]; }
-        // cells with the device's own binary32 origin and scale; one cell of slack on every side
+        // cells with the device's own binary32 origin and scale
         auto cell = [&](double t, float t0, float sc) { return (int)std::floor((t - (double)t0) * (double)sc); };
         std::vector<uint32_t> count((size_t)K * K + 1, 0u);
         for (uint32_t i = 0; i < ns; ++i) {
             const double *b = &box[4 * (size_t)i];
-            Rect r = { cell(b[0], g.u0, g.su) - 1, cell(b[1], g.u0, g.su) + 1, cell(b[2], g.v0, g.sv) - 1, cell(b[3], g.v0, g.sv) + 1 };
+            // slack for the device's binary32 projection of a point (error ~1e-6 (1 + |u|)): 1e-4 (1 + |u|), a twentieth of a
+            // cell at most (a whole cell on every side listed 25 cells for a 3 x 3 footprint instead of 16)
+            const double eu = 1e-4 * (1.0 + std::max(std::fabs(b[0]), std::fabs(b[1]))), ev = 1e-4 * (1.0 + std::max(std::fabs(b[2]), std::fabs(b[3])));
+            Rect r = { cell(b[0] - eu, g.u0, g.su), cell(b[1] + eu, g.u0, g.su), cell(b[2] - ev, g.v0, g.sv), cell(b[3] + ev, g.v0, g.sv) };
             r.u0 = std::max(r.u0, 0); r.v0 = std::max(r.v0, 0); r.u1 = std::min(r.u1, (int)K - 1); r.v1 = std::min(r.v1, (int)K - 1);
             rect[i] = r;
             for (int v = r.v0; v <= r.v1; ++v)

@@ -9,7 +9,7 @@
 // and radius rho with w_c > rho is contained in [tan(th_u - al_u), tan(th_u + al_u)] x [the same in v], th_u = atan2(x_c, w_c),
 // al_u = asin(rho / hypot(x_c, w_c)) - exactly the range of X.U / X.a over the ball, because that ratio depends only on the
 // ball's shadow in the (U, a) plane, a disc of radius rho around (x_c, w_c).  A ball is listed in every cell its rectangle
-// touches, plus one cell on every side (the device computes (u, v) in binary32), with rho = r (1 + 1e-6) + 1e-6 x the
+// touches after widening it by 1e-4 (1 + |u|) (the device computes (u, v) in binary32: error ~1e-6 (1 + |u|)), with rho = r (1 + 1e-6) + 1e-6 x the
 // scene's largest coordinate.  A light gets no grid (valid = 0: its queries walk the whole tree) when a ball reaches
 // behind or close to the light's plane (w_c <= 1.5 rho) or projects at more than ~83 degrees from the axis.
 #pragma once
