@@ -405,6 +405,31 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
         if (use_bvh && ns > 0 && nl > 0 && !(ge && ge[0] == '0'))
             ds.sg_on = nt_shadow_grids_build(sph.data(), ns, lights.data(), nl, (double)ds.max_abs, grids, sg_off, sg_items) > 0 ? 1 : 0;
         if (!ds.sg_on) { grids.assign(std::max<uint32_t>(nl, 1), NtShadowGrid{}); sg_off.clear(); sg_items.clear(); }
+        // ... and room for the grid of the primary rays, rebuilt on the device for every call's eye (nt_eyegrid.cuh):
+        // grid nl, K0 x K0 + 2 offsets (+ the scan's block totals), 48 entries per sphere, the spheres' rectangles
+        const char *ee = getenv("NT_EYE_GRID");
+        ds.eg_on = use_bvh && ns > 0 && !(ee && ee[0] == '0') ? 1 : 0;
+        grids.resize((size_t)nl + 1, NtShadowGrid{});
+        if (ds.eg_on) {
+            uint32_t k0 = 64;
+            while (k0 < 1024 && (double)k0 < 4.0 * std::sqrt((double)ns)) k0 *= 2;
+            ds.eg_k0 = k0;
+            ds.eg_off_base = (uint32_t)sg_off.size();
+            sg_off.resize(sg_off.size() + (size_t)k0 * k0 + 2 + 1024, 0u);
+            ds.eg_items_base = (uint32_t)sg_items.size();
+            ds.eg_items_cap = (uint32_t)std::min<size_t>(std::max<size_t>(48 * (size_t)ns, 65536), (size_t)1 << 30);
+            sg_items.resize(sg_items.size() + ds.eg_items_cap, 0u);
+            double clo[3] = { HUGE_VAL, HUGE_VAL, HUGE_VAL }, chi[3] = { -HUGE_VAL, -HUGE_VAL, -HUGE_VAL };
+            for (uint32_t i = 0; i < ns; ++i)
+                for (int a = 0; a < 3; ++a) { clo[a] = std::min(clo[a], sph[4 * (size_t)i + a]); chi[a] = std::max(chi[a], sph[4 * (size_t)i + a]); }
+            for (int a = 0; a < 3; ++a) { ds.sph_lo[a] = (float)clo[a]; ds.sph_hi[a] = (float)chi[a]; }
+            std::vector<double> boxes(4 * (size_t)ns, 0.0);
+            std::vector<unsigned long long> acc(8, 0ull);
+            const double *d_boxes = nullptr;
+            const unsigned long long *d_acc = nullptr;
+            UP(boxes, d_boxes); UP(acc, d_acc);
+            ds.eg_boxes = const_cast<double *>(d_boxes); ds.eg_acc = const_cast<unsigned long long *>(d_acc);
+        }
         UP(grids, ds.sgrid); UP(sg_off, ds.sg_off); UP(sg_items, ds.sg_items);
     }
 #undef UP

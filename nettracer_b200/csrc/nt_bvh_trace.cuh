@@ -263,6 +263,49 @@ __device__ __forceinline__ void shadow_query_start(const Ctx<R, true> &c, BvhQue
     query_start<R>(c, q, P, Ld, dist, true, k, pass0);
 }
 
+// Nearest-hit query of a PRIMARY ray (origin = the eye of this render call).  With an eye grid (nt_eyegrid.cuh: grid nl, built
+// at the start of the call) the spheres the ray can hit are those its cell lists: the planes first as always, then the walk
+// of the triangle set is armed (pass 4), then the listed spheres are tested with the exact rule - nearest wins, ties to the
+// smallest global id, exactly the leaf step's rule - and their bound goes into the walk.
+template <typename R, typename K>
+__device__ __forceinline__ void primary_query_start(const Ctx<R, true> &c, BvhQuery<R> &q, const V3<R> &o, const V3<R> &d, K &k) {
+    const NtDevScene &s = *c.s;
+    if (s.eg_on) {
+        const NtShadowGrid *g = s.sgrid + s.nl;
+        const uint4 kb = __ldg((const uint4 *)&g->K); // K base valid pad
+        if (kb.z) {
+            query_start<R>(c, q, o, d, Math<R>::inf(), false, k, 4);
+            if (q.done) return; // past every bounded primitive, or a plane nearer than the scene's bounds
+            const float4 g0 = __ldg((const float4 *)g), g1 = __ldg((const float4 *)g + 1), g2 = __ldg((const float4 *)g + 2), g3 = __ldg((const float4 *)g + 3);
+            const float dx = (float)d.x, dy = (float)d.y, dz = (float)d.z;
+            const float w = dx * g0.w + dy * g1.x + dz * g1.y;
+            if (!(w > 0.0f)) return; // pointing away from every sphere
+            const float iw = 1.0f / w;
+            const float fu = ((dx * g1.z + dy * g1.w + dz * g2.x) * iw - g3.x) * g3.z, fv = ((dx * g2.y + dy * g2.z + dz * g2.w) * iw - g3.y) * g3.w;
+            const float kf = (float)kb.x;
+            if (!(fu >= 0.0f && fv >= 0.0f && fu < kf && fv < kf)) return;
+            const unsigned cell = kb.y + (unsigned)fv * kb.x + (unsigned)fu;
+            const uint32_t i0 = __ldg(s.sg_off + cell), i1 = __ldg(s.sg_off + cell + 1);
+            for (uint32_t i = i0; i < i1; ++i) {
+                const int idx = (int)__ldg(s.sg_items + s.eg_items_base + i);
+                R p[4], t;
+                c.ld_sph((unsigned)idx, p);
+                k.sph++;
+                if (!hit_sphere<R>(p, o, d, c.eps, t)) continue;
+                if (t < q.tb) {
+                    q.tb = t; q.best.kind = 0; q.best.idx = idx; q.best.gid = __ldg(s.sph_gid + idx); q.found = true;
+                } else if (t == q.tb) {
+                    const int gid = __ldg(s.sph_gid + idx);
+                    if (gid < q.best.gid) { q.best.kind = 0; q.best.idx = idx; q.best.gid = gid; q.found = true; }
+                }
+            }
+            q.tmaxf = Math<R>::up(q.tb - q.tshift);
+            return;
+        }
+    }
+    query_start<R>(c, q, o, d, Math<R>::inf(), false, k);
+}
+
 template <typename R> __device__ __forceinline__ void query_pop(BvhQuery<R> &q, const int2 *stack) {
     while (q.sp > 0) {
         const int2 e = stack[--q.sp];
@@ -618,7 +661,7 @@ render_bvh_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ 
                         ln.sid = (unsigned)sid; ln.W = R(1); ln.depth = 1; ln.sp = 0; ln.phase = 0; ln.active = true;
                         ln.acc[0] = ln.acc[1] = ln.acc[2] = R(0);
                         k.prim++;
-                        query_start<R>(c, q, eye, ln.d, Math<R>::inf(), false, k);
+                        primary_query_start<R>(c, q, eye, ln.d, k);
                     }
                 }
             }

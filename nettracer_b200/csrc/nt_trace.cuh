@@ -1188,6 +1188,7 @@ inline size_t flat_smem_bytes(const NtDevScene &s, bool bvh) {
 } // namespace nt
 
 #include "nt_bvh_trace.cuh"
+#include "nt_eyegrid.cuh"
 #include "nt_wavefront.cuh"
 
 namespace nt {
@@ -1221,7 +1222,9 @@ inline int launch_render_t(const NtDevScene &s, const NtRenderArgs &a, cudaStrea
             sync_kernel<<<1, 32, 0, st>>>(a.sync_post_ptr, a.sync_post_val, a.sync_wait_ptr, 1, a.sync_wait_val, nullptr, 0, timeouts);
             if (a.n_launches) *a.n_launches += 1;
         }
-        int rc;
+        int rc = 0;
+        if (s.eg_on) rc = launch_eye_grid(s, a.cam, st, a.n_launches); // this call's eye: the primary rays' sphere lists (nt_eyegrid.cuh)
+        if (rc) return rc;
         if (a.wf) rc = launch_wavefront<R>(s, a, st, sms[dev], blocks_per_sm[dev]);
         else {
             render_bvh_kernel<R><<<grid, NT_BLOCK_THREADS, smem, st>>>(s, a);

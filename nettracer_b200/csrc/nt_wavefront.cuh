@@ -213,8 +213,8 @@ wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
                         V3<R> o, d;
                         R W;
                         if (wf_ray<R>(a, w, rec, o, d, W)) {
-                            if (w.level == 1) k.prim++;
-                            query_start<R>(c, q, o, d, Math<R>::inf(), false, k);
+                            if (w.level == 1) { k.prim++; primary_query_start<R>(c, q, o, d, k); }
+                            else query_start<R>(c, q, o, d, Math<R>::inf(), false, k);
                             if constexpr (RAY_IN_SMEM) {
                                 s_ray[0][threadIdx.x] = o.x; s_ray[1][threadIdx.x] = o.y; s_ray[2][threadIdx.x] = o.z;
                                 s_ray[3][threadIdx.x] = d.x; s_ray[4][threadIdx.x] = d.y; s_ray[5][threadIdx.x] = d.z;

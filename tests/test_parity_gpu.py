@@ -160,6 +160,40 @@ def test_bvh_render_paths_agree(mode, monkeypatch):
         assert st[k] == rst[k], k
 
 
+@pytest.mark.parametrize("eye", ["outside", "inside_the_cloud", "beside_the_cloud"])
+def test_bvh_grids_off_equal_on_equal_oracle(eye, monkeypatch):
+    """BVH scenes: occlusion queries test the spheres their light's shadow grid lists and primary rays those of the eye grid
+    (built on the device per call), and both walk only the triangle set of the tree.  With the grids switched off every
+    query walks the whole tree: same image, same ray counters, and the brute-force oracle agrees - also for an eye inside
+    or right beside the sphere cloud (no eye grid: the kernel marks it invalid) and lights there (no shadow grid)."""
+    from nettracer_b200.scene import Camera
+    s, cam = scenes.spheres_and_mesh(n_spheres=1500, mesh_n=40)
+    s.add_light((3.0, 15.0, -4.0), (0.3, 0.3, 0.3))  # inside the slab of spheres: no grid for this light
+    if eye == "inside_the_cloud":
+        cam = Camera(eye=(1.0, 16.0, 2.0), at=(20.0, 10.0, -15.0), up=(0, 1, 0), vfov_deg=70.0)
+    elif eye == "beside_the_cloud":
+        cam = Camera(eye=(47.0, 17.0, 0.0), at=(0.0, 12.0, 0.0), up=(0, 1, 0), vfov_deg=60.0)
+    w, h = 240, 135
+    p = make_params(w, h, 4, 3, cam.resolve(w, h), abi.NT_F64_STRICT)
+    ref, rst = oracle.render(s, p, accel=0)
+    outs = []
+    for grids in ("1", "0"):
+        monkeypatch.setenv("NT_SHADOW_GRID", grids)
+        monkeypatch.setenv("NT_EYE_GRID", grids)
+        for wavefront in ("1", "0"):
+            monkeypatch.setenv("NT_WAVEFRONT", wavefront)
+            with Renderer(s) as r:
+                assert r.info()["uses_bvh"]
+                img, st = r.render_params(p)
+                img2, _ = r.render_params(p)  # the eye grid is rebuilt per call
+            assert np.array_equal(img, img2)
+            assert_images_match(img, ref, f"grids={grids} wavefront={wavefront} eye={eye}")
+            for k in COUNTER_KEYS:
+                assert st[k] == rst[k], (k, grids, wavefront)
+            outs.append(st)
+    assert outs[0]["box_tests"] < outs[2]["box_tests"], "the grids must save box tests"
+
+
 def test_flat_culling_off_equals_on(monkeypatch):
     """NT_CULL=0 renders flat scenes by brute force; the culled default must give the same image and counters."""
     s, cam = scenes.random_mixed(12, 3, 20, seed=8)
