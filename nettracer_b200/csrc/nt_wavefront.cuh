@@ -32,7 +32,8 @@
 #endif
 
 #ifndef NT_WF_SORT_DEFAULT
-#define NT_WF_SORT_DEFAULT 2   // see wf_sort_mode: configs[3] f64 57.7 ms unsorted, 55.8 with 2, 56.0 with 6, 60.4 with 3 (profiles/r04_wf_sort.txt)
+#define NT_WF_SORT_DEFAULT 0   // see wf_sort_mode: configs[3] f64 57.7 ms unsorted, 55.8 with 2, 56.0 with 6, 60.4 with 3 BEFORE the shadow grids
+                               // (profiles/r04_wf_sort.txt); with them the shadow passes are half as long and the sort no longer pays: 38.4 / 39.3
 #endif
 
 #ifndef NT_WF_REPULL

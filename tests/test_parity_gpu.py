@@ -137,13 +137,15 @@ def test_drifted_directions_second_pass_variants(variant, monkeypatch):
 def test_bvh_render_paths_agree(mode, monkeypatch):
     """BVH scenes have two schedules of the same arithmetic: the wavefront pipeline (nt_wavefront.cuh; default,
     here also with a workspace so small that the frame is cut into many chunks, and with its task lists unsorted / sorted
-    before every pass: NT_WF_SORT, default = the shadow tasks of levels >= 2 by what they hit) and the per-lane state machine
+    before every pass: NT_WF_SORT, default unsorted) and the per-lane state machine
     (nt_bvh_trace.cuh; NT_WAVEFRONT=0, and always for trees deeper than 6).  All must equal the oracle bit for bit."""
     depth = 4
     if mode == "wavefront_chunked":
         monkeypatch.setenv("NT_WF_MB", "3")
     elif mode == "wavefront_unsorted":
         monkeypatch.setenv("NT_WF_SORT", "0")
+        monkeypatch.setenv("NT_SHADOW_GRID", "0")
+        monkeypatch.setenv("NT_EYE_GRID", "0")
     elif mode.startswith("wavefront_all_sorts"):
         monkeypatch.setenv("NT_WF_SORT", "7")
         if mode.endswith("chunked"):
