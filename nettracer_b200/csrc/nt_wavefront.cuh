@@ -36,6 +36,9 @@
                                // (profiles/r04_wf_sort.txt); with them the shadow passes are half as long and the sort no longer pays: 38.4 / 39.3
 #endif
 
+#ifndef NT_WF_EARLY_RETIRE
+#define NT_WF_EARLY_RETIRE 1
+#endif
 #ifndef NT_WF_REPULL
 #define NT_WF_REPULL 1
 #endif
@@ -261,6 +264,15 @@ wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
                         }
                     }
                 }
+            }
+        }
+        // an occlusion query can end where it starts - a listed sphere of the light's shadow grid occludes, the ray leaves the
+        // scene's bounds at once: such a lane retires here and counts as idle, or the warp would walk with the few lanes whose
+        // queries are real (the level-2 shadow pass of configs[3] ran at 11 of 32 lanes)
+        if constexpr (SHADOW && NT_WF_EARLY_RETIRE) {
+            if (active && q.done) {
+                if (!q.found) atomicOr(L.vis + rec, 1u << light);
+                active = false;
             }
         }
         const unsigned started = __ballot_sync(0xffffffffu, active);
