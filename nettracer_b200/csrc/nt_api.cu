@@ -410,15 +410,20 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
         const char *ee = getenv("NT_EYE_GRID");
         ds.eg_on = use_bvh && ns > 0 && !(ee && ee[0] == '0') ? 1 : 0;
         grids.resize((size_t)nl + 1, NtShadowGrid{});
+        ds.eg_off = nullptr; ds.eg_items = nullptr; ds.eg_boxes = nullptr; ds.eg_acc = nullptr; ds.eg_items_cap = 0; ds.eg_k0 = 0;
         if (ds.eg_on) {
             uint32_t k0 = 64;
             while (k0 < 1024 && (double)k0 < 4.0 * std::sqrt((double)ns)) k0 *= 2;
             ds.eg_k0 = k0;
-            ds.eg_off_base = (uint32_t)sg_off.size();
-            sg_off.resize(sg_off.size() + (size_t)k0 * k0 + 2 + 1024, 0u);
-            ds.eg_items_base = (uint32_t)sg_items.size();
             ds.eg_items_cap = (uint32_t)std::min<size_t>(std::max<size_t>(48 * (size_t)ns, 65536), (size_t)1 << 30);
-            sg_items.resize(sg_items.size() + ds.eg_items_cap, 0u);
+            const size_t off_bytes = sizeof(uint32_t) * ((size_t)k0 * k0 + 2 + 1024), item_bytes = sizeof(uint32_t) * (size_t)ds.eg_items_cap;
+            void *p_off = nullptr, *p_items = nullptr; // device-only: written by the kernels of nt_eyegrid.cuh
+            cudaError_t ge2 = cudaMalloc(&p_off, off_bytes);
+            if (ge2 == cudaSuccess) { sc->allocs.push_back(p_off); ge2 = cudaMalloc(&p_items, item_bytes); }
+            if (ge2 == cudaSuccess) { sc->allocs.push_back(p_items); ge2 = cudaMemset(p_off, 0, off_bytes); }
+            if (ge2 != cudaSuccess) return fail(ge2 == cudaErrorMemoryAllocation ? NT_ERR_NOMEM : NT_ERR_CUDA, "eye grid cudaMalloc(%zu + %zu): %s", off_bytes, item_bytes, cudaGetErrorString(ge2));
+            sc->device_bytes += off_bytes + item_bytes;
+            ds.eg_off = (uint32_t *)p_off; ds.eg_items = (uint32_t *)p_items;
             double clo[3] = { HUGE_VAL, HUGE_VAL, HUGE_VAL }, chi[3] = { -HUGE_VAL, -HUGE_VAL, -HUGE_VAL };
             for (uint32_t i = 0; i < ns; ++i)
                 for (int a = 0; a < 3; ++a) { clo[a] = std::min(clo[a], sph[4 * (size_t)i + a]); chi[a] = std::max(chi[a], sph[4 * (size_t)i + a]); }

@@ -284,10 +284,10 @@ __device__ __forceinline__ void primary_query_start(const Ctx<R, true> &c, BvhQu
             const float fu = ((dx * g1.z + dy * g1.w + dz * g2.x) * iw - g3.x) * g3.z, fv = ((dx * g2.y + dy * g2.z + dz * g2.w) * iw - g3.y) * g3.w;
             const float kf = (float)kb.x;
             if (!(fu >= 0.0f && fv >= 0.0f && fu < kf && fv < kf)) return;
-            const unsigned cell = kb.y + (unsigned)fv * kb.x + (unsigned)fu;
-            const uint32_t i0 = __ldg(s.sg_off + cell), i1 = __ldg(s.sg_off + cell + 1);
+            const unsigned cell = (unsigned)fv * kb.x + (unsigned)fu;
+            const uint32_t i0 = __ldg(s.eg_off + cell), i1 = __ldg(s.eg_off + cell + 1);
             for (uint32_t i = i0; i < i1; ++i) {
-                const int idx = (int)__ldg(s.sg_items + s.eg_items_base + i);
+                const int idx = (int)__ldg(s.eg_items + i);
                 R p[4], t;
                 c.ld_sph((unsigned)idx, p);
                 k.sph++;

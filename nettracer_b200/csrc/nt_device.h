@@ -115,7 +115,8 @@ struct NtDevScene {
     const NtBvhNode4 *nodes;
     // The same construction for PRIMARY rays: grid nl of sgrid is built on the device at the start of every render call from
     // that call's eye (nt_eyegrid.cuh) - a primary ray tests the spheres its cell lists and walks only the triangle set.
-    uint32_t eg_on, eg_k0, eg_off_base, eg_items_base, eg_items_cap; // off_base: index into sg_off of the grid's K0*K0 + 2 offsets
+    uint32_t eg_on, eg_k0, eg_items_cap;
+    uint32_t *eg_off, *eg_items; // the eye grid's own K0*K0 + 2 offsets (+ 1024 block totals of the scan) and item room (device-only memory)
     float sph_lo[3], sph_hi[3];  // bounds of the sphere CENTRES (the projection's axis points from the eye to their middle)
     double *eg_boxes;            // [ns][4] scratch: projected rectangle of every sphere for the current eye
     unsigned long long *eg_acc;  // [8] scratch: bounds (ordered doubles) umin umax vmin vmax, invalid flag

@@ -75,7 +75,7 @@ static __global__ void eg_setup_kernel(const __grid_constant__ NtDevScene s, con
     for (int k = 0; k < 3; ++k) { g->L[k] = (float)b.L[k]; g->axis[k] = (float)b.axis[k]; g->U[k] = (float)b.U[k]; g->V[k] = (float)b.V[k]; }
     g->u0 = (float)umin; g->v0 = (float)vmin;
     g->su = (float)((double)K / du); g->sv = (float)((double)K / dv);
-    g->K = K; g->base = s.eg_off_base; g->valid = 0; g->pad = 0;
+    g->K = K; g->base = 0; g->valid = 0; g->pad = 0;
 }
 
 // The cells of a sphere's widened rectangle, as nt_shadowgrid.cpp computes them.
@@ -91,8 +91,8 @@ static __global__ void eg_count_fill_kernel(const __grid_constant__ NtDevScene s
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= s.ns || s.eg_acc[4]) return;
     const NtShadowGrid *g = s.sgrid + s.nl;
-    uint32_t *off = const_cast<uint32_t *>(s.sg_off) + s.eg_off_base + 1; // shifted by one: see the header
-    uint32_t *items = const_cast<uint32_t *>(s.sg_items) + s.eg_items_base;
+    uint32_t *off = s.eg_off + 1; // shifted by one: see the header
+    uint32_t *items = s.eg_items;
     int u0, u1, v0, v1;
     eg_cells(s, g, i, u0, u1, v0, v1);
     const unsigned K = g->K;
@@ -161,7 +161,7 @@ inline int launch_eye_grid(const NtDevScene &s, const double *eye, cudaStream_t 
     const double V[3] = { ax[1] * U[2] - ax[2] * U[1], ax[2] * U[0] - ax[0] * U[2], ax[0] * U[1] - ax[1] * U[0] };
     for (int k = 0; k < 3; ++k) { b.axis[k] = ax[k]; b.U[k] = U[k]; b.V[k] = V[k]; }
     const size_t cells = (size_t)s.eg_k0 * s.eg_k0;
-    uint32_t *off = const_cast<uint32_t *>(s.sg_off) + s.eg_off_base;
+    uint32_t *off = s.eg_off;
     cudaMemsetAsync(off, 0, sizeof(uint32_t) * (cells + 2), st);
     eg_init_kernel<<<1, 8, 0, st>>>(s.eg_acc);
     const unsigned T = 256, nb = (s.ns + T - 1) / T, sb = (unsigned)(cells / 1024);
