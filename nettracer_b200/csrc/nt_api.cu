@@ -412,8 +412,7 @@ static int scene_create_impl(const nt_scene_desc *d, int device, nt_scene *sc) {
         grids.resize((size_t)nl + 1, NtShadowGrid{});
         ds.eg_off = nullptr; ds.eg_items = nullptr; ds.eg_boxes = nullptr; ds.eg_acc = nullptr; ds.eg_items_cap = 0; ds.eg_k0 = 0;
         if (ds.eg_on) {
-            uint32_t k0 = 64;
-            while (k0 < 1024 && (double)k0 < 4.0 * std::sqrt((double)ns)) k0 *= 2;
+            const uint32_t k0 = nt_shadow_grid_k0(ns);
             ds.eg_k0 = k0;
             ds.eg_items_cap = (uint32_t)std::min<size_t>(std::max<size_t>(48 * (size_t)ns, 65536), (size_t)1 << 30);
             const size_t off_bytes = sizeof(uint32_t) * ((size_t)k0 * k0 + 2 + 1024), item_bytes = sizeof(uint32_t) * (size_t)ds.eg_items_cap;

@@ -2,9 +2,18 @@
 #include "nt_shadowgrid.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace {
 struct Rect { int u0, u1, v0, v1; };
+}
+
+uint32_t nt_shadow_grid_k0(uint32_t ns) {
+    double mul = 4.0; // cells per axis ~ mul x sqrt(number of spheres); NT_GRID_KMUL: A/B
+    if (const char *e = getenv("NT_GRID_KMUL")) { const double v = atof(e); if (v >= 0.5 && v <= 64.0) mul = v; }
+    uint32_t k = 64;
+    while (k < 1024 && (double)k < mul * std::sqrt((double)ns)) k *= 2;
+    return k;
 }
 
 int nt_shadow_grids_build(const double *sph, uint32_t ns, const double *lights, uint32_t nl, double max_abs,
@@ -15,8 +24,7 @@ int nt_shadow_grids_build(const double *sph, uint32_t ns, const double *lights, 
     double lo[3] = { HUGE_VAL, HUGE_VAL, HUGE_VAL }, hi[3] = { -HUGE_VAL, -HUGE_VAL, -HUGE_VAL };
     for (uint32_t i = 0; i < ns; ++i)
         for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], sph[4 * (size_t)i + a]); hi[a] = std::max(hi[a], sph[4 * (size_t)i + a]); }
-    uint32_t K0 = 64;
-    while (K0 < 1024 && (double)K0 < 4.0 * std::sqrt((double)ns)) K0 *= 2;
+    const uint32_t K0 = nt_shadow_grid_k0(ns);
     int n_valid = 0;
     std::vector<double> box(4 * (size_t)ns);
     std::vector<Rect> rect(ns);

@@ -21,3 +21,5 @@
 // light, and the concatenated offsets / items of all valid lights.  Returns the number of valid grids.
 int nt_shadow_grids_build(const double *sph, uint32_t ns, const double *lights, uint32_t nl, double max_abs,
                           std::vector<NtShadowGrid> &grids, std::vector<uint32_t> &off, std::vector<uint32_t> &items);
+// Cells per axis of a grid over ns spheres before the per-grid coarsening: a power of two in 64 .. 1024, ~4 sqrt(ns).
+uint32_t nt_shadow_grid_k0(uint32_t ns);
