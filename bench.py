@@ -499,8 +499,8 @@ def main():
                                 "rank 0's clock")},
                 "gpu_launches": a.steps * r["launches"],
                 "gpu_launches_note": "per frame on rank 0, counted by the library (nt_scene_info): flat scenes 1 render kernel (exchange flags "
-                                     "are posted inside it); BVH scenes the wavefront pipeline's kernels per level and chunk + sum + "
-                                     "resolve; + 1 flag-wait kernel on rank 0 when n_gpus > 1 (p2p_store) / + deinterleave (gather)",
+                                     "are posted inside it); BVH scenes the 8 small kernels of the eye grid + the wavefront pipeline's kernels per level and chunk "
+                                     "+ sum + resolve; + 1 flag-wait kernel on rank 0 when n_gpus > 1 (p2p_store) / + deinterleave (gather)",
                 "kernel_ms": r["kernel_ms"], "wall_s_timed_region": r["wall"], "clocks": clocks, "roofline": roof}
         if not a.no_frame_check:
             line["frame_check"] = frame_check(r)
