@@ -36,6 +36,9 @@
                                // (profiles/r04_wf_sort.txt); with them the shadow passes are half as long and the sort no longer pays: 38.4 / 39.3
 #endif
 
+#ifndef NT_WF_REFILL_SHADOW
+#define NT_WF_REFILL_SHADOW NT_WF_REFILL // the occlusion passes' own threshold (their walks are short since the shadow grids): 12 / 20 / 26 -> 39.3 / 38.2 / 38.2 ms
+#endif
 #ifndef NT_WF_EARLY_RETIRE
 #define NT_WF_EARLY_RETIRE 1
 #endif
@@ -168,6 +171,7 @@ wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
     c.s = &s; c.v = &v; c.eps = (R)a.eps; c.eps_lo = (R)a.eps_lo; c.max_depth = a.max_depth; c.rules = a.rules;
     stage_scene<R, true>(s, v, c);
     const unsigned lane = threadIdx.x & 31;
+    constexpr int REFILL = SHADOW ? NT_WF_REFILL_SHADOW : NT_WF_REFILL;
     const NtWfLevel &L = w.lv[w.level - 1];
     const unsigned n_rec = CONEPASS ? min(*w.cone_count, w.sweep_cap) : w.level == 1 ? w.n_samples : w.counts[w.level];
     const unsigned long long n_tasks = SHADOW ? (((unsigned long long)n_rec + 31) / 32) * 32 * s.nl : n_rec;
@@ -188,7 +192,7 @@ wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
     for (;;) {
         // ---- refill: idle lanes pull tasks, one atomic per warp ----
         const unsigned idle = __ballot_sync(0xffffffffu, !active);
-        if (!exhausted && (__popc(idle) >= NT_WF_REFILL || idle == 0xffffffffu)) {
+        if (!exhausted && (__popc(idle) >= REFILL || idle == 0xffffffffu)) {
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(cursor, (unsigned long long)__popc(idle));
             base = __shfl_sync(0xffffffffu, base, 0);
@@ -282,7 +286,7 @@ wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
         }
         // sparse tasks - records that hit nothing, lights behind the surface, samples of the last ragged tile start no query -:
         // pull again before walking, or the warp walks with whatever share of its lanes the list happened to fill
-        if (NT_WF_REPULL && !exhausted && __popc(~started) >= NT_WF_REFILL) continue;
+        if (NT_WF_REPULL && !exhausted && __popc(~started) >= REFILL) continue;
         // ---- traversal rounds (as in render_bvh_kernel) until enough lanes have finished ----
         for (;;) {
             for (;;) {
@@ -329,7 +333,7 @@ wf_trace_kernel(const __grid_constant__ NtDevScene s, const __grid_constant__ Nt
                 }
             }
             const unsigned parked = __ballot_sync(0xffffffffu, !active || q.done);
-            if (parked == 0xffffffffu || (!exhausted && __popc(parked) >= NT_WF_REFILL)) break;
+            if (parked == 0xffffffffu || (!exhausted && __popc(parked) >= REFILL)) break;
         }
         // ---- retire finished queries ----
         if (active && q.done) {
